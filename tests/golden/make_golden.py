@@ -1,0 +1,97 @@
+"""Generate the golden fixtures by running the UNMODIFIED reference (``/root/reference``).
+
+Run in the build container only:  ``python tests/golden/make_golden.py``  (writes tests/golden/*.npz).
+The reference is imported through ``refshim`` (numexpr / matplotlib / trimesh stand-ins); nothing of
+it is copied.  Live (scaled) solver state is captured non-invasively: ``RunningHistory.record`` is
+called exactly once per iteration from ``solver_socp``'s own frame (socp/solver_socp.py:746), so the
+caller's locals expose every iterate.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, HERE)
+
+from dots_socp_b200 import synth  # noqa: E402
+import refshim  # noqa: E402
+
+STATE = ("phi", "A", "B", "lambda_c", "mu", "E", "z_fst", "z_mid", "z_end", "beta_fst", "beta_mid", "beta_end")
+SCALARS = ("r", "scale_factor_z", "constant_d")
+
+
+def run_reference(geo, n_time, snap_its=(), **kw):
+    refshim.load()
+    from dot_surface_socp.socp.solver_socp import solver_socp
+    from dot_surface_socp.utils import admm_tools
+
+    snaps, r_hist = {}, {}
+    orig = admm_tools.RunningHistory.record
+
+    def spy(self, current_it=None, kkt_errors=None, history=None):
+        loc = sys._getframe(1).f_locals
+        if current_it not in r_hist and "counter_main" in loc:
+            r_hist[current_it] = float(loc["r"])
+            if current_it in snap_its:
+                d = {k: np.array(loc[k], copy=True) for k in STATE}
+                d.update({k: float(loc[k]) for k in SCALARS})
+                snaps[current_it] = d
+        return orig(self, current_it=current_it, kkt_errors=kkt_errors, history=history)
+
+    admm_tools.RunningHistory.record = spy
+    cwd = os.getcwd()
+    try:
+        sol, hist = solver_socp(n_time, geo, **kw)
+    finally:
+        admm_tools.RunningHistory.record = orig
+        os.chdir(cwd)
+    return sol, hist, snaps, r_hist
+
+
+CASES = {
+    # name: (example, example kwargs, n_time, solver kwargs, snapshot iterations, keep full final solution)
+    "ico2_nt7_c0": ("icosphere2", {}, 7, dict(tol=1e-3, nit=1000), (0, 1, 4, 49), True),
+    "ico2_nt7_c01": ("icosphere2", {}, 7, dict(tol=1e-3, nit=1000, congestion=0.1), (0, 1, 4, 49), True),
+    "plane8_nt6_c0": ("plane8", {}, 6, dict(tol=1e-3, nit=1000), (0, 9), False),
+    "knot_small_nt8_c005": ("knot", dict(n_u=40, n_v=6), 8, dict(tol=1e-3, nit=600, congestion=0.05), (0, 9), False),
+    "ico2_nt15_tol1e-4": ("icosphere2", {}, 15, dict(tol=1e-4, nit=3000), (), False),
+    "ico3_nt31_c0": ("icosphere3", {}, 31, dict(tol=1e-3, nit=1000), (), False),
+    "ico3_nt31_c01": ("icosphere3", {}, 31, dict(tol=1e-3, nit=1000, congestion=0.1), (), False),
+}
+
+
+def main(only=None):
+    for name, (ex, exkw, n_time, kw, snap_its, keep_full) in CASES.items():
+        if only and name not in only:
+            continue
+        geo, scale = synth.example(ex, **exkw)
+        sol, hist, snaps, r_hist = run_reference(geo, n_time, snap_its, **kw)
+        out = dict(
+            vertices=geo["vertices"], triangles=geo["triangles"], mu0=geo["mu0"], mu1=geo["mu1"],
+            n_time=n_time, scale_factor=scale,
+            kw_keys=np.array(list(kw.keys())), kw_vals=np.array([float(v) for v in kw.values()]),
+            iterations=int(hist.kkt_iteration[-1]),
+            kkt_rows=hist.kkt_errors, kkt_iteration=hist.kkt_iteration,
+            r_history=np.array([r_hist[i] for i in sorted(r_hist)]),
+            cost=hist.history["Transportation cost"][-1], objective=hist.history["Objective value"][-1],
+            sol_mu=sol["mu"], sol_phi_grad_t=np.diff(sol["phi"], axis=0),
+        )
+        if keep_full:
+            for k in STATE:
+                out["sol_" + k] = sol[k]
+        for it, d in snaps.items():
+            for k, v in d.items():
+                out[f"it{it}_{k}"] = v
+        out["snap_its"] = np.array(sorted(snaps), dtype=np.int64)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: V={geo['vertices'].shape[0]} iterations={out['iterations']} cost={out['cost']:.12e} "
+              f"-> {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

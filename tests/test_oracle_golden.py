@@ -1,0 +1,88 @@
+"""Pin the CPU oracle (oracle/alm_oracle.py) to outputs of the unmodified reference.
+
+Fixtures: tests/golden/*.npz, written by tests/golden/make_golden.py from /root/reference."""
+import numpy as np
+import pytest
+
+from oracle import alm_oracle as orc
+
+ORACLE_NAMES = dict(phi="phi", A="A", B="B", lambda_c="lam_c", mu="mu", E="E", z_fst="z_fst", z_mid="z_mid",
+                    z_end="z_end", beta_fst="b_fst", beta_mid="b_mid", beta_end="b_end")
+
+
+def rel_err(a, b):
+    scale = max(np.abs(b).max(), 1e-300)
+    return np.abs(a - b).max() / scale
+
+
+def phi_mod_const(phi):
+    return phi - phi.mean()
+
+
+@pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005"])
+def test_iterates_match_reference(golden, name):
+    z, geo, n_time, kw = golden(name)
+    snap_its = [int(i) for i in z["snap_its"]]
+    got = {}
+
+    def trace(it, alm):
+        if it in snap_its:
+            got[it] = (alm.state(), alm.r, alm.s, alm.d)
+
+    sol, info = orc.solve(n_time, geo, trace=trace, **kw)
+    assert info["iterations"] == int(z["iterations"])
+    for it in snap_its:
+        st, r, s, d = got[it]
+        assert r == pytest.approx(float(z[f"it{it}_r"]), rel=1e-12)
+        assert s == float(z[f"it{it}_scale_factor_z"]) and d == float(z[f"it{it}_constant_d"])
+        for ref_name, my_name in ORACLE_NAMES.items():
+            a, b = st[my_name], z[f"it{it}_{ref_name}"]
+            if ref_name == "phi":
+                a, b = phi_mod_const(a), phi_mod_const(b)
+            assert rel_err(a, b) < 1e-9, (it, ref_name, rel_err(a, b))
+    assert info["cost"] == pytest.approx(float(z["cost"]), rel=1e-9)
+    assert info["objective"] == pytest.approx(float(z["objective"]), rel=1e-9)
+    assert rel_err(sol["mu"], z["sol_mu"]) < 1e-8
+    if "sol_z_mid" in z:
+        for ref_name in ORACLE_NAMES:
+            a, b = sol[ref_name], z["sol_" + ref_name]
+            if ref_name == "phi":
+                a, b = phi_mod_const(a), phi_mod_const(b)
+            assert rel_err(a, b) < 1e-8, ref_name
+
+
+@pytest.mark.parametrize("name", ["ico2_nt15_tol1e-4", "ico3_nt31_c0", "ico3_nt31_c01"])
+def test_schedule_and_history_match_reference(golden, name):
+    """Iteration count, which KKT conditions were evaluated when (nan pattern), their values, penalty path, cost."""
+    z, geo, n_time, kw = golden(name)
+    sol, info = orc.solve(n_time, geo, **kw)
+    assert info["iterations"] == int(z["iterations"])
+    ref_rows = z["kkt_rows"]
+    my_rows = info["kkt_rows"].copy()
+    my_rows[-1] = info["final_kkt"]                       # the reference overwrites the last row with the full final check
+    assert my_rows.shape == ref_rows.shape
+    assert np.array_equal(np.isnan(my_rows), np.isnan(ref_rows))
+    m = ~np.isnan(ref_rows)
+    assert np.allclose(my_rows[m], ref_rows[m], rtol=1e-6, atol=1e-12)
+    assert np.allclose(info["r_history"], z["r_history"], rtol=1e-12)
+    assert info["cost"] == pytest.approx(float(z["cost"]), rel=1e-8)
+    assert rel_err(sol["mu"], z["sol_mu"]) < 1e-7
+
+
+def test_operator_identities():
+    """Adjointness / structure checks the survey lists on a small icosphere."""
+    from dots_socp_b200 import synth
+    geo, _ = synth.example("icosphere1")
+    ops = orc.MeshOps(5, geo, build_inverse=False)
+    rng = np.random.default_rng(1)
+    b = rng.standard_normal((6, ops.T, 3))
+    x = rng.standard_normal((5, 2, 3, ops.T, 3))
+    assert np.sum(orc.decouple(b, 1.7) * x) == pytest.approx(np.sum(b * orc.decouple_adjoint(x, 1.7)), rel=1e-12)
+    assert np.allclose(orc.adjoint_time_average(np.array([[1.], [2.], [3.], [4.]]))[:, 0], [0.5, 1.5, 2.5, 3.5, 2.0])
+    m = rng.standard_normal((5, ops.V)); p = rng.standard_normal((6, ops.V))
+    assert np.sum(orc.grad_time(ops.dt, p) * m) == pytest.approx(-np.sum(p * orc.div_time(ops.dt, m)), rel=1e-12)
+    # L = D diag(area_f x 1_3) G, symmetric, zero row sums
+    W = np.repeat(ops.area_f, 3)
+    L2 = ops.D @ (ops.G.multiply(W[:, None])).tocsr()
+    assert abs(L2 - ops.L).max() < 1e-13
+    assert abs(ops.L @ np.ones(ops.V)).max() < 1e-12
