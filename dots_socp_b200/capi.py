@@ -1,0 +1,90 @@
+"""ctypes binding of libdots_b200.so (C-ABI declared in include/dots_b200.h).
+
+The library is the product: there is NO fallback.  ``load()`` raises if the shared object is missing
+or its ABI does not match this mirror of ``dots_ctx_t``."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+ABI_VERSION = 1
+P_R, P_S, P_D, P_CONG, P_TAU, P_EPS, P_COUNT = 0, 1, 2, 3, 4, 5, 8
+
+_i32p, _i64p, _f64p = C.c_void_p, C.c_void_p, C.c_void_p      # raw device/host addresses
+
+
+class DotsCtx(C.Structure):
+    """Field order mirrors ``struct dots_ctx`` exactly (checked against dots_ctx_sizeof() at load)."""
+    _fields_ = (
+        [(n, C.c_int32) for n in ("abi_version", "n_time", "n_vert", "n_tri", "m_pad", "n_nodes", "n_levels", "n_sm")]
+        + [(n, C.c_void_p) for n in (
+            "tri", "hat_grad", "area_f", "area_v", "diag_soc", "vc_ptr", "vc_idx", "qmat",
+            "panels", "nd_off", "nd_s", "nd_b", "nd_child", "nd_panel", "nd_front", "nd_upd",
+            "front_idx", "child_pos", "lvl_ptr", "lvl_items", "lvb_ptr", "lvb_items", "h_lvl_ptr", "h_lvb_ptr")]
+        + [("front_total", C.c_int64)]
+        + [(n, C.c_void_p) for n in (
+            "params", "phi", "A", "lam_c", "mu", "z_fst", "z_end", "b_fst", "b_end", "lam",
+            "bnd0", "bnd1", "B", "E", "b_mid", "z_mid", "corner_nrm", "corner_div",
+            "rhs", "hat", "ywork", "upd", "red_part", "red_out")]
+        + [("red_blocks", C.c_int32), ("reserved0", C.c_int32)]
+    )
+
+
+class DotsError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True):
+    """Load (building with nvcc first when the .so is absent or stale and ``build_if_missing``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if build_if_missing and _build.needs_build():
+        try:
+            _build.build()
+        except Exception as exc:                      # no nvcc on the box: use the shipped .so if there is one
+            if not os.path.exists(path):
+                raise DotsError(f"libdots_b200.so is missing and could not be built: {exc}") from exc
+    if not os.path.exists(path):
+        raise DotsError(f"{path} not found: run `python -m dots_socp_b200.build` (the CUDA library is required)")
+    lib = C.CDLL(path)
+    lib.dots_last_error.restype = C.c_char_p
+    if lib.dots_abi_version() != ABI_VERSION:
+        raise DotsError(f"ABI mismatch: library {lib.dots_abi_version()} binding {ABI_VERSION}")
+    if lib.dots_ctx_sizeof() != C.sizeof(DotsCtx):
+        raise DotsError(f"dots_ctx_t size mismatch: library {lib.dots_ctx_sizeof()} binding {C.sizeof(DotsCtx)}")
+    ctxp, vp, i, d = C.POINTER(DotsCtx), C.c_void_p, C.c_int, C.c_double
+    protos = {
+        "dots_step_phi": (ctxp, vp), "dots_step_vertex": (ctxp, vp), "dots_step_tri": (ctxp, i, vp),
+        "dots_iterate": (ctxp, i, i, vp), "dots_refresh_corner_terms": (ctxp, vp),
+        "dots_scale_dual": (ctxp, d, vp), "dots_scale_z": (ctxp, d, vp), "dots_set_params": (ctxp, vp, vp),
+        "dots_kkt_sums": (ctxp, i, vp, vp), "dots_phi_rhs": (ctxp, vp), "dots_time_transform": (ctxp, i, vp),
+        "dots_mode_solves": (ctxp, vp), "dots_grad_space": (ctxp, vp, vp, vp), "dots_div_space": (ctxp, vp, vp, vp),
+    }
+    for name, args in protos.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = list(args), C.c_int
+    _lib = lib
+    return lib
+
+
+EXPORTS = ("dots_abi_version", "dots_ctx_sizeof", "dots_last_error", "dots_step_phi", "dots_step_vertex",
+           "dots_step_tri", "dots_iterate", "dots_refresh_corner_terms", "dots_scale_dual", "dots_scale_z",
+           "dots_set_params", "dots_kkt_sums", "dots_phi_rhs", "dots_time_transform", "dots_mode_solves",
+           "dots_grad_space", "dots_div_space")
+
+
+def check(code: int, what: str = ""):
+    if code != 0:
+        msg = load().dots_last_error()
+        raise DotsError(f"{what} failed with code {code}: {msg.decode() if msg else ''}")

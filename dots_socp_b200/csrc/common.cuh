@@ -1,0 +1,61 @@
+// Shared helpers for the dots_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/dots_b200.h"
+
+#define DOTS_ERR_BAD_ARG (-1)
+#define DOTS_ERR_ABI (-2)
+
+void dots_set_error(const char *fmt, ...);
+
+#define DOTS_CUDA(call)                                                                          \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            dots_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return (int)e__;                                                                     \
+        }                                                                                        \
+    } while (0)
+
+#define DOTS_LAUNCH_CHECK() DOTS_CUDA(cudaGetLastError())
+
+static inline int dots_check_ctx(const dots_ctx_t *c)
+{
+    if (!c) { dots_set_error("null context"); return DOTS_ERR_BAD_ARG; }
+    if (c->abi_version != DOTS_ABI_VERSION) { dots_set_error("abi mismatch: ctx %d lib %d", c->abi_version, DOTS_ABI_VERSION); return DOTS_ERR_ABI; }
+    if (c->m_pad % 32 != 0 || c->m_pad < c->n_time + 1 || c->m_pad > 128) { dots_set_error("m_pad=%d unsupported (multiple of 32, >= nT+1, <= 128)", c->m_pad); return DOTS_ERR_BAD_ARG; }
+    return 0;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// np.clip semantics: NaN passes through (fmin/fmax would drop it)
+__device__ __forceinline__ double clip01(double x) { return x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x); }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Fixed-order block reduction of NS partial sums per thread; result row written to part[blockIdx.x*8 + slot0 + i].
+template <int NS>
+__device__ __forceinline__ void block_reduce_store(double (&acc)[NS], double *part, int slot0)
+{
+    __shared__ double sm[32][NS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        double v = warp_sum(acc[i]);
+        if (lane == 0) sm[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NS) {
+        double v = 0.0;
+        for (int w = 0; w < nw; ++w) v += sm[w][threadIdx.x];
+        part[(size_t)blockIdx.x * 8 + slot0 + threadIdx.x] = v;
+    }
+}

@@ -1,0 +1,419 @@
+// Fused per-iteration kernels of the inexact semi-proximal ALM (reference: socp/solver_socp.py:656-823).
+//
+// One iteration of the reference touches the 18-wide corner arrays z_mid / beta_mid seven times
+// (projection :988-1042, q-step :1044-1065, multiplier step :716-722).  Here the three steps are
+// re-associated by *where* their data lives:
+//
+//   k_phi_rhs  per (t,v)   : right-hand side of the space-time Laplacian (:976-986)
+//   k_vertex   per (t,v)   : everything that is local to a (time, vertex) pair once the cone norm is
+//                            known: dt_phi, lam, z_fst, z_end (:1017-1042), A, lam_c (:1056-1065),
+//                            mu, beta_fst, beta_end (:718-722)
+//   k_tri      per (tau,f) : everything local to a (time level, triangle) pair: dx_phi (:898-907),
+//                            z_mid (:1041), the adjoint sum (:944-959), B (:1064), E, beta_mid (:719-721)
+//                            and the two corner by-products the NEXT iteration needs - the squared cone
+//                            norms per corner (:998-1014) and the divergence terms per corner (:980).
+//
+// so beta_mid is read once and written once per iteration.  All arithmetic is fp64 and keeps the
+// reference's expression order inside each formula.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// rhs[t][v] = div_t((A + lam_c - mu) area_v) + D((B - E) area_f) - boundary - eps area_v phi      (:979-986)
+__global__ void __launch_bounds__(256) k_phi_rhs(dots_ctx_t c)
+{
+    const int V = c.n_vert, nT = c.n_time, T = c.n_tri;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (v >= V) return;
+    const double dt = 1.0 / nT;
+    const double av = c.area_v[v];
+    const double eps = c.params[DOTS_P_EPS];
+    double divt;
+    if (t == 0) {
+        const size_t i = v;
+        divt = ((c.A[i] + c.lam_c[i] - c.mu[i]) * av) / dt;                                   // :893
+    } else if (t == nT) {
+        const size_t i = (size_t)(nT - 1) * V + v;
+        divt = -((c.A[i] + c.lam_c[i] - c.mu[i]) * av) / dt;                                  // :894
+    } else {
+        const size_t i1 = (size_t)t * V + v, i0 = i1 - V;
+        divt = ((c.A[i1] + c.lam_c[i1] - c.mu[i1]) * av - (c.A[i0] + c.lam_c[i0] - c.mu[i0]) * av) / dt;   // :892
+    }
+    const double *cd = c.corner_div + (size_t)t * 3 * T;
+    double divx = 0.0;
+    for (int q = c.vc_ptr[v], qe = c.vc_ptr[v + 1]; q < qe; ++q) divx += cd[c.vc_idx[q]];
+    const double bnd = (t == 0) ? c.bnd0[v] : ((t == nT) ? c.bnd1[v] : 0.0);
+    const size_t o = (size_t)t * V + v;
+    c.rhs[o] = divt + divx - bnd - eps * av * c.phi[o];
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_vertex(dots_ctx_t c)
+{
+    const int V = c.n_vert, nT = c.n_time, T = c.n_tri;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;                       // 0 .. nT-1
+    if (v >= V) return;
+    const double *prm = c.params;
+    const double r = prm[DOTS_P_R], s = prm[DOTS_P_S], d = prm[DOTS_P_D], cong = prm[DOTS_P_CONG], tau = prm[DOTS_P_TAU];
+    const double dt = 1.0 / nT;
+    const size_t i = (size_t)t * V + v;
+
+    const double dtphi = (c.phi[i + V] - c.phi[i]) / dt;                                      // :884
+
+    // cone norm: corners contribute their side-0 part at level t and their side-1 part at level t+1
+    const double *n0 = c.corner_nrm + ((size_t)t * 2 + 0) * 3 * T;
+    const double *n1 = c.corner_nrm + ((size_t)(t + 1) * 2 + 1) * 3 * T;
+    double nsq = 0.0;
+    for (int q = c.vc_ptr[v], qe = c.vc_ptr[v + 1]; q < qe; ++q) {
+        const int cid = c.vc_idx[q];
+        nsq += n0[cid] + n1[cid];                                                             // :1004-1016
+    }
+    const double A0 = c.A[i], bf = c.b_fst[i], be = c.b_end[i], mu0 = c.mu[i];
+    const double p = d - s * A0 - bf;                                                         // :997
+    const double e = d + s * A0 - be;                                                         // :999
+    const double nrm = sqrt(nsq + e * e);                                                     // :1017
+    const double lam = clip01(0.5 * (1.0 + p / nrm));                                         // :1018
+    const double zf = (lam >= 1.0) ? p : lam * nrm;                                           // :1040
+    const double ze = lam * e;                                                                // :1042
+
+    const double c1 = s * (1.0 + cong * r);                                                   // :1049
+    const double c2 = 1.0 + 2.0 * s * c1;                                                     // :1050
+    const double memo_a = dtphi + mu0;                                                        // :1051
+    const double An = (1.0 / c2) * memo_a + (c1 / c2) * (ze + be - zf - bf);                  // :1062
+    const double lc = (cong * r / (1. + cong * r)) * (memo_a - An);                           // :1065
+
+    c.lam[i] = lam;
+    c.z_fst[i] = zf;
+    c.z_end[i] = ze;
+    c.A[i] = An;
+    c.lam_c[i] = lc;
+    c.mu[i] = mu0 + tau * (dtphi - An - lc);                                                  // :718
+    c.b_fst[i] = bf + tau * (zf + s * An - d);                                                // :720
+    c.b_end[i] = be + tau * (ze - s * An - d);                                                // :722
+}
+
+// ------------------------------------------------------------------------------------------------
+// MODE 0: full step.  MODE 1: full step + store z_mid.  MODE 2: only recompute corner_nrm / corner_div.
+template <int MODE>
+__global__ void __launch_bounds__(128) k_tri(dots_ctx_t c)
+{
+    const int V = c.n_vert, nT = c.n_time;
+    const size_t T = (size_t)c.n_tri;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tau = blockIdx.y;                     // 0 .. nT
+    if (f >= c.n_tri) return;
+    const double *prm = c.params;
+    const double s = prm[DOTS_P_S], step = prm[DOTS_P_TAU];
+    const double cs = s / sqrt(3.0);                                                          // :932, :953
+    const bool has0 = tau < nT, has1 = tau > 0;
+
+    double g[3][3], dg[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        dg[k] = c.diag_soc[k * T + f];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) g[k][x] = c.hat_grad[(k * 3 + x) * T + f];
+    }
+    const double af = c.area_f[f];
+    double *Bp = c.B + (size_t)tau * 3 * T + f;
+    double *Ep = c.E + (size_t)tau * 3 * T + f;
+    double *bm = c.b_mid + (size_t)tau * 18 * T + f;
+    double Bn[3], En[3];
+    double beta[2][3][3];
+#pragma unroll
+    for (int sd = 0; sd < 2; ++sd)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) beta[sd][k][x] = 0.0;
+
+    if (MODE == 2) {
+#pragma unroll
+        for (int x = 0; x < 3; ++x) { Bn[x] = Bp[x * T]; En[x] = Ep[x * T]; }
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            if (sd == 0 ? !has0 : !has1) continue;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int x = 0; x < 3; ++x) beta[sd][k][x] = bm[((sd * 3 + k) * 3 + x) * T];
+        }
+    } else {
+        const int vk[3] = {c.tri[f], c.tri[T + f], c.tri[2 * T + f]};
+        const double *ph = c.phi + (size_t)tau * V;
+        const double p0 = ph[vk[0]], p1 = ph[vk[1]], p2 = ph[vk[2]];
+        double lamk[2][3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lamk[0][k] = has0 ? c.lam[(size_t)tau * V + vk[k]] : 0.0;
+            lamk[1][k] = has1 ? c.lam[(size_t)(tau - 1) * V + vk[k]] : 0.0;
+        }
+        double Bo[3], Eo[3], dx[3], bs[3];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            Bo[x] = Bp[x * T];
+            Eo[x] = Ep[x * T];
+            dx[x] = g[0][x] * p0 + g[1][x] * p1 + g[2][x] * p2;                               // :902-906
+            bs[x] = cs * Bo[x];                                                               // :932
+        }
+        double z[2][3][3];
+        double adj[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            if (sd == 0 ? !has0 : !has1) continue;
+            double sum[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double lt = lamk[sd][k] / dg[k];                                        // :1023
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    const double b = bm[((sd * 3 + k) * 3 + x) * T];
+                    beta[sd][k][x] = b;
+                    const double w = dg[k] * (bs[x] - b);                                     // :998
+                    const double zz = lt * w;                                                 // :1041
+                    z[sd][k][x] = zz;
+                    const double zb = zz + b;                                                 // :1052
+                    sum[x] = (k == 0) ? zb : sum[x] + zb;                                     // np.sum(axis=2) :953
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < 3; ++x) adj[x] = (sd == 0 || !has0) ? cs * sum[x] : adj[x] + cs * sum[x];   // :953-957
+        }
+        const double db = (tau == 0 || tau == nT) ? (1.0 + s * s) : (1.0 + (2.0 * s * s));    // :195-197
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            Bn[x] = (dx[x] + Eo[x] + adj[x]) / db;                                            // :1064
+            En[x] = Eo[x] + step * (dx[x] - Bn[x]);                                           // :719
+            Bp[x * T] = Bn[x];
+            Ep[x * T] = En[x];
+        }
+        double *zm = c.z_mid + (size_t)tau * 18 * T + f;
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            if (sd == 0 ? !has0 : !has1) continue;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    const double bnew = beta[sd][k][x] + step * (z[sd][k][x] - cs * Bn[x]);   // :717, :721
+                    beta[sd][k][x] = bnew;
+                    bm[((sd * 3 + k) * 3 + x) * T] = bnew;
+                    if (MODE == 1) zm[((sd * 3 + k) * 3 + x) * T] = z[sd][k][x];
+                }
+        }
+    }
+
+    // by-products for the next iteration, from the updated (B, E, beta_mid)
+    double *cn = c.corner_nrm + (size_t)tau * 6 * T + f;
+#pragma unroll
+    for (int sd = 0; sd < 2; ++sd) {
+        const bool has = (sd == 0) ? has0 : has1;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double acc = 0.0;
+            if (has) {
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    const double w = dg[k] * (cs * Bn[x] - beta[sd][k][x]);                   // :995-998
+                    acc += w * w;                                                             // :1003-1014
+                }
+            }
+            cn[(sd * 3 + k) * T] = acc;
+        }
+    }
+    double *cd = c.corner_div + (size_t)tau * 3 * T + f;
+    double y[3];
+#pragma unroll
+    for (int x = 0; x < 3; ++x) y[x] = (Bn[x] - En[x]) * af;                                  // :980
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cd[k * T] = -(g[k][0] * y[0] + g[k][1] * y[1] + g[k][2] * y[2]);   // D = -G^T
+}
+
+// ------------------------------------------------------------------------------------------------
+// rescaling helpers (row a12)
+__global__ void k_div_scalar(double *__restrict__ a, size_t n, double f)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = a[i] / f;
+}
+__global__ void k_mul_scalar(double *__restrict__ a, size_t n, double f)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] *= f;
+}
+// mu = s (b_fst - b_end)                                                                      (:387)
+__global__ void k_mu_from_beta(dots_ctx_t c, double s)
+{
+    const size_t n = (size_t)c.n_time * c.n_vert;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        c.mu[i] = s * (c.b_fst[i] - c.b_end[i]);
+}
+// E = -decouple_adjoin_spacial(b_mid, s)                                                      (:388)
+__global__ void k_E_from_beta(dots_ctx_t c, double s)
+{
+    const size_t T = (size_t)c.n_tri;
+    const int nT = c.n_time;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tau = blockIdx.y;
+    if (f >= c.n_tri) return;
+    const double cs = s / sqrt(3.0);
+    const double *bm = c.b_mid + (size_t)tau * 18 * T + f;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+        double out = 0.0;
+        if (tau < nT) out = cs * ((bm[(0 * 3 + x) * T] + bm[(1 * 3 + x) * T]) + bm[(2 * 3 + x) * T]);
+        if (tau > 0) {
+            const double s1 = cs * ((bm[(9 + 0 * 3 + x) * T] + bm[(9 + 1 * 3 + x) * T]) + bm[(9 + 2 * 3 + x) * T]);
+            out = (tau < nT) ? out + s1 : s1;
+        }
+        c.E[((size_t)tau * 3 + x) * T + f] = -out;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// operator-level kernels on the internal layout (rows a5/a6): G phi and D x for all time levels
+__global__ void k_grad_space(dots_ctx_t c, const double *__restrict__ phi, double *__restrict__ out)
+{
+    const size_t T = (size_t)c.n_tri;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x, tau = blockIdx.y;
+    if (f >= c.n_tri) return;
+    const double *ph = phi + (size_t)tau * c.n_vert;
+    const double p0 = ph[c.tri[f]], p1 = ph[c.tri[T + f]], p2 = ph[c.tri[2 * T + f]];
+#pragma unroll
+    for (int x = 0; x < 3; ++x)
+        out[((size_t)tau * 3 + x) * T + f] = c.hat_grad[(0 * 3 + x) * T + f] * p0 + c.hat_grad[(1 * 3 + x) * T + f] * p1 + c.hat_grad[(2 * 3 + x) * T + f] * p2;
+}
+__global__ void k_div_space(dots_ctx_t c, const double *__restrict__ x, double *__restrict__ out)
+{
+    const size_t T = (size_t)c.n_tri;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x, tau = blockIdx.y;
+    if (v >= c.n_vert) return;
+    const double *xt = x + (size_t)tau * 3 * T;
+    double acc = 0.0;
+    for (int q = c.vc_ptr[v], qe = c.vc_ptr[v + 1]; q < qe; ++q) {
+        const int cid = c.vc_idx[q];
+        const size_t k = cid / T, f = cid - k * T;
+        acc += -(c.hat_grad[(k * 3 + 0) * T + f] * xt[f] + c.hat_grad[(k * 3 + 1) * T + f] * xt[T + f] + c.hat_grad[(k * 3 + 2) * T + f] * xt[2 * T + f]);
+    }
+    out[(size_t)tau * c.n_vert + v] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int dots_phi_rhs(const dots_ctx_t *c, void *stream)
+{
+    if (int e = dots_check_ctx(c)) return e;
+    dim3 grid(ceil_div(c->n_vert, 256), c->n_time + 1);
+    k_phi_rhs<<<grid, 256, 0, (cudaStream_t)stream>>>(*c);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_step_vertex(const dots_ctx_t *c, void *stream)
+{
+    if (int e = dots_check_ctx(c)) return e;
+    dim3 grid(ceil_div(c->n_vert, 256), c->n_time);
+    k_vertex<<<grid, 256, 0, (cudaStream_t)stream>>>(*c);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream)
+{
+    if (int e = dots_check_ctx(c)) return e;
+    dim3 grid(ceil_div(c->n_tri, 128), c->n_time + 1);
+    if (write_z) k_tri<1><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);
+    else k_tri<0><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_refresh_corner_terms(const dots_ctx_t *c, void *stream)
+{
+    if (int e = dots_check_ctx(c)) return e;
+    dim3 grid(ceil_div(c->n_tri, 128), c->n_time + 1);
+    k_tri<2><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+static int launch_div(double *a, size_t n, double f, int n_sm, cudaStream_t st)
+{
+    if (!n) return 0;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > n_sm * 16) blocks = n_sm * 16;
+    k_div_scalar<<<blocks, 256, 0, st>>>(a, n, f);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+static int launch_mul(double *a, size_t n, double f, int n_sm, cudaStream_t st)
+{
+    if (!n) return 0;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > n_sm * 16) blocks = n_sm * 16;
+    k_mul_scalar<<<blocks, 256, 0, st>>>(a, n, f);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_scale_dual(const dots_ctx_t *c, double factor, void *stream)
+{
+    if (int e = dots_check_ctx(c)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t a = (size_t)c->n_time * c->n_vert, b = (size_t)(c->n_time + 1) * 3 * c->n_tri, z = (size_t)(c->n_time + 1) * 18 * c->n_tri;
+    int e;
+    if ((e = launch_div(c->mu, a, factor, c->n_sm, st))) return e;                            // :370
+    if ((e = launch_div(c->E, b, factor, c->n_sm, st))) return e;
+    if ((e = launch_div(c->bnd0, c->n_vert, factor, c->n_sm, st))) return e;
+    if ((e = launch_div(c->bnd1, c->n_vert, factor, c->n_sm, st))) return e;
+    if ((e = launch_div(c->b_fst, a, factor, c->n_sm, st))) return e;
+    if ((e = launch_div(c->b_mid, z, factor, c->n_sm, st))) return e;
+    if ((e = launch_div(c->b_end, a, factor, c->n_sm, st))) return e;
+    return dots_refresh_corner_terms(c, stream);
+}
+
+extern "C" int dots_scale_z(const dots_ctx_t *c, double s_cum, void *stream)
+{
+    if (int e = dots_check_ctx(c)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t a = (size_t)c->n_time * c->n_vert, z = (size_t)(c->n_time + 1) * 18 * c->n_tri;
+    int e;
+    if ((e = launch_mul(c->z_fst, a, s_cum, c->n_sm, st))) return e;                          // :383
+    if ((e = launch_mul(c->z_mid, z, s_cum, c->n_sm, st))) return e;
+    if ((e = launch_mul(c->z_end, a, s_cum, c->n_sm, st))) return e;
+    const double inv = 1.0 / s_cum;                                                           // :384
+    if ((e = launch_mul(c->b_fst, a, inv, c->n_sm, st))) return e;
+    if ((e = launch_mul(c->b_mid, z, inv, c->n_sm, st))) return e;
+    if ((e = launch_mul(c->b_end, a, inv, c->n_sm, st))) return e;
+    int blocks = ceil_div((long long)a, 256);
+    if (blocks > c->n_sm * 16) blocks = c->n_sm * 16;
+    k_mu_from_beta<<<blocks, 256, 0, st>>>(*c, s_cum);
+    DOTS_LAUNCH_CHECK();
+    dim3 grid(ceil_div(c->n_tri, 128), c->n_time + 1);
+    k_E_from_beta<<<grid, 128, 0, st>>>(*c, s_cum);
+    DOTS_LAUNCH_CHECK();
+    return 0;   // caller sets params (s, d) and then calls dots_refresh_corner_terms
+}
+
+extern "C" int dots_set_params(const dots_ctx_t *c, const double *host_params, void *stream)
+{
+    if (int e = dots_check_ctx(c)) return e;
+    DOTS_CUDA(cudaMemcpyAsync(c->params, host_params, sizeof(double) * DOTS_P_COUNT, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int dots_grad_space(const dots_ctx_t *c, const double *phi, double *out, void *stream)
+{
+    if (int e = dots_check_ctx(c)) return e;
+    dim3 grid(ceil_div(c->n_tri, 128), c->n_time + 1);
+    k_grad_space<<<grid, 128, 0, (cudaStream_t)stream>>>(*c, phi, out);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dots_div_space(const dots_ctx_t *c, const double *x, double *out, void *stream)
+{
+    if (int e = dots_check_ctx(c)) return e;
+    dim3 grid(ceil_div(c->n_vert, 128), c->n_time + 1);
+    k_div_space<<<grid, 128, 0, (cudaStream_t)stream>>>(*c, x, out);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}

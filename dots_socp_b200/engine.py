@@ -1,0 +1,360 @@
+"""Device-resident ALM state + the calls into libdots_b200.so.
+
+``Engine`` owns what ``solver_socp`` sets up before its loop (reference socp/solver_socp.py:97-270):
+mesh operators, the space-time Laplacian inverse, the state arrays and the scalars (r, scale_factor_z,
+constant_d).  Everything numeric that happens per iteration is a CUDA kernel behind the C-ABI
+(include/dots_b200.h); PyTorch only provides device memory and the stream.  There is no CPU path:
+constructing an Engine without a CUDA device or without the library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import capi, nested, surface
+
+STATE_VERTEX = ("phi", "A", "lam_c", "mu", "z_fst", "z_end", "b_fst", "b_end")
+STATE_TRI = ("B", "E")
+STATE_CORNER = ("b_mid", "z_mid")
+#: reference key (utils/type.py:22-38)  ->  engine field
+REF_KEYS = dict(phi="phi", A="A", B="B", lambda_c="lam_c", mu="mu", E="E", z_fst="z_fst", z_mid="z_mid",
+                z_end="z_end", beta_fst="b_fst", beta_mid="b_mid", beta_end="b_end")
+
+
+def time_basis(n_time: int):
+    """Eigen-decomposition of the Neumann time Laplacian (laplacian_inverse_socp.py:15-31), analytically:
+    Q[t,k] = c_k cos(pi k (t+1/2)/(nT+1)),  lambda_k = -4 nT^2 sin^2(pi k / (2 (nT+1)))."""
+    n = n_time + 1
+    t = np.arange(n)[:, None]
+    k = np.arange(n)[None, :]
+    Q = np.cos(np.pi * k * (t + 0.5) / n)
+    Q[:, 0] = 1.0 / math.sqrt(n)
+    Q[:, 1:] *= math.sqrt(2.0 / n)
+    lam = -4.0 * n_time ** 2 * np.sin(np.pi * np.arange(n) / (2.0 * n)) ** 2
+    return Q, lam
+
+
+def _sweep_items(sym: nested.Symbolic, n_sm: int):
+    """Per-level work items for the forward (row blocks) and backward (column blocks) sweeps."""
+    fwd_ptr, bwd_ptr, fwd, bwd = [0], [0], [], []
+    for nodes in nested.level_schedule(sym):
+        rows_total = int((sym.s[nodes] + sym.b[nodes]).sum())
+        cols_total = int(sym.s[nodes].sum())
+        rb = int(min(32, max(8, -(-rows_total // (4 * n_sm)))))
+        cb = int(min(32, max(8, -(-cols_total // (4 * n_sm)))))
+        for nd in nodes:
+            nrow, ncol = int(sym.s[nd] + sym.b[nd]), int(sym.s[nd])
+            for r0 in range(0, nrow, rb):
+                fwd.append((nd, r0, min(rb, nrow - r0)))
+            for c0 in range(0, ncol, cb):
+                bwd.append((nd, c0, min(cb, ncol - c0)))
+        fwd_ptr.append(len(fwd))
+        bwd_ptr.append(len(bwd))
+    as32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32).reshape(-1, 3))
+    return (np.array(fwd_ptr, dtype=np.int32), as32(fwd) if fwd else np.zeros((0, 3), np.int32),
+            np.array(bwd_ptr, dtype=np.int32), as32(bwd) if bwd else np.zeros((0, 3), np.int32))
+
+
+class Engine:
+    def __init__(self, n_time, geometry, congestion=0.0, eps=0.0, tau=1.9, device=None, leaf_size=24, timings=None):
+        if not torch.cuda.is_available():
+            raise capi.DotsError("dots_socp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = capi.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        torch.cuda.set_device(self.device)
+        t_start = time.perf_counter()
+        tm = timings if timings is not None else {}
+
+        v = np.ascontiguousarray(geometry["vertices"], dtype=np.float64)
+        tri_old = np.ascontiguousarray(geometry["triangles"]).astype(np.int64)
+        self.nT, self.V, self.T = int(n_time), v.shape[0], tri_old.shape[0]
+        nT, V, T = self.nT, self.V, self.T
+        if nT + 1 > 128:
+            raise ValueError("n_time + 1 must be <= 128 (time-mode batch width of the sweep kernels)")
+        self.dt = 1.0 / nT
+        self.cong, self.tau, self.eps = float(congestion), float(tau), float(eps)
+        self.m_pad = 32 * (-(-(nT + 1) // 32))
+
+        # ---- mesh operators (host, vectorised) --------------------------------------------------
+        area_f = surface.triangle_areas(v, tri_old)
+        area_v = surface.incident_area_sum(V, tri_old, area_f) / 3.0                    # solver_socp.py:112
+        hat = surface.hat_gradients(v, tri_old)                                         # (T,3,3) [f,k,xyz]
+        K = surface.stiffness_matrix(v, tri_old)
+        tm["mesh_operators"] = time.perf_counter() - t_start
+
+        # ---- ordering + batched factorisation -----------------------------------------------------
+        t0 = time.perf_counter()
+        sym = nested.analyse(v, K, leaf_size=leaf_size)
+        self.sym = sym
+        self.perm_v = sym.perm                                                          # new -> old
+        tri_new = sym.iperm[tri_old]                                                    # (T,3) in new vertex ids
+        self.perm_f = np.argsort(tri_new.min(axis=1), kind="stable")                    # new -> old triangle
+        tri_new = tri_new[self.perm_f]
+        tm["ordering"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        Q, lam_t = time_basis(nT)
+        self.Q, self.lam_t = Q, lam_t
+        shifts = -lam_t + self.eps                       # (L + (lam - eps) M) = -(K + (|lam| + eps) M)   (laplacian_inverse_socp.py:37-38)
+        panels = nested.factor_batched(sym, K, area_v, shifts, m_pad=self.m_pad)
+        tm["factorization"] = time.perf_counter() - t0
+
+        # ---- upload --------------------------------------------------------------------------------
+        t0 = time.perf_counter()
+        dev = self.device
+        self._keep = {}
+
+        def up(name, arr, dtype):
+            ten = torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(dev)
+            self._keep[name] = ten
+            return ten
+
+        props = torch.cuda.get_device_properties(dev)
+        self.n_sm = props.multi_processor_count
+        area_f_n, area_v_n = area_f[self.perm_f], area_v[self.perm_v]
+        self.area_f_new, self.area_v_new = area_f_n, area_v_n
+        hat_n = hat[self.perm_f]                                                         # (T,3,3)
+        diag = np.sqrt(area_f_n[None, :] / area_v_n[tri_new.T])                          # (3,T)  solver_socp.py:172-180
+        vc_ptr, vc_tri, vc_corner = surface.corner_adjacency(V, tri_new)
+        qpad = np.zeros((nT + 1, self.m_pad))
+        qpad[:, :nT + 1] = Q
+        fwd_ptr, fwd_items, bwd_ptr, bwd_items = _sweep_items(sym, self.n_sm)
+        self._h_fwd_ptr, self._h_bwd_ptr = fwd_ptr, bwd_ptr                              # host copies stay alive
+
+        ctx = capi.DotsCtx()
+        ctx.abi_version, ctx.n_time, ctx.n_vert, ctx.n_tri = capi.ABI_VERSION, nT, V, T
+        ctx.m_pad, ctx.n_nodes, ctx.n_levels, ctx.n_sm = self.m_pad, sym.n_nodes, sym.n_levels, self.n_sm
+        const = dict(
+            tri=up("tri", tri_new.T, np.int32), hat_grad=up("hat_grad", hat_n.transpose(1, 2, 0), np.float64),
+            area_f=up("area_f", area_f_n, np.float64), area_v=up("area_v", area_v_n, np.float64),
+            diag_soc=up("diag_soc", diag, np.float64), vc_ptr=up("vc_ptr", vc_ptr, np.int32),
+            vc_idx=up("vc_idx", vc_corner * T + vc_tri, np.int32), qmat=up("qmat", qpad, np.float64),
+            panels=up("panels", panels, np.float64),
+            nd_off=up("nd_off", sym.off, np.int32), nd_s=up("nd_s", sym.s, np.int32), nd_b=up("nd_b", sym.b, np.int32),
+            nd_child=up("nd_child", sym.child, np.int32), nd_panel=up("nd_panel", sym.panel_off[:-1], np.int64),
+            nd_front=up("nd_front", sym.front_off[:-1], np.int64), nd_upd=up("nd_upd", sym.upd_off[:-1], np.int64),
+            front_idx=up("front_idx", sym.front_idx, np.int32), child_pos=up("child_pos", sym.child_pos, np.int32),
+            lvl_ptr=up("lvl_ptr", fwd_ptr, np.int32), lvl_items=up("lvl_items", fwd_items, np.int32),
+            lvb_ptr=up("lvb_ptr", bwd_ptr, np.int32), lvb_items=up("lvb_items", bwd_items, np.int32))
+        del panels
+        for k, ten in const.items():
+            setattr(ctx, k, ten.data_ptr())
+        ctx.h_lvl_ptr = self._h_fwd_ptr.ctypes.data
+        ctx.h_lvb_ptr = self._h_bwd_ptr.ctypes.data
+        ctx.front_total = int(sym.front_off[-1])
+
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)
+        self.red_blocks = self.n_sm * 4
+        st = dict(params=z(capi.P_COUNT), phi=z(nT + 1, V), lam=z(nT, V), bnd0=z(V), bnd1=z(V),
+                  B=z(nT + 1, 3, T), E=z(nT + 1, 3, T), b_mid=z(nT + 1, 2, 3, 3, T), z_mid=z(nT + 1, 2, 3, 3, T),
+                  corner_nrm=z(nT + 1, 2, 3, T), corner_div=z(nT + 1, 3, T),
+                  rhs=z(nT + 1, V), hat=z(V, self.m_pad), ywork=z(V, self.m_pad),
+                  upd=z(max(1, int(sym.upd_off[-1])), self.m_pad), red_part=z(self.red_blocks, 8), red_out=z(8))
+        for name in ("A", "lam_c", "mu", "z_fst", "z_end", "b_fst", "b_end"):
+            st[name] = z(nT, V)
+        self.t = st
+        for k, ten in st.items():
+            setattr(ctx, k, ten.data_ptr())
+        ctx.red_blocks = self.red_blocks
+        self.ctx = ctx
+        self._ctxp = C.byref(ctx)
+        self._host_out = np.zeros(8)
+        self._host_params = np.zeros(capi.P_COUNT)
+
+        # ---- scalars of the reference driver (:97, :267-270, :296-313, :318-321) ------------------
+        self.r, self.s, self.d = 1.0, 1.0, 1.0
+        mu0 = np.asarray(geometry["mu0"], dtype=np.float64)[self.perm_v]
+        mu1 = np.asarray(geometry["mu1"], dtype=np.float64)[self.perm_v]
+        b0, b1 = -mu0 / (self.r * self.dt), mu1 / (self.r * self.dt)
+        st["bnd0"].copy_(torch.from_numpy(b0))
+        st["bnd1"].copy_(torch.from_numpy(b1))
+        self.norm_bnd = self.r * self.dt * math.sqrt((np.sum((b0 / area_v_n) ** 2 * area_v_n)
+                                                      + np.sum((b1 / area_v_n) ** 2 * area_v_n)) / (nT + 1))
+        self.area_mesh = float(np.sum(area_f))
+        self.norm_d = math.sqrt(2 * self.area_mesh)
+        ma_v, ma_f = float(np.mean(area_v)), float(np.mean(area_f))
+        self.k_prim_q = np.mean([ma_v, ma_f])
+        self.k_prim_z = np.mean([ma_v, ma_f, ma_v])
+        self.k_dual_a = ma_v
+        self.k_dual_b = np.mean([ma_v, ma_f])
+        self.k_comp_rho, self.k_comp_m = ma_v, ma_f
+        self.z_valid = True                              # z_mid = 0 is the reference's initial z_mid (:245)
+        self.launches = 0
+        self._push_params()
+        torch.cuda.synchronize(dev)
+        tm["upload"] = time.perf_counter() - t0
+        tm["setup_total"] = time.perf_counter() - t_start
+        self.timings = tm
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _push_params(self):
+        p = self._host_params
+        p[capi.P_R], p[capi.P_S], p[capi.P_D] = self.r, self.s, self.d
+        p[capi.P_CONG], p[capi.P_TAU], p[capi.P_EPS] = self.cong, self.tau, self.eps
+        capi.check(self.lib.dots_set_params(self._ctxp, p.ctypes.data, self.stream), "dots_set_params")
+
+    def launches_per_iteration(self):
+        """Kernel launches of one dots_iterate step: rhs, 2 transforms, one sweep launch per non-empty level
+        and direction, vertex, triangle."""
+        n_f = int(np.count_nonzero(np.diff(self._h_fwd_ptr)))
+        n_b = int(np.count_nonzero(np.diff(self._h_bwd_ptr)))
+        return 5 + n_f + n_b
+
+    # ------------------------------------------------------------------ the iteration
+    def iterate(self, n=1, write_z=False):
+        capi.check(self.lib.dots_iterate(self._ctxp, int(n), int(bool(write_z)), self.stream), "dots_iterate")
+        self.launches += n * self.launches_per_iteration()
+        self.z_valid = bool(write_z)
+
+    def adjust_penalty(self, f):                                                         # :367-371
+        self.r *= f
+        self._push_params()
+        capi.check(self.lib.dots_scale_dual(self._ctxp, float(f), self.stream), "dots_scale_dual")
+        self.launches += 8
+
+    def scale_z(self, f):                                                                # :373-395
+        self.s *= f
+        self.d *= f
+        self.norm_d *= f
+        capi.check(self.lib.dots_scale_z(self._ctxp, float(self.s), self.stream), "dots_scale_z")
+        self._push_params()
+        capi.check(self.lib.dots_refresh_corner_terms(self._ctxp, self.stream), "dots_refresh_corner_terms")
+        self.launches += 9
+
+    def set_scalars(self, r=None, s=None, d=None, norm_d=None):
+        """Overwrite the driver scalars (tests / warm starts) and push them to the device."""
+        if r is not None: self.r = float(r)
+        if s is not None: self.s = float(s)
+        if d is not None: self.d = float(d)
+        if norm_d is not None: self.norm_d = float(norm_d)
+        self._push_params()
+
+    def grad_space_into(self, src, dst):
+        """t[dst] = G t[src] for all time levels (vanilla_grad_space, solver_socp.py:898-907)."""
+        capi.check(self.lib.dots_grad_space(self._ctxp, self.t[src].data_ptr(), self.t[dst].data_ptr(), self.stream), "dots_grad_space")
+        self.launches += 1
+
+    def E_from_beta(self, scale):
+        """E = -decouple_adjoin_spacial(b_mid, scale) (warm-start default, solver_socp.py:250); rare, so plain tensor ops."""
+        self.t["E"].copy_(-(scale / math.sqrt(3.0)) * self.t["b_mid"].sum(dim=2).sum(dim=1))
+
+    def refresh(self):
+        capi.check(self.lib.dots_refresh_corner_terms(self._ctxp, self.stream), "dots_refresh_corner_terms")
+        self.launches += 1
+
+    # ------------------------------------------------------------------ residuals
+    def sums(self, which):
+        capi.check(self.lib.dots_kkt_sums(self._ctxp, int(which), self._host_out.ctypes.data, self.stream), "dots_kkt_sums")
+        self.launches += 3
+        return self._host_out.copy()
+
+    def kkt(self, i):
+        """Relative KKT residual i as [value, value] (conditions 0-3) or [value, None] (4-6):
+        the two-valued convention of solver_socp.py:589-643 with prim_scale = dual_scale = 1."""
+        nT, sq = self.nT, math.sqrt
+        if i == 1 and not self.z_valid:
+            raise capi.DotsError("KKT #1 needs z_mid of the current iteration: call iterate(..., write_z=True)")
+        o = self.sums(i)
+        v, t = o[0:4], o[4:8]
+        tn, sn = 1.0 / nT, 1.0 / (nT + 1)
+        if i == 0:                                                                       # :433-450
+            norm_sum = sq(v[1] * tn + t[1] * sn) + sq(v[2] * tn + t[2] * sn) + sq(v[3] * tn)
+            val = sq(v[0] * tn + t[0] * sn) / (self.k_prim_q / 1.0 + norm_sum)
+            return [val, val]
+        if i == 1:                                                                       # :452-464
+            val = sq(v[0] * tn + v[1] * tn + t[0] * tn) / (self.k_prim_z / 1.0 + self.norm_d)
+            return [val, val]
+        if i == 2:                                                                       # :466-482
+            val = sq(v[0] * sn) / (self.k_dual_a / 1.0 + self.norm_bnd)
+            return [val, val]
+        if i == 3:                                                                       # :484-503
+            norm_sum = self.r * (sq(v[0] * tn + t[0] * sn) + sq(v[1] * tn + t[1] * sn))
+            val = self.r * sq(v[2] * tn + t[2] * sn) / (self.k_dual_b / 1.0 + norm_sum)
+            return [val, val]
+        if i == 4:                                                                       # :505-526
+            return [sq(v[2] * tn) / (self.k_comp_rho + sq(v[0] * tn) + sq(v[1] * tn)), None]
+        if i == 5:                                                                       # :528-547
+            return [sq(t[2] * sn) / (self.k_comp_m + sq(t[0] * sn) + sq(t[1] * sn)), None]
+        if i == 6:                                                                       # :549-559
+            return [sq(v[2] * tn) / (self.k_comp_rho + sq(v[0] * tn) + sq(v[1] * tn)), None]
+        raise IndexError(i)
+
+    def objective(self):                                                                 # :417-431
+        o = self.sums(7)
+        cost = self.dt * (o[0] + o[1])
+        if self.cong > 10 ** (-10):
+            return cost, cost - 1. / (2. * self.cong) * (o[2] / self.nT)
+        return cost, cost
+
+    # ------------------------------------------------------------------ layout conversion (host <-> device)
+    def _perm_v_t(self):
+        if "perm_v_t" not in self._keep:
+            self._keep["perm_v_t"] = torch.from_numpy(self.perm_v.astype(np.int64)).to(self.device)
+            self._keep["perm_f_t"] = torch.from_numpy(self.perm_f.astype(np.int64)).to(self.device)
+        return self._keep["perm_v_t"], self._keep["perm_f_t"]
+
+    def to_internal(self, name, ref):
+        """Reference-layout array (numpy or torch) -> internal-layout device tensor."""
+        pv, pf = self._perm_v_t()
+        x = torch.as_tensor(ref, dtype=torch.float64).to(self.device)
+        if name in STATE_VERTEX or name in ("lam", "rhs"):
+            return x[:, pv].contiguous()
+        if name in STATE_TRI:
+            return x[:, pf, :].permute(0, 2, 1).contiguous()
+        if name in STATE_CORNER:
+            nT, T = self.nT, self.T
+            out = torch.zeros((nT + 1, 2, 3, 3, T), dtype=torch.float64, device=self.device)
+            out[:nT, 0] = x[:, 0][:, :, pf, :].permute(0, 1, 3, 2)
+            out[1:, 1] = x[:, 1][:, :, pf, :].permute(0, 1, 3, 2)
+            return out
+        raise KeyError(name)
+
+    def from_internal(self, name, ten=None):
+        """Internal device tensor -> reference-layout device tensor (fresh)."""
+        pv, pf = self._perm_v_t()
+        x = self.t[name] if ten is None else ten
+        if name in STATE_VERTEX or name in ("lam", "rhs"):
+            out = torch.empty_like(x)
+            out[:, pv] = x
+            return out
+        if name in STATE_TRI:
+            out = torch.empty((x.shape[0], self.T, 3), dtype=torch.float64, device=self.device)
+            out[:, pf, :] = x.permute(0, 2, 1)
+            return out
+        if name in STATE_CORNER:
+            nT, T = self.nT, self.T
+            out = torch.empty((nT, 2, 3, T, 3), dtype=torch.float64, device=self.device)
+            out[:, 0][:, :, pf, :] = x[:nT, 0].permute(0, 1, 3, 2)
+            out[:, 1][:, :, pf, :] = x[1:, 1].permute(0, 1, 3, 2)
+            return out
+        raise KeyError(name)
+
+    def set_state(self, **arrays):
+        """Overwrite state fields from reference-layout arrays, then rebuild the derived corner terms."""
+        for name, ref in arrays.items():
+            self.t[name].copy_(self.to_internal(name, ref))
+        self.z_valid = "z_mid" in arrays
+        self.refresh()
+
+    def get_state(self, names=None):
+        names = names or (STATE_VERTEX + STATE_TRI + STATE_CORNER)
+        return {n: self.from_internal(n).cpu().numpy() for n in names}
+
+    def solution(self):
+        """Un-scaled solution dict with the reference's keys and layouts (:397-405, :855-869)."""
+        if not self.z_valid:
+            raise capi.DotsError("z_mid was not materialised on the last iteration")
+        r, s = self.r, self.s
+        scale = dict(phi=1.0, A=1.0, B=1.0, lam_c=1.0, z_fst=1.0 / s, z_mid=1.0 / s, z_end=1.0 / s,
+                     mu=r, E=r, b_fst=r * s, b_mid=r * s, b_end=r * s)
+        out = {}
+        for key, name in REF_KEYS.items():
+            out[key] = (self.from_internal(name) * scale[name]).cpu().numpy()
+        return out

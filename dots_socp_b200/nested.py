@@ -1,0 +1,259 @@
+"""Host-side setup of the per-mode shifted surface-Laplacian solves (row a8 of SURVEY.md section 8).
+
+The reference factorises ``L + (lambda_a - eps) diag(area_v)`` once per time mode with SuperLU
+(utils/laplacian_inverse_socp.py:34-41) and calls the ``nT+1`` solve closures one after another
+(:58-59).  All those matrices share one sparsity pattern and differ by a diagonal shift, so here
+they are factorised TOGETHER, batched over the mode index, with one nested-dissection ordering:
+
+* ``dissect``        geometric nested dissection (recursive coordinate bisection, vertex separators)
+                     -> elimination order + separator tree.
+* ``symbolic``       multifrontal structure: every tree node owns a contiguous block S of the new
+                     ordering and a boundary set B of ancestor vertices; its front is dense
+                     (|S|+|B|)^2.
+* ``factor_batched`` numeric multifrontal Cholesky of ``K + shift_m * diag(mass)`` for all modes m at
+                     once (K = -L is the PSD cotan stiffness matrix).  What is stored per node is the
+                     *solve-ready* panel  P = [ inv(L11) ; L21 inv(L11) ]  (lower triangle of the first
+                     block, |B| x |S| second block) laid out ``[row][col][mode]`` with the mode index
+                     fastest, which is the layout the CUDA level-scheduled kernels stream.
+
+With that panel the forward sweep is one dense mat-vec per node, ``[y_S ; -du_B] = P r_S`` and the
+backward sweep is its transpose: no sequential triangular recurrences are left inside a node, the
+only dependencies are parent/child ones (tree levels).
+
+Mode 0 (shift 0, eps = 0) is singular along the constant vector: the last pivot is pinned, which
+returns the solution with that vertex at 0 (the reference returns an arbitrary constant, SURVEY.md
+appendix B); everything downstream only uses differences of phi.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sp
+
+
+# ----------------------------------------------------------------------------- ordering
+@dataclass
+class _Node:
+    own: np.ndarray                       # old vertex ids owned (eliminated) by this node
+    kids: list = field(default_factory=list)
+
+
+def dissect(coords: np.ndarray, adj: sp.csr_matrix, leaf_size: int = 24):
+    """Recursive coordinate bisection with vertex separators.  Returns the root ``_Node``.
+
+    Iterative (explicit stack) so deep trees do not hit the recursion limit."""
+    n = coords.shape[0]
+    side = np.full(n, -1, dtype=np.int8)          # scratch: -1 outside the current subset
+    indptr, indices = adj.indptr, adj.indices
+    root = _Node(own=np.empty(0, dtype=np.int64))
+    stack = [(root, np.arange(n, dtype=np.int64))]
+    while stack:
+        node, verts = stack.pop()
+        if verts.size <= leaf_size:
+            node.own = verts
+            continue
+        x = coords[verts]
+        axis = int(np.argmax(x.max(axis=0) - x.min(axis=0)))
+        order = np.argsort(x[:, axis], kind="stable")
+        half = verts.size // 2
+        left, right = verts[order[:half]], verts[order[half:]]
+        side[left], side[right] = 0, 1
+        # boundary of each half: vertices with a neighbour in the other half
+        def frontier(part, other_side):
+            starts, ends = indptr[part], indptr[part + 1]
+            counts = ends - starts
+            rows = np.repeat(np.arange(part.size), counts)
+            offs = np.arange(counts.sum()) - np.repeat(np.cumsum(counts) - counts, counts)
+            nbr = indices[np.repeat(starts, counts) + offs]
+            hit = side[nbr] == other_side
+            mask = np.zeros(part.size, dtype=bool)
+            mask[rows[hit]] = True
+            return mask
+        fl, fr = frontier(left, 1), frontier(right, 0)
+        if fl.sum() <= fr.sum():
+            sep, left = left[fl], left[~fl]
+        else:
+            sep, right = right[fr], right[~fr]
+        side[verts] = -1
+        node.own = sep
+        for part in (left, right):
+            if part.size:
+                kid = _Node(own=np.empty(0, dtype=np.int64))
+                node.kids.append(kid)
+                stack.append((kid, part))
+    return root
+
+
+# ----------------------------------------------------------------------------- symbolic structure
+@dataclass
+class Symbolic:
+    n: int
+    perm: np.ndarray            # new -> old vertex id
+    iperm: np.ndarray           # old -> new
+    n_nodes: int
+    off: np.ndarray             # first new index owned by node
+    s: np.ndarray               # |S|
+    b: np.ndarray               # |B|
+    level: np.ndarray           # 0 = leaves ... root = max
+    parent: np.ndarray
+    child: np.ndarray           # (n_nodes, 2) ids or -1
+    front_off: np.ndarray       # offset of the node's front rows in ``front_idx``   (n_nodes+1)
+    front_idx: np.ndarray       # new vertex index of every front row (S rows then B rows, ascending)
+    child_pos: np.ndarray       # (2, sum n_i): row of child slot's update vector feeding this front row, or -1
+    panel_off: np.ndarray       # offset of the node's panel, in entries (n_nodes+1)
+    upd_off: np.ndarray         # offset of the node's update vector, in rows      (n_nodes+1)
+
+    @property
+    def n_levels(self):
+        return int(self.level.max()) + 1
+
+    @property
+    def panel_entries(self):
+        return int(self.panel_off[-1])
+
+
+def panel_size(s, b):
+    return s * (s + 1) // 2 + b * s
+
+
+def symbolic(root: _Node, adj: sp.csr_matrix) -> Symbolic:
+    n = adj.shape[0]
+    # post-order (children before parents), iterative
+    order, stack = [], [(root, False)]
+    while stack:
+        node, seen = stack.pop()
+        if seen:
+            order.append(node)
+        else:
+            stack.append((node, True))
+            for kid in reversed(node.kids):
+                stack.append((kid, False))
+    ids = {id(nd): i for i, nd in enumerate(order)}
+    n_nodes = len(order)
+    perm = np.concatenate([nd.own for nd in order]).astype(np.int64)
+    assert perm.size == n and np.unique(perm).size == n, "dissection must cover every vertex exactly once"
+    iperm = np.empty(n, dtype=np.int64)
+    iperm[perm] = np.arange(n)
+    s = np.array([nd.own.size for nd in order], dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(s)[:-1]]).astype(np.int64)
+    parent = np.full(n_nodes, -1, dtype=np.int64)
+    child = np.full((n_nodes, 2), -1, dtype=np.int64)
+    level = np.zeros(n_nodes, dtype=np.int64)
+    for i, nd in enumerate(order):
+        for slot, kid in enumerate(nd.kids):
+            k = ids[id(kid)]
+            parent[k] = i
+            child[i, slot] = k
+            level[i] = max(level[i], level[k] + 1)
+    adj_new = adj[perm][:, perm].tocsr()
+    adj_new.sort_indices()
+    indptr, indices = adj_new.indptr, adj_new.indices
+    bsets = [None] * n_nodes
+    b = np.zeros(n_nodes, dtype=np.int64)
+    for i in range(n_nodes):                                    # post-order: children are ready
+        lo, hi = off[i], off[i] + s[i]
+        nbr = indices[indptr[lo]:indptr[hi]]
+        parts = [nbr[nbr >= hi]]
+        for k in child[i]:
+            if k >= 0:
+                bk = bsets[k]
+                parts.append(bk[bk >= hi])
+        bsets[i] = np.unique(np.concatenate(parts)) if parts else np.empty(0, dtype=np.int64)
+        b[i] = bsets[i].size
+    nfront = s + b
+    front_off = np.concatenate([[0], np.cumsum(nfront)]).astype(np.int64)
+    front_idx = np.empty(front_off[-1], dtype=np.int64)
+    child_pos = np.full((2, front_off[-1]), -1, dtype=np.int64)
+    for i in range(n_nodes):
+        f0 = front_off[i]
+        rows = np.concatenate([np.arange(off[i], off[i] + s[i]), bsets[i]])
+        front_idx[f0:f0 + nfront[i]] = rows
+        for slot, k in enumerate(child[i]):
+            if k >= 0 and b[k]:
+                where = np.searchsorted(rows, bsets[k])
+                assert np.array_equal(rows[where], bsets[k]), "child boundary must embed in the parent front"
+                child_pos[slot, f0 + where] = np.arange(b[k])
+    panel_off = np.concatenate([[0], np.cumsum([panel_size(int(a), int(c)) for a, c in zip(s, b)])]).astype(np.int64)
+    upd_off = np.concatenate([[0], np.cumsum(b)]).astype(np.int64)
+    return Symbolic(n=n, perm=perm, iperm=iperm, n_nodes=n_nodes, off=off, s=s, b=b, level=level, parent=parent,
+                    child=child, front_off=front_off, front_idx=front_idx, child_pos=child_pos,
+                    panel_off=panel_off, upd_off=upd_off)
+
+
+def analyse(vertices: np.ndarray, K: sp.csr_matrix, leaf_size: int = 24) -> Symbolic:
+    adj = K.copy().tocsr()
+    adj.setdiag(0)
+    adj.eliminate_zeros()
+    return symbolic(dissect(np.asarray(vertices, dtype=np.float64), adj, leaf_size), adj)
+
+
+# ----------------------------------------------------------------------------- numeric factorisation
+def factor_batched(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shifts: np.ndarray, m_pad: int | None = None,
+                   pin_singular: bool = True, out: np.ndarray | None = None) -> np.ndarray:
+    """Solve-ready panels of ``K + shifts[m] * diag(mass)`` for every mode m.
+
+    Returns ``panels`` of shape (panel_entries, m_pad) float64, C-contiguous (mode fastest).  Modes
+    ``>= len(shifts)`` (padding) hold identity-like data (inverse diagonal 1, zeros elsewhere)."""
+    shifts = np.asarray(shifts, dtype=np.float64)
+    n_modes = shifts.size
+    m_pad = m_pad or n_modes
+    Kp = K[sym.perm][:, sym.perm].tocsr()
+    Kp.sort_indices()
+    massp = np.asarray(mass, dtype=np.float64)[sym.perm]
+    indptr, indices, data = Kp.indptr, Kp.indices, Kp.data
+    panels = out if out is not None else np.zeros((sym.panel_entries, m_pad))
+    singular = [m for m in range(n_modes) if shifts[m] == 0.0] if pin_singular else []
+    pin_value = float(Kp.diagonal().mean())
+    updates = [None] * sym.n_nodes
+    for i in range(sym.n_nodes):
+        s, b = int(sym.s[i]), int(sym.b[i])
+        nf = s + b
+        lo = int(sym.off[i])
+        rows = sym.front_idx[sym.front_off[i]:sym.front_off[i] + nf]
+        F = np.zeros((n_modes, nf, nf))
+        # original entries with a row in S (upper part col >= lo); mirrored
+        a0, a1 = indptr[lo], indptr[lo + s]
+        r = np.repeat(np.arange(s), np.diff(indptr[lo:lo + s + 1]))
+        c_new, v = indices[a0:a1], data[a0:a1]
+        keep = c_new >= lo
+        r, c_new, v = r[keep], c_new[keep], v[keep]
+        c = np.searchsorted(rows, c_new)
+        F[:, r, c] = v[None, :]
+        F[:, c, r] = v[None, :]
+        d = np.arange(s)
+        F[:, d, d] += shifts[:, None] * massp[None, lo:lo + s]
+        if i == sym.n_nodes - 1:
+            for m in singular:
+                F[m, s - 1, s - 1] += pin_value
+        for slot in range(2):
+            k = int(sym.child[i, slot])
+            if k >= 0 and sym.b[k]:
+                cp = sym.child_pos[slot, sym.front_off[i]:sym.front_off[i] + nf]
+                where = np.nonzero(cp >= 0)[0]
+                where = where[np.argsort(cp[where])]
+                F[:, where[:, None], where[None, :]] += updates[k]
+                updates[k] = None
+        if s == 0:                                              # empty separator: just forward the children's updates
+            updates[i] = F if b else None
+            continue
+        L11 = np.linalg.cholesky(F[:, :s, :s])
+        Linv = np.linalg.inv(L11)
+        tri = np.tril_indices(s)
+        p0 = int(sym.panel_off[i])
+        ntri = s * (s + 1) // 2
+        panels[p0:p0 + ntri, :n_modes] = Linv[:, tri[0], tri[1]].T
+        if m_pad > n_modes:
+            panels[p0 + np.arange(s) * (np.arange(s) + 1) // 2 + np.arange(s), n_modes:] = 1.0
+        if b:
+            L21 = F[:, s:, :s] @ np.swapaxes(Linv, 1, 2)
+            W21 = L21 @ Linv
+            panels[p0 + ntri:p0 + ntri + b * s, :n_modes] = W21.reshape(n_modes, b * s).T
+            updates[i] = F[:, s:, s:] - L21 @ np.swapaxes(L21, 1, 2)
+    return panels
+
+
+# ----------------------------------------------------------------------------- level schedule for the kernels
+def level_schedule(sym: Symbolic):
+    """Nodes grouped by tree level (leaves first).  Returns list of int64 arrays of node ids."""
+    return [np.nonzero(sym.level == lv)[0].astype(np.int64) for lv in range(sym.n_levels)]

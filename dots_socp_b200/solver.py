@@ -1,0 +1,237 @@
+"""Drop-in solver callables for ``dot_surface_socp.interface.run_dot_surface(opts, solver=...)``.
+
+Mirrors the reference's solver plug-in surface:
+
+* ``solver_socp(n_time, geometry, **kw) -> (SolutionSocpData-shaped dict, run history)``
+      same keyword names, defaults, error behaviour and output keys/shapes as
+      dot_surface_socp/socp/solver_socp.py:25-41,855-871;
+* ``solver_raw``  = SOCP units -> DOT units            (socp/solver_decorator.py:10-26, utils/type.py:48-65)
+* ``solver``      = ... on the time-centred grid       (socp/solver_decorator.py:29-54)
+
+The outer loop below restates solver_socp.py:565-871 on host scalars; every array operation of an
+iteration is a CUDA kernel launched through libdots_b200.so (``engine.Engine``).  The host only syncs
+on the iterations whose KKT residuals the reference's lazy validator would evaluate; the iterations
+in between are enqueued back to back.
+"""
+from __future__ import annotations
+
+import logging
+import math
+import time
+
+import numpy as np
+import torch
+
+from .engine import Engine, REF_KEYS
+from .history import RunHistory, LOG_KKT, LOG_SCALING, LOG_INFO
+from .schedule import LazyResidualCheck, PenaltySchedule, max_or_none
+
+KKT_LABELS = ["SOC & Org : Primal Feasibility (q)", "SOC       : Primal Feasibility (z)",
+              "SOC & Org : Dual Feasibility (alpha)", "SOC       : Dual Feasibility (beta)",
+              "      Org : ||rho - Pi+(rho + Fq)||", "      Org : ||m - rho o B||",
+              "      Org : ||cong. rho - lambda_c||"]
+KKT_SHORT = ["Prim(phi, q)", "Prim(q, z)", "Dual(alpha)", "Dual(beta)", "Comp(rho, f(q))", "Comp(m, rho o B)",
+             "Comp(rho, cong.)"]
+STEP_TAG = "Step 1-3 (fused Lap / SOC-Proj / Q & Lambda / Multiplier, GPU)"
+STOP_SET, PRIM_SET, DUAL_SET = (0, 2, 4, 5), (0, 1), (2, 3)
+
+
+def _validate_checkpoints(tol_checkpoints, tol):
+    """solver_socp.py:85-94."""
+    if tol_checkpoints is None:
+        return None
+    if not isinstance(tol_checkpoints, list) or not tol_checkpoints:
+        raise ValueError("tol_checkpoints must be a non-empty list")
+    for i, c in enumerate(tol_checkpoints):
+        if not (isinstance(c, (int, float)) and 0 < c < 1):
+            raise ValueError(f"Invalid checkpoint value at index {i}: {c}. Must be between 0 and 1")
+        if c < tol:
+            raise ValueError(f"Checkpoint value must be greater than tol. However, checkpoint ({c}) < tol ({tol})")
+    return sorted(tol_checkpoints, reverse=True)
+
+
+def _warm_start(eng: Engine, init):
+    """solver_socp.py:239-250: any subset of the solution keys; missing ones get the reference's defaults."""
+    nT, V, T = eng.nT, eng.V, eng.T
+    dev = eng.device
+    get = lambda k, shape: torch.as_tensor(init[k], dtype=torch.float64, device=dev) if k in init else torch.zeros(shape, dtype=torch.float64, device=dev)
+    phi = get("phi", (nT + 1, V))
+    st = dict(phi=phi, lam_c=get("lambda_c", (nT, V)), z_fst=get("z_fst", (nT, V)), z_end=get("z_end", (nT, V)),
+              z_mid=get("z_mid", (nT, 2, 3, T, 3)), b_fst=get("beta_fst", (nT, V)), b_end=get("beta_end", (nT, V)),
+              b_mid=get("beta_mid", (nT, 2, 3, T, 3)))
+    st["A"] = get("A", None) if "A" in init else torch.diff(phi, dim=0) / eng.dt
+    eng.set_state(**st)
+    if "B" in init:
+        eng.set_state(B=init["B"])
+    else:
+        eng.grad_space_into("phi", "B")
+    if "mu" in init:
+        eng.set_state(mu=init["mu"])
+    else:
+        eng.t["mu"].copy_(eng.t["b_fst"] - eng.t["b_end"])
+    if "E" in init:
+        eng.set_state(E=init["E"])
+    else:
+        eng.E_from_beta(1.0)
+    eng.refresh()
+    eng.z_valid = True
+
+
+def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8), tol=1e-4, tau=1.90,
+                is_palm=False, is_multi_threads=True, is_z_scaling=True, is_constant_scaling=False,
+                check_kkt_step_by_step=False, init_solution=None, tol_checkpoints=None, time_limit=1000,
+                device=None, leaf_size=24, show_progress=False, return_engine=False):
+    """B200 implementation of ``dot_surface_socp.socp.solver_socp.solver_socp``.
+
+    Extra keyword arguments (``device``, ``leaf_size``, ``show_progress``, ``return_engine``) are additions;
+    ``is_multi_threads`` is accepted and ignored (the two reference threads become stream order).
+    ``is_palm=True`` and ``is_constant_scaling=True`` are solver-only knobs that the reference's CLI /
+    interface cannot reach (interface.py:275-284); they are not built and raise."""
+    if is_palm or is_constant_scaling:
+        raise NotImplementedError("is_palm / is_constant_scaling are not part of the B200 hot path (see DESIGN.md)")
+    logging.basicConfig(level=LOG_INFO, format="%(message)s")
+    tol_checkpoints = _validate_checkpoints(tol_checkpoints, tol)
+    checkpoints = []
+
+    eng = Engine(n_time, geometry, congestion=congestion, eps=eps, tau=tau, device=device, leaf_size=leaf_size)
+    logging.log(LOG_KKT, f"---- Experiment info ".ljust(42, "-") + "\n"
+                f"Congestion parameter: {congestion}Number of discretization points in time: {n_time}\n"
+                f"Number of discretization vertices: {eng.V}\nNumber of discretization triangles: {eng.T}\nStepsize: {tau}")
+    if init_solution:
+        _warm_start(eng, init_solution)
+
+    hist = RunHistory(max_record_numbers=max(nit, 1), kkt_labels=KKT_LABELS, kkt_short_labels=KKT_SHORT, name="SOCP",
+                      show_progress=show_progress)
+    sched = PenaltySchedule()
+    lazy = LazyResidualCheck([(lambda i=i: eng.kkt(i)) for i in range(7)], tol)
+    hist.setup_time = dict(eng.timings)
+
+    hist.start()                                                                          # :565
+    hist.create_tol_progress(target_tol=tol)
+    prim_gap = 1.0 + 1.0 * np.exp(-100 * congestion)                                      # :568
+    if is_z_scaling:
+        logging.log(LOG_SCALING, "Initially scale z with z factor: 2.0")
+        eng.scale_z(2.0)                                                                  # :571-572
+    use_org = False
+    it, passed = -1, False
+    ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_a.record()
+    pending = False                                  # GPU work enqueued since ev_a
+    kkt_seconds = 0.0
+    start = time.perf_counter()                                                           # :655
+    for it in range(nit):                                                                 # :656
+        if is_z_scaling and sched.z_rescale_due(it, hist.get_current_kkt_errors()):       # :661-666
+            row = hist.get_current_kkt_errors()
+            with np.errstate(all="ignore"):
+                f = prim_gap * float(np.sqrt(np.float64(row[1]) / np.float64(row[0])))
+            if f > 1.25:
+                logging.log(LOG_SCALING, f"Rescale z at iteration {it} with z factor: {f}")
+                eng.scale_z(f)
+        # The wall-clock limit is sampled before the step is enqueued (the reference samples it after
+        # its synchronous steps, :725): the decision whether z_mid must be stored has to precede the launch.
+        time_up = (time.perf_counter() - start) > time_limit
+        adjust = sched.due(it) or time_up                                                 # :726
+        required = list(PRIM_SET + DUAL_SET) if adjust else None                          # :728-731
+        if adjust:
+            lazy.restart_ticks()                                                          # :735-736
+        will_check = check_kkt_step_by_step or lazy.will_fire(required) or it == nit - 1
+        eng.iterate(1, write_z=will_check)                                                # Steps 1-3, :674-722
+        pending = True
+
+        cost = lagr = None
+        if will_check and pending:
+            ev_b.record()
+        t_k = time.perf_counter()
+        if not check_kkt_step_by_step:
+            passed, _ = lazy.evaluate(required)                                           # :738
+        else:
+            passed, _ = lazy.evaluate(list(range(7)))                                     # :770
+            cost, lagr = eng.objective()                                                  # :773-775
+        errs = lazy.collect()                                                             # :739-740
+        org = [e[0] for e in errs]
+        sec = [e[1] for e in errs]
+        if will_check:
+            torch.cuda.current_stream(eng.device).synchronize()
+            hist.add_time(STEP_TAG, ev_a.elapsed_time(ev_b) * 1e-3)
+            kkt_seconds += time.perf_counter() - t_k
+            ev_a.record()
+            pending = False
+        if adjust and not check_kkt_step_by_step:
+            lazy.restart_ticks()                                                          # :742-743
+        hist.record(current_it=it, kkt_errors=org,
+                    history=None if cost is None else {"Transportation cost": cost, "Objective value": lagr})
+        error = max_or_none([org[k] for k in STOP_SET])                                   # :751
+        if error is not None and not check_kkt_step_by_step:
+            lazy.adapt(error)                                                             # :753-754
+        if error is not None and (check_kkt_step_by_step or not adjust):
+            hist.show_tol_progress(it, error)                                             # :757-768
+
+        if tol_checkpoints and error is not None and error <= tol_checkpoints[0]:         # :790-801
+            checkpoints.append(dict(mu=(eng.r * eng.from_internal("mu")).cpu().numpy(),
+                                    E=(eng.r * eng.from_internal("E")).cpu().numpy(),
+                                    iteration=it, time=hist.get_running_time(), kkt=np.array(org, dtype=object)))
+            tol_checkpoints.pop(0)
+
+        if passed or time_up:                                                             # :804
+            break
+        mx = max_or_none(sec)                                                             # :808-810
+        if mx is not None and mx < 5 * tol:
+            use_org = True
+        if adjust:                                                                        # :813-823
+            src = org if use_org else sec
+            gap = max_or_none([src[k] for k in PRIM_SET]) / max_or_none([src[k] for k in DUAL_SET])
+            eng.adjust_penalty(sched.next_penalty(eng.r, gap) / eng.r)
+
+    final = [eng.kkt(i)[0] for i in range(7)]                                             # :826-828
+    cost, lagr = eng.objective()                                                          # :829-831
+    hist.record(current_it=it, kkt_errors=final, history={"Transportation cost": cost, "Objective value": lagr})
+    hist.end()                                                                            # :844
+    hist.kkt_seconds = kkt_seconds
+    hist.evaluations = list(lazy.evaluations)
+    hist.gpu_launches = eng.launches
+    solution = eng.solution()                                                             # :845, :855-869
+    solution["checkpoints"] = checkpoints if checkpoints else None
+    logging.log(LOG_INFO, "---- Overview of solution ".ljust(42, "-") + "\n"
+                f"Congestion norm: {np.linalg.norm(solution['lambda_c'] - congestion * solution['mu']):.2f}\n"
+                f"Number of iterations: {it}\nIteration time: {hist.running_time:.2f}")
+    if return_engine:
+        return solution, hist, eng
+    return solution, hist.as_reference_history()
+
+
+# ----------------------------------------------------------------------------- decorators
+def translate_solution_socp_to_dot(solution_socp, geom):
+    """utils/type.py:48-65: densities -> masses (mu * area_v / 3, E * area_f)."""
+    av = np.asarray(geom["area_vertices"])[None, :] / 3.0
+    af = np.asarray(geom["area_triangles"])[None, :, None]
+    out = dict(mu=solution_socp["mu"] * av, E=solution_socp["E"] * af)
+    if solution_socp.get("checkpoints"):
+        out["checkpoints"] = [dict(mu=c["mu"] * av, E=c["E"] * af, iteration=c["iteration"], time=c["time"], kkt=c["kkt"])
+                              for c in solution_socp["checkpoints"]]
+    return out
+
+
+def _centre_in_time(sol, mu0, mu1):
+    """socp/solver_decorator.py:32-34."""
+    mid = 0.5 * (sol["mu"][:-1] + sol["mu"][1:])
+    sol["mu"] = np.concatenate([mu0[None, :], mid, mu1[None, :]], axis=0)
+
+
+def solver_raw(n_time, geometry, **kwargs):
+    """DOT-unit solution on the staggered time grid (reference name ``dot_solver_socp``)."""
+    sol, hist = solver_socp(n_time, geometry, **kwargs)
+    return translate_solution_socp_to_dot(sol, geometry), hist
+
+
+def solver(n_time, geometry, **kwargs):
+    """DOT-unit solution on the time-centred grid incl. mu0 / mu1 (reference name ``dot_solver_socp_center``)."""
+    sol, hist = solver_raw(n_time, geometry, **kwargs)
+    mu0, mu1 = np.asarray(geometry["mu0"]), np.asarray(geometry["mu1"])
+    _centre_in_time(sol, mu0, mu1)
+    for c in sol.get("checkpoints") or []:
+        _centre_in_time(c, mu0, mu1)
+    return sol, hist
+
+
+solver_raw.__name__ = "dot_solver_socp"
+solver.__name__ = "dot_solver_socp_center"

@@ -1,0 +1,158 @@
+/*
+ * dots_b200.h - C-ABI of the B200-native DOTs-SOCP hot path (libdots_b200.so).
+ *
+ * The reference (chlhnu/DOTs-SOCP) is pure Python and has no FFI of its own; the boundary it offers
+ * is the solver plug-in  solver(n_time, geometry, **kwargs) -> (solution, run_history)
+ * (dot_surface_socp/interface.py:106-122,295-299).  This header is what a host language binds to run
+ * the inner ALM iteration of dot_surface_socp/socp/solver_socp.py:656-823 on one B200; the Python
+ * mirror of the reference interface that sits on top of it is dots_socp_b200/solver.py, and the
+ * ctypes binding a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every array pointer is a DEVICE pointer to C-contiguous fp64 / int32 / int64 storage owned by the
+ *     caller (PyTorch tensors in the shipped host code); nothing is allocated or freed here except
+ *     CUDA graphs cached inside a dots_graph_t;
+ *   - every call takes the CUDA stream to enqueue on (a cudaStream_t passed as void*) and returns
+ *     immediately (no hidden synchronisation) unless its comment says "synchronises";
+ *   - return value: 0 on success, otherwise a negative dots error or a positive cudaError_t;
+ *     dots_last_error() gives the message of the last failure on the calling thread;
+ *   - INTERNAL LAYOUT.  Vertices are numbered in the nested-dissection elimination order, triangles
+ *     are renumbered for locality, and per-triangle data is structure-of-arrays with the triangle
+ *     index fastest:
+ *         vertex fields   phi[t][v]                 t = 0..nT      (reference: (nT+1, V))
+ *                         A, lam_c, mu, z_fst, z_end, b_fst, b_end, lam  [t][v], t = 0..nT-1
+ *         triangle fields B, E  [tau][xyz][f]        tau = 0..nT    (reference: (nT+1, T, 3))
+ *         corner fields   b_mid, z_mid [tau][side][k][xyz][f]       (reference: (nT, 2, 3, T, 3) indexed
+ *                         [t][s][k][f][xyz] with tau = t + s, side = s; the slots (tau=0, side=1) and
+ *                         (tau=nT, side=0) do not exist in the reference and stay zero)
+ *     The host side (dots_socp_b200/layout.py) converts between the reference layout and this one.
+ */
+#ifndef DOTS_B200_H
+#define DOTS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DOTS_ABI_VERSION 1
+
+/* scalar block read by the kernels from device memory (so CUDA graphs stay valid across penalty updates) */
+enum {
+    DOTS_P_R = 0,        /* penalty r                      (solver_socp.py:97, :367-371)              */
+    DOTS_P_S,            /* scale_factor_z                 (:321, :373-395)                           */
+    DOTS_P_D,            /* constant_d                     (:320)                                     */
+    DOTS_P_CONG,         /* congestion                     (:28)                                      */
+    DOTS_P_TAU,          /* multiplier step tau            (:32)                                      */
+    DOTS_P_EPS,          /* Laplacian regularisation eps   (:30)                                      */
+    DOTS_P_COUNT = 8
+};
+
+/* Problem description + device storage.  Filled by the host side once; passed to every call. */
+typedef struct dots_ctx {
+    int32_t abi_version;
+    int32_t n_time;            /* nT: number of time intervals                                        */
+    int32_t n_vert;            /* V                                                                   */
+    int32_t n_tri;             /* T                                                                   */
+    int32_t m_pad;             /* number of time modes nT+1 padded to a multiple of 32                */
+    int32_t n_nodes;           /* separator-tree nodes                                                */
+    int32_t n_levels;          /* separator-tree levels                                               */
+    int32_t n_sm;              /* multiprocessor count (grid sizing)                                  */
+
+    /* ---- mesh constants (read-only) ---- */
+    const int32_t *tri;        /* [3][T]    vertex of corner k of triangle f                          */
+    const double  *hat_grad;   /* [3][3][T] hat-function gradients g[k][xyz][f]  (surface_pre_computations_socp.py:30-37) */
+    const double  *area_f;     /* [T]                                                                 */
+    const double  *area_v;     /* [V]       (sum of incident |f|)/3               (solver_socp.py:112) */
+    const double  *diag_soc;   /* [3][T]    sqrt(|f| / area_v[tri[k][f]])         (:172-192)           */
+    const int32_t *vc_ptr;     /* [V+1]     CSR vertex -> incident corners                            */
+    const int32_t *vc_idx;     /* [3T]      corner ids k*T+f, ascending per vertex                    */
+    const double  *qmat;       /* [nT+1][m_pad] time eigenbasis Q[t][mode] (laplacian_inverse_socp.py:31) */
+
+    /* ---- batched multifrontal factor of K + shift_mode*diag(area_v) (dots_socp_b200/nested.py) ---- */
+    const double  *panels;     /* [panel_entries][m_pad]                                              */
+    const int32_t *nd_off;     /* [n_nodes] first vertex owned                                        */
+    const int32_t *nd_s;       /* [n_nodes] |S|                                                       */
+    const int32_t *nd_b;       /* [n_nodes] |B|                                                       */
+    const int32_t *nd_child;   /* [n_nodes][2] child node ids or -1                                   */
+    const int64_t *nd_panel;   /* [n_nodes] panel offset (entries)                                    */
+    const int64_t *nd_front;   /* [n_nodes] offset into front_idx / child_pos                         */
+    const int64_t *nd_upd;     /* [n_nodes] offset of the update vector (rows)                        */
+    const int32_t *front_idx;  /* [sum(s+b)] vertex of every front row                                */
+    const int32_t *child_pos;  /* [2][sum(s+b)] row in the child's update vector or -1                */
+    const int32_t *lvl_ptr;    /* [n_levels+1] ranges into lvl_items                                  */
+    const int32_t *lvl_items;  /* work items (node, first row, n rows) as int32 triples, forward      */
+    const int32_t *lvb_ptr;    /* [n_levels+1] ranges into lvb_items                                  */
+    const int32_t *lvb_items;  /* work items (node, first col, n cols) as int32 triples, backward     */
+    const int32_t *h_lvl_ptr;  /* HOST copies of lvl_ptr / lvb_ptr (grid sizing of the per-level launches) */
+    const int32_t *h_lvb_ptr;
+    int64_t front_total;       /* sum(s+b)                                                            */
+
+    /* ---- ALM state (read-write) ---- */
+    double *params;            /* [DOTS_P_COUNT]                                                      */
+    double *phi, *A, *lam_c, *mu, *z_fst, *z_end, *b_fst, *b_end, *lam;
+    double *bnd0, *bnd1;       /* [V] rows t=0 and t=nT of boundary_time_with_area (:267-270)         */
+    double *B, *E;
+    double *b_mid, *z_mid;
+    double *corner_nrm;        /* [nT+1][2][3][T] per-corner squared norms feeding the next projection */
+    double *corner_div;        /* [nT+1][3][T]    per-corner divergence terms feeding the next rhs     */
+
+    /* ---- work space ---- */
+    double *rhs;               /* [nT+1][V]                                                           */
+    double *hat;               /* [V][m_pad]  transformed rhs, then solution                          */
+    double *ywork;             /* [V][m_pad]  forward-sweep result                                    */
+    double *upd;               /* [sum b][m_pad] update vectors                                       */
+    double *red_part;          /* [red_blocks][8] block partial sums                                  */
+    double *red_out;           /* [8] reduced sums (device)                                           */
+    int32_t red_blocks;
+    int32_t reserved0;
+} dots_ctx_t;
+
+/* ------------------------------------------------------------------------------------------------ */
+int  dots_abi_version(void);
+int  dots_ctx_sizeof(void);                      /* sizeof(dots_ctx_t): the binding checks its mirror  */
+const char *dots_last_error(void);
+
+/* ---- one ALM iteration, fused (rows a1-a8 of SURVEY.md section 8) ---------------------------------
+ * dots_step_phi   : rhs assembly + time transform + per-mode solves + inverse transform -> phi
+ *                   (vanilla_solve_laplacian solver_socp.py:976-986, __laplacian_invert laplacian_inverse_socp.py:52-61)
+ * dots_step_vertex: per (t,v): dt_phi, cone multiplier lam, z_fst/z_end, A, lam_c, mu, b_fst, b_end
+ *                   (vertex halves of vanilla_solve_proj_soc :988-1042, vanilla_solve_q_lambda :1044-1065, Step 3 :716-722)
+ * dots_step_tri   : per (tau,f): dx_phi, z_mid, B, E, b_mid and the corner terms of the next iteration
+ *                   (triangle halves of the same three steps + decouple_spacial :923-942 / adjoint :944-959)
+ *                   write_z != 0 also stores z_mid (needed by KKT #1 and by the returned solution).
+ * dots_iterate    : n_iter x (phi, vertex, tri); write_z applies to the last one.                    */
+int dots_step_phi(const dots_ctx_t *c, void *stream);
+int dots_step_vertex(const dots_ctx_t *c, void *stream);
+int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream);
+int dots_iterate(const dots_ctx_t *c, int n_iter, int write_z, void *stream);
+
+/* recompute corner_nrm / corner_div from (B, E, b_mid) after the state was set or rescaled */
+int dots_refresh_corner_terms(const dots_ctx_t *c, void *stream);
+
+/* ---- rescaling (row a12) --------------------------------------------------------------------------
+ * dots_scale_dual: adjust_penalty :367-371  (mu, E, boundary, b_* divided by factor) + refresh.
+ * dots_scale_z   : scale_variable_z :373-395 with cumulative factor s_cum (z_* *= s_cum, b_* /= s_cum,
+ *                  mu = s_cum (b_fst - b_end), E = -adjoint(b_mid; s_cum)) + refresh.
+ * The caller updates params[] itself (dots_set_params).                                              */
+int dots_scale_dual(const dots_ctx_t *c, double factor, void *stream);
+int dots_scale_z(const dots_ctx_t *c, double s_cum, void *stream);
+int dots_set_params(const dots_ctx_t *c, const double *host_params, void *stream);
+
+/* ---- residuals (rows a9-a11).  Writes the raw weighted sums (un-normalised, un-rooted) of KKT condition
+ * `which` (0..6, order of solver_socp.py:591-639) or of the objective (which = 7) into host_out[8].
+ * Synchronises the stream.  Slot meaning per condition is documented in dots_socp_b200/solver.py.   */
+int dots_kkt_sums(const dots_ctx_t *c, int which, double *host_out, void *stream);
+
+/* ---- operator-level entry points on the internal layout (rows a5, a6, a7, a8) ---------------------- */
+int dots_phi_rhs(const dots_ctx_t *c, void *stream);                       /* -> c->rhs                */
+int dots_time_transform(const dots_ctx_t *c, int inverse, void *stream);   /* rhs -> hat / hat -> phi   */
+int dots_mode_solves(const dots_ctx_t *c, void *stream);                   /* hat <- (K+shift M)^-1 hat */
+int dots_grad_space(const dots_ctx_t *c, const double *phi, double *out, void *stream);  /* [nT+1][3][T] */
+int dots_div_space(const dots_ctx_t *c, const double *x, double *out, void *stream);     /* [nT+1][V]    */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOTS_B200_H */

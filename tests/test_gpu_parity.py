@@ -1,0 +1,224 @@
+"""GPU parity: the CUDA hot path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (fp64, north_star): per-iterate primal/dual iterates within 1e-8 relative (phi modulo its
+additive constant), identical iteration counts, transport cost within 1e-6 relative.  Operator-level
+checks use 1e-11 or tighter.  Nothing here reads /root/reference (it does not exist on the GPU box);
+the reference's own outputs enter through the committed fixtures in tests/golden."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import alm_oracle as orc          # noqa: E402  (checker only)
+from dots_socp_b200 import synth              # noqa: E402
+from dots_socp_b200.engine import Engine      # noqa: E402
+from dots_socp_b200 import solver as b200     # noqa: E402
+
+O2E = dict(phi="phi", A="A", B="B", lam_c="lam_c", mu="mu", E="E", z_fst="z_fst", z_mid="z_mid", z_end="z_end",
+           b_fst="b_fst", b_mid="b_mid", b_end="b_end")
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def centred(phi, w):
+    return phi - (phi * w[None, :]).sum() / (w.sum() * phi.shape[0])
+
+
+def make_pair(example, n_time, congestion=0.0, leaf=8, **exkw):
+    geo, _ = synth.example(example, **exkw)
+    alm = orc.OracleALM(n_time, geo, congestion=congestion)
+    eng = Engine(n_time, geo, congestion=congestion, leaf_size=leaf)
+    eng.scale_z(2.0)
+    return geo, alm, eng
+
+
+def push_state(alm, eng):
+    st = alm.state()
+    eng.set_scalars(r=alm.r, s=alm.s, d=alm.d, norm_d=alm.norm_d)
+    eng.set_state(**{O2E[k]: v for k, v in st.items()})
+    b = alm.bnd
+    eng.t["bnd0"].copy_(torch.from_numpy(b[0][eng.perm_v]))
+    eng.t["bnd1"].copy_(torch.from_numpy(b[-1][eng.perm_v]))
+
+
+def compare_states(alm, eng, tol, label=""):
+    got = eng.get_state()
+    ref = alm.state()
+    worst = {}
+    for k, v in ref.items():
+        a, b = got[O2E[k]], v
+        if k == "phi":
+            a, b = centred(a, alm.ops.area_v), centred(b, alm.ops.area_v)
+        worst[k] = rel(a, b)
+    bad = {k: e for k, e in worst.items() if not e < tol}
+    assert not bad, f"{label} mismatch {bad} (all: {worst})"
+    return worst
+
+
+# ---------------------------------------------------------------------------------------------- operators
+@pytest.mark.parametrize("example,n_time,leaf", [("icosphere2", 7, 8), ("plane8", 6, 6), ("icosphere3", 31, 16),
+                                                 ("icosphere2", 40, 8)])
+def test_laplacian_inverse_rows_a7_a8(example, n_time, leaf):
+    """rhs assembly, time transform, per-mode solves, inverse transform vs the oracle's SuperLU path."""
+    geo, alm, eng = make_pair(example, n_time, congestion=0.05, leaf=leaf)
+    rng = np.random.default_rng(3)
+    o = alm.ops
+    alm.A, alm.lam_c, alm.mu = (rng.standard_normal((n_time, o.V)) for _ in range(3))
+    alm.B, alm.E = (rng.standard_normal((n_time + 1, o.T, 3)) for _ in range(2))
+    push_state(alm, eng)
+    rhs_ref = o.phi_rhs(alm.A, alm.B, alm.lam_c, alm.mu, alm.E, alm.bnd, alm.phi)
+    from dots_socp_b200 import capi
+    capi.check(eng.lib.dots_phi_rhs(eng._ctxp, eng.stream))
+    rhs = eng.from_internal("rhs", eng.t["rhs"]).cpu().numpy()
+    assert rel(rhs, rhs_ref) < 1e-12
+    capi.check(eng.lib.dots_step_phi(eng._ctxp, eng.stream))
+    phi = eng.from_internal("phi").cpu().numpy()
+    phi_ref = o.lap_inv(rhs_ref)
+    assert rel(centred(phi, o.area_v), centred(phi_ref, o.area_v)) < 1e-9
+    # what the iteration consumes are the gradients of phi
+    assert rel(orc.grad_time(o.dt, phi), orc.grad_time(o.dt, phi_ref)) < 1e-9
+    assert rel(orc.grad_space(o.G, phi), orc.grad_space(o.G, phi_ref)) < 1e-9
+    # residual of the space-time operator itself
+    lap = orc.div_time(o.dt, o.area_v[None] * orc.grad_time(o.dt, phi)) + orc.div_space(o.D, o.area_f[None, :, None] * orc.grad_space(o.G, phi))
+    assert rel(lap, rhs_ref) < 1e-9
+
+
+def test_grad_div_space_rows_a5_a6():
+    geo, alm, eng = make_pair("icosphere2", 5)
+    o = alm.ops
+    rng = np.random.default_rng(4)
+    phi = rng.standard_normal((6, o.V))
+    x = rng.standard_normal((6, o.T, 3))
+    from dots_socp_b200 import capi
+    phi_i, x_i = eng.to_internal("phi", phi), eng.to_internal("B", x)
+    g_out, d_out = torch.empty_like(eng.t["B"]), torch.empty_like(eng.t["phi"])
+    capi.check(eng.lib.dots_grad_space(eng._ctxp, phi_i.data_ptr(), g_out.data_ptr(), eng.stream))
+    capi.check(eng.lib.dots_div_space(eng._ctxp, x_i.data_ptr(), d_out.data_ptr(), eng.stream))
+    assert rel(eng.from_internal("B", g_out).cpu().numpy(), orc.grad_space(o.G, phi)) < 1e-13
+    assert rel(eng.from_internal("phi", d_out).cpu().numpy(), orc.div_space(o.D, x)) < 1e-13
+
+
+@pytest.mark.parametrize("congestion", [0.0, 0.1])
+def test_fused_step_rows_a1_a4(congestion):
+    """Projection + q/lambda + multiplier update from a random state with a prescribed phi."""
+    n_time = 6
+    geo, alm, eng = make_pair("icosphere2", n_time, congestion=congestion)
+    o = alm.ops
+    rng = np.random.default_rng(5)
+    for name in ("A", "lam_c", "mu", "b_fst", "b_end"):
+        setattr(alm, name, rng.standard_normal((n_time, o.V)))
+    for name in ("B", "E"):
+        setattr(alm, name, rng.standard_normal((n_time + 1, o.T, 3)))
+    alm.b_mid = rng.standard_normal((n_time, 2, 3, o.T, 3))
+    alm.phi = rng.standard_normal((n_time + 1, o.V))
+    alm.r = 1.7
+    push_state(alm, eng)
+    # oracle: Step 1-2, Step 2, Step 3 with this phi (no Laplacian solve)
+    s, d, tau = alm.s, alm.d, alm.tau
+    alm.z_fst, alm.z_mid, alm.z_end = o.proj_soc(alm.A, alm.B, alm.b_fst, alm.b_mid, alm.b_end, d, s)
+    alm.dt_phi, alm.dx_phi = orc.grad_time(o.dt, alm.phi), orc.grad_space(o.G, alm.phi)
+    alm.step_q()
+    alm.Bd_new = orc.decouple(alm.B, s)
+    alm.mu = alm.mu + tau * (alm.dt_phi - alm.A - alm.lam_c)
+    alm.E = alm.E + tau * (alm.dx_phi - alm.B)
+    alm.b_fst = alm.b_fst + tau * (alm.z_fst + s * alm.A - d)
+    alm.b_mid = alm.b_mid + tau * (alm.z_mid - alm.Bd_new)
+    alm.b_end = alm.b_end + tau * (alm.z_end - s * alm.A - d)
+    from dots_socp_b200 import capi
+    capi.check(eng.lib.dots_step_vertex(eng._ctxp, eng.stream))
+    capi.check(eng.lib.dots_step_tri(eng._ctxp, 1, eng.stream))
+    compare_states(alm, eng, 1e-12, "fused step")
+
+
+# ---------------------------------------------------------------------------------------------- iterates
+@pytest.mark.parametrize("example,n_time,congestion,exkw", [
+    ("icosphere2", 7, 0.0, {}), ("icosphere2", 7, 0.1, {}), ("plane8", 6, 0.0, {}),
+    ("knot", 8, 0.05, dict(n_u=40, n_v=6)), ("icosphere3", 31, 0.0, {})])
+def test_iterates_match_oracle(example, n_time, congestion, exkw):
+    geo, alm, eng = make_pair(example, n_time, congestion=congestion, **exkw)
+    done = 0
+    for k in (1, 2, 5, 50):
+        for _ in range(k - done):
+            alm.iterate()
+        eng.iterate(k - done, write_z=True)
+        done = k
+        compare_states(alm, eng, 1e-8, f"{example} nT={n_time} k={k}")
+        if k == 5:                                   # penalty update + z rescale in the middle of the run
+            alm.adjust_penalty(1.35)
+            eng.adjust_penalty(1.35)
+            alm.scale_z(1.3)
+            eng.scale_z(1.3)
+            compare_states(alm, eng, 1e-8, "after rescale")
+
+
+def test_kkt_and_objective_rows_a9_a11():
+    geo, alm, eng = make_pair("icosphere2", 7, congestion=0.1)
+    for _ in range(12):
+        alm.iterate()
+    eng.iterate(12, write_z=True)
+    for i in range(7):
+        got, ref = eng.kkt(i), alm.kkt(i)
+        assert got[0] == pytest.approx(ref[0], rel=1e-8), (i, got, ref)
+        assert (got[1] is None) == (ref[1] is None)
+    c_got, c_ref = eng.objective(), alm.objective()
+    assert c_got[0] == pytest.approx(c_ref[0], rel=1e-8) and c_got[1] == pytest.approx(c_ref[1], rel=1e-8)
+
+
+# ---------------------------------------------------------------------------------------------- end to end
+@pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005",
+                                  "ico2_nt15_tol1e-4", "ico3_nt31_c0", "ico3_nt31_c01"])
+def test_solver_matches_reference_fixture(golden, name):
+    """Through the public solver_socp: iteration count, KKT schedule (which residual on which iteration), penalty
+    path, transport cost and the returned mu against the fixtures generated by the unmodified reference."""
+    z, geo, n_time, kw = golden(name)
+    sol, hist, eng = b200.solver_socp(n_time, geo, leaf_size=8, return_engine=True, **kw)
+    assert int(hist.kkt_iteration[-1]) == int(z["iterations"])
+    ref_rows = z["kkt_rows"]
+    assert hist.kkt_errors.shape == ref_rows.shape
+    assert np.array_equal(np.isnan(hist.kkt_errors), np.isnan(ref_rows))
+    m = ~np.isnan(ref_rows)
+    assert np.allclose(hist.kkt_errors[m], ref_rows[m], rtol=1e-6, atol=1e-12)
+    cost = hist.history["Transportation cost"][-1]
+    assert cost == pytest.approx(float(z["cost"]), rel=1e-6)
+    assert math.sqrt(2 * cost) == pytest.approx(math.sqrt(2 * float(z["cost"])), rel=1e-6)          # W2
+    assert rel(sol["mu"], z["sol_mu"]) < 1e-6
+    assert sol["z_mid"].shape == (n_time, 2, 3, geo["triangles"].shape[0], 3)
+    if "sol_z_mid" in z:
+        for key in ("A", "B", "lambda_c", "E", "z_fst", "z_mid", "z_end", "beta_fst", "beta_mid", "beta_end"):
+            assert rel(sol[key], z["sol_" + key]) < 1e-6, key
+
+
+def test_drop_in_decorators_and_checkpoints():
+    geo, _ = synth.example("icosphere2")
+    sol, hist = b200.solver(7, geo, tol=1e-3, nit=400, tol_checkpoints=[1e-1, 1e-2], leaf_size=8)
+    V = geo["vertices"].shape[0]
+    assert sol["mu"].shape == (8, V)                                  # centred grid incl. mu0, mu1
+    assert np.allclose(sol["mu"][0], geo["mu0"]) and np.allclose(sol["mu"][-1], geo["mu1"])
+    assert np.allclose(sol["mu"].sum(axis=1), 1.0, atol=5e-3)         # mass conservation per time layer
+    assert sol["checkpoints"] and sol["checkpoints"][0]["mu"].shape == (8, V)
+    with pytest.raises(ValueError):
+        b200.solver_socp(7, geo, tol=1e-3, tol_checkpoints=[1e-4])
+
+
+def test_large_problem_properties():
+    """Full-size style check (size-independent properties): solve residual of the space-time operator and
+    feasibility of the cone projection on a 10k-vertex icosphere with nT=63."""
+    geo, _ = synth.example("icosphere5")
+    n_time = 63
+    eng = Engine(n_time, geo, leaf_size=24)
+    eng.scale_z(2.0)
+    eng.iterate(3, write_z=True)
+    st = eng.get_state(("phi", "z_fst", "z_end", "z_mid", "A", "lam_c", "mu", "B", "E"))
+    ops = orc.MeshOps(n_time, geo, build_inverse=False)
+    # cone feasibility in the area-weighted metric: ||u|| <= z_fst   
+    zsq = (ops.diag_soc[None, None, :, :, None] * st["z_mid"]) ** 2
+    corner = zsq.sum(axis=(1, 4)).reshape(n_time, 3 * ops.T)
+    nrm = np.sqrt(ops.M_oneT.dot(corner.T).T + st["z_end"] ** 2)
+    assert (nrm <= st["z_fst"] * (1 + 1e-12) + 1e-12).all()
+    assert np.isfinite(st["phi"]).all()

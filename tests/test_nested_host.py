@@ -1,0 +1,91 @@
+"""Host-side checks of the nested-dissection multifrontal setup (dots_socp_b200/nested.py).
+
+The numpy sweep below walks the same panel layout the CUDA kernels stream, so a layout or index-map
+bug shows up here without a GPU."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from dots_socp_b200 import nested, surface, synth
+
+
+def panel_rows(sym, panels, i):
+    """Dense (s+b, s, M) view of node i's panel (upper triangle of the first block zero)."""
+    s, b = int(sym.s[i]), int(sym.b[i])
+    p0 = int(sym.panel_off[i])
+    out = np.zeros((s + b, s, panels.shape[1]))
+    tri = np.tril_indices(s)
+    out[tri[0], tri[1]] = panels[p0:p0 + s * (s + 1) // 2]
+    if b and s:
+        out[s:] = panels[p0 + s * (s + 1) // 2:p0 + nested.panel_size(s, b)].reshape(b, s, -1)
+    return out
+
+
+def sweep_solve(sym, panels, rhs):
+    """rhs: (n, M) in NEW ordering. Forward (leaves->root) then backward, mirroring the kernels."""
+    n, M = rhs.shape
+    y = np.zeros_like(rhs)
+    upd = [None] * sym.n_nodes
+    for i in np.argsort(sym.level, kind="stable"):
+        s, b = int(sym.s[i]), int(sym.b[i])
+        f0 = sym.front_off[i]
+        P = panel_rows(sym, panels, i)
+        r = np.zeros((s + b, M))
+        r[:s] = rhs[sym.off[i]:sym.off[i] + s]
+        for slot in range(2):
+            k = sym.child[i, slot]
+            if k >= 0 and sym.b[k]:
+                cp = sym.child_pos[slot, f0:f0 + s + b]
+                hit = cp >= 0
+                r[hit] += upd[k][cp[hit]]
+        out = np.einsum("ijm,jm->im", P, r[:s])
+        y[sym.off[i]:sym.off[i] + s] = out[:s]
+        upd[i] = r[s:] - out[s:]
+    x = np.zeros_like(rhs)
+    for i in np.argsort(-sym.level, kind="stable"):
+        s, b = int(sym.s[i]), int(sym.b[i])
+        f0 = sym.front_off[i]
+        P = panel_rows(sym, panels, i)
+        v = np.concatenate([y[sym.off[i]:sym.off[i] + s], -x[sym.front_idx[f0 + s:f0 + s + b]]], axis=0)
+        x[sym.off[i]:sym.off[i] + s] = np.einsum("ijm,im->jm", P, v)
+    return x
+
+
+@pytest.mark.parametrize("example,leaf", [("icosphere2", 8), ("icosphere3", 24), ("plane8", 6), ("knot", 16)])
+def test_batched_factor_solves_all_modes(example, leaf):
+    kw = dict(n_u=60, n_v=6) if example == "knot" else {}
+    geo, _ = synth.example(example, **kw)
+    v, t = geo["vertices"], geo["triangles"]
+    K = surface.stiffness_matrix(v, t)
+    mass = surface.incident_area_sum(v.shape[0], t, surface.triangle_areas(v, t)) / 3.0
+    sym = nested.analyse(v, K, leaf_size=leaf)
+    assert sorted(sym.perm.tolist()) == list(range(v.shape[0]))
+    n_time = 7
+    k = np.arange(n_time + 1)
+    shifts = 4.0 * n_time ** 2 * np.sin(np.pi * k / (2 * (n_time + 1))) ** 2
+    panels = nested.factor_batched(sym, K, mass, shifts, m_pad=8)
+    rng = np.random.default_rng(0)
+    rhs_old = rng.standard_normal((v.shape[0], 8))
+    rhs_old[:, 0] -= rhs_old[:, 0].mean()                  # compatible rhs for the singular mode
+    x_new = sweep_solve(sym, panels, rhs_old[sym.perm])
+    x_old = np.empty_like(x_new)
+    x_old[sym.perm] = x_new
+    for m in range(1, 8):
+        A = (K + shifts[m] * sp.diags(mass)).tocsc()
+        ref = spla.spsolve(A, rhs_old[:, m])
+        assert np.abs(x_old[:, m] - ref).max() / np.abs(ref).max() < 1e-11
+    # mode 0: K x = b up to the pinned constant
+    res = K @ x_old[:, 0] - rhs_old[:, 0]
+    assert np.abs(res).max() / np.abs(rhs_old[:, 0]).max() < 1e-10
+
+
+def test_levels_respect_tree():
+    geo, _ = synth.example("icosphere3")
+    K = surface.stiffness_matrix(geo["vertices"], geo["triangles"])
+    sym = nested.analyse(geo["vertices"], K, leaf_size=16)
+    for i in range(sym.n_nodes):
+        for k in sym.child[i]:
+            if k >= 0:
+                assert sym.level[k] < sym.level[i] and sym.parent[k] == i
+    assert sym.parent[sym.n_nodes - 1] == -1
