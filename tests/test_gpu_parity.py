@@ -16,7 +16,7 @@ torch = pytest.importorskip("torch")
 from oracle import alm_oracle as orc          # noqa: E402  (checker only)
 from dots_socp_b200 import synth              # noqa: E402
 from dots_socp_b200.engine import Engine      # noqa: E402
-from dots_socp_b200 import solver as b200     # noqa: E402
+import dots_socp_b200 as b200                  # noqa: E402
 
 O2E = dict(phi="phi", A="A", B="B", lam_c="lam_c", mu="mu", E="E", z_fst="z_fst", z_mid="z_mid", z_end="z_end",
            b_fst="b_fst", b_mid="b_mid", b_end="b_end")
