@@ -99,7 +99,8 @@ class Engine:
         Q, lam_t = time_basis(nT)
         self.Q, self.lam_t = Q, lam_t
         shifts = -lam_t + self.eps                       # (L + (lam - eps) M) = -(K + (|lam| + eps) M)   (laplacian_inverse_socp.py:37-38)
-        panels = nested.factor_batched(sym, K, area_v, shifts, m_pad=self.m_pad)
+        panels = nested.factor_batched_device(sym, K, area_v, shifts, m_pad=self.m_pad, device=self.device)
+        torch.cuda.synchronize(self.device)
         tm["factorization"] = time.perf_counter() - t0
 
         # ---- upload --------------------------------------------------------------------------------
@@ -132,14 +133,14 @@ class Engine:
             area_f=up("area_f", area_f_n, np.float64), area_v=up("area_v", area_v_n, np.float64),
             diag_soc=up("diag_soc", diag, np.float64), vc_ptr=up("vc_ptr", vc_ptr, np.int32),
             vc_idx=up("vc_idx", vc_corner * T + vc_tri, np.int32), qmat=up("qmat", qpad, np.float64),
-            panels=up("panels", panels, np.float64),
+            panels=panels,
             nd_off=up("nd_off", sym.off, np.int32), nd_s=up("nd_s", sym.s, np.int32), nd_b=up("nd_b", sym.b, np.int32),
             nd_child=up("nd_child", sym.child, np.int32), nd_panel=up("nd_panel", sym.panel_off[:-1], np.int64),
             nd_front=up("nd_front", sym.front_off[:-1], np.int64), nd_upd=up("nd_upd", sym.upd_off[:-1], np.int64),
             front_idx=up("front_idx", sym.front_idx, np.int32), child_pos=up("child_pos", sym.child_pos, np.int32),
             lvl_ptr=up("lvl_ptr", fwd_ptr, np.int32), lvl_items=up("lvl_items", fwd_items, np.int32),
             lvb_ptr=up("lvb_ptr", bwd_ptr, np.int32), lvb_items=up("lvb_items", bwd_items, np.int32))
-        del panels
+        self._keep["panels"] = panels
         for k, ten in const.items():
             setattr(ctx, k, ten.data_ptr())
         ctx.h_lvl_ptr = self._h_fwd_ptr.ctypes.data

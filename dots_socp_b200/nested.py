@@ -257,3 +257,78 @@ def factor_batched(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shifts: np
 def level_schedule(sym: Symbolic):
     """Nodes grouped by tree level (leaves first).  Returns list of int64 arrays of node ids."""
     return [np.nonzero(sym.level == lv)[0].astype(np.int64) for lv in range(sym.n_levels)]
+
+
+def factor_batched_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shifts: np.ndarray, m_pad: int, device,
+                          pin_singular: bool = True):
+    """Same numeric factorisation as ``factor_batched`` but with the dense front algebra on the GPU.
+
+    SETUP path (row (f)1 of SURVEY.md section 8), not the per-iteration hot path: the batched dense
+    Cholesky / triangular-solve / GEMM calls go through torch.linalg (cuSOLVER / cuBLAS) on fp64 tensors
+    of shape (modes, n, n).  Returns the panel tensor (panel_entries, m_pad) on ``device``."""
+    import torch
+
+    shifts_t = torch.as_tensor(np.asarray(shifts, dtype=np.float64), device=device)
+    n_modes = shifts_t.numel()
+    Kp = K[sym.perm][:, sym.perm].tocsr()
+    Kp.sort_indices()
+    massp = torch.as_tensor(np.asarray(mass, dtype=np.float64)[sym.perm], device=device)
+    indptr, indices, data = Kp.indptr, Kp.indices, Kp.data
+    panels = torch.zeros((sym.panel_entries, m_pad), dtype=torch.float64, device=device)
+    singular = [m for m in range(n_modes) if float(shifts[m]) == 0.0] if pin_singular else []
+    pin_value = float(Kp.diagonal().mean())
+    updates = [None] * sym.n_nodes
+    tril_cache = {}
+    dev_i64 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int64), device=device)
+    for i in range(sym.n_nodes):
+        s, b = int(sym.s[i]), int(sym.b[i])
+        nf = s + b
+        lo = int(sym.off[i])
+        f0 = int(sym.front_off[i])
+        rows = sym.front_idx[f0:f0 + nf]
+        F = torch.zeros((n_modes, nf, nf), dtype=torch.float64, device=device)
+        if s:
+            a0, a1 = indptr[lo], indptr[lo + s]
+            r = np.repeat(np.arange(s), np.diff(indptr[lo:lo + s + 1]))
+            c_new, v = indices[a0:a1], data[a0:a1]
+            keep = c_new >= lo
+            r, c_new, v = r[keep], c_new[keep], v[keep]
+            c = np.searchsorted(rows, c_new)
+            rt, ct = dev_i64(r), dev_i64(c)
+            vt = torch.as_tensor(v, device=device)
+            F[:, rt, ct] = vt
+            F[:, ct, rt] = vt
+            d = torch.arange(s, device=device)
+            F[:, d, d] += shifts_t[:, None] * massp[None, lo:lo + s]
+            if i == sym.n_nodes - 1:
+                for m in singular:
+                    F[m, s - 1, s - 1] += pin_value
+        for slot in range(2):
+            k = int(sym.child[i, slot])
+            if k >= 0 and sym.b[k]:
+                cp = sym.child_pos[slot, f0:f0 + nf]
+                where = np.nonzero(cp >= 0)[0]
+                where = dev_i64(where[np.argsort(cp[where])])
+                F[:, where[:, None], where[None, :]] += updates[k]
+                updates[k] = None
+        if s == 0:
+            updates[i] = F if b else None
+            continue
+        L11 = torch.linalg.cholesky(F[:, :s, :s])
+        eye = torch.eye(s, dtype=torch.float64, device=device).expand(n_modes, s, s)
+        Linv = torch.linalg.solve_triangular(L11, eye, upper=False)
+        if s not in tril_cache:
+            tril_cache[s] = torch.tril_indices(s, s, device=device)
+        tri = tril_cache[s]
+        p0 = int(sym.panel_off[i])
+        ntri = s * (s + 1) // 2
+        panels[p0:p0 + ntri, :n_modes] = Linv[:, tri[0], tri[1]].T
+        if m_pad > n_modes:
+            dd = torch.arange(s, device=device)
+            panels[p0 + dd * (dd + 1) // 2 + dd, n_modes:] = 1.0
+        if b:
+            L21 = F[:, s:, :s] @ Linv.mT
+            W21 = L21 @ Linv
+            panels[p0 + ntri:p0 + ntri + b * s, :n_modes] = W21.reshape(n_modes, b * s).T
+            updates[i] = F[:, s:, s:] - L21 @ L21.mT
+    return panels

@@ -80,8 +80,11 @@ def corner_maps(n_v, triangles, area):
 # =============================================================================
 # space-time Laplacian inverse  (utils/laplacian_inverse_socp.py)
 # =============================================================================
-def build_laplacian_inverse(n_time, dt, area_v, L, eps=0.0):
-    """Ref :11-50: dense eigh of the Neumann time Laplacian, one sparse LU per time mode."""
+def build_laplacian_inverse(n_time, dt, area_v, L, eps=0.0, n_threads=1):
+    """Ref :11-50: dense eigh of the Neumann time Laplacian, one sparse LU per time mode.
+
+    ``n_threads > 1`` (bench.py's CPU arm only) factorises / solves the independent modes from a thread pool
+    (SuperLU releases the GIL); the arithmetic per mode is unchanged."""
     n = n_time + 1
     Lt = np.zeros((n, n))
     i = np.arange(1, n_time)
@@ -90,13 +93,24 @@ def build_laplacian_inverse(n_time, dt, area_v, L, eps=0.0):
     Lt *= 1 / (dt ** 2)
     lam, Q = np.linalg.eigh(Lt)                                                    # :31
     mass = sp.diags([area_v], [0])
-    solves = [spla.splu((L + (lam[a] - eps) * mass).tocsc()).solve for a in range(n)]   # :35-41 (factorized == splu.solve)
+    make = lambda a: spla.splu((L + (lam[a] - eps) * mass).tocsc()).solve            # :35-41 (factorized == splu.solve)
+    pool = None
+    if n_threads > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(n_threads)
+        solves = list(pool.map(make, range(n)))
+    else:
+        solves = [make(a) for a in range(n)]
 
     def invert(rhs):                                                               # :52-61
         hat = np.array(np.dot(Q.T, rhs))
         sol = np.zeros_like(hat)
-        for a in range(n):
-            sol[a, :] = solves[a](hat[a, :])
+        if pool is not None:
+            for a, x in enumerate(pool.map(lambda a: solves[a](hat[a, :]), range(n))):
+                sol[a, :] = x
+        else:
+            for a in range(n):
+                sol[a, :] = solves[a](hat[a, :])
         return np.array(np.dot(Q, sol))
 
     return invert, lam, Q
@@ -156,7 +170,7 @@ def adjoint_time_average(x):                               # :961-974  correlate
 class MeshOps:
     """Everything ``solver_socp`` prepares before its loop (ref :97-236)."""
 
-    def __init__(self, n_time, geometry, eps=0.0, build_inverse=True):
+    def __init__(self, n_time, geometry, eps=0.0, build_inverse=True, n_threads=1):
         v = np.asarray(geometry["vertices"], dtype=np.float64)
         t = np.asarray(geometry["triangles"])
         self.nT, self.V, self.T = n_time, v.shape[0], t.shape[0]
@@ -181,7 +195,7 @@ class MeshOps:
         self.eps = eps
         self.area_mesh = np.sum(self.area_f)
         if build_inverse:
-            self.lap_inv, self.lam_t, self.Q = build_laplacian_inverse(n_time, self.dt, self.area_v, self.L, eps)
+            self.lap_inv, self.lam_t, self.Q = build_laplacian_inverse(n_time, self.dt, self.area_v, self.L, eps, n_threads)
 
     # weighted norms (:215-218)
     def nsq_center(self, a): return weighted_norm_sq(self.w_center, self.nT + 1, a)
@@ -403,8 +417,18 @@ class OracleALM:
         o, tau, s, d = self.ops, self.tau, self.s, self.d
         if self.is_palm:
             self.step_q()
-        phi = o.solve_laplacian(self.A, self.B, self.lam_c, self.mu, self.E, self.bnd, self.phi)
-        self.z_fst, self.z_mid, self.z_end = o.proj_soc(self.A, self.B, self.b_fst, self.b_mid, self.b_end, d, s)
+        if getattr(self, "two_threads", False):          # the reference's default is_multi_threads=True (:674-696)
+            import threading
+            box = {}
+            th = threading.Thread(target=lambda: box.setdefault("phi", o.solve_laplacian(
+                self.A, self.B, self.lam_c, self.mu, self.E, self.bnd, self.phi)))
+            th.start()
+            self.z_fst, self.z_mid, self.z_end = o.proj_soc(self.A, self.B, self.b_fst, self.b_mid, self.b_end, d, s)
+            th.join()
+            phi = box["phi"]
+        else:
+            phi = o.solve_laplacian(self.A, self.B, self.lam_c, self.mu, self.E, self.bnd, self.phi)
+            self.z_fst, self.z_mid, self.z_end = o.proj_soc(self.A, self.B, self.b_fst, self.b_mid, self.b_end, d, s)
         self.phi = phi
         self.dt_phi = grad_time(o.dt, self.phi)
         self.dx_phi = grad_space(o.G, self.phi)

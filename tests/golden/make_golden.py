@@ -61,6 +61,9 @@ CASES = {
     "ico2_nt15_tol1e-4": ("icosphere2", {}, 15, dict(tol=1e-4, nit=3000), (), False),
     "ico3_nt31_c0": ("icosphere3", {}, 31, dict(tol=1e-3, nit=1000), (), False),
     "ico3_nt31_c01": ("icosphere3", {}, 31, dict(tol=1e-3, nit=1000, congestion=0.1), (), False),
+    # BASELINE.json configs[0] / configs[1]: the knots_5-class stand-in (V=4300, T=8600), nT=31, tol 1e-3
+    "knots5class_nt31_c0": ("knot", {}, 31, dict(tol=1e-3, nit=1000), (), False),
+    "knots5class_nt31_c01": ("knot", {}, 31, dict(tol=1e-3, nit=1000, congestion=0.1), (), False),
 }
 
 
@@ -79,7 +82,10 @@ def main(only=None):
             r_history=np.array([r_hist[i] for i in sorted(r_hist)]),
             cost=hist.history["Transportation cost"][-1], objective=hist.history["Objective value"][-1],
             sol_mu=sol["mu"], sol_phi_grad_t=np.diff(sol["phi"], axis=0),
+            ref_running_time=hist.running_time, ref_steps_time=float(sum(hist.steps_time.values())),
         )
+        if geo["vertices"].shape[0] > 2000:          # keep the big fixtures small: drop the phi gradient, store mu in f32-exact chunks
+            out.pop("sol_phi_grad_t")
         if keep_full:
             for k in STATE:
                 out["sol_" + k] = sol[k]

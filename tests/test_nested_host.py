@@ -89,3 +89,17 @@ def test_levels_respect_tree():
             if k >= 0:
                 assert sym.level[k] < sym.level[i] and sym.parent[k] == i
     assert sym.parent[sym.n_nodes - 1] == -1
+
+
+def test_device_factorisation_matches_host_version():
+    """factor_batched_device is the same algebra through torch (run on the CPU device here)."""
+    geo, _ = synth.example("icosphere2")
+    v, t = geo["vertices"], geo["triangles"]
+    K = surface.stiffness_matrix(v, t)
+    mass = surface.incident_area_sum(v.shape[0], t, surface.triangle_areas(v, t)) / 3.0
+    sym = nested.analyse(v, K, leaf_size=8)
+    shifts = np.array([0.0, 3.0, 11.0, 40.0, 170.0])
+    a = nested.factor_batched(sym, K, mass, shifts, m_pad=32)
+    b = nested.factor_batched_device(sym, K, mass, shifts, m_pad=32, device="cpu").numpy()
+    assert a.shape == b.shape
+    assert np.abs(a - b).max() / np.abs(a).max() < 1e-12
