@@ -9,7 +9,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 P_R, P_S, P_D, P_CONG, P_TAU, P_EPS, P_COUNT = 0, 1, 2, 3, 4, 5, 8
 
 _i32p, _i64p, _f64p = C.c_void_p, C.c_void_p, C.c_void_p      # raw device/host addresses
@@ -22,7 +22,8 @@ class DotsCtx(C.Structure):
         + [(n, C.c_void_p) for n in (
             "tri", "hat_grad", "area_f", "area_v", "diag_soc", "vc_ptr", "vc_idx", "qmat",
             "panels", "nd_off", "nd_s", "nd_b", "nd_child", "nd_panel", "nd_front", "nd_upd",
-            "front_idx", "child_pos", "lvl_ptr", "lvl_items", "lvb_ptr", "lvb_items", "h_lvl_ptr", "h_lvb_ptr")]
+            "front_idx", "child_pos", "lvl_ptr", "lvl_items", "lvb_ptr", "lvb_items", "lvn_nodes", "h_lvl_ptr", "h_lvb_ptr",
+            "h_lvn_ptr", "h_lvl_wpr", "h_lvb_cw")]
         + [("front_total", C.c_int64)]
         + [(n, C.c_void_p) for n in (
             "params", "phi", "A", "lam_c", "mu", "z_fst", "z_end", "b_fst", "b_end", "lam",

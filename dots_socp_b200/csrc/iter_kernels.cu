@@ -95,18 +95,23 @@ __global__ void __launch_bounds__(256) k_vertex(dots_ctx_t c)
 
 // ------------------------------------------------------------------------------------------------
 // MODE 0: full step.  MODE 1: full step + store z_mid.  MODE 2: only recompute corner_nrm / corner_div.
+// One thread owns triangle f for TRI_TCH consecutive time levels, so the mesh constants (hat gradients, cone
+// diagonal, vertex ids) are loaded once per chunk and lam[tau] is reused as lam[tau-1] of the next level.
+// beta_mid is streamed twice per level from the same thread (second time out of L1) instead of being held in
+// 36 registers: that keeps the kernel at 4 CTAs/SM.
+#define TRI_TCH 8
 template <int MODE>
-__global__ void __launch_bounds__(128) k_tri(dots_ctx_t c)
+__global__ void __launch_bounds__(128, 4) k_tri(dots_ctx_t c)
 {
     const int V = c.n_vert, nT = c.n_time;
     const size_t T = (size_t)c.n_tri;
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    const int tau = blockIdx.y;                     // 0 .. nT
     if (f >= c.n_tri) return;
+    const int tau_begin = blockIdx.y * TRI_TCH;
+    const int tau_end = min(tau_begin + TRI_TCH, nT + 1);
     const double *prm = c.params;
     const double s = prm[DOTS_P_S], step = prm[DOTS_P_TAU];
     const double cs = s / sqrt(3.0);                                                          // :932, :953
-    const bool has0 = tau < nT, has1 = tau > 0;
 
     double g[3][3], dg[3];
 #pragma unroll
@@ -116,118 +121,109 @@ __global__ void __launch_bounds__(128) k_tri(dots_ctx_t c)
         for (int x = 0; x < 3; ++x) g[k][x] = c.hat_grad[(k * 3 + x) * T + f];
     }
     const double af = c.area_f[f];
-    double *Bp = c.B + (size_t)tau * 3 * T + f;
-    double *Ep = c.E + (size_t)tau * 3 * T + f;
-    double *bm = c.b_mid + (size_t)tau * 18 * T + f;
-    double Bn[3], En[3];
-    double beta[2][3][3];
+    int vk[3] = {0, 0, 0};
+    double lam_prev[3] = {0.0, 0.0, 0.0};
+    if (MODE != 2) {
+        vk[0] = c.tri[f]; vk[1] = c.tri[T + f]; vk[2] = c.tri[2 * T + f];
+        if (tau_begin > 0) {
 #pragma unroll
-    for (int sd = 0; sd < 2; ++sd)
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int x = 0; x < 3; ++x) beta[sd][k][x] = 0.0;
+            for (int k = 0; k < 3; ++k) lam_prev[k] = c.lam[(size_t)(tau_begin - 1) * V + vk[k]];
+        }
+    }
 
-    if (MODE == 2) {
+    for (int tau = tau_begin; tau < tau_end; ++tau) {
+        const bool has0 = tau < nT, has1 = tau > 0;
+        double *Bp = c.B + (size_t)tau * 3 * T + f;
+        double *Ep = c.E + (size_t)tau * 3 * T + f;
+        double *bm = c.b_mid + (size_t)tau * 18 * T + f;
+        double Bn[3], En[3];
+        double lamk[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+        double bs[3] = {0.0, 0.0, 0.0};
+
+        if (MODE == 2) {
 #pragma unroll
-        for (int x = 0; x < 3; ++x) { Bn[x] = Bp[x * T]; En[x] = Ep[x * T]; }
-#pragma unroll
-        for (int sd = 0; sd < 2; ++sd) {
-            if (sd == 0 ? !has0 : !has1) continue;
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-#pragma unroll
-                for (int x = 0; x < 3; ++x) beta[sd][k][x] = bm[((sd * 3 + k) * 3 + x) * T];
-        }
-    } else {
-        const int vk[3] = {c.tri[f], c.tri[T + f], c.tri[2 * T + f]};
-        const double *ph = c.phi + (size_t)tau * V;
-        const double p0 = ph[vk[0]], p1 = ph[vk[1]], p2 = ph[vk[2]];
-        double lamk[2][3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            lamk[0][k] = has0 ? c.lam[(size_t)tau * V + vk[k]] : 0.0;
-            lamk[1][k] = has1 ? c.lam[(size_t)(tau - 1) * V + vk[k]] : 0.0;
-        }
-        double Bo[3], Eo[3], dx[3], bs[3];
-#pragma unroll
-        for (int x = 0; x < 3; ++x) {
-            Bo[x] = Bp[x * T];
-            Eo[x] = Ep[x * T];
-            dx[x] = g[0][x] * p0 + g[1][x] * p1 + g[2][x] * p2;                               // :902-906
-            bs[x] = cs * Bo[x];                                                               // :932
-        }
-        double z[2][3][3];
-        double adj[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-        for (int sd = 0; sd < 2; ++sd) {
-            if (sd == 0 ? !has0 : !has1) continue;
-            double sum[3];
+            for (int x = 0; x < 3; ++x) { Bn[x] = Bp[x * T]; En[x] = Ep[x * T]; }
+        } else {
+            const double *ph = c.phi + (size_t)tau * V;
+            const double p0 = ph[vk[0]], p1 = ph[vk[1]], p2 = ph[vk[2]];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const double lt = lamk[sd][k] / dg[k];                                        // :1023
-#pragma unroll
-                for (int x = 0; x < 3; ++x) {
-                    const double b = bm[((sd * 3 + k) * 3 + x) * T];
-                    beta[sd][k][x] = b;
-                    const double w = dg[k] * (bs[x] - b);                                     // :998
-                    const double zz = lt * w;                                                 // :1041
-                    z[sd][k][x] = zz;
-                    const double zb = zz + b;                                                 // :1052
-                    sum[x] = (k == 0) ? zb : sum[x] + zb;                                     // np.sum(axis=2) :953
-                }
+                lamk[0][k] = has0 ? c.lam[(size_t)tau * V + vk[k]] : 0.0;
+                lamk[1][k] = lam_prev[k];
             }
+            double Eo[3], dx[3];
 #pragma unroll
-            for (int x = 0; x < 3; ++x) adj[x] = (sd == 0 || !has0) ? cs * sum[x] : adj[x] + cs * sum[x];   // :953-957
-        }
-        const double db = (tau == 0 || tau == nT) ? (1.0 + s * s) : (1.0 + (2.0 * s * s));    // :195-197
+            for (int x = 0; x < 3; ++x) {
+                const double Bo = Bp[x * T];
+                Eo[x] = Ep[x * T];
+                dx[x] = g[0][x] * p0 + g[1][x] * p1 + g[2][x] * p2;                           // :902-906
+                bs[x] = cs * Bo;                                                              // :932
+            }
+            double adj[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-        for (int x = 0; x < 3; ++x) {
-            Bn[x] = (dx[x] + Eo[x] + adj[x]) / db;                                            // :1064
-            En[x] = Eo[x] + step * (dx[x] - Bn[x]);                                           // :719
-            Bp[x * T] = Bn[x];
-            Ep[x * T] = En[x];
+            for (int sd = 0; sd < 2; ++sd) {
+                if (sd == 0 ? !has0 : !has1) continue;
+                double sum[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double lt = lamk[sd][k] / dg[k];                                    // :1023
+#pragma unroll
+                    for (int x = 0; x < 3; ++x) {
+                        const double b = bm[((sd * 3 + k) * 3 + x) * T];
+                        const double w = dg[k] * (bs[x] - b);                                 // :998
+                        const double zb = lt * w + b;                                         // :1041, :1052
+                        sum[x] = (k == 0) ? zb : sum[x] + zb;                                 // np.sum(axis=2) :953
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x < 3; ++x) adj[x] = (sd == 0 || !has0) ? cs * sum[x] : adj[x] + cs * sum[x];   // :953-957
+            }
+            const double db = (tau == 0 || tau == nT) ? (1.0 + s * s) : (1.0 + (2.0 * s * s));    // :195-197
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                Bn[x] = (dx[x] + Eo[x] + adj[x]) / db;                                        // :1064
+                En[x] = Eo[x] + step * (dx[x] - Bn[x]);                                       // :719
+                Bp[x * T] = Bn[x];
+                Ep[x * T] = En[x];
+            }
         }
+
+        // second pass over beta_mid: multiplier update (:721) + the per-corner terms of the NEXT iteration
         double *zm = c.z_mid + (size_t)tau * 18 * T + f;
+        double *cn = c.corner_nrm + (size_t)tau * 6 * T + f;
 #pragma unroll
         for (int sd = 0; sd < 2; ++sd) {
-            if (sd == 0 ? !has0 : !has1) continue;
+            const bool has = (sd == 0) ? has0 : has1;
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
+            for (int k = 0; k < 3; ++k) {
+                double acc = 0.0;
+                if (has) {
+                    const double lt = lamk[sd][k] / dg[k];
 #pragma unroll
-                for (int x = 0; x < 3; ++x) {
-                    const double bnew = beta[sd][k][x] + step * (z[sd][k][x] - cs * Bn[x]);   // :717, :721
-                    beta[sd][k][x] = bnew;
-                    bm[((sd * 3 + k) * 3 + x) * T] = bnew;
-                    if (MODE == 1) zm[((sd * 3 + k) * 3 + x) * T] = z[sd][k][x];
+                    for (int x = 0; x < 3; ++x) {
+                        double b = bm[((sd * 3 + k) * 3 + x) * T];
+                        if (MODE != 2) {
+                            const double zz = lt * (dg[k] * (bs[x] - b));                     // same arithmetic as pass one
+                            b = b + step * (zz - cs * Bn[x]);                                 // :717, :721
+                            bm[((sd * 3 + k) * 3 + x) * T] = b;
+                            if (MODE == 1) zm[((sd * 3 + k) * 3 + x) * T] = zz;
+                        }
+                        const double w = dg[k] * (cs * Bn[x] - b);                            // :995-998
+                        acc += w * w;                                                         // :1003-1014
+                    }
                 }
-        }
-    }
-
-    // by-products for the next iteration, from the updated (B, E, beta_mid)
-    double *cn = c.corner_nrm + (size_t)tau * 6 * T + f;
-#pragma unroll
-    for (int sd = 0; sd < 2; ++sd) {
-        const bool has = (sd == 0) ? has0 : has1;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            double acc = 0.0;
-            if (has) {
-#pragma unroll
-                for (int x = 0; x < 3; ++x) {
-                    const double w = dg[k] * (cs * Bn[x] - beta[sd][k][x]);                   // :995-998
-                    acc += w * w;                                                             // :1003-1014
-                }
+                cn[(sd * 3 + k) * T] = acc;
             }
-            cn[(sd * 3 + k) * T] = acc;
         }
+        double *cd = c.corner_div + (size_t)tau * 3 * T + f;
+        double y[3];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) y[x] = (Bn[x] - En[x]) * af;                              // :980
+#pragma unroll
+        for (int k = 0; k < 3; ++k) cd[k * T] = -(g[k][0] * y[0] + g[k][1] * y[1] + g[k][2] * y[2]);   // D = -G^T
+#pragma unroll
+        for (int k = 0; k < 3; ++k) lam_prev[k] = lamk[0][k];
     }
-    double *cd = c.corner_div + (size_t)tau * 3 * T + f;
-    double y[3];
-#pragma unroll
-    for (int x = 0; x < 3; ++x) y[x] = (Bn[x] - En[x]) * af;                                  // :980
-#pragma unroll
-    for (int k = 0; k < 3; ++k) cd[k * T] = -(g[k][0] * y[0] + g[k][1] * y[1] + g[k][2] * y[2]);   // D = -G^T
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -319,7 +315,7 @@ extern "C" int dots_step_vertex(const dots_ctx_t *c, void *stream)
 extern "C" int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
-    dim3 grid(ceil_div(c->n_tri, 128), c->n_time + 1);
+    dim3 grid(ceil_div(c->n_tri, 128), ceil_div(c->n_time + 1, TRI_TCH));
     if (write_z) k_tri<1><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);
     else k_tri<0><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);
     DOTS_LAUNCH_CHECK();
@@ -329,7 +325,7 @@ extern "C" int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream)
 extern "C" int dots_refresh_corner_terms(const dots_ctx_t *c, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
-    dim3 grid(ceil_div(c->n_tri, 128), c->n_time + 1);
+    dim3 grid(ceil_div(c->n_tri, 128), ceil_div(c->n_time + 1, TRI_TCH));
     k_tri<2><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);
     DOTS_LAUNCH_CHECK();
     return 0;

@@ -15,8 +15,6 @@
 
 #define SWEEP_THREADS 256
 #define SWEEP_WARPS 8
-#define SWEEP_MAX_RPW 4          // rows (forward) / columns (backward) per warp
-#define SWEEP_CHUNK 32           // staged vector rows per shared-memory chunk
 
 // ------------------------------------------------------------------------------------------------
 // forward transform: hat[v][k] = sum_t Q[t][k] rhs[t][v]
@@ -72,137 +70,169 @@ __device__ __forceinline__ size_t panel_row_off(int row, int s)
     return (row < s) ? (size_t)row * (row + 1) / 2 : (size_t)s * (s + 1) / 2 + (size_t)(row - s) * s;
 }
 
-// Forward sweep, one tree level.  Block = one work item (node, first row, n rows <= 32).
-//   r_S   = hat_S + (children's updates landing on S)
-//   y_S   = inv(L11) r_S                       -> ywork
-//   upd_B = (children's updates landing on B) - (L21 inv(L11)) r_S   -> this node's update vector
-template <int MP>
-__global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_fwd(dots_ctx_t c, int item0)
+// Gather step of the forward sweep, one tree level: r_S = hat_S + (children's updates landing on S), in place.
+// Block = one node of the level (leaves have no children and are skipped by the host).
+__global__ void __launch_bounds__(256) k_sweep_gather(dots_ctx_t c, int node0)
 {
-    __shared__ double rs[SWEEP_CHUNK * 32 * MP];
-    const int M = 32 * MP;
-    const int *it = c.lvl_items + 3 * (size_t)(item0 + blockIdx.x);
-    const int node = it[0], row0 = it[1], nrows = it[2];
+    const int M = c.m_pad;
+    const int node = c.lvn_nodes[node0 + blockIdx.x];
     const int s = c.nd_s[node], off = c.nd_off[node];
     const int ch0 = c.nd_child[2 * node], ch1 = c.nd_child[2 * node + 1];
     const double *u0 = (ch0 >= 0) ? c.upd + (size_t)c.nd_upd[ch0] * M : nullptr;
     const double *u1 = (ch1 >= 0) ? c.upd + (size_t)c.nd_upd[ch1] * M : nullptr;
     const int32_t *cp0 = c.child_pos + c.nd_front[node];
     const int32_t *cp1 = cp0 + c.front_total;
+    for (int i = threadIdx.x; i < s * M; i += blockDim.x) {
+        const int j = i / M, m = i - j * M;
+        const int a = cp0[j], b = cp1[j];
+        double r = c.hat[(size_t)(off + j) * M + m];
+        if (u0 && a >= 0) r += u0[(size_t)a * M + m];
+        if (u1 && b >= 0) r += u1[(size_t)b * M + m];
+        c.hat[(size_t)(off + j) * M + m] = r;
+    }
+}
+
+// Forward sweep, one tree level.  Block = one work item (node, first row, n rows).
+//   y_S   = inv(L11) r_S                                               -> ywork
+//   upd_B = (children's updates landing on B) - (L21 inv(L11)) r_S     -> this node's update vector
+// WPR warps share one panel row (interleaved columns, partial sums combined through shared memory in a fixed
+// order); 8/WPR rows are in flight per pass.  Every panel entry is streamed exactly once, as M*8-byte rows.
+template <int MP, int WPR>
+__global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_fwd(dots_ctx_t c, int item0)
+{
+    constexpr int M = 32 * MP;
+    constexpr int ROWS = SWEEP_WARPS / WPR;
+    __shared__ double red[(WPR > 1) ? SWEEP_WARPS * M : 1];
+    const int *it = c.lvl_items + 3 * (size_t)(item0 + blockIdx.x);
+    const int node = it[0], row0 = it[1], nrows = it[2];
+    const int s = c.nd_s[node], off = c.nd_off[node], b_rows = c.nd_b[node];
+    const int ch0 = c.nd_child[2 * node], ch1 = c.nd_child[2 * node + 1];
+    const double *u0 = (ch0 >= 0) ? c.upd + (size_t)c.nd_upd[ch0] * M : nullptr;
+    const double *u1 = (ch1 >= 0) ? c.upd + (size_t)c.nd_upd[ch1] * M : nullptr;
+    const int32_t *cp0 = c.child_pos + c.nd_front[node];
+    const int32_t *cp1 = cp0 + c.front_total;
     const double *panel = c.panels + (size_t)c.nd_panel[node] * M;
+    const double *rvec = c.hat + (size_t)off * M;
+    double *myupd = c.upd + (size_t)c.nd_upd[node] * M;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    // rows of this warp: row0 + warp + SWEEP_WARPS*q
-    double acc[SWEEP_MAX_RPW][MP];
-#pragma unroll
-    for (int q = 0; q < SWEEP_MAX_RPW; ++q)
-#pragma unroll
-        for (int m = 0; m < MP; ++m) acc[q][m] = 0.0;
-
+    const int rslot = warp / WPR, cslot = warp % WPR;
     const int last_row = row0 + nrows - 1;
-    const int jmax = min(s, last_row + 1);          // columns any row of this item touches
-    for (int j0 = 0; j0 < jmax; j0 += SWEEP_CHUNK) {
-        const int jc = min(SWEEP_CHUNK, jmax - j0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < jc * M; i += SWEEP_THREADS) {
-            const int jj = i / M, m = i - jj * M, j = j0 + jj;
-            double r = c.hat[(size_t)(off + j) * M + m];
-            const int a = cp0[j], b = cp1[j];
-            if (u0 && a >= 0) r += u0[(size_t)a * M + m];
-            if (u1 && b >= 0) r += u1[(size_t)b * M + m];
-            rs[jj * M + m] = r;
-        }
-        __syncthreads();
+
+    for (int base = row0; base <= last_row; base += ROWS) {
+        const int row = base + rslot;
+        const bool valid = row <= last_row;
+        double acc[MP];
 #pragma unroll
-        for (int q = 0; q < SWEEP_MAX_RPW; ++q) {
-            const int row = row0 + warp + SWEEP_WARPS * q;
-            if (row > last_row) break;
+        for (int m = 0; m < MP; ++m) acc[m] = 0.0;
+        if (valid) {
             const int len = min(row + 1, s);
-            const int je = min(jc, len - j0);
-            if (je <= 0) continue;
-            const double *pr = panel + (panel_row_off(row, s) + j0) * M + lane;
-            for (int jj = 0; jj < je; ++jj) {
+            const double *pr = panel + panel_row_off(row, s) * M + lane;
+            const double *rv = rvec + lane;
+            int j = cslot;
+            for (; j + 3 * WPR < len; j += 4 * WPR) {
+                double p[4][MP], r[4][MP];
 #pragma unroll
-                for (int m = 0; m < MP; ++m) acc[q][m] += pr[(size_t)jj * M + 32 * m] * rs[jj * M + 32 * m + lane];
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int m = 0; m < MP; ++m) {
+                        p[u][m] = __ldcs(pr + (size_t)(j + u * WPR) * M + 32 * m);
+                        r[u][m] = rv[(size_t)(j + u * WPR) * M + 32 * m];
+                    }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int m = 0; m < MP; ++m) acc[m] += p[u][m] * r[u][m];
+            }
+            for (; j < len; j += WPR) {
+#pragma unroll
+                for (int m = 0; m < MP; ++m) acc[m] += __ldcs(pr + (size_t)j * M + 32 * m) * rv[(size_t)j * M + 32 * m];
             }
         }
-    }
-    const int b_rows = c.nd_b[node];
-    double *myupd = c.upd + (size_t)c.nd_upd[node] * M;
+        if (WPR > 1) {
+            __syncthreads();
 #pragma unroll
-    for (int q = 0; q < SWEEP_MAX_RPW; ++q) {
-        const int row = row0 + warp + SWEEP_WARPS * q;
-        if (row > last_row) break;
-        if (row < s) {
+            for (int m = 0; m < MP; ++m) red[warp * M + 32 * m + lane] = acc[m];
+            __syncthreads();
+            if (cslot == 0) {
 #pragma unroll
-            for (int m = 0; m < MP; ++m) c.ywork[(size_t)(off + row) * M + 32 * m + lane] = acc[q][m];
-        } else if (row - s < b_rows) {
-            const int a = cp0[row], b = cp1[row];
+                for (int m = 0; m < MP; ++m) {
+                    double v = 0.0;
 #pragma unroll
-            for (int m = 0; m < MP; ++m) {
-                double val = 0.0;
-                if (u0 && a >= 0) val += u0[(size_t)a * M + 32 * m + lane];
-                if (u1 && b >= 0) val += u1[(size_t)b * M + 32 * m + lane];
-                myupd[(size_t)(row - s) * M + 32 * m + lane] = val - acc[q][m];
+                    for (int w = 0; w < WPR; ++w) v += red[(rslot * WPR + w) * M + 32 * m + lane];
+                    acc[m] = v;
+                }
+            }
+        }
+        if (valid && cslot == 0) {
+            if (row < s) {
+#pragma unroll
+                for (int m = 0; m < MP; ++m) c.ywork[(size_t)(off + row) * M + 32 * m + lane] = acc[m];
+            } else if (row - s < b_rows) {
+                const int a = cp0[row], b = cp1[row];
+#pragma unroll
+                for (int m = 0; m < MP; ++m) {
+                    double val = 0.0;
+                    if (u0 && a >= 0) val += u0[(size_t)a * M + 32 * m + lane];
+                    if (u1 && b >= 0) val += u1[(size_t)b * M + 32 * m + lane];
+                    myupd[(size_t)(row - s) * M + 32 * m + lane] = val - acc[m];
+                }
             }
         }
     }
 }
 
-// Backward sweep, one tree level.  Block = one work item (node, first column, n columns <= 32).
+// Backward sweep, one tree level.  Block = one work item (node, first column, n columns <= CW).
 //   x_S = inv(L11)^T y_S - (L21 inv(L11))^T x_B          (x of the ancestors is already final in `hat`)
 // The reference's per-mode matrix is L + (lambda - eps) M = -(K + shift M)  (laplacian_inverse_socp.py:37-38), so what
 // is stored in `hat` is xt = -x; substituting gives  xt_S = P^T (-[y_S ; xt_B]):  the sign costs nothing.
-template <int MP>
+// The 8 warps of a block interleave over the panel rows (each row contributes n_cols*M*8 contiguous bytes) and
+// their partial column sums are combined through shared memory in a fixed order.
+template <int MP, int CW>
 __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_bwd(dots_ctx_t c, int item0)
 {
-    __shared__ double vs[SWEEP_CHUNK * 32 * MP];
-    const int M = 32 * MP;
+    constexpr int M = 32 * MP;
+    __shared__ double red[SWEEP_WARPS * CW * M];
     const int *it = c.lvb_items + 3 * (size_t)(item0 + blockIdx.x);
     const int node = it[0], col0 = it[1], ncols = it[2];
     const int s = c.nd_s[node], b = c.nd_b[node], off = c.nd_off[node];
     const int32_t *fidx = c.front_idx + c.nd_front[node];
     const double *panel = c.panels + (size_t)c.nd_panel[node] * M;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int last_col = col0 + ncols - 1;
+    const int nrows = s + b;
 
-    // columns of this warp: col0 + warp*RPW + q   (adjacent columns -> contiguous panel reads)
-    const int rpw = (ncols + SWEEP_WARPS - 1) / SWEEP_WARPS;
-    const int cbase = col0 + warp * rpw;
-    double acc[SWEEP_MAX_RPW][MP];
+    double acc[CW][MP];
 #pragma unroll
-    for (int q = 0; q < SWEEP_MAX_RPW; ++q)
+    for (int q = 0; q < CW; ++q)
 #pragma unroll
         for (int m = 0; m < MP; ++m) acc[q][m] = 0.0;
 
-    const int nrows = s + b;
-    for (int i0 = col0; i0 < nrows; i0 += SWEEP_CHUNK) {     // rows < col0 never touch these columns
-        const int ic = min(SWEEP_CHUNK, nrows - i0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < ic * M; i += SWEEP_THREADS) {
-            const int ii = i / M, m = i - ii * M, row = i0 + ii;
-            vs[ii * M + m] = -((row < s) ? c.ywork[(size_t)(off + row) * M + m] : c.hat[(size_t)fidx[row] * M + m]);
-        }
-        __syncthreads();
-        for (int ii = 0; ii < ic; ++ii) {
-            const int row = i0 + ii;
-            const double *pr = panel + panel_row_off(row, s) * M + lane;
+#pragma unroll 4
+    for (int row = col0 + warp; row < nrows; row += SWEEP_WARPS) {     // rows < col0 never touch these columns
+        const double *vsrc = (row < s) ? c.ywork + (size_t)(off + row) * M : c.hat + (size_t)fidx[row] * M;
+        const double *pr = panel + (panel_row_off(row, s) + col0) * M + lane;
+        const int qe = (row < s) ? min(ncols, row - col0 + 1) : ncols;    // lower triangle of inv(L11) only
+        double v[MP];
 #pragma unroll
-            for (int q = 0; q < SWEEP_MAX_RPW; ++q) {
-                const int col = cbase + q;
-                if (q >= rpw || col > last_col) break;
-                if (row < s && col > row) continue;            // upper triangle of inv(L11) is zero / not stored
+        for (int m = 0; m < MP; ++m) v[m] = -vsrc[32 * m + lane];
 #pragma unroll
-                for (int m = 0; m < MP; ++m) acc[q][m] += pr[(size_t)col * M + 32 * m] * vs[ii * M + 32 * m + lane];
+        for (int q = 0; q < CW; ++q) {
+            if (q < qe) {
+#pragma unroll
+                for (int m = 0; m < MP; ++m) acc[q][m] += __ldcs(pr + (size_t)q * M + 32 * m) * v[m];
             }
         }
     }
 #pragma unroll
-    for (int q = 0; q < SWEEP_MAX_RPW; ++q) {
-        const int col = cbase + q;
-        if (q >= rpw || col > last_col) break;
+    for (int q = 0; q < CW; ++q)
 #pragma unroll
-        for (int m = 0; m < MP; ++m) c.hat[(size_t)(off + col) * M + 32 * m + lane] = acc[q][m];
+        for (int m = 0; m < MP; ++m) red[(warp * CW + q) * M + 32 * m + lane] = acc[q][m];
+    __syncthreads();
+    for (int o = threadIdx.x; o < ncols * M; o += SWEEP_THREADS) {
+        const int q = o / M, m = o - q * M;
+        double vsum = 0.0;
+#pragma unroll
+        for (int w = 0; w < SWEEP_WARPS; ++w) vsum += red[(w * CW + q) * M + m];
+        c.hat[(size_t)(off + col0 + q) * M + m] = vsum;
     }
 }
 
@@ -211,12 +241,31 @@ template <int MP>
 static int launch_sweeps(const dots_ctx_t *c, cudaStream_t st)
 {
     for (int lv = 0; lv < c->n_levels; ++lv) {
+        const int g0 = c->h_lvn_ptr[lv], gn = c->h_lvn_ptr[lv + 1] - g0;
+        if (lv > 0 && gn > 0) { k_sweep_gather<<<gn, 256, 0, st>>>(*c, g0); DOTS_LAUNCH_CHECK(); }
         const int i0 = c->h_lvl_ptr[lv], n = c->h_lvl_ptr[lv + 1] - i0;
-        if (n > 0) { k_sweep_fwd<MP><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); DOTS_LAUNCH_CHECK(); }
+        if (n <= 0) continue;
+        switch (c->h_lvl_wpr[lv]) {
+        case 1: k_sweep_fwd<MP, 1><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
+        case 2: k_sweep_fwd<MP, 2><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
+        case 4: k_sweep_fwd<MP, 4><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
+        default: k_sweep_fwd<MP, 8><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
+        }
+        DOTS_LAUNCH_CHECK();
     }
     for (int lv = c->n_levels - 1; lv >= 0; --lv) {
         const int i0 = c->h_lvb_ptr[lv], n = c->h_lvb_ptr[lv + 1] - i0;
-        if (n > 0) { k_sweep_bwd<MP><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); DOTS_LAUNCH_CHECK(); }
+        if (n <= 0) continue;
+        switch (c->h_lvb_cw[lv]) {
+        case 1: k_sweep_bwd<MP, 1><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
+        case 2: k_sweep_bwd<MP, 2><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
+        case 4: k_sweep_bwd<MP, 4><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
+        default:
+            if (MP * 8 * SWEEP_WARPS * 32 * 8 <= 48 * 1024) { k_sweep_bwd<MP, (MP <= 3 ? 8 : 4)><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); }
+            else { dots_set_error("column block 8 unsupported for m_pad=%d", 32 * MP); return DOTS_ERR_BAD_ARG; }
+            break;
+        }
+        DOTS_LAUNCH_CHECK();
     }
     return 0;
 }

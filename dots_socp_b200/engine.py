@@ -38,25 +38,42 @@ def time_basis(n_time: int):
     return Q, lam
 
 
-def _sweep_items(sym: nested.Symbolic, n_sm: int):
-    """Per-level work items for the forward (row blocks) and backward (column blocks) sweeps."""
-    fwd_ptr, bwd_ptr, fwd, bwd = [0], [0], [], []
+def _sweep_items(sym: nested.Symbolic, n_sm: int, m_pad: int):
+    """Per-level launch plan of the two sweeps.
+
+    forward : items (node, first row, n rows); ``wpr`` warps share a panel row (1 for the small leaf fronts,
+              up to 8 for the long rows of the top separators) so that every level exposes >= ~8 blocks per SM
+              whenever it has the rows for it;
+    backward: items (node, first column, n columns <= cw)."""
+    fwd_ptr, bwd_ptr, node_ptr, fwd, bwd, nodes_flat, wprs, cws = [0], [0], [0], [], [], [], [], []
+    cw_cap = 4 if m_pad > 96 else 8
     for nodes in nested.level_schedule(sym):
-        rows_total = int((sym.s[nodes] + sym.b[nodes]).sum())
-        cols_total = int(sym.s[nodes].sum())
-        rb = int(min(32, max(8, -(-rows_total // (4 * n_sm)))))
-        cb = int(min(32, max(8, -(-cols_total // (4 * n_sm)))))
+        s_l, b_l = sym.s[nodes].astype(np.int64), sym.b[nodes].astype(np.int64)
+        rows_total, cols_total = int((s_l + b_l).sum()), int(s_l.sum())
+        work = s_l * (s_l + 1) // 2 + s_l * b_l
+        s_eff = float((s_l * work).sum() / max(1, work.sum()))
+        wpr = 1 if s_eff < 48 else 2 if s_eff < 128 else 4 if s_eff < 320 else 8
+        rows_per_pass = 8 // wpr
+        passes = int(min(8, max(1, rows_total // (rows_per_pass * 8 * n_sm))))
+        rb = rows_per_pass * passes
+        cw = next((w for w in (8, 4, 2, 1) if w <= cw_cap and cols_total // w >= 4 * n_sm), 1)
         for nd in nodes:
             nrow, ncol = int(sym.s[nd] + sym.b[nd]), int(sym.s[nd])
             for r0 in range(0, nrow, rb):
                 fwd.append((nd, r0, min(rb, nrow - r0)))
-            for c0 in range(0, ncol, cb):
-                bwd.append((nd, c0, min(cb, ncol - c0)))
+            for c0 in range(0, ncol, cw):
+                bwd.append((nd, c0, min(cw, ncol - c0)))
+        with_kids = [int(nd) for nd in nodes if (sym.child[nd] >= 0).any() and sym.s[nd] > 0]
+        nodes_flat += with_kids
+        node_ptr.append(len(nodes_flat))
         fwd_ptr.append(len(fwd))
         bwd_ptr.append(len(bwd))
-    as32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32).reshape(-1, 3))
-    return (np.array(fwd_ptr, dtype=np.int32), as32(fwd) if fwd else np.zeros((0, 3), np.int32),
-            np.array(bwd_ptr, dtype=np.int32), as32(bwd) if bwd else np.zeros((0, 3), np.int32))
+        wprs.append(wpr)
+        cws.append(cw)
+    as32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32).reshape(-1, 3)) if a else np.zeros((0, 3), np.int32)
+    i32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32))
+    return dict(fwd_ptr=i32(fwd_ptr), fwd_items=as32(fwd), bwd_ptr=i32(bwd_ptr), bwd_items=as32(bwd),
+                node_ptr=i32(node_ptr), nodes=i32(nodes_flat if nodes_flat else [0]), wpr=i32(wprs), cw=i32(cws))
 
 
 class Engine:
@@ -122,8 +139,10 @@ class Engine:
         vc_ptr, vc_tri, vc_corner = surface.corner_adjacency(V, tri_new)
         qpad = np.zeros((nT + 1, self.m_pad))
         qpad[:, :nT + 1] = Q
-        fwd_ptr, fwd_items, bwd_ptr, bwd_items = _sweep_items(sym, self.n_sm)
-        self._h_fwd_ptr, self._h_bwd_ptr = fwd_ptr, bwd_ptr                              # host copies stay alive
+        plan = _sweep_items(sym, self.n_sm, self.m_pad)
+        self.plan = plan                                                                 # host arrays stay alive
+        fwd_ptr, fwd_items, bwd_ptr, bwd_items = plan["fwd_ptr"], plan["fwd_items"], plan["bwd_ptr"], plan["bwd_items"]
+        self._h_fwd_ptr, self._h_bwd_ptr = fwd_ptr, bwd_ptr
 
         ctx = capi.DotsCtx()
         ctx.abi_version, ctx.n_time, ctx.n_vert, ctx.n_tri = capi.ABI_VERSION, nT, V, T
@@ -139,12 +158,16 @@ class Engine:
             nd_front=up("nd_front", sym.front_off[:-1], np.int64), nd_upd=up("nd_upd", sym.upd_off[:-1], np.int64),
             front_idx=up("front_idx", sym.front_idx, np.int32), child_pos=up("child_pos", sym.child_pos, np.int32),
             lvl_ptr=up("lvl_ptr", fwd_ptr, np.int32), lvl_items=up("lvl_items", fwd_items, np.int32),
-            lvb_ptr=up("lvb_ptr", bwd_ptr, np.int32), lvb_items=up("lvb_items", bwd_items, np.int32))
+            lvb_ptr=up("lvb_ptr", bwd_ptr, np.int32), lvb_items=up("lvb_items", bwd_items, np.int32),
+            lvn_nodes=up("lvn_nodes", plan["nodes"], np.int32))
         self._keep["panels"] = panels
         for k, ten in const.items():
             setattr(ctx, k, ten.data_ptr())
         ctx.h_lvl_ptr = self._h_fwd_ptr.ctypes.data
         ctx.h_lvb_ptr = self._h_bwd_ptr.ctypes.data
+        ctx.h_lvn_ptr = plan["node_ptr"].ctypes.data
+        ctx.h_lvl_wpr = plan["wpr"].ctypes.data
+        ctx.h_lvb_cw = plan["cw"].ctypes.data
         ctx.front_total = int(sym.front_off[-1])
 
         z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)
@@ -206,7 +229,8 @@ class Engine:
         and direction, vertex, triangle."""
         n_f = int(np.count_nonzero(np.diff(self._h_fwd_ptr)))
         n_b = int(np.count_nonzero(np.diff(self._h_bwd_ptr)))
-        return 5 + n_f + n_b
+        n_g = int(np.count_nonzero(np.diff(self.plan["node_ptr"])[1:]))
+        return 5 + n_f + n_b + n_g
 
     # ------------------------------------------------------------------ the iteration
     def iterate(self, n=1, write_z=False):

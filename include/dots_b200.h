@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DOTS_ABI_VERSION 1
+#define DOTS_ABI_VERSION 2
 
 /* scalar block read by the kernels from device memory (so CUDA graphs stay valid across penalty updates) */
 enum {
@@ -85,8 +85,12 @@ typedef struct dots_ctx {
     const int32_t *lvl_items;  /* work items (node, first row, n rows) as int32 triples, forward      */
     const int32_t *lvb_ptr;    /* [n_levels+1] ranges into lvb_items                                  */
     const int32_t *lvb_items;  /* work items (node, first col, n cols) as int32 triples, backward     */
+    const int32_t *lvn_nodes;  /* node ids grouped by level (gather step of the forward sweep)        */
     const int32_t *h_lvl_ptr;  /* HOST copies of lvl_ptr / lvb_ptr (grid sizing of the per-level launches) */
     const int32_t *h_lvb_ptr;
+    const int32_t *h_lvn_ptr;  /* HOST [n_levels+1] ranges into lvn_nodes                             */
+    const int32_t *h_lvl_wpr;  /* HOST [n_levels] warps sharing one panel row in the forward sweep (1,2,4,8) */
+    const int32_t *h_lvb_cw;   /* HOST [n_levels] columns per block in the backward sweep (1,2,4,8)   */
     int64_t front_total;       /* sum(s+b)                                                            */
 
     /* ---- ALM state (read-write) ---- */
