@@ -17,50 +17,83 @@
 #define SWEEP_WARPS 8
 
 // ------------------------------------------------------------------------------------------------
-// forward transform: hat[v][k] = sum_t Q[t][k] rhs[t][v]
-#define TT_TILE 32
-__global__ void __launch_bounds__(256) k_time_fwd(dots_ctx_t c)
+// Time transforms as fp64 tensor-core GEMMs (DMMA, mma.sync.m8n8k4.f64: the only fp64 tensor path - tcgen05 has
+// no f64 kind).  Per 64-vertex tile:   C[64][N] = A[64][K] * B[K][N]
+//   DIR 0 (laplacian_inverse_socp.py:54)  hat[v][k] = sum_t rhs[t][v] Q[t][k]   A = rhs^T, B = Q,   K = nT+1, N = m_pad
+//   DIR 1 (laplacian_inverse_socp.py:61)  phi[t][v] = sum_k hat[v][k] Q[t][k]   A = hat,   B = Q^T, K = m_pad, N = nT+1
+// B (the time eigenbasis) is loaded into shared memory once per block; blocks are persistent over vertex tiles.
+// Leading dimensions lda = K+4, ldb = N+8 make both fragment loads bank-conflict free.
+#define TT_VT 64
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(256) k_time_mma(dots_ctx_t c, int n_tiles)
 {
     extern __shared__ double sm[];
     const int nt1 = c.n_time + 1, M = c.m_pad, V = c.n_vert;
-    double *Qs = sm;                       // [nt1][M]
-    double *Xs = sm + (size_t)nt1 * M;     // [nt1][TT_TILE]
-    const int v0 = blockIdx.x * TT_TILE;
-    for (int i = threadIdx.x; i < nt1 * M; i += blockDim.x) Qs[i] = c.qmat[i];
-    for (int i = threadIdx.x; i < nt1 * TT_TILE; i += blockDim.x) {
-        const int t = i / TT_TILE, vv = i % TT_TILE;
-        Xs[i] = (v0 + vv < V) ? c.rhs[(size_t)t * V + v0 + vv] : 0.0;
+    const int K = (DIR == 0) ? ((nt1 + 3) & ~3) : M;
+    const int N = (DIR == 0) ? M : ((nt1 + 7) & ~7);
+    const int lda = K + 4, ldb = N + 8, NT = N / 8;
+    double *Bs = sm;                       // [K][ldb]
+    double *As = sm + (size_t)K * ldb;     // [TT_VT][lda]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (DIR == 0) {
+        for (int i = tid; i < K * N; i += 256) {
+            const int p = i / N, j = i - p * N;
+            Bs[p * ldb + j] = (p < nt1) ? c.qmat[(size_t)p * M + j] : 0.0;
+        }
+    } else {
+        for (int i = tid; i < N * K; i += 256) {
+            const int j = i / K, p = i - j * K;
+            Bs[p * ldb + j] = (j < nt1) ? c.qmat[(size_t)j * M + p] : 0.0;
+        }
     }
-    __syncthreads();
-    for (int o = threadIdx.x; o < TT_TILE * M; o += blockDim.x) {
-        const int vv = o / M, k = o % M;
-        if (v0 + vv >= V) continue;
-        double acc = 0.0;
-        for (int t = 0; t < nt1; ++t) acc += Qs[t * M + k] * Xs[t * TT_TILE + vv];
-        c.hat[(size_t)(v0 + vv) * M + k] = acc;
-    }
-}
-
-// inverse transform: phi[t][v] = sum_k Q[t][k] hat[v][k]
-__global__ void __launch_bounds__(256) k_time_bwd(dots_ctx_t c)
-{
-    extern __shared__ double sm[];
-    const int nt1 = c.n_time + 1, M = c.m_pad, V = c.n_vert, Mp = M + 1;
-    double *Qs = sm;                       // [nt1][M]
-    double *Hs = sm + (size_t)nt1 * M;     // [TT_TILE][M+1]
-    const int v0 = blockIdx.x * TT_TILE;
-    for (int i = threadIdx.x; i < nt1 * M; i += blockDim.x) Qs[i] = c.qmat[i];
-    for (int i = threadIdx.x; i < TT_TILE * M; i += blockDim.x) {
-        const int vv = i / M, k = i % M;
-        Hs[vv * Mp + k] = (v0 + vv < V) ? c.hat[(size_t)(v0 + vv) * M + k] : 0.0;
-    }
-    __syncthreads();
-    for (int o = threadIdx.x; o < nt1 * TT_TILE; o += blockDim.x) {
-        const int t = o / TT_TILE, vv = o % TT_TILE;
-        if (v0 + vv >= V) continue;
-        double acc = 0.0;
-        for (int k = 0; k < nt1; ++k) acc += Qs[t * M + k] * Hs[vv * Mp + k];
-        c.phi[(size_t)t * V + v0 + vv] = acc;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int v0 = tile * TT_VT;
+        __syncthreads();
+        if (DIR == 0) {
+            for (int i = tid; i < K * TT_VT; i += 256) {
+                const int p = i / TT_VT, vv = i - p * TT_VT;
+                As[vv * lda + p] = (p < nt1 && v0 + vv < V) ? c.rhs[(size_t)p * V + v0 + vv] : 0.0;
+            }
+        } else {
+            for (int i = tid; i < TT_VT * K; i += 256) {
+                const int vv = i / K, p = i - vv * K;
+                As[vv * lda + p] = (v0 + vv < V) ? c.hat[(size_t)(v0 + vv) * M + p] : 0.0;
+            }
+        }
+        __syncthreads();
+        double acc[16][2];
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+        const double *ap = As + (8 * warp + (lane >> 2)) * lda + (lane & 3);
+        const double *bp = Bs + (lane & 3) * ldb + (lane >> 2);
+        for (int p0 = 0; p0 < K; p0 += 4) {
+            const double a = ap[p0];
+#pragma unroll
+            for (int nt = 0; nt < 16; ++nt) {
+                if (nt < NT) dmma_m8n8k4(acc[nt][0], acc[nt][1], a, bp[(size_t)p0 * ldb + nt * 8]);
+            }
+        }
+        const int vrow = v0 + 8 * warp + (lane >> 2);
+        if (vrow < V) {
+#pragma unroll
+            for (int nt = 0; nt < 16; ++nt) {
+                if (nt < NT) {
+                    const int j = nt * 8 + 2 * (lane & 3);
+                    if (DIR == 0) {
+                        *reinterpret_cast<double2 *>(c.hat + (size_t)vrow * M + j) = make_double2(acc[nt][0], acc[nt][1]);
+                    } else {
+                        if (j < nt1) c.phi[(size_t)j * V + vrow] = acc[nt][0];
+                        if (j + 1 < nt1) c.phi[(size_t)(j + 1) * V + vrow] = acc[nt][1];
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -71,19 +104,20 @@ __device__ __forceinline__ size_t panel_row_off(int row, int s)
 }
 
 // Gather step of the forward sweep, one tree level: r_S = hat_S + (children's updates landing on S), in place.
-// Block = one node of the level (leaves have no children and are skipped by the host).
-__global__ void __launch_bounds__(256) k_sweep_gather(dots_ctx_t c, int node0)
+// Block = one item (node, first S row, n rows) of the level's gather list (leaves have no children: no items).
+__global__ void __launch_bounds__(256) k_sweep_gather(dots_ctx_t c, int item0)
 {
     const int M = c.m_pad;
-    const int node = c.lvn_nodes[node0 + blockIdx.x];
-    const int s = c.nd_s[node], off = c.nd_off[node];
+    const int *it = c.lvn_nodes + 3 * (size_t)(item0 + blockIdx.x);
+    const int node = it[0], j0 = it[1], nj = it[2];
+    const int off = c.nd_off[node];
     const int ch0 = c.nd_child[2 * node], ch1 = c.nd_child[2 * node + 1];
     const double *u0 = (ch0 >= 0) ? c.upd + (size_t)c.nd_upd[ch0] * M : nullptr;
     const double *u1 = (ch1 >= 0) ? c.upd + (size_t)c.nd_upd[ch1] * M : nullptr;
     const int32_t *cp0 = c.child_pos + c.nd_front[node];
     const int32_t *cp1 = cp0 + c.front_total;
-    for (int i = threadIdx.x; i < s * M; i += blockDim.x) {
-        const int j = i / M, m = i - j * M;
+    for (int i = threadIdx.x; i < nj * M; i += blockDim.x) {
+        const int j = j0 + i / M, m = i % M;
         const int a = cp0[j], b = cp1[j];
         double r = c.hat[(size_t)(off + j) * M + m];
         if (u0 && a >= 0) r += u0[(size_t)a * M + m];
@@ -289,24 +323,19 @@ extern "C" int dots_time_transform(const dots_ctx_t *c, int inverse, void *strea
     if (int e = dots_check_ctx(c)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     const int nt1 = c->n_time + 1, M = c->m_pad;
-    const int grid = ceil_div(c->n_vert, TT_TILE);
-    if (!inverse) {
-        const size_t smem = ((size_t)nt1 * M + (size_t)nt1 * TT_TILE) * sizeof(double);
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            DOTS_CUDA(cudaFuncSetAttribute(k_time_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
-        k_time_fwd<<<grid, 256, smem, st>>>(*c);
-    } else {
-        const size_t smem = ((size_t)nt1 * M + (size_t)TT_TILE * (M + 1)) * sizeof(double);
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            DOTS_CUDA(cudaFuncSetAttribute(k_time_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
-        k_time_bwd<<<grid, 256, smem, st>>>(*c);
+    const int K = inverse ? M : ((nt1 + 3) & ~3), N = inverse ? ((nt1 + 7) & ~7) : M;
+    const size_t smem = ((size_t)K * (N + 8) + (size_t)TT_VT * (K + 4)) * sizeof(double);
+    const int n_tiles = ceil_div(c->n_vert, TT_VT);
+    const int per_sm = (smem <= 72 * 1024) ? 3 : (smem <= 110 * 1024 ? 2 : 1);
+    const int grid = n_tiles < c->n_sm * per_sm ? n_tiles : c->n_sm * per_sm;
+    static size_t configured[2] = {0, 0};
+    if (smem > 48 * 1024 && smem > configured[inverse ? 1 : 0]) {
+        if (inverse) DOTS_CUDA(cudaFuncSetAttribute(k_time_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else DOTS_CUDA(cudaFuncSetAttribute(k_time_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[inverse ? 1 : 0] = smem;
     }
+    if (inverse) k_time_mma<1><<<grid, 256, smem, st>>>(*c, n_tiles);
+    else k_time_mma<0><<<grid, 256, smem, st>>>(*c, n_tiles);
     DOTS_LAUNCH_CHECK();
     return 0;
 }

@@ -52,7 +52,7 @@ def _sweep_items(sym: nested.Symbolic, n_sm: int, m_pad: int):
         rows_total, cols_total = int((s_l + b_l).sum()), int(s_l.sum())
         work = s_l * (s_l + 1) // 2 + s_l * b_l
         s_eff = float((s_l * work).sum() / max(1, work.sum()))
-        wpr = 1 if s_eff < 48 else 2 if s_eff < 128 else 4 if s_eff < 320 else 8
+        wpr = 1 if s_eff < 32 else 2 if s_eff < 96 else 4 if s_eff < 256 else 8
         rows_per_pass = 8 // wpr
         passes = int(min(8, max(1, rows_total // (rows_per_pass * 8 * n_sm))))
         rb = rows_per_pass * passes
@@ -63,8 +63,10 @@ def _sweep_items(sym: nested.Symbolic, n_sm: int, m_pad: int):
                 fwd.append((nd, r0, min(rb, nrow - r0)))
             for c0 in range(0, ncol, cw):
                 bwd.append((nd, c0, min(cw, ncol - c0)))
-        with_kids = [int(nd) for nd in nodes if (sym.child[nd] >= 0).any() and sym.s[nd] > 0]
-        nodes_flat += with_kids
+        for nd in nodes:
+            if (sym.child[nd] >= 0).any():
+                for j0 in range(0, int(sym.s[nd]), 32):
+                    nodes_flat.append((int(nd), j0, min(32, int(sym.s[nd]) - j0)))
         node_ptr.append(len(nodes_flat))
         fwd_ptr.append(len(fwd))
         bwd_ptr.append(len(bwd))
@@ -73,7 +75,7 @@ def _sweep_items(sym: nested.Symbolic, n_sm: int, m_pad: int):
     as32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32).reshape(-1, 3)) if a else np.zeros((0, 3), np.int32)
     i32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32))
     return dict(fwd_ptr=i32(fwd_ptr), fwd_items=as32(fwd), bwd_ptr=i32(bwd_ptr), bwd_items=as32(bwd),
-                node_ptr=i32(node_ptr), nodes=i32(nodes_flat if nodes_flat else [0]), wpr=i32(wprs), cw=i32(cws))
+                node_ptr=i32(node_ptr), nodes=as32(nodes_flat) if nodes_flat else np.zeros((1, 3), np.int32), wpr=i32(wprs), cw=i32(cws))
 
 
 class Engine:

@@ -85,7 +85,7 @@ typedef struct dots_ctx {
     const int32_t *lvl_items;  /* work items (node, first row, n rows) as int32 triples, forward      */
     const int32_t *lvb_ptr;    /* [n_levels+1] ranges into lvb_items                                  */
     const int32_t *lvb_items;  /* work items (node, first col, n cols) as int32 triples, backward     */
-    const int32_t *lvn_nodes;  /* node ids grouped by level (gather step of the forward sweep)        */
+    const int32_t *lvn_nodes;  /* gather work items (node, first S row, n rows) grouped by level      */
     const int32_t *h_lvl_ptr;  /* HOST copies of lvl_ptr / lvb_ptr (grid sizing of the per-level launches) */
     const int32_t *h_lvb_ptr;
     const int32_t *h_lvn_ptr;  /* HOST [n_levels+1] ranges into lvn_nodes                             */
