@@ -71,6 +71,7 @@ def load(build_if_missing: bool = True):
         "dots_scale_dual": (ctxp, d, vp), "dots_scale_z": (ctxp, d, vp), "dots_set_params": (ctxp, vp, vp),
         "dots_kkt_sums": (ctxp, i, vp, vp), "dots_phi_rhs": (ctxp, vp), "dots_time_transform": (ctxp, i, vp),
         "dots_mode_solves": (ctxp, vp), "dots_grad_space": (ctxp, vp, vp, vp), "dots_div_space": (ctxp, vp, vp, vp),
+        "dots_graph_create": (ctxp, i, vp, C.POINTER(vp)), "dots_graph_launch": (vp, vp), "dots_graph_destroy": (vp,),
     }
     for name, args in protos.items():
         fn = getattr(lib, name)
@@ -82,7 +83,7 @@ def load(build_if_missing: bool = True):
 EXPORTS = ("dots_abi_version", "dots_ctx_sizeof", "dots_last_error", "dots_step_phi", "dots_step_vertex",
            "dots_step_tri", "dots_iterate", "dots_refresh_corner_terms", "dots_scale_dual", "dots_scale_z",
            "dots_set_params", "dots_kkt_sums", "dots_phi_rhs", "dots_time_transform", "dots_mode_solves",
-           "dots_grad_space", "dots_div_space")
+           "dots_grad_space", "dots_div_space", "dots_graph_create", "dots_graph_launch", "dots_graph_destroy")
 
 
 def check(code: int, what: str = ""):

@@ -359,3 +359,47 @@ extern "C" int dots_iterate(const dots_ctx_t *c, int n_iter, int write_z, void *
     }
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-graph form of one iteration: the ~45 launches of dots_iterate(1) are captured once and replayed with a
+// single cudaGraphLaunch (launch latency matters for the small meshes: knots_5-class is ~60 us of HBM traffic).
+// Scalars (r, s, d, ...) live in device memory (ctx->params), so the graph stays valid across penalty updates.
+struct dots_graph {
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+};
+
+extern "C" int dots_graph_create(const dots_ctx_t *c, int write_z, void *stream, dots_graph_t **out)
+{
+    if (int e = dots_check_ctx(c)) return e;
+    if (!out) { dots_set_error("null output handle"); return DOTS_ERR_BAD_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    dots_graph *g = new dots_graph{nullptr, nullptr};
+    DOTS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int e = dots_iterate(c, 1, write_z, stream);
+    cudaError_t ce = cudaStreamEndCapture(st, &g->graph);
+    if (e || ce != cudaSuccess) {
+        if (!e) dots_set_error("cudaStreamEndCapture -> %s", cudaGetErrorString(ce));
+        delete g;
+        return e ? e : (int)ce;
+    }
+    DOTS_CUDA(cudaGraphInstantiate(&g->exec, g->graph, 0));
+    *out = g;
+    return 0;
+}
+
+extern "C" int dots_graph_launch(dots_graph_t *g, void *stream)
+{
+    if (!g || !g->exec) { dots_set_error("null graph"); return DOTS_ERR_BAD_ARG; }
+    DOTS_CUDA(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int dots_graph_destroy(dots_graph_t *g)
+{
+    if (!g) return 0;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    return 0;
+}

@@ -208,6 +208,7 @@ class Engine:
         self.k_dual_b = np.mean([ma_v, ma_f])
         self.k_comp_rho, self.k_comp_m = ma_v, ma_f
         self.z_valid = True                              # z_mid = 0 is the reference's initial z_mid (:245)
+        self.use_graphs, self._warm, self._graphs = True, False, {}
         self.launches = 0
         self._push_params()
         torch.cuda.synchronize(dev)
@@ -236,9 +237,35 @@ class Engine:
 
     # ------------------------------------------------------------------ the iteration
     def iterate(self, n=1, write_z=False):
-        capi.check(self.lib.dots_iterate(self._ctxp, int(n), int(bool(write_z)), self.stream), "dots_iterate")
+        """n ALM iterations (Steps 1-3); ``write_z`` stores z_mid on the last one.  After the first call the
+        iteration is replayed from a captured CUDA graph (one per write_z flavour) unless ``use_graphs`` is off."""
+        n, write_z = int(n), bool(write_z)
+        st = self.stream
+        if not self.use_graphs or not self._warm:
+            capi.check(self.lib.dots_iterate(self._ctxp, n, int(write_z), st), "dots_iterate")
+            self._warm = True
+        else:
+            for i in range(n):
+                wz = write_z and i == n - 1
+                key = (int(wz), st)
+                if key not in self._graphs:
+                    h = C.c_void_p()
+                    capi.check(self.lib.dots_graph_create(self._ctxp, int(wz), st, C.byref(h)), "dots_graph_create")
+                    self._graphs[key] = h
+                capi.check(self.lib.dots_graph_launch(self._graphs[key], st), "dots_graph_launch")
         self.launches += n * self.launches_per_iteration()
-        self.z_valid = bool(write_z)
+        self.z_valid = write_z
+
+    def close(self):
+        for h in self._graphs.values():
+            self.lib.dots_graph_destroy(h)
+        self._graphs = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def adjust_penalty(self, f):                                                         # :367-371
         self.r *= f

@@ -132,6 +132,14 @@ int dots_step_vertex(const dots_ctx_t *c, void *stream);
 int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream);
 int dots_iterate(const dots_ctx_t *c, int n_iter, int write_z, void *stream);
 
+/* One iteration captured as a CUDA graph (same work as dots_iterate(c, 1, write_z)); the context must outlive it and
+ * must not be modified afterwards (scalars go through dots_set_params, which the graph picks up).  Call
+ * dots_iterate once before creating a graph (first-use kernel attributes are set outside of stream capture). */
+typedef struct dots_graph dots_graph_t;
+int dots_graph_create(const dots_ctx_t *c, int write_z, void *stream, dots_graph_t **out);
+int dots_graph_launch(dots_graph_t *g, void *stream);
+int dots_graph_destroy(dots_graph_t *g);
+
 /* recompute corner_nrm / corner_div from (B, E, b_mid) after the state was set or rescaled */
 int dots_refresh_corner_terms(const dots_ctx_t *c, void *stream);
 

@@ -172,12 +172,13 @@ def test_kkt_and_objective_rows_a9_a11():
 
 # ---------------------------------------------------------------------------------------------- end to end
 @pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005",
-                                  "ico2_nt15_tol1e-4", "ico3_nt31_c0", "ico3_nt31_c01"])
+                                  "ico2_nt15_tol1e-4", "ico3_nt31_c0", "ico3_nt31_c01",
+                                  "knots5class_nt31_c0", "knots5class_nt31_c01"])       # BASELINE configs[0], [1]
 def test_solver_matches_reference_fixture(golden, name):
     """Through the public solver_socp: iteration count, KKT schedule (which residual on which iteration), penalty
     path, transport cost and the returned mu against the fixtures generated by the unmodified reference."""
     z, geo, n_time, kw = golden(name)
-    sol, hist, eng = b200.solver_socp(n_time, geo, leaf_size=8, return_engine=True, **kw)
+    sol, hist, eng = b200.solver_socp(n_time, geo, leaf_size=8 if geo["vertices"].shape[0] < 2000 else 24, return_engine=True, **kw)
     assert int(hist.kkt_iteration[-1]) == int(z["iterations"])
     ref_rows = z["kkt_rows"]
     assert hist.kkt_errors.shape == ref_rows.shape

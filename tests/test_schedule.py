@@ -54,7 +54,8 @@ def replay(rows, tol, nit):
     return nit - 1, np.array(asked), np.array(r_hist)
 
 
-@pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt15_tol1e-4", "ico3_nt31_c0", "ico3_nt31_c01", "knot_small_nt8_c005"])
+@pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt15_tol1e-4", "ico3_nt31_c0", "ico3_nt31_c01", "knot_small_nt8_c005",
+                                  "knots5class_nt31_c0", "knots5class_nt31_c01"])
 def test_replay_of_reference_decisions(golden, name):
     z, geo, n_time, kw = golden(name)
     rows = z["kkt_rows"].copy()
