@@ -226,7 +226,7 @@ def run_own(args):
         barrier()
         ev0.record()
         for _ in range(args.steps):
-            capi.check(lib.dots_iterate(ctxp, 1, 0, stream))
+            eng.iterate(1)                                 # one cudaGraphLaunch per ALM iteration
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)

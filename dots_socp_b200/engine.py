@@ -208,7 +208,7 @@ class Engine:
         self.k_dual_b = np.mean([ma_v, ma_f])
         self.k_comp_rho, self.k_comp_m = ma_v, ma_f
         self.z_valid = True                              # z_mid = 0 is the reference's initial z_mid (:245)
-        self.use_graphs, self._warm, self._graphs = True, False, {}
+        self.use_graphs, self._warm, self._graphs, self._cap_stream = True, False, {}, None
         self.launches = 0
         self._push_params()
         torch.cuda.synchronize(dev)
@@ -249,8 +249,13 @@ class Engine:
                 wz = write_z and i == n - 1
                 key = (int(wz), st)
                 if key not in self._graphs:
+                    # capture on a private stream (the legacy default stream cannot be captured); capturing does
+                    # not execute anything, and the instantiated graph is launched on the caller's stream
+                    if self._cap_stream is None:
+                        self._cap_stream = torch.cuda.Stream(self.device)
                     h = C.c_void_p()
-                    capi.check(self.lib.dots_graph_create(self._ctxp, int(wz), st, C.byref(h)), "dots_graph_create")
+                    capi.check(self.lib.dots_graph_create(self._ctxp, int(wz), self._cap_stream.cuda_stream, C.byref(h)),
+                               "dots_graph_create")
                     self._graphs[key] = h
                 capi.check(self.lib.dots_graph_launch(self._graphs[key], st), "dots_graph_launch")
         self.launches += n * self.launches_per_iteration()
