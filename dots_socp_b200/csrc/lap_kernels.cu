@@ -126,60 +126,94 @@ __global__ void __launch_bounds__(256) k_sweep_gather(dots_ctx_t c, int item0)
     }
 }
 
-// Forward sweep, one tree level.  Block = one work item (node, first row, n rows).
-//   y_S   = inv(L11) r_S                                               -> ywork
-//   upd_B = (children's updates landing on B) - (L21 inv(L11)) r_S     -> this node's update vector
-// WPR warps share one panel row (interleaved columns, partial sums combined through shared memory in a fixed
-// order); 8/WPR rows are in flight per pass.  Every panel entry is streamed exactly once, as M*8-byte rows.
-template <int MP, int WPR>
-__global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_fwd(dots_ctx_t c, int item0)
+__device__ __forceinline__ size_t panel_col_off(int col, int s, int b)     // column-major copy: offset of column `col`
+{
+    return (size_t)col * (s + b) - (size_t)col * (col - 1) / 2;
+}
+__device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes)     // bytes % 16 == 0; SASS: UBLKPF.L2
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// One tree level of a sweep.  Block = one work item (node, first output, n outputs).
+//   DIR 0, forward : output = panel row i of the row-major panel  (columns [0, min(i+1,s)))
+//        y_S   = inv(L11) r_S                                               -> ywork
+//        upd_B = (children's updates landing on B) - (L21 inv(L11)) r_S     -> this node's update vector
+//   DIR 1, backward: output = panel column j of the column-major copy (rows [j, s+b))
+//        xt_S = P^T (-[y_S ; xt_B])      (x of the ancestors is final in `hat`; the reference's per-mode matrix is
+//        L + (lambda - eps) M = -(K + shift M), laplacian_inverse_socp.py:37-38, so what is stored is xt = -x)
+// In both directions an output's data is ONE contiguous run of len*M doubles.  WPR warps share an output (interleaved
+// entries, partial sums combined through shared memory in a fixed order), 8/WPR outputs are in flight per pass, and
+// the run of the pass after next is pulled into L2 with one bulk prefetch (cp.async.bulk.prefetch.L2) so that the
+// demand loads mostly see L2 latency instead of DRAM latency (ncu before: >80 % long_scoreboard).
+template <int MP, int WPR, int DIR>
+__global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_run(dots_ctx_t c, int item0)
 {
     constexpr int M = 32 * MP;
     constexpr int ROWS = SWEEP_WARPS / WPR;
     __shared__ double red[(WPR > 1) ? SWEEP_WARPS * M : 1];
-    const int *it = c.lvl_items + 3 * (size_t)(item0 + blockIdx.x);
-    const int node = it[0], row0 = it[1], nrows = it[2];
+    const int *it = (DIR == 0 ? c.lvl_items : c.lvb_items) + 3 * (size_t)(item0 + blockIdx.x);
+    const int node = it[0], o0 = it[1], n_o = it[2];
     const int s = c.nd_s[node], off = c.nd_off[node], b_rows = c.nd_b[node];
     const int ch0 = c.nd_child[2 * node], ch1 = c.nd_child[2 * node + 1];
-    const double *u0 = (ch0 >= 0) ? c.upd + (size_t)c.nd_upd[ch0] * M : nullptr;
-    const double *u1 = (ch1 >= 0) ? c.upd + (size_t)c.nd_upd[ch1] * M : nullptr;
+    const double *u0 = (DIR == 0 && ch0 >= 0) ? c.upd + (size_t)c.nd_upd[ch0] * M : nullptr;
+    const double *u1 = (DIR == 0 && ch1 >= 0) ? c.upd + (size_t)c.nd_upd[ch1] * M : nullptr;
     const int32_t *cp0 = c.child_pos + c.nd_front[node];
     const int32_t *cp1 = cp0 + c.front_total;
-    const double *panel = c.panels + (size_t)c.nd_panel[node] * M;
-    const double *rvec = c.hat + (size_t)off * M;
+    const int32_t *fidx = c.front_idx + c.nd_front[node];
+    const double *panel = (DIR == 0 ? c.panels : c.panels_t) + (size_t)c.nd_panel[node] * M;
     double *myupd = c.upd + (size_t)c.nd_upd[node] * M;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rslot = warp / WPR, cslot = warp % WPR;
-    const int last_row = row0 + nrows - 1;
+    const int last = o0 + n_o - 1;
 
-    for (int base = row0; base <= last_row; base += ROWS) {
-        const int row = base + rslot;
-        const bool valid = row <= last_row;
+    auto out_len = [&](int o) { return DIR == 0 ? min(o + 1, s) : s + b_rows - o; };
+    auto out_off = [&](int o) { return DIR == 0 ? panel_row_off(o, s) : panel_col_off(o, s, b_rows); };
+    auto prefetch = [&](int o) {
+        if (cslot == 0 && lane == 0 && o <= last) {
+            const int len = out_len(o);
+            if (len > 0) l2_prefetch_bulk(panel + out_off(o) * M, (uint32_t)len * M * 8u);
+        }
+    };
+    prefetch(o0 + rslot);
+    prefetch(o0 + ROWS + rslot);
+
+    for (int base = o0; base <= last; base += ROWS) {
+        const int o = base + rslot;
+        const bool valid = o <= last;
+        prefetch(o + 2 * ROWS);
         double acc[MP];
 #pragma unroll
         for (int m = 0; m < MP; ++m) acc[m] = 0.0;
         if (valid) {
-            const int len = min(row + 1, s);
-            const double *pr = panel + panel_row_off(row, s) * M + lane;
-            const double *rv = rvec + lane;
-            int j = cslot;
-            for (; j + 3 * WPR < len; j += 4 * WPR) {
+            const int len = out_len(o);
+            const double *pr = panel + out_off(o) * M + lane;
+            auto vptr = [&](int e) -> const double * {
+                if (DIR == 0) return c.hat + (size_t)(off + e) * M + lane;
+                const int row = o + e;
+                return (row < s ? c.ywork + (size_t)(off + row) * M : c.hat + (size_t)fidx[row] * M) + lane;
+            };
+            int e = cslot;
+            for (; e + 3 * WPR < len; e += 4 * WPR) {
                 double p[4][MP], r[4][MP];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < 4; ++u) {
+                    const double *vp = vptr(e + u * WPR);
 #pragma unroll
                     for (int m = 0; m < MP; ++m) {
-                        p[u][m] = __ldcs(pr + (size_t)(j + u * WPR) * M + 32 * m);
-                        r[u][m] = rv[(size_t)(j + u * WPR) * M + 32 * m];
+                        p[u][m] = __ldcs(pr + (size_t)(e + u * WPR) * M + 32 * m);
+                        r[u][m] = vp[32 * m];
                     }
+                }
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
 #pragma unroll
                     for (int m = 0; m < MP; ++m) acc[m] += p[u][m] * r[u][m];
             }
-            for (; j < len; j += WPR) {
+            for (; e < len; e += WPR) {
+                const double *vp = vptr(e);
 #pragma unroll
-                for (int m = 0; m < MP; ++m) acc[m] += __ldcs(pr + (size_t)j * M + 32 * m) * rv[(size_t)j * M + 32 * m];
+                for (int m = 0; m < MP; ++m) acc[m] += __ldcs(pr + (size_t)e * M + 32 * m) * vp[32 * m];
             }
         }
         if (WPR > 1) {
@@ -198,79 +232,40 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_fwd(dots_ctx_t c, int i
             }
         }
         if (valid && cslot == 0) {
-            if (row < s) {
+            if (DIR == 1) {
 #pragma unroll
-                for (int m = 0; m < MP; ++m) c.ywork[(size_t)(off + row) * M + 32 * m + lane] = acc[m];
-            } else if (row - s < b_rows) {
-                const int a = cp0[row], b = cp1[row];
+                for (int m = 0; m < MP; ++m) c.hat[(size_t)(off + o) * M + 32 * m + lane] = -acc[m];
+            } else if (o < s) {
+#pragma unroll
+                for (int m = 0; m < MP; ++m) c.ywork[(size_t)(off + o) * M + 32 * m + lane] = acc[m];
+            } else if (o - s < b_rows) {
+                const int a = cp0[o], b = cp1[o];
 #pragma unroll
                 for (int m = 0; m < MP; ++m) {
                     double val = 0.0;
                     if (u0 && a >= 0) val += u0[(size_t)a * M + 32 * m + lane];
                     if (u1 && b >= 0) val += u1[(size_t)b * M + 32 * m + lane];
-                    myupd[(size_t)(row - s) * M + 32 * m + lane] = val - acc[m];
+                    myupd[(size_t)(o - s) * M + 32 * m + lane] = val - acc[m];
                 }
             }
         }
     }
 }
 
-// Backward sweep, one tree level.  Block = one work item (node, first column, n columns <= CW).
-//   x_S = inv(L11)^T y_S - (L21 inv(L11))^T x_B          (x of the ancestors is already final in `hat`)
-// The reference's per-mode matrix is L + (lambda - eps) M = -(K + shift M)  (laplacian_inverse_socp.py:37-38), so what
-// is stored in `hat` is xt = -x; substituting gives  xt_S = P^T (-[y_S ; xt_B]):  the sign costs nothing.
-// The 8 warps of a block interleave over the panel rows (each row contributes n_cols*M*8 contiguous bytes) and
-// their partial column sums are combined through shared memory in a fixed order.
-template <int MP, int CW>
-__global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_bwd(dots_ctx_t c, int item0)
+// ------------------------------------------------------------------------------------------------
+template <int MP, int DIR>
+static int launch_level(const dots_ctx_t *c, int wpr, int i0, int n, cudaStream_t st)
 {
-    constexpr int M = 32 * MP;
-    __shared__ double red[SWEEP_WARPS * CW * M];
-    const int *it = c.lvb_items + 3 * (size_t)(item0 + blockIdx.x);
-    const int node = it[0], col0 = it[1], ncols = it[2];
-    const int s = c.nd_s[node], b = c.nd_b[node], off = c.nd_off[node];
-    const int32_t *fidx = c.front_idx + c.nd_front[node];
-    const double *panel = c.panels + (size_t)c.nd_panel[node] * M;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nrows = s + b;
-
-    double acc[CW][MP];
-#pragma unroll
-    for (int q = 0; q < CW; ++q)
-#pragma unroll
-        for (int m = 0; m < MP; ++m) acc[q][m] = 0.0;
-
-#pragma unroll 4
-    for (int row = col0 + warp; row < nrows; row += SWEEP_WARPS) {     // rows < col0 never touch these columns
-        const double *vsrc = (row < s) ? c.ywork + (size_t)(off + row) * M : c.hat + (size_t)fidx[row] * M;
-        const double *pr = panel + (panel_row_off(row, s) + col0) * M + lane;
-        const int qe = (row < s) ? min(ncols, row - col0 + 1) : ncols;    // lower triangle of inv(L11) only
-        double v[MP];
-#pragma unroll
-        for (int m = 0; m < MP; ++m) v[m] = -vsrc[32 * m + lane];
-#pragma unroll
-        for (int q = 0; q < CW; ++q) {
-            if (q < qe) {
-#pragma unroll
-                for (int m = 0; m < MP; ++m) acc[q][m] += __ldcs(pr + (size_t)q * M + 32 * m) * v[m];
-            }
-        }
+    switch (wpr) {
+    case 1: k_sweep_run<MP, 1, DIR><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
+    case 2: k_sweep_run<MP, 2, DIR><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
+    case 4: k_sweep_run<MP, 4, DIR><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
+    default: k_sweep_run<MP, 8, DIR><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
     }
-#pragma unroll
-    for (int q = 0; q < CW; ++q)
-#pragma unroll
-        for (int m = 0; m < MP; ++m) red[(warp * CW + q) * M + 32 * m + lane] = acc[q][m];
-    __syncthreads();
-    for (int o = threadIdx.x; o < ncols * M; o += SWEEP_THREADS) {
-        const int q = o / M, m = o - q * M;
-        double vsum = 0.0;
-#pragma unroll
-        for (int w = 0; w < SWEEP_WARPS; ++w) vsum += red[(w * CW + q) * M + m];
-        c.hat[(size_t)(off + col0 + q) * M + m] = vsum;
-    }
+    DOTS_LAUNCH_CHECK();
+    return 0;
 }
 
-// ------------------------------------------------------------------------------------------------
 template <int MP>
 static int launch_sweeps(const dots_ctx_t *c, cudaStream_t st)
 {
@@ -279,34 +274,22 @@ static int launch_sweeps(const dots_ctx_t *c, cudaStream_t st)
         if (lv > 0 && gn > 0) { k_sweep_gather<<<gn, 256, 0, st>>>(*c, g0); DOTS_LAUNCH_CHECK(); }
         const int i0 = c->h_lvl_ptr[lv], n = c->h_lvl_ptr[lv + 1] - i0;
         if (n <= 0) continue;
-        switch (c->h_lvl_wpr[lv]) {
-        case 1: k_sweep_fwd<MP, 1><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
-        case 2: k_sweep_fwd<MP, 2><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
-        case 4: k_sweep_fwd<MP, 4><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
-        default: k_sweep_fwd<MP, 8><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
-        }
-        DOTS_LAUNCH_CHECK();
+        if (int e = launch_level<MP, 0>(c, c->h_lvl_wpr[lv], i0, n, st)) return e;
     }
     for (int lv = c->n_levels - 1; lv >= 0; --lv) {
         const int i0 = c->h_lvb_ptr[lv], n = c->h_lvb_ptr[lv + 1] - i0;
         if (n <= 0) continue;
-        switch (c->h_lvb_cw[lv]) {
-        case 1: k_sweep_bwd<MP, 1><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
-        case 2: k_sweep_bwd<MP, 2><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
-        case 4: k_sweep_bwd<MP, 4><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
-        default:
-            if (MP * 8 * SWEEP_WARPS * 32 * 8 <= 48 * 1024) { k_sweep_bwd<MP, (MP <= 3 ? 8 : 4)><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); }
-            else { dots_set_error("column block 8 unsupported for m_pad=%d", 32 * MP); return DOTS_ERR_BAD_ARG; }
-            break;
-        }
-        DOTS_LAUNCH_CHECK();
+        if (int e = launch_level<MP, 1>(c, c->h_lvb_cw[lv], i0, n, st)) return e;
     }
     return 0;
 }
 
+int dots_mode_solves_persistent(const dots_ctx_t *c, void *stream);   // sweep_tma.cu
+
 extern "C" int dots_mode_solves(const dots_ctx_t *c, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
+    if (c->sweep_mode == 1) return dots_mode_solves_persistent(c, stream);
     cudaStream_t st = (cudaStream_t)stream;
     switch (c->m_pad / 32) {
     case 1: return launch_sweeps<1>(c, st);

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import time
 
 import numpy as np
@@ -39,47 +40,71 @@ def time_basis(n_time: int):
 
 
 def _sweep_items(sym: nested.Symbolic, n_sm: int, m_pad: int):
-    """Per-level launch plan of the two sweeps.
+    """Per-level launch plan of the two sweeps (one launch per level and direction).
 
-    forward : items (node, first row, n rows); ``wpr`` warps share a panel row (1 for the small leaf fronts,
-              up to 8 for the long rows of the top separators) so that every level exposes >= ~8 blocks per SM
-              whenever it has the rows for it;
-    backward: items (node, first column, n columns <= cw)."""
+    Items are (node, first output, n outputs): outputs are panel rows in the forward sweep and panel columns (of the
+    column-major copy) in the backward sweep.  ``wpr`` warps share one output: 1 for the short runs of the leaf
+    fronts, up to 8 for the long runs of the top separators, so every level exposes >= ~8 blocks per SM whenever it
+    has the outputs for it."""
     fwd_ptr, bwd_ptr, node_ptr, fwd, bwd, nodes_flat, wprs, cws = [0], [0], [0], [], [], [], [], []
-    cw_cap = 4 if m_pad > 96 else 8
+
+    def pick(len_eff, total):
+        wpr = 1 if len_eff < 32 else 2 if len_eff < 96 else 4 if len_eff < 256 else 8
+        per_pass = 8 // wpr
+        passes = int(min(8, max(1, total // (per_pass * 8 * n_sm))))
+        return wpr, per_pass * passes
+
     for nodes in nested.level_schedule(sym):
         s_l, b_l = sym.s[nodes].astype(np.int64), sym.b[nodes].astype(np.int64)
-        rows_total, cols_total = int((s_l + b_l).sum()), int(s_l.sum())
-        work = s_l * (s_l + 1) // 2 + s_l * b_l
-        s_eff = float((s_l * work).sum() / max(1, work.sum()))
-        wpr = 1 if s_eff < 32 else 2 if s_eff < 96 else 4 if s_eff < 256 else 8
-        rows_per_pass = 8 // wpr
-        passes = int(min(8, max(1, rows_total // (rows_per_pass * 8 * n_sm))))
-        rb = rows_per_pass * passes
-        cw = next((w for w in (8, 4, 2, 1) if w <= cw_cap and cols_total // w >= 4 * n_sm), 1)
+        work = np.maximum(1, s_l * (s_l + 1) // 2 + s_l * b_l)
+        s_eff = float((s_l * work).sum() / work.sum())
+        col_eff = float(((s_l / 2 + b_l) * work).sum() / work.sum())
+        wpr, rb = pick(s_eff, int((s_l + b_l).sum()))
+        cw, cb = pick(col_eff, int(s_l.sum()))
         for nd in nodes:
             nrow, ncol = int(sym.s[nd] + sym.b[nd]), int(sym.s[nd])
-            for r0 in range(0, nrow, rb):
-                fwd.append((nd, r0, min(rb, nrow - r0)))
-            for c0 in range(0, ncol, cw):
-                bwd.append((nd, c0, min(cw, ncol - c0)))
-        for nd in nodes:
+            fwd += [(int(nd), r0, min(rb, nrow - r0)) for r0 in range(0, nrow, rb)]
+            bwd += [(int(nd), c0, min(cb, ncol - c0)) for c0 in range(0, ncol, cb)]
             if (sym.child[nd] >= 0).any():
-                for j0 in range(0, int(sym.s[nd]), 32):
-                    nodes_flat.append((int(nd), j0, min(32, int(sym.s[nd]) - j0)))
+                nodes_flat += [(int(nd), j0, min(32, ncol - j0)) for j0 in range(0, ncol, 32)]
         node_ptr.append(len(nodes_flat))
         fwd_ptr.append(len(fwd))
         bwd_ptr.append(len(bwd))
         wprs.append(wpr)
         cws.append(cw)
-    as32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32).reshape(-1, 3)) if a else np.zeros((0, 3), np.int32)
+    as32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32).reshape(-1, 3)) if a else np.zeros((1, 3), np.int32)
     i32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32))
     return dict(fwd_ptr=i32(fwd_ptr), fwd_items=as32(fwd), bwd_ptr=i32(bwd_ptr), bwd_items=as32(bwd),
-                node_ptr=i32(node_ptr), nodes=as32(nodes_flat) if nodes_flat else np.zeros((1, 3), np.int32), wpr=i32(wprs), cw=i32(cws))
+                node_ptr=i32(node_ptr), nodes=as32(nodes_flat), wpr=i32(wprs), cw=i32(cws))
+
+
+def _sweep_items_persistent(sym: nested.Symbolic, n_blocks: int):
+    """Work items (node, first output, n outputs <= 8) of the persistent TMA-fed sweep kernel, per level.
+
+    n outputs is chosen per level so that the level has about one item per resident block when it is small (the
+    top separators) and 8 outputs per item when it is large (the leaves)."""
+    fwd_ptr, bwd_ptr, fwd, bwd = [0], [0], [], []
+    for nodes in nested.level_schedule(sym):
+        rows_total = int((sym.s[nodes] + sym.b[nodes]).sum())
+        cols_total = int(sym.s[nodes].sum())
+        rb = int(min(8, max(1, rows_total // n_blocks)))
+        cb = int(min(8, max(1, cols_total // n_blocks)))
+        for nd in nodes:
+            nrow, ncol = int(sym.s[nd] + sym.b[nd]), int(sym.s[nd])
+            fwd += [(int(nd), r0, min(rb, nrow - r0)) for r0 in range(0, nrow, rb)]
+            bwd += [(int(nd), c0, min(cb, ncol - c0)) for c0 in range(0, ncol, cb)]
+        fwd_ptr.append(len(fwd))
+        bwd_ptr.append(len(bwd))
+    as32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32).reshape(-1, 3)) if a else np.zeros((1, 3), np.int32)
+    i32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32))
+    n_lv = len(fwd_ptr) - 1
+    return dict(fwd_ptr=i32(fwd_ptr), fwd_items=as32(fwd), bwd_ptr=i32(bwd_ptr), bwd_items=as32(bwd),
+                node_ptr=i32([0] * (n_lv + 1)), nodes=np.zeros((1, 3), np.int32), wpr=i32([1] * n_lv), cw=i32([1] * n_lv))
 
 
 class Engine:
-    def __init__(self, n_time, geometry, congestion=0.0, eps=0.0, tau=1.9, device=None, leaf_size=24, timings=None):
+    def __init__(self, n_time, geometry, congestion=0.0, eps=0.0, tau=1.9, device=None, leaf_size=24, timings=None,
+                 sweep_mode=None):
         if not torch.cuda.is_available():
             raise capi.DotsError("dots_socp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = capi.load()
@@ -118,7 +143,12 @@ class Engine:
         Q, lam_t = time_basis(nT)
         self.Q, self.lam_t = Q, lam_t
         shifts = -lam_t + self.eps                       # (L + (lam - eps) M) = -(K + (|lam| + eps) M)   (laplacian_inverse_socp.py:37-38)
-        panels = nested.factor_batched_device(sym, K, area_v, shifts, m_pad=self.m_pad, device=self.device)
+        if sweep_mode is None:
+            sweep_mode = int(os.environ.get("DOTS_SWEEP_MODE", "0"))
+        self.sweep_mode = int(sweep_mode)
+        panels = nested.factor_batched_device(sym, K, area_v, shifts, m_pad=self.m_pad, device=self.device,
+                                              transposed=True)
+        panels, panels_t = panels
         torch.cuda.synchronize(self.device)
         tm["factorization"] = time.perf_counter() - t0
 
@@ -141,7 +171,9 @@ class Engine:
         vc_ptr, vc_tri, vc_corner = surface.corner_adjacency(V, tri_new)
         qpad = np.zeros((nT + 1, self.m_pad))
         qpad[:, :nT + 1] = Q
-        plan = _sweep_items(sym, self.n_sm, self.m_pad)
+        self.sweep_grid = 2 * self.n_sm if self.m_pad <= 96 else self.n_sm
+        plan = (_sweep_items_persistent(sym, self.sweep_grid) if self.sweep_mode == 1
+                else _sweep_items(sym, self.n_sm, self.m_pad))
         self.plan = plan                                                                 # host arrays stay alive
         fwd_ptr, fwd_items, bwd_ptr, bwd_items = plan["fwd_ptr"], plan["fwd_items"], plan["bwd_ptr"], plan["bwd_items"]
         self._h_fwd_ptr, self._h_bwd_ptr = fwd_ptr, bwd_ptr
@@ -163,6 +195,13 @@ class Engine:
             lvb_ptr=up("lvb_ptr", bwd_ptr, np.int32), lvb_items=up("lvb_items", bwd_items, np.int32),
             lvn_nodes=up("lvn_nodes", plan["nodes"], np.int32))
         self._keep["panels"] = panels
+        if panels_t is not None:
+            self._keep["panels_t"] = panels_t
+            ctx.panels_t = panels_t.data_ptr()
+        ctx.sweep_mode, ctx.sweep_grid = self.sweep_mode, self.sweep_grid
+        self._keep["phase_clock"] = torch.zeros(2 * sym.n_levels + 1, dtype=torch.int64, device=dev)
+        if os.environ.get("DOTS_PHASE_CLOCK"):
+            ctx.phase_clock = self._keep["phase_clock"].data_ptr()
         for k, ten in const.items():
             setattr(ctx, k, ten.data_ptr())
         ctx.h_lvl_ptr = self._h_fwd_ptr.ctypes.data
@@ -230,6 +269,8 @@ class Engine:
     def launches_per_iteration(self):
         """Kernel launches of one dots_iterate step: rhs, 2 transforms, one sweep launch per non-empty level
         and direction, vertex, triangle."""
+        if self.sweep_mode == 1:
+            return 6                                   # rhs, 2 transforms, persistent sweeps, vertex, triangle
         n_f = int(np.count_nonzero(np.diff(self._h_fwd_ptr)))
         n_b = int(np.count_nonzero(np.diff(self._h_bwd_ptr)))
         n_g = int(np.count_nonzero(np.diff(self.plan["node_ptr"])[1:]))

@@ -260,12 +260,14 @@ def level_schedule(sym: Symbolic):
 
 
 def factor_batched_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shifts: np.ndarray, m_pad: int, device,
-                          pin_singular: bool = True):
+                          pin_singular: bool = True, transposed: bool = False):
     """Same numeric factorisation as ``factor_batched`` but with the dense front algebra on the GPU.
 
     SETUP path (row (f)1 of SURVEY.md section 8), not the per-iteration hot path: the batched dense
     Cholesky / triangular-solve / GEMM calls go through torch.linalg (cuSOLVER / cuBLAS) on fp64 tensors
-    of shape (modes, n, n).  Returns the panel tensor (panel_entries, m_pad) on ``device``."""
+    of shape (modes, n, n).  Returns the panel tensor (panel_entries, m_pad) on ``device``; with
+    ``transposed=True`` also the column-major copy (per node: column j holds rows j..s+b-1 of the stacked panel)
+    that the backward sweep streams."""
     import torch
 
     shifts_t = torch.as_tensor(np.asarray(shifts, dtype=np.float64), device=device)
@@ -275,6 +277,8 @@ def factor_batched_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shi
     massp = torch.as_tensor(np.asarray(mass, dtype=np.float64)[sym.perm], device=device)
     indptr, indices, data = Kp.indptr, Kp.indices, Kp.data
     panels = torch.zeros((sym.panel_entries, m_pad), dtype=torch.float64, device=device)
+    panels_t = torch.zeros((sym.panel_entries, m_pad), dtype=torch.float64, device=device) if transposed else None
+    triu_cache = {}
     singular = [m for m in range(n_modes) if float(shifts[m]) == 0.0] if pin_singular else []
     pin_value = float(Kp.diagonal().mean())
     updates = [None] * sym.n_nodes
@@ -326,9 +330,19 @@ def factor_batched_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shi
         if m_pad > n_modes:
             dd = torch.arange(s, device=device)
             panels[p0 + dd * (dd + 1) // 2 + dd, n_modes:] = 1.0
+        W21 = None
         if b:
             L21 = F[:, s:, :s] @ Linv.mT
             W21 = L21 @ Linv
             panels[p0 + ntri:p0 + ntri + b * s, :n_modes] = W21.reshape(n_modes, b * s).T
             updates[i] = F[:, s:, s:] - L21 @ L21.mT
-    return panels
+        if transposed:
+            stacked = Linv if W21 is None else torch.cat([Linv, W21], dim=1)          # (modes, s+b, s)
+            if (s, b) not in triu_cache:
+                triu_cache[(s, b)] = torch.ones((s, s + b), dtype=torch.bool, device=device).triu()
+            mask = triu_cache[(s, b)]                                                   # (col j, row i) with i >= j
+            panels_t[p0:p0 + ntri + b * s, :n_modes] = stacked.mT[:, mask].T
+            if m_pad > n_modes:
+                jj = torch.arange(s, device=device)
+                panels_t[p0 + jj * (s + b) - jj * (jj - 1) // 2, n_modes:] = 1.0
+    return (panels, panels_t) if transposed else panels

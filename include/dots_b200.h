@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DOTS_ABI_VERSION 2
+#define DOTS_ABI_VERSION 4
 
 /* scalar block read by the kernels from device memory (so CUDA graphs stay valid across penalty updates) */
 enum {
@@ -71,7 +71,8 @@ typedef struct dots_ctx {
     const double  *qmat;       /* [nT+1][m_pad] time eigenbasis Q[t][mode] (laplacian_inverse_socp.py:31) */
 
     /* ---- batched multifrontal factor of K + shift_mode*diag(area_v) (dots_socp_b200/nested.py) ---- */
-    const double  *panels;     /* [panel_entries][m_pad]                                              */
+    const double  *panels;     /* [panel_entries][m_pad]  per node row-major: rows of [inv(L11) ; L21 inv(L11)]  */
+    const double  *panels_t;   /* same entries, per node column-major (column j holds rows j..s+b-1): backward sweep */
     const int32_t *nd_off;     /* [n_nodes] first vertex owned                                        */
     const int32_t *nd_s;       /* [n_nodes] |S|                                                       */
     const int32_t *nd_b;       /* [n_nodes] |B|                                                       */
@@ -90,7 +91,7 @@ typedef struct dots_ctx {
     const int32_t *h_lvb_ptr;
     const int32_t *h_lvn_ptr;  /* HOST [n_levels+1] ranges into lvn_nodes                             */
     const int32_t *h_lvl_wpr;  /* HOST [n_levels] warps sharing one panel row in the forward sweep (1,2,4,8) */
-    const int32_t *h_lvb_cw;   /* HOST [n_levels] columns per block in the backward sweep (1,2,4,8)   */
+    const int32_t *h_lvb_cw;   /* HOST [n_levels] warps sharing one panel column in the backward sweep (1,2,4,8) */
     int64_t front_total;       /* sum(s+b)                                                            */
 
     /* ---- ALM state (read-write) ---- */
@@ -110,7 +111,10 @@ typedef struct dots_ctx {
     double *red_part;          /* [red_blocks][8] block partial sums                                  */
     double *red_out;           /* [8] reduced sums (device)                                           */
     int32_t red_blocks;
+    int32_t sweep_mode;        /* 0: one launch per tree level and direction; 1: persistent TMA-fed cooperative kernel */
+    int32_t sweep_grid;        /* blocks of the persistent kernel (0 = 2 per SM)                       */
     int32_t reserved0;
+    uint64_t *phase_clock;     /* optional [2*n_levels+1]: %globaltimer (ns) at the start and after each sweep phase */
 } dots_ctx_t;
 
 /* ------------------------------------------------------------------------------------------------ */

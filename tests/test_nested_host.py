@@ -103,3 +103,24 @@ def test_device_factorisation_matches_host_version():
     b = nested.factor_batched_device(sym, K, mass, shifts, m_pad=32, device="cpu").numpy()
     assert a.shape == b.shape
     assert np.abs(a - b).max() / np.abs(a).max() < 1e-12
+
+
+def test_transposed_panel_copy_is_column_major_view_of_the_same_entries():
+    geo, _ = synth.example("icosphere2")
+    v, t = geo["vertices"], geo["triangles"]
+    K = surface.stiffness_matrix(v, t)
+    mass = surface.incident_area_sum(v.shape[0], t, surface.triangle_areas(v, t)) / 3.0
+    sym = nested.analyse(v, K, leaf_size=8)
+    shifts = np.array([0.0, 3.0, 11.0])
+    p, pt = nested.factor_batched_device(sym, K, mass, shifts, m_pad=32, device="cpu", transposed=True)
+    p, pt = p.numpy(), pt.numpy()
+    for i in range(sym.n_nodes):
+        s, b = int(sym.s[i]), int(sym.b[i])
+        if s == 0:
+            continue
+        P = panel_rows(sym, p, i)                       # (s+b, s, M), upper triangle zero
+        p0 = int(sym.panel_off[i])
+        for j in range(s):
+            col_off = j * (s + b) - j * (j - 1) // 2
+            got = pt[p0 + col_off:p0 + col_off + (s + b - j)]
+            assert np.array_equal(got, P[j:, j])
