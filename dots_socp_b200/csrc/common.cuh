@@ -25,11 +25,13 @@ static inline int dots_check_ctx(const dots_ctx_t *c)
 {
     if (!c) { dots_set_error("null context"); return DOTS_ERR_BAD_ARG; }
     if (c->abi_version != DOTS_ABI_VERSION) { dots_set_error("abi mismatch: ctx %d lib %d", c->abi_version, DOTS_ABI_VERSION); return DOTS_ERR_ABI; }
-    if (c->m_pad % 32 != 0 || c->m_pad < c->n_time + 1 || c->m_pad > 128) { dots_set_error("m_pad=%d unsupported (multiple of 32, >= nT+1, <= 128)", c->m_pad); return DOTS_ERR_BAD_ARG; }
+    if (!(c->m_pad == 8 || c->m_pad == 16 || (c->m_pad % 32 == 0 && c->m_pad >= 32 && c->m_pad <= 128))) { dots_set_error("m_pad=%d unsupported (8, 16, 32, 64, 96, 128)", c->m_pad); return DOTS_ERR_BAD_ARG; }
+    if (c->lvl_begin < 0 || c->lvl_end > c->n_time + 1 || c->lvl_begin >= c->lvl_end) { dots_set_error("bad level range [%d, %d)", c->lvl_begin, c->lvl_end); return DOTS_ERR_BAD_ARG; }
     return 0;
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline int dots_t_end(const dots_ctx_t *c) { return c->lvl_end < c->n_time ? c->lvl_end : c->n_time; }   // staggered steps owned: [lvl_begin, t_end)
 
 // np.clip semantics: NaN passes through (fmin/fmax would drop it)
 __device__ __forceinline__ double clip01(double x) { return x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x); }

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) k_phi_rhs(dots_ctx_t c)
 {
     const int V = c.n_vert, nT = c.n_time, T = c.n_tri;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;
+    const int t = c.lvl_begin + blockIdx.y;
     if (v >= V) return;
     const double dt = 1.0 / nT;
     const double av = c.area_v[v];
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) k_vertex(dots_ctx_t c)
 {
     const int V = c.n_vert, nT = c.n_time, T = c.n_tri;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;                       // 0 .. nT-1
+    const int t = c.lvl_begin + blockIdx.y;         // owned staggered steps
     if (v >= V) return;
     const double *prm = c.params;
     const double r = prm[DOTS_P_R], s = prm[DOTS_P_S], d = prm[DOTS_P_D], cong = prm[DOTS_P_CONG], tau = prm[DOTS_P_TAU];
@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(128, 4) k_tri(dots_ctx_t c)
     const size_t T = (size_t)c.n_tri;
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= c.n_tri) return;
-    const int tau_begin = blockIdx.y * TRI_TCH;
-    const int tau_end = min(tau_begin + TRI_TCH, nT + 1);
+    const int tau_begin = c.lvl_begin + blockIdx.y * TRI_TCH;
+    const int tau_end = min(tau_begin + TRI_TCH, c.lvl_end);
     const double *prm = c.params;
     const double s = prm[DOTS_P_S], step = prm[DOTS_P_TAU];
     const double cs = s / sqrt(3.0);                                                          // :932, :953
@@ -251,8 +251,8 @@ __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c)
     const int nf = min(TRI_TILE, c.n_tri - f0);
     const int f = f0 + tid;
     const bool active = tid < nf;
-    const int tau_begin = blockIdx.y * TRI_TMA_TCH;
-    const int tau_end = min(tau_begin + TRI_TMA_TCH, nT + 1);
+    const int tau_begin = c.lvl_begin + blockIdx.y * TRI_TMA_TCH;
+    const int tau_end = min(tau_begin + TRI_TMA_TCH, c.lvl_end);
     const double *prm = c.params;
     const double s = prm[DOTS_P_S], step = prm[DOTS_P_TAU];
     const double cs = s / sqrt(3.0);
@@ -405,10 +405,9 @@ __global__ void k_mul_scalar(double *__restrict__ a, size_t n, double f)
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] *= f;
 }
 // mu = s (b_fst - b_end)                                                                      (:387)
-__global__ void k_mu_from_beta(dots_ctx_t c, double s)
+__global__ void k_mu_from_beta(dots_ctx_t c, double s, size_t i0, size_t n)
 {
-    const size_t n = (size_t)c.n_time * c.n_vert;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    for (size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         c.mu[i] = s * (c.b_fst[i] - c.b_end[i]);
 }
 // E = -decouple_adjoin_spacial(b_mid, s)                                                      (:388)
@@ -417,7 +416,7 @@ __global__ void k_E_from_beta(dots_ctx_t c, double s)
     const size_t T = (size_t)c.n_tri;
     const int nT = c.n_time;
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    const int tau = blockIdx.y;
+    const int tau = c.lvl_begin + blockIdx.y;
     if (f >= c.n_tri) return;
     const double cs = s / sqrt(3.0);
     const double *bm = c.b_mid + (size_t)tau * 18 * T + f;
@@ -438,7 +437,7 @@ __global__ void k_E_from_beta(dots_ctx_t c, double s)
 __global__ void k_grad_space(dots_ctx_t c, const double *__restrict__ phi, double *__restrict__ out)
 {
     const size_t T = (size_t)c.n_tri;
-    const int f = blockIdx.x * blockDim.x + threadIdx.x, tau = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x, tau = c.lvl_begin + blockIdx.y;
     if (f >= c.n_tri) return;
     const double *ph = phi + (size_t)tau * c.n_vert;
     const double p0 = ph[c.tri[f]], p1 = ph[c.tri[T + f]], p2 = ph[c.tri[2 * T + f]];
@@ -449,7 +448,7 @@ __global__ void k_grad_space(dots_ctx_t c, const double *__restrict__ phi, doubl
 __global__ void k_div_space(dots_ctx_t c, const double *__restrict__ x, double *__restrict__ out)
 {
     const size_t T = (size_t)c.n_tri;
-    const int v = blockIdx.x * blockDim.x + threadIdx.x, tau = blockIdx.y;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x, tau = c.lvl_begin + blockIdx.y;
     if (v >= c.n_vert) return;
     const double *xt = x + (size_t)tau * 3 * T;
     double acc = 0.0;
@@ -465,7 +464,7 @@ __global__ void k_div_space(dots_ctx_t c, const double *__restrict__ x, double *
 extern "C" int dots_phi_rhs(const dots_ctx_t *c, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
-    dim3 grid(ceil_div(c->n_vert, 256), c->n_time + 1);
+    dim3 grid(ceil_div(c->n_vert, 256), c->lvl_end - c->lvl_begin);
     k_phi_rhs<<<grid, 256, 0, (cudaStream_t)stream>>>(*c);
     DOTS_LAUNCH_CHECK();
     return 0;
@@ -474,7 +473,8 @@ extern "C" int dots_phi_rhs(const dots_ctx_t *c, void *stream)
 extern "C" int dots_step_vertex(const dots_ctx_t *c, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
-    dim3 grid(ceil_div(c->n_vert, 256), c->n_time);
+    if (dots_t_end(c) <= c->lvl_begin) return 0;
+    dim3 grid(ceil_div(c->n_vert, 256), dots_t_end(c) - c->lvl_begin);
     k_vertex<<<grid, 256, 0, (cudaStream_t)stream>>>(*c);
     DOTS_LAUNCH_CHECK();
     return 0;
@@ -490,11 +490,11 @@ extern "C" int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream)
             DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM));
             configured = true;
         }
-        dim3 grid(ceil_div(c->n_tri, TRI_TILE), ceil_div(c->n_time + 1, TRI_TMA_TCH));
+        dim3 grid(ceil_div(c->n_tri, TRI_TILE), ceil_div(c->lvl_end - c->lvl_begin, TRI_TMA_TCH));
         if (write_z) k_tri_tma<1><<<grid, TRI_TILE, TRI_TMA_SMEM, (cudaStream_t)stream>>>(*c);
         else k_tri_tma<0><<<grid, TRI_TILE, TRI_TMA_SMEM, (cudaStream_t)stream>>>(*c);
     } else {
-        dim3 grid(ceil_div(c->n_tri, 128), ceil_div(c->n_time + 1, TRI_TCH));
+        dim3 grid(ceil_div(c->n_tri, 128), ceil_div(c->lvl_end - c->lvl_begin, TRI_TCH));
         if (write_z) k_tri<1><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);
         else k_tri<0><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);
     }
@@ -505,7 +505,7 @@ extern "C" int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream)
 extern "C" int dots_refresh_corner_terms(const dots_ctx_t *c, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
-    dim3 grid(ceil_div(c->n_tri, 128), ceil_div(c->n_time + 1, TRI_TCH));
+    dim3 grid(ceil_div(c->n_tri, 128), ceil_div(c->lvl_end - c->lvl_begin, TRI_TCH));
     k_tri<2><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);
     DOTS_LAUNCH_CHECK();
     return 0;
@@ -534,15 +534,17 @@ extern "C" int dots_scale_dual(const dots_ctx_t *c, double factor, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t a = (size_t)c->n_time * c->n_vert, b = (size_t)(c->n_time + 1) * 3 * c->n_tri, z = (size_t)(c->n_time + 1) * 18 * c->n_tri;
+    const size_t V = c->n_vert, T = c->n_tri;
+    const size_t l0 = c->lvl_begin, nl = c->lvl_end - c->lvl_begin, nt = dots_t_end(c) - c->lvl_begin;
     int e;
-    if ((e = launch_div(c->mu, a, factor, c->n_sm, st))) return e;                            // :370
-    if ((e = launch_div(c->E, b, factor, c->n_sm, st))) return e;
-    if ((e = launch_div(c->bnd0, c->n_vert, factor, c->n_sm, st))) return e;
-    if ((e = launch_div(c->bnd1, c->n_vert, factor, c->n_sm, st))) return e;
-    if ((e = launch_div(c->b_fst, a, factor, c->n_sm, st))) return e;
-    if ((e = launch_div(c->b_mid, z, factor, c->n_sm, st))) return e;
-    if ((e = launch_div(c->b_end, a, factor, c->n_sm, st))) return e;
+    // mu carries one halo step in front (t = lvl_begin-1), scaled here so that it stays consistent without an exchange
+    if ((e = launch_div(c->mu + ((long long)l0 - 1) * (long long)V, (nt + 1) * V, factor, c->n_sm, st))) return e;     // :370
+    if ((e = launch_div(c->E + l0 * 3 * T, nl * 3 * T, factor, c->n_sm, st))) return e;
+    if ((e = launch_div(c->bnd0, V, factor, c->n_sm, st))) return e;
+    if ((e = launch_div(c->bnd1, V, factor, c->n_sm, st))) return e;
+    if ((e = launch_div(c->b_fst + l0 * V, nt * V, factor, c->n_sm, st))) return e;
+    if ((e = launch_div(c->b_mid + l0 * 18 * T, nl * 18 * T, factor, c->n_sm, st))) return e;
+    if ((e = launch_div(c->b_end + l0 * V, nt * V, factor, c->n_sm, st))) return e;
     return dots_refresh_corner_terms(c, stream);
 }
 
@@ -550,20 +552,24 @@ extern "C" int dots_scale_z(const dots_ctx_t *c, double s_cum, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t a = (size_t)c->n_time * c->n_vert, z = (size_t)(c->n_time + 1) * 18 * c->n_tri;
+    const size_t V = c->n_vert, T = c->n_tri;
+    const size_t l0 = c->lvl_begin, nl = c->lvl_end - c->lvl_begin, nt = dots_t_end(c) - c->lvl_begin;
+    const size_t a = nt * V, z = nl * 18 * T;
     int e;
-    if ((e = launch_mul(c->z_fst, a, s_cum, c->n_sm, st))) return e;                          // :383
-    if ((e = launch_mul(c->z_mid, z, s_cum, c->n_sm, st))) return e;
-    if ((e = launch_mul(c->z_end, a, s_cum, c->n_sm, st))) return e;
+    if ((e = launch_mul(c->z_fst + l0 * V, a, s_cum, c->n_sm, st))) return e;                 // :383
+    if ((e = launch_mul(c->z_mid + l0 * 18 * T, z, s_cum, c->n_sm, st))) return e;
+    if ((e = launch_mul(c->z_end + l0 * V, a, s_cum, c->n_sm, st))) return e;
     const double inv = 1.0 / s_cum;                                                           // :384
-    if ((e = launch_mul(c->b_fst, a, inv, c->n_sm, st))) return e;
-    if ((e = launch_mul(c->b_mid, z, inv, c->n_sm, st))) return e;
-    if ((e = launch_mul(c->b_end, a, inv, c->n_sm, st))) return e;
-    int blocks = ceil_div((long long)a, 256);
-    if (blocks > c->n_sm * 16) blocks = c->n_sm * 16;
-    k_mu_from_beta<<<blocks, 256, 0, st>>>(*c, s_cum);
-    DOTS_LAUNCH_CHECK();
-    dim3 grid(ceil_div(c->n_tri, 128), c->n_time + 1);
+    if ((e = launch_mul(c->b_fst + l0 * V, a, inv, c->n_sm, st))) return e;
+    if ((e = launch_mul(c->b_mid + l0 * 18 * T, z, inv, c->n_sm, st))) return e;
+    if ((e = launch_mul(c->b_end + l0 * V, a, inv, c->n_sm, st))) return e;
+    if (a) {
+        int blocks = ceil_div((long long)a, 256);
+        if (blocks > c->n_sm * 16) blocks = c->n_sm * 16;
+        k_mu_from_beta<<<blocks, 256, 0, st>>>(*c, s_cum, l0 * V, l0 * V + a);                // halo step of mu: host exchange
+        DOTS_LAUNCH_CHECK();
+    }
+    dim3 grid(ceil_div(c->n_tri, 128), c->lvl_end - c->lvl_begin);
     k_E_from_beta<<<grid, 128, 0, st>>>(*c, s_cum);
     DOTS_LAUNCH_CHECK();
     return 0;   // caller sets params (s, d) and then calls dots_refresh_corner_terms
@@ -579,7 +585,7 @@ extern "C" int dots_set_params(const dots_ctx_t *c, const double *host_params, v
 extern "C" int dots_grad_space(const dots_ctx_t *c, const double *phi, double *out, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
-    dim3 grid(ceil_div(c->n_tri, 128), c->n_time + 1);
+    dim3 grid(ceil_div(c->n_tri, 128), c->lvl_end - c->lvl_begin);
     k_grad_space<<<grid, 128, 0, (cudaStream_t)stream>>>(*c, phi, out);
     DOTS_LAUNCH_CHECK();
     return 0;
@@ -588,7 +594,7 @@ extern "C" int dots_grad_space(const dots_ctx_t *c, const double *phi, double *o
 extern "C" int dots_div_space(const dots_ctx_t *c, const double *x, double *out, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
-    dim3 grid(ceil_div(c->n_vert, 128), c->n_time + 1);
+    dim3 grid(ceil_div(c->n_vert, 128), c->lvl_end - c->lvl_begin);
     k_div_space<<<grid, 128, 0, (cudaStream_t)stream>>>(*c, x, out);
     DOTS_LAUNCH_CHECK();
     return 0;

@@ -34,8 +34,10 @@ __global__ void __launch_bounds__(KKT_THREADS) k_kkt_vertex(dots_ctx_t c, int wh
     const double r = prm[DOTS_P_R], s = prm[DOTS_P_S], d = prm[DOTS_P_D], cong = prm[DOTS_P_CONG];
     const double dt = 1.0 / nT;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    const size_t n = (which == 2) ? (size_t)(nT + 1) * V : (size_t)nT * V;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    // owned range: levels [lvl_begin, lvl_end) for the centred residual (#2), staggered steps otherwise
+    const int t_end = (which == 2) ? c.lvl_end : min(c.lvl_end, nT);
+    const size_t i0 = (size_t)c.lvl_begin * V, n = (size_t)max(t_end, c.lvl_begin) * V;
+    for (size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int t = (int)(i / V), v = (int)(i - (size_t)t * V);
         const double av = c.area_v[v];
         switch (which) {
@@ -101,10 +103,8 @@ __global__ void __launch_bounds__(KKT_THREADS) k_kkt_vertex(dots_ctx_t c, int wh
             acc[0] += rho * rho * av; acc[1] += lc * lc * av; acc[2] += res * res * av;
         } break;
         case 7: {                                                          // objective :417-431
-            if (t == 0) {
-                acc[0] += c.phi[v] * (r * c.bnd0[v]);
-                acc[1] += c.phi[(size_t)nT * V + v] * (r * c.bnd1[v]);
-            }
+            if (t == 0) acc[0] += c.phi[v] * (r * c.bnd0[v]);
+            if (t == nT - 1) acc[1] += c.phi[(size_t)nT * V + v] * (r * c.bnd1[v]);
             const double lc = c.lam_c[i];
             acc[2] += lc * lc * av;
         } break;
@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(KKT_THREADS) k_kkt_tri(dots_ctx_t c, int which
     const double r = prm[DOTS_P_R], s = prm[DOTS_P_S];
     const double cs = s / sqrt(3.0);
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    const size_t n = (size_t)(nT + 1) * T;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t i0 = (size_t)c.lvl_begin * T, n = (size_t)c.lvl_end * T;
+    for (size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int tau = (int)(i / T);
         const size_t f = i - (size_t)tau * T;
         const double af = c.area_f[f];

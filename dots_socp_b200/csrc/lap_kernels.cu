@@ -19,9 +19,10 @@
 // ------------------------------------------------------------------------------------------------
 // Time transforms as fp64 tensor-core GEMMs (DMMA, mma.sync.m8n8k4.f64: the only fp64 tensor path - tcgen05 has
 // no f64 kind).  Per 64-vertex tile:   C[64][N] = A[64][K] * B[K][N]
-//   DIR 0 (laplacian_inverse_socp.py:54)  hat[v][k] = sum_t rhs[t][v] Q[t][k]   A = rhs^T, B = Q,   K = nT+1, N = m_pad
-//   DIR 1 (laplacian_inverse_socp.py:61)  phi[t][v] = sum_k hat[v][k] Q[t][k]   A = hat,   B = Q^T, K = m_pad, N = nT+1
-// B (the time eigenbasis) is loaded into shared memory once per block; blocks are persistent over vertex tiles.
+//   DIR 0 (laplacian_inverse_socp.py:54)  hat[v][k] = sum_t rhs[t][v] Q[t][k]   A = rhs^T, B = qf (all levels x own modes)
+//   DIR 1 (laplacian_inverse_socp.py:61)  phi[t][v] = sum_k hat[v][k] Q[t][k]   A = hat_all, B = qb (all modes x own levels)
+// B (a slice of the time eigenbasis prepared by the host: this rank's modes / levels) is loaded into shared memory once
+// per block; blocks are persistent over vertex tiles.
 // Leading dimensions lda = K+4, ldb = N+8 make both fragment loads bank-conflict free.
 #define TT_VT 64
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b)
@@ -35,22 +36,16 @@ __global__ void __launch_bounds__(256) k_time_mma(dots_ctx_t c, int n_tiles)
 {
     extern __shared__ double sm[];
     const int nt1 = c.n_time + 1, M = c.m_pad, V = c.n_vert;
-    const int K = (DIR == 0) ? ((nt1 + 3) & ~3) : M;
-    const int N = (DIR == 0) ? M : ((nt1 + 7) & ~7);
+    const int K = (DIR == 0) ? c.tt_kf : c.tt_kb;
+    const int N = (DIR == 0) ? M : c.tt_nb;
+    const double *Bg = (DIR == 0) ? c.qf : c.qb;           // [K][N], built by the host for this rank
     const int lda = K + 4, ldb = N + 8, NT = N / 8;
     double *Bs = sm;                       // [K][ldb]
     double *As = sm + (size_t)K * ldb;     // [TT_VT][lda]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (DIR == 0) {
-        for (int i = tid; i < K * N; i += 256) {
-            const int p = i / N, j = i - p * N;
-            Bs[p * ldb + j] = (p < nt1) ? c.qmat[(size_t)p * M + j] : 0.0;
-        }
-    } else {
-        for (int i = tid; i < N * K; i += 256) {
-            const int j = i / K, p = i - j * K;
-            Bs[p * ldb + j] = (j < nt1) ? c.qmat[(size_t)j * M + p] : 0.0;
-        }
+    for (int i = tid; i < K * N; i += 256) {
+        const int p = i / N, j = i - p * N;
+        Bs[p * ldb + j] = Bg[i];
     }
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int v0 = tile * TT_VT;
@@ -63,7 +58,8 @@ __global__ void __launch_bounds__(256) k_time_mma(dots_ctx_t c, int n_tiles)
         } else {
             for (int i = tid; i < TT_VT * K; i += 256) {
                 const int vv = i / K, p = i - vv * K;
-                As[vv * lda + p] = (v0 + vv < V) ? c.hat[(size_t)(v0 + vv) * M + p] : 0.0;
+                const int rk = p / M, pos = p - rk * M;     // gathered layout [rank][v][m_pad]
+                As[vv * lda + p] = (v0 + vv < V) ? c.hat_all[((size_t)rk * V + v0 + vv) * M + pos] : 0.0;
             }
         }
         __syncthreads();
@@ -88,8 +84,8 @@ __global__ void __launch_bounds__(256) k_time_mma(dots_ctx_t c, int n_tiles)
                     if (DIR == 0) {
                         *reinterpret_cast<double2 *>(c.hat + (size_t)vrow * M + j) = make_double2(acc[nt][0], acc[nt][1]);
                     } else {
-                        if (j < nt1) c.phi[(size_t)j * V + vrow] = acc[nt][0];
-                        if (j + 1 < nt1) c.phi[(size_t)(j + 1) * V + vrow] = acc[nt][1];
+                        if (j < c.tt_nout) c.phi[(size_t)(c.lvl_begin + j) * V + vrow] = acc[nt][0];
+                        if (j + 1 < c.tt_nout) c.phi[(size_t)(c.lvl_begin + j + 1) * V + vrow] = acc[nt][1];
                     }
                 }
             }
@@ -146,10 +142,15 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) 
 // entries, partial sums combined through shared memory in a fixed order), 8/WPR outputs are in flight per pass, and
 // the run of the pass after next is pulled into L2 with one bulk prefetch (cp.async.bulk.prefetch.L2) so that the
 // demand loads mostly see L2 latency instead of DRAM latency (ncu before: >80 % long_scoreboard).
-template <int MP, int WPR, int DIR>
+// ML = modes of this rank (8, 16, 32, 64, 96, 128).  ML >= 32: lane = mode (+32 per register); ML < 32: a warp covers
+// G = 32/ML consecutive entries at once (lane = entry-in-group * ML + mode) and folds the groups with shuffles.
+template <int ML, int WPR, int DIR>
 __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_run(dots_ctx_t c, int item0)
 {
-    constexpr int M = 32 * MP;
+    constexpr int M = ML;
+    constexpr int MP = (ML >= 32) ? ML / 32 : 1;
+    constexpr int G = (ML >= 32) ? 1 : 32 / ML;
+    constexpr int LSTRIDE = (ML >= 32) ? 32 : 0;       // register m of a lane is mode lane + 32 m (only ML >= 32)
     constexpr int ROWS = SWEEP_WARPS / WPR;
     __shared__ double red[(WPR > 1) ? SWEEP_WARPS * M : 1];
     const int *it = (DIR == 0 ? c.lvl_items : c.lvb_items) + 3 * (size_t)(item0 + blockIdx.x);
@@ -163,14 +164,17 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_run(dots_ctx_t c, int i
     const int32_t *fidx = c.front_idx + c.nd_front[node];
     const double *panel = (DIR == 0 ? c.panels : c.panels_t) + (size_t)c.nd_panel[node] * M;
     double *myupd = c.upd + (size_t)c.nd_upd[node] * M;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = (G > 1) ? lane_id / ML : 0;        // entry slot inside the warp
+    const int lane = (G > 1) ? lane_id % ML : lane_id; // mode index of register 0
     const int rslot = warp / WPR, cslot = warp % WPR;
+    const int estep = WPR * G, e_first = cslot * G + grp;
     const int last = o0 + n_o - 1;
 
     auto out_len = [&](int o) { return DIR == 0 ? min(o + 1, s) : s + b_rows - o; };
     auto out_off = [&](int o) { return DIR == 0 ? panel_row_off(o, s) : panel_col_off(o, s, b_rows); };
     auto prefetch = [&](int o) {
-        if (cslot == 0 && lane == 0 && o <= last) {
+        if (cslot == 0 && lane_id == 0 && o <= last) {
             const int len = out_len(o);
             if (len > 0) l2_prefetch_bulk(panel + out_off(o) * M, (uint32_t)len * M * 8u);
         }
@@ -193,16 +197,16 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_run(dots_ctx_t c, int i
                 const int row = o + e;
                 return (row < s ? c.ywork + (size_t)(off + row) * M : c.hat + (size_t)fidx[row] * M) + lane;
             };
-            int e = cslot;
-            for (; e + 3 * WPR < len; e += 4 * WPR) {
+            int e = e_first;
+            for (; e + 3 * estep < len; e += 4 * estep) {
                 double p[4][MP], r[4][MP];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const double *vp = vptr(e + u * WPR);
+                    const double *vp = vptr(e + u * estep);
 #pragma unroll
                     for (int m = 0; m < MP; ++m) {
-                        p[u][m] = __ldcs(pr + (size_t)(e + u * WPR) * M + 32 * m);
-                        r[u][m] = vp[32 * m];
+                        p[u][m] = __ldcs(pr + (size_t)(e + u * estep) * M + LSTRIDE * m);
+                        r[u][m] = vp[LSTRIDE * m];
                     }
                 }
 #pragma unroll
@@ -210,42 +214,47 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_run(dots_ctx_t c, int i
 #pragma unroll
                     for (int m = 0; m < MP; ++m) acc[m] += p[u][m] * r[u][m];
             }
-            for (; e < len; e += WPR) {
+            for (; e < len; e += estep) {
                 const double *vp = vptr(e);
 #pragma unroll
-                for (int m = 0; m < MP; ++m) acc[m] += __ldcs(pr + (size_t)e * M + 32 * m) * vp[32 * m];
+                for (int m = 0; m < MP; ++m) acc[m] += __ldcs(pr + (size_t)e * M + LSTRIDE * m) * vp[LSTRIDE * m];
             }
         }
+        if (G > 1) {                                           // fold the entry slots of the warp (fixed order)
+#pragma unroll
+            for (int o2 = ML; o2 < 32; o2 <<= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o2);
+        }
+        const bool writer = (G > 1) ? (grp == 0) : true;
         if (WPR > 1) {
             __syncthreads();
 #pragma unroll
-            for (int m = 0; m < MP; ++m) red[warp * M + 32 * m + lane] = acc[m];
+            for (int m = 0; m < MP; ++m) if (writer) red[warp * M + LSTRIDE * m + lane] = acc[m];
             __syncthreads();
             if (cslot == 0) {
 #pragma unroll
                 for (int m = 0; m < MP; ++m) {
                     double v = 0.0;
 #pragma unroll
-                    for (int w = 0; w < WPR; ++w) v += red[(rslot * WPR + w) * M + 32 * m + lane];
+                    for (int w = 0; w < WPR; ++w) v += red[(rslot * WPR + w) * M + LSTRIDE * m + lane];
                     acc[m] = v;
                 }
             }
         }
-        if (valid && cslot == 0) {
+        if (valid && cslot == 0 && writer) {
             if (DIR == 1) {
 #pragma unroll
-                for (int m = 0; m < MP; ++m) c.hat[(size_t)(off + o) * M + 32 * m + lane] = -acc[m];
+                for (int m = 0; m < MP; ++m) c.hat[(size_t)(off + o) * M + LSTRIDE * m + lane] = -acc[m];
             } else if (o < s) {
 #pragma unroll
-                for (int m = 0; m < MP; ++m) c.ywork[(size_t)(off + o) * M + 32 * m + lane] = acc[m];
+                for (int m = 0; m < MP; ++m) c.ywork[(size_t)(off + o) * M + LSTRIDE * m + lane] = acc[m];
             } else if (o - s < b_rows) {
                 const int a = cp0[o], b = cp1[o];
 #pragma unroll
                 for (int m = 0; m < MP; ++m) {
                     double val = 0.0;
-                    if (u0 && a >= 0) val += u0[(size_t)a * M + 32 * m + lane];
-                    if (u1 && b >= 0) val += u1[(size_t)b * M + 32 * m + lane];
-                    myupd[(size_t)(o - s) * M + 32 * m + lane] = val - acc[m];
+                    if (u0 && a >= 0) val += u0[(size_t)a * M + LSTRIDE * m + lane];
+                    if (u1 && b >= 0) val += u1[(size_t)b * M + LSTRIDE * m + lane];
+                    myupd[(size_t)(o - s) * M + LSTRIDE * m + lane] = val - acc[m];
                 }
             }
         }
@@ -253,20 +262,20 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_run(dots_ctx_t c, int i
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int MP, int DIR>
+template <int ML, int DIR>
 static int launch_level(const dots_ctx_t *c, int wpr, int i0, int n, cudaStream_t st)
 {
     switch (wpr) {
-    case 1: k_sweep_run<MP, 1, DIR><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
-    case 2: k_sweep_run<MP, 2, DIR><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
-    case 4: k_sweep_run<MP, 4, DIR><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
-    default: k_sweep_run<MP, 8, DIR><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
+    case 1: k_sweep_run<ML, 1, DIR><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
+    case 2: k_sweep_run<ML, 2, DIR><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
+    case 4: k_sweep_run<ML, 4, DIR><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
+    default: k_sweep_run<ML, 8, DIR><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
     }
     DOTS_LAUNCH_CHECK();
     return 0;
 }
 
-template <int MP>
+template <int ML>
 static int launch_sweeps(const dots_ctx_t *c, cudaStream_t st)
 {
     for (int lv = 0; lv < c->n_levels; ++lv) {
@@ -274,12 +283,12 @@ static int launch_sweeps(const dots_ctx_t *c, cudaStream_t st)
         if (lv > 0 && gn > 0) { k_sweep_gather<<<gn, 256, 0, st>>>(*c, g0); DOTS_LAUNCH_CHECK(); }
         const int i0 = c->h_lvl_ptr[lv], n = c->h_lvl_ptr[lv + 1] - i0;
         if (n <= 0) continue;
-        if (int e = launch_level<MP, 0>(c, c->h_lvl_wpr[lv], i0, n, st)) return e;
+        if (int e = launch_level<ML, 0>(c, c->h_lvl_wpr[lv], i0, n, st)) return e;
     }
     for (int lv = c->n_levels - 1; lv >= 0; --lv) {
         const int i0 = c->h_lvb_ptr[lv], n = c->h_lvb_ptr[lv + 1] - i0;
         if (n <= 0) continue;
-        if (int e = launch_level<MP, 1>(c, c->h_lvb_cw[lv], i0, n, st)) return e;
+        if (int e = launch_level<ML, 1>(c, c->h_lvb_cw[lv], i0, n, st)) return e;
     }
     return 0;
 }
@@ -291,11 +300,13 @@ extern "C" int dots_mode_solves(const dots_ctx_t *c, void *stream)
     if (int e = dots_check_ctx(c)) return e;
     if (c->sweep_mode == 1) return dots_mode_solves_persistent(c, stream);
     cudaStream_t st = (cudaStream_t)stream;
-    switch (c->m_pad / 32) {
-    case 1: return launch_sweeps<1>(c, st);
-    case 2: return launch_sweeps<2>(c, st);
-    case 3: return launch_sweeps<3>(c, st);
-    case 4: return launch_sweeps<4>(c, st);
+    switch (c->m_pad) {
+    case 8: return launch_sweeps<8>(c, st);
+    case 16: return launch_sweeps<16>(c, st);
+    case 32: return launch_sweeps<32>(c, st);
+    case 64: return launch_sweeps<64>(c, st);
+    case 96: return launch_sweeps<96>(c, st);
+    case 128: return launch_sweeps<128>(c, st);
     }
     dots_set_error("m_pad=%d unsupported", c->m_pad);
     return DOTS_ERR_BAD_ARG;
@@ -305,8 +316,8 @@ extern "C" int dots_time_transform(const dots_ctx_t *c, int inverse, void *strea
 {
     if (int e = dots_check_ctx(c)) return e;
     cudaStream_t st = (cudaStream_t)stream;
-    const int nt1 = c->n_time + 1, M = c->m_pad;
-    const int K = inverse ? M : ((nt1 + 3) & ~3), N = inverse ? ((nt1 + 7) & ~7) : M;
+    const int K = inverse ? c->tt_kb : c->tt_kf, N = inverse ? c->tt_nb : c->m_pad;
+    if (K % 4 || N % 8 || N > 128 || K <= 0) { dots_set_error("time transform shape K=%d N=%d unsupported", K, N); return DOTS_ERR_BAD_ARG; }
     const size_t smem = ((size_t)K * (N + 8) + (size_t)TT_VT * (K + 4)) * sizeof(double);
     const int n_tiles = ceil_div(c->n_vert, TT_VT);
     const int per_sm = (smem <= 72 * 1024) ? 3 : (smem <= 110 * 1024 ? 2 : 1);

@@ -278,6 +278,7 @@ static int launch_persistent(const dots_ctx_t *c, cudaStream_t st)
 int dots_mode_solves_persistent(const dots_ctx_t *c, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
+    if (c->m_pad % 32) { dots_set_error("persistent sweep needs m_pad >= 32 (got %d)", c->m_pad); return DOTS_ERR_BAD_ARG; }
     switch (c->m_pad / 32) {
     case 1: return launch_persistent<1>(c, st);
     case 2: return launch_persistent<2>(c, st);

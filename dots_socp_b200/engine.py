@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import capi, nested, surface
+from . import dist as dd
 
 STATE_VERTEX = ("phi", "A", "lam_c", "mu", "z_fst", "z_end", "b_fst", "b_end")
 STATE_TRI = ("B", "E")
@@ -103,8 +104,10 @@ def _sweep_items_persistent(sym: nested.Symbolic, n_blocks: int):
 
 
 class Engine:
+    """One rank's share of the problem.  ``comm`` (dist.Comm) spans the ranks; None / single rank = whole problem."""
+
     def __init__(self, n_time, geometry, congestion=0.0, eps=0.0, tau=1.9, device=None, leaf_size=24, timings=None,
-                 sweep_mode=None):
+                 sweep_mode=None, comm=None):
         if not torch.cuda.is_available():
             raise capi.DotsError("dots_socp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = capi.load()
@@ -112,16 +115,17 @@ class Engine:
         torch.cuda.set_device(self.device)
         t_start = time.perf_counter()
         tm = timings if timings is not None else {}
+        self.comm = comm if comm is not None else dd.Comm()
 
         v = np.ascontiguousarray(geometry["vertices"], dtype=np.float64)
         tri_old = np.ascontiguousarray(geometry["triangles"]).astype(np.int64)
         self.nT, self.V, self.T = int(n_time), v.shape[0], tri_old.shape[0]
         nT, V, T = self.nT, self.V, self.T
-        if nT + 1 > 128:
-            raise ValueError("n_time + 1 must be <= 128 (time-mode batch width of the sweep kernels)")
+        self.part = dd.partition(nT, self.comm.rank, self.comm.world)
+        part = self.part
         self.dt = 1.0 / nT
         self.cong, self.tau, self.eps = float(congestion), float(tau), float(eps)
-        self.m_pad = 32 * (-(-(nT + 1) // 32))
+        self.m_pad = part.m_pad
 
         # ---- mesh operators (host, vectorised) --------------------------------------------------
         area_f = surface.triangle_areas(v, tri_old)
@@ -130,7 +134,7 @@ class Engine:
         K = surface.stiffness_matrix(v, tri_old)
         tm["mesh_operators"] = time.perf_counter() - t_start
 
-        # ---- ordering + batched factorisation -----------------------------------------------------
+        # ---- ordering + batched factorisation (this rank's time modes only) -------------------------
         t0 = time.perf_counter()
         sym = nested.analyse(v, K, leaf_size=leaf_size)
         self.sym = sym
@@ -142,13 +146,12 @@ class Engine:
         t0 = time.perf_counter()
         Q, lam_t = time_basis(nT)
         self.Q, self.lam_t = Q, lam_t
-        shifts = -lam_t + self.eps                       # (L + (lam - eps) M) = -(K + (|lam| + eps) M)   (laplacian_inverse_socp.py:37-38)
+        shifts = (-lam_t + self.eps)[part.lvl_begin:part.lvl_end]   # (L + (lam - eps) M) = -(K + (|lam| + eps) M)   (laplacian_inverse_socp.py:37-38)
         if sweep_mode is None:
             sweep_mode = int(os.environ.get("DOTS_SWEEP_MODE", "0"))
         self.sweep_mode = int(sweep_mode)
-        panels = nested.factor_batched_device(sym, K, area_v, shifts, m_pad=self.m_pad, device=self.device,
-                                              transposed=True)
-        panels, panels_t = panels
+        panels, panels_t = nested.factor_batched_device(sym, K, area_v, shifts, m_pad=self.m_pad, device=self.device,
+                                                        transposed=True)
         torch.cuda.synchronize(self.device)
         tm["factorization"] = time.perf_counter() - t0
 
@@ -169,8 +172,7 @@ class Engine:
         hat_n = hat[self.perm_f]                                                         # (T,3,3)
         diag = np.sqrt(area_f_n[None, :] / area_v_n[tri_new.T])                          # (3,T)  solver_socp.py:172-180
         vc_ptr, vc_tri, vc_corner = surface.corner_adjacency(V, tri_new)
-        qpad = np.zeros((nT + 1, self.m_pad))
-        qpad[:, :nT + 1] = Q
+        qf, qb, n_phi_out = dd.transform_matrices(Q, part)
         self.sweep_grid = 2 * self.n_sm if self.m_pad <= 96 else self.n_sm
         plan = (_sweep_items_persistent(sym, self.sweep_grid) if self.sweep_mode == 1
                 else _sweep_items(sym, self.n_sm, self.m_pad))
@@ -181,12 +183,14 @@ class Engine:
         ctx = capi.DotsCtx()
         ctx.abi_version, ctx.n_time, ctx.n_vert, ctx.n_tri = capi.ABI_VERSION, nT, V, T
         ctx.m_pad, ctx.n_nodes, ctx.n_levels, ctx.n_sm = self.m_pad, sym.n_nodes, sym.n_levels, self.n_sm
+        ctx.lvl_begin, ctx.lvl_end, ctx.n_ranks = part.lvl_begin, part.lvl_end, part.world
+        ctx.tt_kf, ctx.tt_kb, ctx.tt_nb, ctx.tt_nout = qf.shape[0], qb.shape[0], qb.shape[1], n_phi_out
         const = dict(
             tri=up("tri", tri_new.T, np.int32), hat_grad=up("hat_grad", hat_n.transpose(1, 2, 0), np.float64),
             area_f=up("area_f", area_f_n, np.float64), area_v=up("area_v", area_v_n, np.float64),
             diag_soc=up("diag_soc", diag, np.float64), vc_ptr=up("vc_ptr", vc_ptr, np.int32),
-            vc_idx=up("vc_idx", vc_corner * T + vc_tri, np.int32), qmat=up("qmat", qpad, np.float64),
-            panels=panels,
+            vc_idx=up("vc_idx", vc_corner * T + vc_tri, np.int32), qf=up("qf", qf, np.float64), qb=up("qb", qb, np.float64),
+            panels=panels, panels_t=panels_t,
             nd_off=up("nd_off", sym.off, np.int32), nd_s=up("nd_s", sym.s, np.int32), nd_b=up("nd_b", sym.b, np.int32),
             nd_child=up("nd_child", sym.child, np.int32), nd_panel=up("nd_panel", sym.panel_off[:-1], np.int64),
             nd_front=up("nd_front", sym.front_off[:-1], np.int64), nd_upd=up("nd_upd", sym.upd_off[:-1], np.int64),
@@ -194,14 +198,7 @@ class Engine:
             lvl_ptr=up("lvl_ptr", fwd_ptr, np.int32), lvl_items=up("lvl_items", fwd_items, np.int32),
             lvb_ptr=up("lvb_ptr", bwd_ptr, np.int32), lvb_items=up("lvb_items", bwd_items, np.int32),
             lvn_nodes=up("lvn_nodes", plan["nodes"], np.int32))
-        self._keep["panels"] = panels
-        if panels_t is not None:
-            self._keep["panels_t"] = panels_t
-            ctx.panels_t = panels_t.data_ptr()
-        ctx.sweep_mode, ctx.sweep_grid = self.sweep_mode, self.sweep_grid
-        self._keep["phase_clock"] = torch.zeros(2 * sym.n_levels + 1, dtype=torch.int64, device=dev)
-        if os.environ.get("DOTS_PHASE_CLOCK"):
-            ctx.phase_clock = self._keep["phase_clock"].data_ptr()
+        self._keep["panels"], self._keep["panels_t"] = panels, panels_t
         for k, ten in const.items():
             setattr(ctx, k, ten.data_ptr())
         ctx.h_lvl_ptr = self._h_fwd_ptr.ctypes.data
@@ -210,32 +207,45 @@ class Engine:
         ctx.h_lvl_wpr = plan["wpr"].ctypes.data
         ctx.h_lvb_cw = plan["cw"].ctypes.data
         ctx.front_total = int(sym.front_off[-1])
+        ctx.sweep_mode, ctx.sweep_grid = self.sweep_mode, self.sweep_grid
+        self._keep["phase_clock"] = torch.zeros(2 * sym.n_levels + 1, dtype=torch.int64, device=dev)
+        if os.environ.get("DOTS_PHASE_CLOCK"):
+            ctx.phase_clock = self._keep["phase_clock"].data_ptr()
 
+        # ---- state: level-indexed slabs (+ halo levels), addressed through virtual bases -------------------
+        l0, l1, te = part.lvl_begin, part.lvl_end, part.t_end
+        S = lambda lo, hi, *row: dd.SlabStore(lo, hi, row, dev)
+        self.slab = dict(
+            phi=S(l0, l1 + 1, V), lam=S(l0 - 1, te, V), A=S(l0 - 1, te, V), lam_c=S(l0 - 1, te, V), mu=S(l0 - 1, te, V),
+            z_fst=S(l0, te, V), z_end=S(l0, te, V), b_fst=S(l0, te, V), b_end=S(l0, te, V),
+            B=S(l0, l1 + 1, 3, T), E=S(l0, l1, 3, T), b_mid=S(l0, l1, 2, 3, 3, T), z_mid=S(l0, l1, 2, 3, 3, T),
+            corner_nrm=S(l0, l1 + 1, 2, 3, T), corner_div=S(l0, l1, 3, T))
+        for name, st_ in self.slab.items():
+            setattr(ctx, name, st_.base_ptr)
         z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)
         self.red_blocks = self.n_sm * 4
-        st = dict(params=z(capi.P_COUNT), phi=z(nT + 1, V), lam=z(nT, V), bnd0=z(V), bnd1=z(V),
-                  B=z(nT + 1, 3, T), E=z(nT + 1, 3, T), b_mid=z(nT + 1, 2, 3, 3, T), z_mid=z(nT + 1, 2, 3, 3, T),
-                  corner_nrm=z(nT + 1, 2, 3, T), corner_div=z(nT + 1, 3, T),
-                  rhs=z(nT + 1, V), hat=z(V, self.m_pad), ywork=z(V, self.m_pad),
-                  upd=z(max(1, int(sym.upd_off[-1])), self.m_pad), red_part=z(self.red_blocks, 8), red_out=z(8))
-        for name in ("A", "lam_c", "mu", "z_fst", "z_end", "b_fst", "b_end"):
-            st[name] = z(nT, V)
-        self.t = st
-        for k, ten in st.items():
+        hat_local = z(V, self.m_pad)
+        self.t = dict(params=z(capi.P_COUNT), bnd0=z(V), bnd1=z(V), rhs=z(part.world * part.chunk, V),
+                      hat=hat_local, hat_all=hat_local if part.world == 1 else z(part.world, V, self.m_pad),
+                      ywork=z(V, self.m_pad), upd=z(max(1, int(sym.upd_off[-1])), self.m_pad),
+                      red_part=z(self.red_blocks, 8), red_out=z(8))
+        for k, ten in self.t.items():
             setattr(ctx, k, ten.data_ptr())
         ctx.red_blocks = self.red_blocks
         self.ctx = ctx
         self._ctxp = C.byref(ctx)
         self._host_out = np.zeros(8)
         self._host_params = np.zeros(capi.P_COUNT)
+        self._halo_v = z(4, V)
+        self._halo_c = z(3, T)
 
         # ---- scalars of the reference driver (:97, :267-270, :296-313, :318-321) ------------------
         self.r, self.s, self.d = 1.0, 1.0, 1.0
         mu0 = np.asarray(geometry["mu0"], dtype=np.float64)[self.perm_v]
         mu1 = np.asarray(geometry["mu1"], dtype=np.float64)[self.perm_v]
         b0, b1 = -mu0 / (self.r * self.dt), mu1 / (self.r * self.dt)
-        st["bnd0"].copy_(torch.from_numpy(b0))
-        st["bnd1"].copy_(torch.from_numpy(b1))
+        self.t["bnd0"].copy_(torch.from_numpy(b0))
+        self.t["bnd1"].copy_(torch.from_numpy(b1))
         self.norm_bnd = self.r * self.dt * math.sqrt((np.sum((b0 / area_v_n) ** 2 * area_v_n)
                                                       + np.sum((b1 / area_v_n) ** 2 * area_v_n)) / (nT + 1))
         self.area_mesh = float(np.sum(area_f))
@@ -247,7 +257,7 @@ class Engine:
         self.k_dual_b = np.mean([ma_v, ma_f])
         self.k_comp_rho, self.k_comp_m = ma_v, ma_f
         self.z_valid = True                              # z_mid = 0 is the reference's initial z_mid (:245)
-        self.use_graphs, self._warm, self._graphs, self._cap_stream = True, False, {}, None
+        self.use_graphs, self._warm, self._graphs, self._cap_stream = part.world == 1, False, {}, None
         self.launches = 0
         self._push_params()
         torch.cuda.synchronize(dev)
@@ -267,22 +277,64 @@ class Engine:
         capi.check(self.lib.dots_set_params(self._ctxp, p.ctypes.data, self.stream), "dots_set_params")
 
     def launches_per_iteration(self):
-        """Kernel launches of one dots_iterate step: rhs, 2 transforms, one sweep launch per non-empty level
-        and direction, vertex, triangle."""
+        """Kernel launches of one iteration: rhs, 2 transforms, the sweep launches, vertex, triangle."""
         if self.sweep_mode == 1:
-            return 6                                   # rhs, 2 transforms, persistent sweeps, vertex, triangle
+            return 6
         n_f = int(np.count_nonzero(np.diff(self._h_fwd_ptr)))
         n_b = int(np.count_nonzero(np.diff(self._h_bwd_ptr)))
         n_g = int(np.count_nonzero(np.diff(self.plan["node_ptr"])[1:]))
         return 5 + n_f + n_b + n_g
 
+    def _call(self, fn, *args):
+        capi.check(getattr(self.lib, fn)(self._ctxp, *args, self.stream), fn)
+
+    # ------------------------------------------------------------------ halo exchanges (no-ops on one rank)
+    def exchange_vertex_halo(self):
+        """(lam, A, lam_c, mu) of the last owned step -> step lvl_begin-1 of the next rank."""
+        if not self.comm.enabled:
+            return
+        part, sl = self.part, self.slab
+        send = None
+        if part.rank + 1 < part.world and part.n_steps > 0:
+            send = torch.stack([sl[n].level(part.t_end - 1) for n in ("lam", "A", "lam_c", "mu")])
+        recv = self._halo_v if part.rank > 0 else None
+        self.comm.shift(send_next=send, recv_prev=recv)
+        if recv is not None:
+            for i, n in enumerate(("lam", "A", "lam_c", "mu")):
+                sl[n].level(part.lvl_begin - 1).copy_(recv[i])
+
+    def exchange_corner_halo(self):
+        """side-1 corner norms of the first owned level -> level lvl_end of the previous rank."""
+        if not self.comm.enabled:
+            return
+        part, sl = self.part, self.slab
+        send = sl["corner_nrm"].level(part.lvl_begin)[1].contiguous() if part.rank > 0 else None
+        recv = self._halo_c if part.rank + 1 < part.world else None
+        self.comm.shift(send_prev=send, recv_next=recv)
+        if recv is not None:
+            sl["corner_nrm"].level(part.lvl_end)[1].copy_(recv)
+
+    def exchange_B_halo(self):
+        """B of the first owned level -> level lvl_end of the previous rank (only KKT #4 reads it)."""
+        if not self.comm.enabled:
+            return
+        part, sl = self.part, self.slab
+        send = sl["B"].level(part.lvl_begin).contiguous() if part.rank > 0 else None
+        recv = self._halo_c if part.rank + 1 < part.world else None
+        self.comm.shift(send_prev=send, recv_next=recv)
+        if recv is not None:
+            sl["B"].level(part.lvl_end).copy_(recv)
+
     # ------------------------------------------------------------------ the iteration
     def iterate(self, n=1, write_z=False):
-        """n ALM iterations (Steps 1-3); ``write_z`` stores z_mid on the last one.  After the first call the
-        iteration is replayed from a captured CUDA graph (one per write_z flavour) unless ``use_graphs`` is off."""
+        """n ALM iterations (Steps 1-3); ``write_z`` stores z_mid on the last one.  On one GPU the iteration is
+        replayed from a captured CUDA graph after the first call (one per write_z flavour)."""
         n, write_z = int(n), bool(write_z)
         st = self.stream
-        if not self.use_graphs or not self._warm:
+        if self.comm.enabled:
+            for i in range(n):
+                self._iterate_sharded(write_z and i == n - 1)
+        elif not self.use_graphs or not self._warm:
             capi.check(self.lib.dots_iterate(self._ctxp, n, int(write_z), st), "dots_iterate")
             self._warm = True
         else:
@@ -302,6 +354,20 @@ class Engine:
         self.launches += n * self.launches_per_iteration()
         self.z_valid = write_z
 
+    def _iterate_sharded(self, write_z):
+        """One iteration across ranks: the same kernels on this rank's slab / modes + the exchanges of dist.py."""
+        part, comm, t = self.part, self.comm, self.t
+        self._call("dots_phi_rhs")                                                     # own levels of rhs
+        comm.all_gather_into(t["rhs"], t["rhs"][part.rank * part.chunk:(part.rank + 1) * part.chunk])
+        self._call("dots_time_transform", 0)                                           # all levels -> own modes
+        self._call("dots_mode_solves")
+        comm.all_gather_into(t["hat_all"], t["hat"])
+        self._call("dots_time_transform", 1)                                           # all modes -> own levels (+halo)
+        self._call("dots_step_vertex")
+        self.exchange_vertex_halo()
+        self._call("dots_step_tri", int(write_z))
+        self.exchange_corner_halo()
+
     def close(self):
         for h in self._graphs.values():
             self.lib.dots_graph_destroy(h)
@@ -317,6 +383,7 @@ class Engine:
         self.r *= f
         self._push_params()
         capi.check(self.lib.dots_scale_dual(self._ctxp, float(f), self.stream), "dots_scale_dual")
+        self.exchange_corner_halo()
         self.launches += 8
 
     def scale_z(self, f):                                                                # :373-395
@@ -325,8 +392,9 @@ class Engine:
         self.norm_d *= f
         capi.check(self.lib.dots_scale_z(self._ctxp, float(self.s), self.stream), "dots_scale_z")
         self._push_params()
-        capi.check(self.lib.dots_refresh_corner_terms(self._ctxp, self.stream), "dots_refresh_corner_terms")
-        self.launches += 9
+        self.exchange_vertex_halo()
+        self.refresh()
+        self.launches += 8
 
     def set_scalars(self, r=None, s=None, d=None, norm_d=None):
         """Overwrite the driver scalars (tests / warm starts) and push them to the device."""
@@ -337,23 +405,26 @@ class Engine:
         self._push_params()
 
     def grad_space_into(self, src, dst):
-        """t[dst] = G t[src] for all time levels (vanilla_grad_space, solver_socp.py:898-907)."""
-        capi.check(self.lib.dots_grad_space(self._ctxp, self.t[src].data_ptr(), self.t[dst].data_ptr(), self.stream), "dots_grad_space")
+        """slab[dst] = G slab[src] on the owned levels (vanilla_grad_space, solver_socp.py:898-907)."""
+        capi.check(self.lib.dots_grad_space(self._ctxp, self.slab[src].base_ptr, self.slab[dst].base_ptr, self.stream), "dots_grad_space")
         self.launches += 1
 
     def E_from_beta(self, scale):
         """E = -decouple_adjoin_spacial(b_mid, scale) (warm-start default, solver_socp.py:250); rare, so plain tensor ops."""
-        self.t["E"].copy_(-(scale / math.sqrt(3.0)) * self.t["b_mid"].sum(dim=2).sum(dim=1))
+        part = self.part
+        bm = self.slab["b_mid"].levels(part.lvl_begin, part.lvl_end)
+        self.slab["E"].levels(part.lvl_begin, part.lvl_end).copy_(-(scale / math.sqrt(3.0)) * bm.sum(dim=2).sum(dim=1))
 
     def refresh(self):
         capi.check(self.lib.dots_refresh_corner_terms(self._ctxp, self.stream), "dots_refresh_corner_terms")
+        self.exchange_corner_halo()
         self.launches += 1
 
     # ------------------------------------------------------------------ residuals
     def sums(self, which):
         capi.check(self.lib.dots_kkt_sums(self._ctxp, int(which), self._host_out.ctypes.data, self.stream), "dots_kkt_sums")
         self.launches += 3
-        return self._host_out.copy()
+        return self.comm.sum_in_rank_order(self._host_out.copy(), self.device)
 
     def kkt(self, i):
         """Relative KKT residual i as [value, value] (conditions 0-3) or [value, None] (4-6):
@@ -361,6 +432,8 @@ class Engine:
         nT, sq = self.nT, math.sqrt
         if i == 1 and not self.z_valid:
             raise capi.DotsError("KKT #1 needs z_mid of the current iteration: call iterate(..., write_z=True)")
+        if i == 4:
+            self.exchange_B_halo()
         o = self.sums(i)
         v, t = o[0:4], o[4:8]
         tn, sn = 1.0 / nT, 1.0 / (nT + 1)
@@ -401,7 +474,7 @@ class Engine:
         return self._keep["perm_v_t"], self._keep["perm_f_t"]
 
     def to_internal(self, name, ref):
-        """Reference-layout array (numpy or torch) -> internal-layout device tensor."""
+        """Reference-layout array (numpy or torch, ALL time levels) -> internal-layout device tensor (all levels)."""
         pv, pf = self._perm_v_t()
         x = torch.as_tensor(ref, dtype=torch.float64).to(self.device)
         if name in STATE_VERTEX or name in ("lam", "rhs"):
@@ -416,10 +489,21 @@ class Engine:
             return out
         raise KeyError(name)
 
+    def full(self, name):
+        """All time levels of a state field in the internal layout (gathered from the ranks when sharded)."""
+        n_total = self.nT + 1 if name in ("phi", "rhs") + STATE_TRI + STATE_CORNER else self.nT
+        if name == "rhs":
+            return self.t["rhs"][:n_total]
+        st_ = self.slab[name]
+        hi = self.part.lvl_end if n_total == self.nT + 1 else self.part.t_end
+        if not self.comm.enabled:
+            return st_.levels(0, n_total)
+        return dd.gather_levels(self.comm, self.part, st_, n_total, owned_hi=hi)
+
     def from_internal(self, name, ten=None):
-        """Internal device tensor -> reference-layout device tensor (fresh)."""
+        """Internal tensor with all time levels (default: the current state field) -> reference-layout device tensor."""
         pv, pf = self._perm_v_t()
-        x = self.t[name] if ten is None else ten
+        x = self.full(name) if ten is None else ten
         if name in STATE_VERTEX or name in ("lam", "rhs"):
             out = torch.empty_like(x)
             out[:, pv] = x
@@ -436,10 +520,17 @@ class Engine:
             return out
         raise KeyError(name)
 
+    def _store(self, name, internal_full):
+        """Copy this rank's levels (incl. the halo levels it backs) of a full internal array into its slab."""
+        st_ = self.slab[name]
+        lo, hi = max(st_.lo, 0), min(st_.hi, internal_full.shape[0])
+        if hi > lo:
+            st_.levels(lo, hi).copy_(internal_full[lo:hi])
+
     def set_state(self, **arrays):
-        """Overwrite state fields from reference-layout arrays, then rebuild the derived corner terms."""
+        """Overwrite state fields from reference-layout arrays (all levels), then rebuild the derived corner terms."""
         for name, ref in arrays.items():
-            self.t[name].copy_(self.to_internal(name, ref))
+            self._store(name, self.to_internal(name, ref))
         self.z_valid = "z_mid" in arrays
         self.refresh()
 

@@ -54,21 +54,19 @@ def _warm_start(eng: Engine, init):
     """solver_socp.py:239-250: any subset of the solution keys; missing ones get the reference's defaults."""
     nT, V, T = eng.nT, eng.V, eng.T
     dev = eng.device
-    get = lambda k, shape: torch.as_tensor(init[k], dtype=torch.float64, device=dev) if k in init else torch.zeros(shape, dtype=torch.float64, device=dev)
+    get = lambda k, shape: (torch.as_tensor(init[k], dtype=torch.float64, device=dev) if k in init
+                            else torch.zeros(shape, dtype=torch.float64, device=dev))
     phi = get("phi", (nT + 1, V))
+    bf, be = get("beta_fst", (nT, V)), get("beta_end", (nT, V))
     st = dict(phi=phi, lam_c=get("lambda_c", (nT, V)), z_fst=get("z_fst", (nT, V)), z_end=get("z_end", (nT, V)),
-              z_mid=get("z_mid", (nT, 2, 3, T, 3)), b_fst=get("beta_fst", (nT, V)), b_end=get("beta_end", (nT, V)),
-              b_mid=get("beta_mid", (nT, 2, 3, T, 3)))
-    st["A"] = get("A", None) if "A" in init else torch.diff(phi, dim=0) / eng.dt
+              z_mid=get("z_mid", (nT, 2, 3, T, 3)), b_fst=bf, b_end=be, b_mid=get("beta_mid", (nT, 2, 3, T, 3)),
+              A=get("A", None) if "A" in init else torch.diff(phi, dim=0) / eng.dt,
+              mu=get("mu", None) if "mu" in init else bf - be)
     eng.set_state(**st)
     if "B" in init:
         eng.set_state(B=init["B"])
     else:
         eng.grad_space_into("phi", "B")
-    if "mu" in init:
-        eng.set_state(mu=init["mu"])
-    else:
-        eng.t["mu"].copy_(eng.t["b_fst"] - eng.t["b_end"])
     if "E" in init:
         eng.set_state(E=init["E"])
     else:
@@ -80,10 +78,12 @@ def _warm_start(eng: Engine, init):
 def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8), tol=1e-4, tau=1.90,
                 is_palm=False, is_multi_threads=True, is_z_scaling=True, is_constant_scaling=False,
                 check_kkt_step_by_step=False, init_solution=None, tol_checkpoints=None, time_limit=1000,
-                device=None, leaf_size=24, show_progress=False, return_engine=False):
+                device=None, leaf_size=24, show_progress=False, return_engine=False, comm=None):
     """B200 implementation of ``dot_surface_socp.socp.solver_socp.solver_socp``.
 
-    Extra keyword arguments (``device``, ``leaf_size``, ``show_progress``, ``return_engine``) are additions;
+    Extra keyword arguments (``device``, ``leaf_size``, ``show_progress``, ``return_engine``, ``comm``) are additions;
+    with torch.distributed initialised (one process per GPU) the problem is sharded over the ranks of ``comm``
+    (default: the world group) and every rank returns the full solution;
     ``is_multi_threads`` is accepted and ignored (the two reference threads become stream order).
     ``is_palm=True`` and ``is_constant_scaling=True`` are solver-only knobs that the reference's CLI /
     interface cannot reach (interface.py:275-284); they are not built and raise."""
@@ -93,7 +93,7 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
     tol_checkpoints = _validate_checkpoints(tol_checkpoints, tol)
     checkpoints = []
 
-    eng = Engine(n_time, geometry, congestion=congestion, eps=eps, tau=tau, device=device, leaf_size=leaf_size)
+    eng = Engine(n_time, geometry, congestion=congestion, eps=eps, tau=tau, device=device, leaf_size=leaf_size, comm=comm)
     logging.log(LOG_KKT, f"---- Experiment info ".ljust(42, "-") + "\n"
                 f"Congestion parameter: {congestion}Number of discretization points in time: {n_time}\n"
                 f"Number of discretization vertices: {eng.V}\nNumber of discretization triangles: {eng.T}\nStepsize: {tau}")

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DOTS_ABI_VERSION 4
+#define DOTS_ABI_VERSION 5
 
 /* scalar block read by the kernels from device memory (so CUDA graphs stay valid across penalty updates) */
 enum {
@@ -55,7 +55,7 @@ typedef struct dots_ctx {
     int32_t n_time;            /* nT: number of time intervals                                        */
     int32_t n_vert;            /* V                                                                   */
     int32_t n_tri;             /* T                                                                   */
-    int32_t m_pad;             /* number of time modes nT+1 padded to a multiple of 32                */
+    int32_t m_pad;             /* time modes solved by THIS rank, padded to 8, 16, 32, 64, 96 or 128   */
     int32_t n_nodes;           /* separator-tree nodes                                                */
     int32_t n_levels;          /* separator-tree levels                                               */
     int32_t n_sm;              /* multiprocessor count (grid sizing)                                  */
@@ -68,7 +68,10 @@ typedef struct dots_ctx {
     const double  *diag_soc;   /* [3][T]    sqrt(|f| / area_v[tri[k][f]])         (:172-192)           */
     const int32_t *vc_ptr;     /* [V+1]     CSR vertex -> incident corners                            */
     const int32_t *vc_idx;     /* [3T]      corner ids k*T+f, ascending per vertex                    */
-    const double  *qmat;       /* [nT+1][m_pad] time eigenbasis Q[t][mode] (laplacian_inverse_socp.py:31) */
+    const double  *qf;         /* [tt_kf][m_pad]   forward transform matrix: rows = time levels (all), columns = this rank's modes
+                                  (Q[t][mode] of laplacian_inverse_socp.py:31, zero padded)             */
+    const double  *qb;         /* [tt_kb][tt_nb]   inverse transform matrix: rows = gathered modes (rank-major, padded),
+                                  columns = the phi levels this rank needs (lvl_begin .. lvl_begin+tt_nout-1) */
 
     /* ---- batched multifrontal factor of K + shift_mode*diag(area_v) (dots_socp_b200/nested.py) ---- */
     const double  *panels;     /* [panel_entries][m_pad]  per node row-major: rows of [inv(L11) ; L21 inv(L11)]  */
@@ -94,6 +97,19 @@ typedef struct dots_ctx {
     const int32_t *h_lvb_cw;   /* HOST [n_levels] warps sharing one panel column in the backward sweep (1,2,4,8) */
     int64_t front_total;       /* sum(s+b)                                                            */
 
+    /* ---- sharding (one process per GPU; all 0 / full range on a single GPU) ----
+     * Time-slab: this rank owns the time levels [lvl_begin, lvl_end) of every level-indexed array and the staggered
+     * steps [lvl_begin, min(lvl_end, nT)).  State pointers below are VIRTUAL bases: element (level, ...) of an array
+     * is at base + level*stride exactly as on one GPU, but only the owned levels (+ the halo levels named in
+     * DESIGN.md section 5) are backed by memory.  Time-mode: the sweeps run on this rank's m_pad modes only.       */
+    int32_t lvl_begin, lvl_end;
+    int32_t n_ranks;
+    int32_t tt_kf;             /* rows of qf (nT+1 rounded up to 4)                                   */
+    int32_t tt_kb;             /* rows of qb (n_ranks * m_pad)                                        */
+    int32_t tt_nb;             /* columns of qb (tt_nout rounded up to 8)                             */
+    int32_t tt_nout;           /* phi levels written by the inverse transform                         */
+    int32_t reserved1;
+
     /* ---- ALM state (read-write) ---- */
     double *params;            /* [DOTS_P_COUNT]                                                      */
     double *phi, *A, *lam_c, *mu, *z_fst, *z_end, *b_fst, *b_end, *lam;
@@ -104,8 +120,9 @@ typedef struct dots_ctx {
     double *corner_div;        /* [nT+1][3][T]    per-corner divergence terms feeding the next rhs     */
 
     /* ---- work space ---- */
-    double *rhs;               /* [nT+1][V]                                                           */
-    double *hat;               /* [V][m_pad]  transformed rhs, then solution                          */
+    double *rhs;               /* [nT+1 (padded to n_ranks equal slabs)][V], NOT virtual: every rank holds all levels */
+    double *hat;               /* [V][m_pad]  transformed rhs, then solution (this rank's modes)      */
+    double *hat_all;           /* [n_ranks][V][m_pad] all ranks' solutions (== hat on one GPU)        */
     double *ywork;             /* [V][m_pad]  forward-sweep result                                    */
     double *upd;               /* [sum b][m_pad] update vectors                                       */
     double *red_part;          /* [red_blocks][8] block partial sums                                  */

@@ -1,0 +1,83 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices; skipped otherwise): the sharded path must reproduce the single-GPU path
+and the reference fixtures - same iteration count, same KKT schedule, iterates within 1e-8."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+import torch.distributed as dist          # noqa: E402
+import torch.multiprocessing as mp        # noqa: E402
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, name, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from conftest import load_golden
+        import dots_socp_b200 as b200
+        from dots_socp_b200.engine import Engine
+        from dots_socp_b200 import dist as dd
+        z, geo, n_time, kw = load_golden(name)
+        # (1) k iterations, sharded vs whole, same process: states gathered from the ranks
+        comm = dd.Comm()
+        eng = Engine(n_time, geo, congestion=kw.get("congestion", 0.0), leaf_size=8, comm=comm)
+        eng.scale_z(2.0)
+        eng.iterate(7, write_z=True)
+        eng.adjust_penalty(1.35)
+        eng.iterate(5, write_z=True)
+        st = eng.get_state()
+        kk = [eng.kkt(i)[0] for i in range(7)]
+        cost = eng.objective()
+        # (2) full solve through the public API
+        sol, hist = b200.solver_socp(n_time, geo, leaf_size=8, **kw)
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "multi.npz"), kkt=np.array(kk), cost=np.array(cost), iters=int(hist.kkt_iteration[-1]),
+                     rows=hist.kkt_errors, sol_mu=sol["mu"], sol_z_mid=sol["z_mid"], **{"st_" + k: v for k, v in st.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("name", ["ico2_nt7_c01", "ico3_nt31_c0"])
+def test_sharded_solver_matches_single_gpu_and_reference(tmp_path, golden, name, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    z, geo, n_time, kw = golden(name)
+    if (world - 1) * -(-(n_time + 1) // world) >= n_time + 1:
+        pytest.skip("more ranks than time levels")
+    mp.spawn(_worker, args=(world, _free_port(), name, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(os.path.join(str(tmp_path), "multi.npz"))
+    # single-GPU run of the same sequence in this process
+    from dots_socp_b200.engine import Engine
+    eng = Engine(n_time, geo, congestion=kw.get("congestion", 0.0), leaf_size=8)
+    eng.scale_z(2.0)
+    eng.iterate(7, write_z=True)
+    eng.adjust_penalty(1.35)
+    eng.iterate(5, write_z=True)
+    ref = eng.get_state()
+    for k, v in ref.items():
+        a = got["st_" + k]
+        if k == "phi":
+            a, v = a - a.mean(), v - v.mean()
+        err = np.abs(a - v).max() / max(np.abs(v).max(), 1e-300)
+        assert err < 1e-8, (k, err)
+    assert np.allclose(got["kkt"], [eng.kkt(i)[0] for i in range(7)], rtol=1e-8)
+    assert np.allclose(got["cost"], eng.objective(), rtol=1e-8)
+    # against the reference fixture
+    assert int(got["iters"]) == int(z["iterations"])
+    assert np.array_equal(np.isnan(got["rows"]), np.isnan(z["kkt_rows"]))
+    m = ~np.isnan(z["kkt_rows"])
+    assert np.allclose(got["rows"][m], z["kkt_rows"][m], rtol=1e-6, atol=1e-12)
+    assert np.abs(got["sol_mu"] - z["sol_mu"]).max() / np.abs(z["sol_mu"]).max() < 1e-6

@@ -97,7 +97,8 @@ def test_grad_div_space_rows_a5_a6():
     x = rng.standard_normal((6, o.T, 3))
     from dots_socp_b200 import capi
     phi_i, x_i = eng.to_internal("phi", phi), eng.to_internal("B", x)
-    g_out, d_out = torch.empty_like(eng.t["B"]), torch.empty_like(eng.t["phi"])
+    g_out = torch.empty((6, 3, o.T), dtype=torch.float64, device=eng.device)
+    d_out = torch.empty((6, o.V), dtype=torch.float64, device=eng.device)
     capi.check(eng.lib.dots_grad_space(eng._ctxp, phi_i.data_ptr(), g_out.data_ptr(), eng.stream))
     capi.check(eng.lib.dots_div_space(eng._ctxp, x_i.data_ptr(), d_out.data_ptr(), eng.stream))
     assert rel(eng.from_internal("B", g_out).cpu().numpy(), orc.grad_space(o.G, phi)) < 1e-13

@@ -19,4 +19,4 @@ torch.cuda.synchronize()
 print("launches per iteration", eng.launches_per_iteration(), "levels", eng.sym.n_levels, flush=True)
 eng.iterate(n_it, write_z=False)
 torch.cuda.synchronize()
-print("done", float(eng.t["phi"].abs().max()))
+print("done", float(eng.slab["phi"].data.abs().max()))
