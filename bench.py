@@ -34,6 +34,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("DOTS_KEEP_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its banner on stdout; stdout carries exactly one JSON line
 
 import numpy as np
 
@@ -200,7 +202,7 @@ def run_own(args):
     iters = int(hist.kkt_iteration[-1]) + 1
     setup_s = eng.timings["setup_total"]
     loop_s = wall - setup_s                               # loop + KKT syncs + solution download to host numpy
-    h2d = sum(t.numel() * t.element_size() for t in eng._keep.values()) - eng._keep["panels"].numel() * 8
+    h2d = sum(t.numel() * t.element_size() for k, t in eng._keep.items() if k not in ("panels", "panels_t", "phase_clock"))
     d2h_solution = sum(v.nbytes for v in sol.values() if isinstance(v, np.ndarray))
     d2h = d2h_solution + 64 * (sum(hist.evaluations) + 8)
     e2e = {"value": iters / loop_s, "unit": UNIT, "h2d_bytes_per_step": h2d / iters, "d2h_bytes_per_step": d2h / iters,
@@ -238,33 +240,46 @@ def run_own(args):
     value = 1e3 / ms_per_step
 
     # ---- per-kernel-group durations, measured live (second pass, events between the step calls) ------
-    groups = {"k_phi_rhs": [], "k_time_fwd+k_time_bwd": [], "k_sweep_fwd+k_sweep_bwd": [], "k_vertex": [], "k_tri": []}
+    names = ["k_phi_rhs", "comm:all_gather(rhs)", "k_time_fwd", "k_sweep_fwd+k_sweep_bwd", "comm:all_gather(hat)", "k_time_bwd",
+             "k_vertex", "comm:halo(vertex)", "k_tri", "comm:halo(corner)"]
+    part, comm, tt = eng.part, eng.comm, eng.t
+    steps_fn = [
+        lambda: capi.check(lib.dots_phi_rhs(ctxp, stream)),
+        lambda: comm.all_gather_into(tt["rhs"], tt["rhs"][part.rank * part.chunk:(part.rank + 1) * part.chunk]),
+        lambda: capi.check(lib.dots_time_transform(ctxp, 0, stream)),
+        lambda: capi.check(lib.dots_mode_solves(ctxp, stream)),
+        lambda: comm.all_gather_into(tt["hat_all"], tt["hat"]),
+        lambda: capi.check(lib.dots_time_transform(ctxp, 1, stream)),
+        lambda: capi.check(lib.dots_step_vertex(ctxp, stream)),
+        lambda: eng.exchange_vertex_halo(),
+        lambda: capi.check(lib.dots_step_tri(ctxp, 0, stream)),
+        lambda: eng.exchange_corner_halo(),
+    ]
     n_probe = min(args.steps, 20)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(7)] for _ in range(n_probe)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(n_probe)]
+    barrier()
     for i in range(n_probe):
-        e = evs[i]
-        e[0].record(); capi.check(lib.dots_phi_rhs(ctxp, stream))
-        e[1].record(); capi.check(lib.dots_time_transform(ctxp, 0, stream))
-        e[2].record(); capi.check(lib.dots_mode_solves(ctxp, stream))
-        e[3].record(); capi.check(lib.dots_time_transform(ctxp, 1, stream))
-        e[4].record(); capi.check(lib.dots_step_vertex(ctxp, stream))
-        e[5].record(); capi.check(lib.dots_step_tri(ctxp, 0, stream))
-        e[6].record()
+        for j, fn in enumerate(steps_fn):
+            evs[i][j].record()
+            if world > 1 or not names[j].startswith("comm:"):
+                fn()
+        evs[i][-1].record()
     torch.cuda.synchronize()
-    for e in evs:
-        groups["k_phi_rhs"].append(e[0].elapsed_time(e[1]))
-        groups["k_time_fwd+k_time_bwd"].append(e[1].elapsed_time(e[2]) + e[3].elapsed_time(e[4]))
-        groups["k_sweep_fwd+k_sweep_bwd"].append(e[2].elapsed_time(e[3]))
-        groups["k_vertex"].append(e[4].elapsed_time(e[5]))
-        groups["k_tri"].append(e[5].elapsed_time(e[6]))
+    raw = {n: float(np.mean([e[j].elapsed_time(e[j + 1]) for e in evs])) for j, n in enumerate(names)}
+    if world > 1:
+        tmax = torch.tensor([raw[n] for n in names], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        raw = {n: float(v) for n, v in zip(names, tmax.tolist())}
+    groups = {"k_phi_rhs": raw["k_phi_rhs"], "k_time_fwd+k_time_bwd": raw["k_time_fwd"] + raw["k_time_bwd"],
+              "k_sweep_fwd+k_sweep_bwd": raw["k_sweep_fwd+k_sweep_bwd"], "k_vertex": raw["k_vertex"], "k_tri": raw["k_tri"]}
+    comm_ms = {n: round(raw[n], 4) for n in names if n.startswith("comm:")} if world > 1 else {}
     peak, peak_src = peaks()
-    kb = kernel_bytes(V, T, n_time, eng.m_pad, eng.sym)
+    kb = {k: v / world for k, v in kernel_bytes(V, T, n_time, n_time + 1, eng.sym).items()}     # per GPU
     kernels = {}
-    for name, times in groups.items():
-        t_ms = float(np.mean(times))
+    for name, t_ms in groups.items():
         kernels[name] = {"ms": round(t_ms, 4), "bytes": kb[name], "gbs": round(kb[name] / t_ms / 1e6, 1),
                          "frac": round(kb[name] / t_ms / 1e6 / peak, 4)}
-    total_ms = sum(k["ms"] for k in kernels.values())
+    total_ms = sum(k["ms"] for k in kernels.values()) + sum(comm_ms.values())
     for k in kernels.values():
         k["share"] = round(k["ms"] / total_ms, 4)
     dom = max(kernels, key=lambda n: kernels[n]["ms"])
@@ -274,15 +289,16 @@ def run_own(args):
         with open(tpath) as f:
             traffic = json.load(f).get(args.workload, {}).get(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_launch": kb[dom], "ms_per_launch": kernels[dom]["ms"], "kernels": kernels}
+                "frac": kernels[dom]["frac"], "traffic": traffic if world == 1 else None, "peak_source": peak_src,
+                "bytes_per_launch": kb[dom], "ms_per_launch": kernels[dom]["ms"], "kernels": kernels,
+                "per_gpu": True, "comm_ms": comm_ms}
     ref_bytes = reference_bytes_per_iteration(V, T, n_time, eng.sym.panel_entries, n_time + 1)
-    own_bytes = sum(kb.values())
+    own_bytes = sum(kb.values()) * world
     roofline["iteration"] = {
         "reference_algorithmic_bytes": ref_bytes, "achieved_vs_reference_bytes_gbs": round(ref_bytes / ms_per_step / 1e6, 1),
-        "frac_vs_reference_bytes": round(ref_bytes / ms_per_step / 1e6 / peak, 4),
+        "frac_vs_reference_bytes": round(ref_bytes / ms_per_step / 1e6 / (peak * world), 4),
         "fused_unique_bytes": own_bytes, "achieved_fused_gbs": round(own_bytes / ms_per_step / 1e6, 1),
-        "frac_fused": round(own_bytes / ms_per_step / 1e6 / peak, 4),
+        "frac_fused": round(own_bytes / ms_per_step / 1e6 / (peak * world), 4), "peak_all_gpus_gbs": peak * world,
         "note": "reference bytes = SURVEY 8(d) formula 8(27a+10b+8c+7z)+F on the reference's data structures; the fused "
                 "iteration moves fewer bytes, so its fraction of that figure may exceed 1"}
 
@@ -291,6 +307,8 @@ def run_own(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "n_vertices": V, "n_triangles": T, "n_time": n_time, "congestion": cong,
                        "tol": 1e-3, "time_modes": n_time + 1, "leaf_size": args.leaf,
+                       "sharding": (f"{world} ranks: time slabs of {eng.part.chunk} levels for the streaming kernels, "
+                                    f"{eng.part.chunk} time modes per rank for the sweeps" if world > 1 else "single GPU"),
                        "l2": "working set per iteration >> 126 MB L2 (no flush needed)" if V > 20000 else
                              "working set fits in L2 (small config): numbers are launch/latency bound"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": args.steps * eng.launches_per_iteration(),
