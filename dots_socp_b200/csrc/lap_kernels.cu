@@ -321,7 +321,10 @@ extern "C" int dots_time_transform(const dots_ctx_t *c, int inverse, void *strea
     const size_t smem = ((size_t)K * (N + 8) + (size_t)TT_VT * (K + 4)) * sizeof(double);
     const int n_tiles = ceil_div(c->n_vert, TT_VT);
     const int per_sm = (smem <= 72 * 1024) ? 3 : (smem <= 110 * 1024 ? 2 : 1);
-    const int grid = n_tiles < c->n_sm * per_sm ? n_tiles : c->n_sm * per_sm;
+    // a small B (sharded ranks: few modes / levels) is cheap to reload, so one tile per block lets the hardware overlap
+    // the tile loads of different blocks; the single-GPU B (36-140 KB) is loaded once per persistent block instead
+    const bool small_b = (size_t)K * N * sizeof(double) <= 16 * 1024;
+    const int grid = (small_b || n_tiles < c->n_sm * per_sm) ? n_tiles : c->n_sm * per_sm;
     static size_t configured[2] = {0, 0};
     if (smem > 48 * 1024 && smem > configured[inverse ? 1 : 0]) {
         if (inverse) DOTS_CUDA(cudaFuncSetAttribute(k_time_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -258,6 +258,9 @@ class Engine:
         self.k_comp_rho, self.k_comp_m = ma_v, ma_f
         self.z_valid = True                              # z_mid = 0 is the reference's initial z_mid (:245)
         self.use_graphs, self._warm, self._graphs, self._cap_stream = part.world == 1, False, {}, None
+        # capturing NCCL collectives in a CUDA graph gained only ~4 % at N=2 and hung at process-group teardown: opt-in
+        self.use_sharded_graphs = os.environ.get("DOTS_SHARDED_GRAPHS", "0") == "1"
+        self._tgraphs, self._tgraph_warm, self.graph_error = {}, {}, None
         self.launches = 0
         self._push_params()
         torch.cuda.synchronize(dev)
@@ -333,7 +336,7 @@ class Engine:
         st = self.stream
         if self.comm.enabled:
             for i in range(n):
-                self._iterate_sharded(write_z and i == n - 1)
+                self._iterate_sharded_graphed(write_z and i == n - 1)
         elif not self.use_graphs or not self._warm:
             capi.check(self.lib.dots_iterate(self._ctxp, n, int(write_z), st), "dots_iterate")
             self._warm = True
@@ -368,10 +371,32 @@ class Engine:
         self._call("dots_step_tri", int(write_z))
         self.exchange_corner_halo()
 
+    def _iterate_sharded_graphed(self, write_z):
+        """Replay the sharded iteration (kernels + NCCL collectives) from a torch CUDA graph; the first two calls of each
+        flavour run eagerly (NCCL connection set-up, first-use kernel attributes), a failed capture falls back to eager."""
+        key = int(bool(write_z))
+        if not self.use_sharded_graphs or self._tgraph_warm.get(key, 0) < 2:
+            self._tgraph_warm[key] = self._tgraph_warm.get(key, 0) + 1
+            return self._iterate_sharded(write_z)
+        if key not in self._tgraphs:
+            try:
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._iterate_sharded(write_z)
+                self._tgraphs[key] = g
+            except Exception as exc:                     # capture unsupported for some op: stay eager
+                self.use_sharded_graphs = False
+                self.graph_error = repr(exc)
+                torch.cuda.synchronize(self.device)
+                return self._iterate_sharded(write_z)
+        self._tgraphs[key].replay()
+
     def close(self):
         for h in self._graphs.values():
             self.lib.dots_graph_destroy(h)
         self._graphs = {}
+        self._tgraphs = {}
 
     def __del__(self):
         try:
