@@ -11,9 +11,10 @@ Own arm (default)
   value    : iterations/s, state resident in HBM, K steps enqueued back to back, CUDA events on the launch
              stream, barrier + synchronize on both sides, max over ranks.  The per-iteration working set
              (>10 GB) is far larger than the 126 MB L2, so no explicit L2 flush is needed.
-  e2e      : the same metric through the public plug-in call solver_socp(n_time, geometry) with HOST numpy
-             geometry in and HOST numpy solution out, solved to tol=1e-3: iterations / (loop time incl. the
-             lazy KKT reductions + device->host read of their scalars + final solution download); the one-off
+  e2e      : the same metric through the public plug-in call solver(n_time, geometry) (the callable handed to
+             run_dot_surface) with HOST numpy geometry in and the HOST numpy DOT solution (mu, E) out, solved to
+             tol=1e-3: iterations / (loop time incl. the lazy KKT reductions + device->host read of their
+             scalars + final solution download); the one-off
              setup (ordering, batched factorisation, upload) is reported beside it, as the reference's own
              timers do.
   roofline : the dominant kernel's unique bytes per launch / its mean duration measured live with CUDA events.
@@ -209,8 +210,9 @@ def run_own(args):
 
     # ---- end to end through the public plug-in API (host buffers in, host buffers out) -------------
     t0 = time.perf_counter()
-    sol, hist, eng = b200.solver_socp(n_time, geo, congestion=cong, tol=1e-3, nit=args.e2e_nit, return_engine=True,
-                                      leaf_size=args.leaf)
+    # the plug-in callable run_dot_surface(opts, solver=...) receives: DOT-unit mu (centred grid) and E come back
+    sol, hist, eng = b200.solver(n_time, geo, congestion=cong, tol=1e-3, nit=args.e2e_nit, return_engine=True,
+                                 leaf_size=args.leaf)
     wall = time.perf_counter() - t0
     iters = int(hist.kkt_iteration[-1]) + 1
     setup_s = eng.timings["setup_total"]

@@ -563,14 +563,19 @@ class Engine:
         names = names or (STATE_VERTEX + STATE_TRI + STATE_CORNER)
         return {n: self.from_internal(n).cpu().numpy() for n in names}
 
-    def solution(self):
-        """Un-scaled solution dict with the reference's keys and layouts (:397-405, :855-869)."""
-        if not self.z_valid:
+    def solution(self, keys=None):
+        """Un-scaled solution dict with the reference's keys and layouts (:397-405, :855-869).
+
+        ``keys`` restricts what is converted and downloaded (the DOT-unit decorators only need ``mu`` and ``E``; the two
+        18-wide corner arrays are 3 GB each at the headline size)."""
+        keys = tuple(REF_KEYS) if keys is None else tuple(keys)
+        if "z_mid" in keys and not self.z_valid:
             raise capi.DotsError("z_mid was not materialised on the last iteration")
         r, s = self.r, self.s
         scale = dict(phi=1.0, A=1.0, B=1.0, lam_c=1.0, z_fst=1.0 / s, z_mid=1.0 / s, z_end=1.0 / s,
                      mu=r, E=r, b_fst=r * s, b_mid=r * s, b_end=r * s)
         out = {}
-        for key, name in REF_KEYS.items():
+        for key in keys:
+            name = REF_KEYS[key]
             out[key] = (self.from_internal(name) * scale[name]).cpu().numpy()
         return out

@@ -78,12 +78,13 @@ def _warm_start(eng: Engine, init):
 def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8), tol=1e-4, tau=1.90,
                 is_palm=False, is_multi_threads=True, is_z_scaling=True, is_constant_scaling=False,
                 check_kkt_step_by_step=False, init_solution=None, tol_checkpoints=None, time_limit=1000,
-                device=None, leaf_size=24, show_progress=False, return_engine=False, comm=None):
+                device=None, leaf_size=24, show_progress=False, return_engine=False, comm=None, solution_keys=None):
     """B200 implementation of ``dot_surface_socp.socp.solver_socp.solver_socp``.
 
     Extra keyword arguments (``device``, ``leaf_size``, ``show_progress``, ``return_engine``, ``comm``) are additions;
     with torch.distributed initialised (one process per GPU) the problem is sharded over the ranks of ``comm``
-    (default: the world group) and every rank returns the full solution;
+    (default: the world group) and every rank returns the full solution; ``solution_keys`` limits which of the twelve
+    solution arrays are converted and copied to the host (default: all, as the reference returns them);
     ``is_multi_threads`` is accepted and ignored (the two reference threads become stream order).
     ``is_palm=True`` and ``is_constant_scaling=True`` are solver-only knobs that the reference's CLI /
     interface cannot reach (interface.py:275-284); they are not built and raise."""
@@ -189,10 +190,12 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
     hist.kkt_seconds = kkt_seconds
     hist.evaluations = list(lazy.evaluations)
     hist.gpu_launches = eng.launches
-    solution = eng.solution()                                                             # :845, :855-869
+    solution = eng.solution(solution_keys)                                                # :845, :855-869
     solution["checkpoints"] = checkpoints if checkpoints else None
+    cong_norm = (f"{np.linalg.norm(solution['lambda_c'] - congestion * solution['mu']):.2f}"
+                 if "lambda_c" in solution and "mu" in solution else "n/a")
     logging.log(LOG_INFO, "---- Overview of solution ".ljust(42, "-") + "\n"
-                f"Congestion norm: {np.linalg.norm(solution['lambda_c'] - congestion * solution['mu']):.2f}\n"
+                f"Congestion norm: {cong_norm}\n"
                 f"Number of iterations: {it}\nIteration time: {hist.running_time:.2f}")
     if return_engine:
         return solution, hist, eng
@@ -218,19 +221,23 @@ def _centre_in_time(sol, mu0, mu1):
 
 
 def solver_raw(n_time, geometry, **kwargs):
-    """DOT-unit solution on the staggered time grid (reference name ``dot_solver_socp``)."""
-    sol, hist = solver_socp(n_time, geometry, **kwargs)
-    return translate_solution_socp_to_dot(sol, geometry), hist
+    """DOT-unit solution on the staggered time grid (reference name ``dot_solver_socp``).
+
+    Only ``mu`` and ``E`` (what the DOT solution consists of, utils/type.py:40-65) leave the device."""
+    kwargs.setdefault("solution_keys", ("mu", "E"))
+    res = solver_socp(n_time, geometry, **kwargs)
+    return (translate_solution_socp_to_dot(res[0], geometry),) + tuple(res[1:])
 
 
 def solver(n_time, geometry, **kwargs):
     """DOT-unit solution on the time-centred grid incl. mu0 / mu1 (reference name ``dot_solver_socp_center``)."""
-    sol, hist = solver_raw(n_time, geometry, **kwargs)
+    res = solver_raw(n_time, geometry, **kwargs)
+    sol = res[0]
     mu0, mu1 = np.asarray(geometry["mu0"]), np.asarray(geometry["mu1"])
     _centre_in_time(sol, mu0, mu1)
     for c in sol.get("checkpoints") or []:
         _centre_in_time(c, mu0, mu1)
-    return sol, hist
+    return res if len(res) > 2 else (sol, res[1])
 
 
 solver_raw.__name__ = "dot_solver_socp"

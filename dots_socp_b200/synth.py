@@ -95,15 +95,17 @@ def hex_plane(n: int):
     verts = np.stack([x, ii * dy, np.zeros_like(x)], axis=-1).reshape(-1, 3)
     vid = lambda a, b: a * cols + b
     tris = []
-    for r in range(rows - 1):
-        j = np.arange(cols - 1)
+    j = np.arange(cols - 1)
+    for r in range(rows - 1):                # triangle order of the reference generator: per cell, first / second triangle
         if r % 2 == 0:
-            tris.append(np.stack([vid(r, j), vid(r, j + 1), vid(r + 1, j)], axis=1))
-            tris.append(np.stack([vid(r, j + 1), vid(r + 1, j + 1), vid(r + 1, j)], axis=1))
+            first = np.stack([vid(r, j), vid(r, j + 1), vid(r + 1, j)], axis=1)
+            second = np.stack([vid(r, j + 1), vid(r + 1, j + 1), vid(r + 1, j)], axis=1)
+            tris.append(np.stack([first, second], axis=1).reshape(-1, 3))
         else:
-            tris.append(np.stack([vid(r, j), vid(r + 1, j + 1), vid(r + 1, j)], axis=1))
-            jp = j[1:]
-            tris.append(np.stack([vid(r, jp - 1), vid(r, jp), vid(r + 1, jp)], axis=1))
+            first = np.stack([vid(r, j), vid(r + 1, j + 1), vid(r + 1, j)], axis=1)
+            second = np.stack([vid(r, j - 1), vid(r, j), vid(r + 1, j)], axis=1)
+            both = np.stack([first, second], axis=1).reshape(-1, 3)
+            tris.append(np.concatenate([first[:1], both[2:]], axis=0))      # cell j = 0 has no second triangle
     return verts, np.concatenate(tris, axis=0).astype(np.int64)
 
 

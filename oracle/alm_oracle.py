@@ -508,7 +508,7 @@ class OracleALM:
 
 
 def solve(n_time, geometry, congestion=0.0, nit=1000, eps=0.0, tol=1e-4, tau=1.9, is_palm=False,
-          is_z_scaling=True, time_limit=1000, trace=None, ops=None):
+          is_z_scaling=True, time_limit=1000, trace=None, ops=None, check_kkt_step_by_step=False):
     """The reference's outer loop (:565-871) around OracleALM.  Returns (solution, info).
 
     ``info``: iterations (= last 0-based index, what the reference prints), kkt rows (nan = not
@@ -517,7 +517,7 @@ def solve(n_time, geometry, congestion=0.0, nit=1000, eps=0.0, tol=1e-4, tau=1.9
     t0 = time.perf_counter()
     prim_gap = 1.0 + 1.0 * np.exp(-100 * congestion)                                       # :568
     lazy = LazyKKT([(lambda i=i: alm.kkt(i)) for i in range(7)], tol)
-    rows, its, r_hist = [], [], []
+    rows, its, r_hist, costs = [], [], [], []
     last_adjust, z_rescales, use_org = -1, 0, False
     last_row = np.full(7, np.inf)
     it, passed = -1, False
@@ -534,18 +534,22 @@ def solve(n_time, geometry, congestion=0.0, nit=1000, eps=0.0, tol=1e-4, tau=1.9
             last_adjust = it
         adjust = due or time_up
         required = [0, 1, 2, 3] if adjust else None
-        if adjust:
-            lazy.reset_counter()
-        passed, _ = lazy.validate(required)                                                # :738
+        if check_kkt_step_by_step:                                                         # :769-787
+            passed, _ = lazy.validate(list(range(7)))
+            costs.append(alm.objective())
+        else:
+            if adjust:
+                lazy.reset_counter()
+            passed, _ = lazy.validate(required)                                            # :738
         errs = lazy.pop_errors()
         org = [e[0] for e in errs]
         sec = [e[1] for e in errs]
-        if adjust:
+        if adjust and not check_kkt_step_by_step:
             lazy.reset_counter()
         last_row = np.array([np.nan if v is None else v for v in org], dtype=float)        # record(): None -> nan
         rows.append(last_row); its.append(it); r_hist.append(alm.r)
         err = _max_skip_none([org[k] for k in (0, 2, 4, 5)])                               # :751
-        if err is not None:
+        if err is not None and not check_kkt_step_by_step:
             lazy.retune(err)
         if trace is not None:
             trace(it, alm)
@@ -561,6 +565,6 @@ def solve(n_time, geometry, congestion=0.0, nit=1000, eps=0.0, tol=1e-4, tau=1.9
     final = [alm.kkt(i)[0] for i in range(7)]                                              # :826-828
     cost, lagr = alm.objective()
     info = dict(iterations=it, converged=bool(passed), kkt_rows=np.array(rows), kkt_iteration=np.array(its),
-                r_history=np.array(r_hist), final_kkt=np.array(final), cost=cost, objective=lagr,
+                r_history=np.array(r_hist), final_kkt=np.array(final), cost=cost, objective=lagr, cost_history=np.array(costs),
                 running_time=time.perf_counter() - t0, r=alm.r, scale_z=alm.s)
     return alm.solution(), info

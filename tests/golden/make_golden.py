@@ -62,6 +62,10 @@ CASES = {
     "ico3_nt31_c0": ("icosphere3", {}, 31, dict(tol=1e-3, nit=1000), (), False),
     "ico3_nt31_c01": ("icosphere3", {}, 31, dict(tol=1e-3, nit=1000, congestion=0.1), (), False),
     # BASELINE.json configs[0] / configs[1]: the knots_5-class stand-in (V=4300, T=8600), nT=31, tol 1e-3
+    # --detail_runhist mode (check_kkt_step_by_step, solver_socp.py:769-787): all 7 residuals + objective every iteration
+    "ico2_nt7_stepwise": ("icosphere2", {}, 7, dict(tol=1e-3, nit=400, congestion=0.05, check_kkt_step_by_step=True), (0, 9), False),
+    # the reference's OWN example pipeline: load_example('plane', n_space=20) + normalize_geometry (survey: 328 iterations)
+    "refplane20_nt15": ("@reference:plane:20", {}, 15, dict(tol=1e-3, nit=1000), (0, 9), False),
     "knots5class_nt31_c0": ("knot", {}, 31, dict(tol=1e-3, nit=1000), (), False),
     "knots5class_nt31_c01": ("knot", {}, 31, dict(tol=1e-3, nit=1000, congestion=0.1), (), False),
 }
@@ -71,7 +75,18 @@ def main(only=None):
     for name, (ex, exkw, n_time, kw, snap_its, keep_full) in CASES.items():
         if only and name not in only:
             continue
-        geo, scale = synth.example(ex, **exkw)
+        if ex.startswith("@reference:"):
+            _, ex_name, n_space = ex.split(":")
+            refshim.load()
+            cwd = os.getcwd()
+            os.chdir(refshim.REFERENCE_ROOT)
+            from dot_surface_socp.data.load_example import load_example
+            from dot_surface_socp.socp.data_preprocessing import normalize_geometry
+            _, raw_geo, _ = load_example(example_name=ex_name, kwargs_generating_mesh={"n": int(n_space)})
+            geo, scale = normalize_geometry(raw_geo)
+            os.chdir(cwd)
+        else:
+            geo, scale = synth.example(ex, **exkw)
         sol, hist, snaps, r_hist = run_reference(geo, n_time, snap_its, **kw)
         out = dict(
             vertices=geo["vertices"], triangles=geo["triangles"], mu0=geo["mu0"], mu1=geo["mu1"],
@@ -81,6 +96,7 @@ def main(only=None):
             kkt_rows=hist.kkt_errors, kkt_iteration=hist.kkt_iteration,
             r_history=np.array([r_hist[i] for i in sorted(r_hist)]),
             cost=hist.history["Transportation cost"][-1], objective=hist.history["Objective value"][-1],
+            cost_history=hist.history["Transportation cost"], objective_history=hist.history["Objective value"],
             sol_mu=sol["mu"], sol_phi_grad_t=np.diff(sol["phi"], axis=0),
             ref_running_time=hist.running_time, ref_steps_time=float(sum(hist.steps_time.values())),
         )

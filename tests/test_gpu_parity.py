@@ -174,7 +174,8 @@ def test_kkt_and_objective_rows_a9_a11():
 # ---------------------------------------------------------------------------------------------- end to end
 @pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005",
                                   "ico2_nt15_tol1e-4", "ico3_nt31_c0", "ico3_nt31_c01",
-                                  "knots5class_nt31_c0", "knots5class_nt31_c01"])       # BASELINE configs[0], [1]
+                                  "knots5class_nt31_c0", "knots5class_nt31_c01",        # BASELINE configs[0], [1]
+                                  "ico2_nt7_stepwise", "refplane20_nt15"])
 def test_solver_matches_reference_fixture(golden, name):
     """Through the public solver_socp: iteration count, KKT schedule (which residual on which iteration), penalty
     path, transport cost and the returned mu against the fixtures generated by the unmodified reference."""
@@ -188,6 +189,8 @@ def test_solver_matches_reference_fixture(golden, name):
     assert np.allclose(hist.kkt_errors[m], ref_rows[m], rtol=1e-6, atol=1e-12)
     cost = hist.history["Transportation cost"][-1]
     assert cost == pytest.approx(float(z["cost"]), rel=1e-6)
+    if kw.get("check_kkt_step_by_step"):                   # --detail_runhist: the cost is recorded every iteration
+        assert np.allclose(hist.history["Transportation cost"], z["cost_history"], rtol=1e-6)
     assert math.sqrt(2 * cost) == pytest.approx(math.sqrt(2 * float(z["cost"])), rel=1e-6)          # W2
     assert rel(sol["mu"], z["sol_mu"]) < 1e-6
     assert sol["z_mid"].shape == (n_time, 2, 3, geo["triangles"].shape[0], 3)

@@ -19,7 +19,8 @@ def phi_mod_const(phi):
     return phi - phi.mean()
 
 
-@pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005"])
+@pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005",
+                                  "ico2_nt7_stepwise", "refplane20_nt15"])
 def test_iterates_match_reference(golden, name):
     z, geo, n_time, kw = golden(name)
     snap_its = [int(i) for i in z["snap_its"]]
@@ -67,6 +68,27 @@ def test_schedule_and_history_match_reference(golden, name):
     assert np.allclose(info["r_history"], z["r_history"], rtol=1e-12)
     assert info["cost"] == pytest.approx(float(z["cost"]), rel=1e-8)
     assert rel_err(sol["mu"], z["sol_mu"]) < 1e-7
+
+
+def test_stepwise_mode_records_every_residual_and_the_cost_each_iteration(golden):
+    z, geo, n_time, kw = golden("ico2_nt7_stepwise")
+    sol, info = orc.solve(n_time, geo, **kw)
+    assert info["iterations"] == int(z["iterations"])
+    assert not np.isnan(info["kkt_rows"]).any()
+    assert np.allclose(info["kkt_rows"][:-1], z["kkt_rows"][:-1], rtol=1e-6, atol=1e-12)
+    ref_cost = z["cost_history"]
+    assert np.allclose(np.array(info["cost_history"])[:-1, 0], ref_cost[:-1], rtol=1e-8)
+
+
+def test_synthetic_plane_is_the_references_plane_generator(golden):
+    """dots_socp_b200.synth.hex_plane + normalize_geometry reproduce data/meshes/plane.py + data_preprocessing.py."""
+    from dots_socp_b200 import synth
+    z, geo, n_time, kw = golden("refplane20_nt15")
+    mine, scale = synth.example("plane20")
+    assert np.array_equal(mine["triangles"], geo["triangles"])
+    assert np.allclose(mine["vertices"], geo["vertices"], atol=1e-14)
+    assert np.allclose(mine["mu0"], geo["mu0"], rtol=1e-12) and np.allclose(mine["mu1"], geo["mu1"], rtol=1e-12)
+    assert scale == pytest.approx(float(z["scale_factor"]), rel=1e-14)
 
 
 def test_operator_identities():
