@@ -346,7 +346,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default="icosphere7_nt63", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-nit", type=int, default=1000, dest="e2e_nit")
-    ap.add_argument("--leaf", type=int, default=24)
+    ap.add_argument("--leaf", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
     args = ap.parse_args()
     if args.impl == "reference":

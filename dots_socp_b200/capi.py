@@ -35,6 +35,14 @@ class DotsCtx(C.Structure):
     )
 
 
+class FrontArgs(C.Structure):
+    """Mirror of ``dots_front_args_t`` (setup: small-front factorisation launch)."""
+    _fields_ = ([("nodes", C.c_void_p), ("n_modes", C.c_int32), ("m_pad", C.c_int32)]
+                + [(n, C.c_void_p) for n in ("nd_off", "nd_s", "nd_b", "nd_child", "nd_panel", "nd_front", "nd_upd", "parent_pos",
+                                             "u_ptr", "a_ptr", "a_pos", "a_val", "mass", "shifts", "panels", "panels_t")]
+                + [("pin_node", C.c_int32), ("reserved", C.c_int32), ("pin_value", C.c_double)])
+
+
 class DotsError(RuntimeError):
     pass
 
@@ -74,6 +82,7 @@ def load(build_if_missing: bool = True):
         "dots_kkt_sums": (ctxp, i, vp, vp), "dots_phi_rhs": (ctxp, vp), "dots_time_transform": (ctxp, i, vp),
         "dots_mode_solves": (ctxp, vp), "dots_grad_space": (ctxp, vp, vp, vp), "dots_div_space": (ctxp, vp, vp, vp),
         "dots_graph_create": (ctxp, i, vp, C.POINTER(vp)), "dots_graph_launch": (vp, vp), "dots_graph_destroy": (vp,),
+        "dots_factor_small_fronts": (C.POINTER(FrontArgs), i, i, vp), "dots_front_nmax": (),
     }
     for name, args in protos.items():
         fn = getattr(lib, name)
@@ -85,7 +94,8 @@ def load(build_if_missing: bool = True):
 EXPORTS = ("dots_abi_version", "dots_ctx_sizeof", "dots_last_error", "dots_step_phi", "dots_step_vertex",
            "dots_step_tri", "dots_iterate", "dots_refresh_corner_terms", "dots_scale_dual", "dots_scale_z",
            "dots_set_params", "dots_kkt_sums", "dots_phi_rhs", "dots_time_transform", "dots_mode_solves",
-           "dots_grad_space", "dots_div_space", "dots_graph_create", "dots_graph_launch", "dots_graph_destroy")
+           "dots_grad_space", "dots_div_space", "dots_graph_create", "dots_graph_launch", "dots_graph_destroy",
+           "dots_factor_small_fronts", "dots_front_nmax")
 
 
 def check(code: int, what: str = ""):

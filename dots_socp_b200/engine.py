@@ -106,7 +106,7 @@ def _sweep_items_persistent(sym: nested.Symbolic, n_blocks: int):
 class Engine:
     """One rank's share of the problem.  ``comm`` (dist.Comm) spans the ranks; None / single rank = whole problem."""
 
-    def __init__(self, n_time, geometry, congestion=0.0, eps=0.0, tau=1.9, device=None, leaf_size=24, timings=None,
+    def __init__(self, n_time, geometry, congestion=0.0, eps=0.0, tau=1.9, device=None, leaf_size=16, timings=None,
                  sweep_mode=None, comm=None):
         if not torch.cuda.is_available():
             raise capi.DotsError("dots_socp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -150,8 +150,14 @@ class Engine:
         if sweep_mode is None:
             sweep_mode = int(os.environ.get("DOTS_SWEEP_MODE", "0"))
         self.sweep_mode = int(sweep_mode)
-        panels, panels_t = nested.factor_batched_device(sym, K, area_v, shifts, m_pad=self.m_pad, device=self.device,
-                                                        transposed=True)
+        self.factor_stats = {}
+        if os.environ.get("DOTS_FACTOR", "hybrid") == "library":
+            panels, panels_t = nested.factor_batched_device(sym, K, area_v, shifts, m_pad=self.m_pad, device=self.device,
+                                                            transposed=True)
+        else:
+            panels, panels_t = nested.factor_hybrid_device(sym, K, area_v, shifts, self.m_pad, self.device, self.lib,
+                                                           lambda: torch.cuda.current_stream(self.device).cuda_stream,
+                                                           stats=self.factor_stats)
         torch.cuda.synchronize(self.device)
         tm["factorization"] = time.perf_counter() - t0
 

@@ -346,3 +346,161 @@ def factor_batched_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shi
                 jj = torch.arange(s, device=device)
                 panels_t[p0 + jj * (s + b) - jj * (jj - 1) // 2, n_modes:] = 1.0
     return (panels, panels_t) if transposed else panels
+
+
+# ----------------------------------------------------------------------------- hybrid device factorisation (row f1)
+def front_maps(sym: Symbolic, Kp: sp.csr_matrix):
+    """Index maps of the assembly, fully vectorised:
+
+    a_pos[q]      front position (in the front of the node that owns row(q)) of CSR entry q of the permuted matrix,
+                  -1 when the column lies below the owner's first vertex (already eliminated);
+    parent_pos[p] front row, in the PARENT's front, of boundary row p of every node (concatenated like ``upd_off``)."""
+    n = sym.n
+    node_of = np.repeat(np.arange(sym.n_nodes), sym.s)                       # owner node of every vertex (new ids)
+    nfront = (sym.s + sym.b).astype(np.int64)
+    front_node = np.repeat(np.arange(sym.n_nodes), nfront)
+    keys = front_node * np.int64(n) + sym.front_idx                           # globally sorted: nodes ascending, rows ascending
+    rows = np.repeat(np.arange(n), np.diff(Kp.indptr))
+    owner = node_of[rows]
+    cols = Kp.indices.astype(np.int64)
+    hit = np.searchsorted(keys, owner * np.int64(n) + cols)
+    hit = np.minimum(hit, keys.size - 1)
+    ok = (cols >= sym.off[owner]) & (keys[hit] == owner * np.int64(n) + cols)
+    a_pos = np.where(ok, hit - sym.front_off[owner], -1).astype(np.int32)
+    # boundary rows of every node inside the parent's front
+    bnd_node = np.repeat(np.arange(sym.n_nodes), sym.b)
+    within = np.arange(bnd_node.size) - np.repeat(sym.upd_off[:-1], sym.b)
+    bnd_vertex = sym.front_idx[sym.front_off[bnd_node] + sym.s[bnd_node] + within]
+    par = sym.parent[bnd_node]
+    hit = np.searchsorted(keys, par * np.int64(n) + bnd_vertex)
+    hit = np.minimum(hit, keys.size - 1)
+    assert np.all((par < 0) | (keys[hit] == par * np.int64(n) + bnd_vertex)), "child boundary must embed in the parent front"
+    parent_pos = np.where(par >= 0, hit - sym.front_off[np.maximum(par, 0)], -1).astype(np.int32)
+    return a_pos, parent_pos
+
+
+def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shifts: np.ndarray, m_pad: int, device, lib,
+                         stream_fn, stats: dict | None = None):
+    """Numeric factorisation on the GPU, level by level: small fronts by the hand-written ``k_front_small`` kernel (one
+    block per node and mode), the few large fronts near the root by batched dense torch.linalg calls.  Returns
+    (panels, panels_t), both (panel_entries, m_pad) on ``device``."""
+    import ctypes as C
+    import torch
+    from . import capi
+
+    n_modes = int(len(shifts))
+    nmax = int(lib.dots_front_nmax())
+    Kp = K[sym.perm][:, sym.perm].tocsr()
+    Kp.sort_indices()
+    a_pos, parent_pos = front_maps(sym, Kp)
+    dev = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device=device)
+    shifts_t = dev(shifts, np.float64)
+    massp = dev(np.asarray(mass, dtype=np.float64)[sym.perm], np.float64)
+    t = dict(nd_off=dev(sym.off, np.int32), nd_s=dev(sym.s, np.int32), nd_b=dev(sym.b, np.int32),
+             nd_child=dev(sym.child, np.int32), nd_panel=dev(sym.panel_off[:-1], np.int64),
+             nd_front=dev(sym.front_off[:-1], np.int64), nd_upd=dev(sym.upd_off[:-1], np.int64),
+             parent_pos=dev(parent_pos, np.int32), a_ptr=dev(Kp.indptr, np.int64), a_pos=dev(a_pos, np.int32),
+             a_val=dev(Kp.data, np.float64))
+    panels = torch.zeros((sym.panel_entries, m_pad), dtype=torch.float64, device=device)
+    panels_t = torch.zeros((sym.panel_entries, m_pad), dtype=torch.float64, device=device)
+    u_ptr_host = np.zeros(sym.n_nodes, dtype=np.int64)
+    u_ptr_dev = torch.zeros(sym.n_nodes, dtype=torch.int64, device=device)
+    u_view = {}                                           # node -> (b, b, m_pad) view of its update matrix
+    level_buf = {}
+    levels = level_schedule(sym)
+    last_use = {}
+    for lv, nodes in enumerate(levels):
+        par_lv = [int(sym.level[sym.parent[nd]]) for nd in nodes if sym.parent[nd] >= 0]
+        last_use[lv] = max(par_lv) if par_lv else lv
+    pin_node = sym.n_nodes - 1
+    pin_value = float(Kp.diagonal().mean())
+    singular = [m for m in range(n_modes) if float(shifts[m]) == 0.0]
+    tril_cache, triu_cache = {}, {}
+    dev_i64 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int64), device=device)
+    n_small = n_large = 0
+
+    args = capi.FrontArgs()
+    args.n_modes, args.m_pad = n_modes, m_pad
+    for k in ("nd_off", "nd_s", "nd_b", "nd_child", "nd_panel", "nd_front", "nd_upd", "parent_pos", "a_ptr", "a_pos", "a_val"):
+        setattr(args, k, t[k].data_ptr())
+    args.mass, args.shifts = massp.data_ptr(), shifts_t.data_ptr()
+    args.panels, args.panels_t = panels.data_ptr(), panels_t.data_ptr()
+    args.u_ptr = u_ptr_dev.data_ptr()
+    args.pin_node, args.pin_value = pin_node, pin_value
+
+    for lv, nodes in enumerate(levels):
+        b_l = sym.b[nodes].astype(np.int64)
+        offs = np.concatenate([[0], np.cumsum(b_l * b_l)])
+        buf = torch.empty((max(1, int(offs[-1])), m_pad), dtype=torch.float64, device=device)
+        level_buf[lv] = buf
+        for nd, o0, bb in zip(nodes, offs[:-1], b_l):
+            if bb:
+                u_view[int(nd)] = buf[int(o0):int(o0 + bb * bb)].view(int(bb), int(bb), m_pad)
+                u_ptr_host[nd] = buf.data_ptr() + int(o0) * m_pad * 8
+        u_ptr_dev.copy_(torch.from_numpy(u_ptr_host))
+        nfront = sym.s[nodes] + sym.b[nodes]
+        small = nodes[nfront <= nmax]
+        large = nodes[nfront > nmax]
+        if small.size:
+            nodes_dev = dev(small, np.int32)
+            args.nodes = nodes_dev.data_ptr()
+            capi.check(lib.dots_factor_small_fronts(C.byref(args), int(small.size), int(nfront[nfront <= nmax].max()), stream_fn()),
+                       "dots_factor_small_fronts")
+            n_small += int(small.size)
+        for i in large:                                                    # batched dense algebra over the modes
+            i = int(i)
+            s, b = int(sym.s[i]), int(sym.b[i])
+            nf, lo, f0 = s + b, int(sym.off[i]), int(sym.front_off[i])
+            F = torch.zeros((n_modes, nf, nf), dtype=torch.float64, device=device)
+            if s:
+                q0, q1 = int(Kp.indptr[lo]), int(Kp.indptr[lo + s])
+                r = np.repeat(np.arange(s), np.diff(Kp.indptr[lo:lo + s + 1]))
+                c, v = a_pos[q0:q1], Kp.data[q0:q1]
+                keep = c >= 0
+                rt, ct, vt = dev_i64(r[keep]), dev_i64(c[keep]), torch.as_tensor(v[keep], device=device)
+                F[:, rt, ct] = vt
+                F[:, ct, rt] = vt
+                d = torch.arange(s, device=device)
+                F[:, d, d] += shifts_t[:, None] * massp[None, lo:lo + s]
+                if i == pin_node:
+                    for m in singular:
+                        F[m, s - 1, s - 1] += pin_value
+            for slot in range(2):
+                k = int(sym.child[i, slot])
+                if k >= 0 and sym.b[k]:
+                    pp = dev_i64(parent_pos[int(sym.upd_off[k]):int(sym.upd_off[k + 1])])
+                    F[:, pp[:, None], pp[None, :]] += u_view[k][:, :, :n_modes].permute(2, 0, 1)
+            if s == 0:
+                if b:
+                    u_view[i][:, :, :n_modes] = F.permute(1, 2, 0)
+                continue
+            L11 = torch.linalg.cholesky(F[:, :s, :s])
+            eye = torch.eye(s, dtype=torch.float64, device=device).expand(n_modes, s, s)
+            Linv = torch.linalg.solve_triangular(L11, eye, upper=False)
+            if s not in tril_cache:
+                tril_cache[s] = torch.tril_indices(s, s, device=device)
+            tri = tril_cache[s]
+            p0, ntri = int(sym.panel_off[i]), s * (s + 1) // 2
+            panels[p0:p0 + ntri, :n_modes] = Linv[:, tri[0], tri[1]].T
+            W21 = None
+            if b:
+                L21 = F[:, s:, :s] @ Linv.mT
+                W21 = L21 @ Linv
+                panels[p0 + ntri:p0 + ntri + b * s, :n_modes] = W21.reshape(n_modes, b * s).T
+                u_view[i][:, :, :n_modes] = (F[:, s:, s:] - L21 @ L21.mT).permute(1, 2, 0)
+            stacked = Linv if W21 is None else torch.cat([Linv, W21], dim=1)
+            if (s, b) not in triu_cache:
+                triu_cache[(s, b)] = torch.ones((s, s + b), dtype=torch.bool, device=device).triu()
+            panels_t[p0:p0 + ntri + b * s, :n_modes] = stacked.mT[:, triu_cache[(s, b)]].T
+            if m_pad > n_modes:
+                jj = torch.arange(s, device=device)
+                panels[p0 + jj * (jj + 1) // 2 + jj, n_modes:] = 1.0
+                panels_t[p0 + jj * (s + b) - jj * (jj - 1) // 2, n_modes:] = 1.0
+            n_large += 1
+        for old in [k for k, lu in last_use.items() if lu <= lv and k in level_buf and k < lv]:
+            for nd in levels[old]:
+                u_view.pop(int(nd), None)
+            del level_buf[old]
+    if stats is not None:
+        stats.update(small_fronts=n_small, large_fronts=n_large, front_nmax=nmax)
+    return panels, panels_t

@@ -78,7 +78,7 @@ def _warm_start(eng: Engine, init):
 def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8), tol=1e-4, tau=1.90,
                 is_palm=False, is_multi_threads=True, is_z_scaling=True, is_constant_scaling=False,
                 check_kkt_step_by_step=False, init_solution=None, tol_checkpoints=None, time_limit=1000,
-                device=None, leaf_size=24, show_progress=False, return_engine=False, comm=None, solution_keys=None):
+                device=None, leaf_size=16, show_progress=False, return_engine=False, comm=None, solution_keys=None):
     """B200 implementation of ``dot_surface_socp.socp.solver_socp.solver_socp``.
 
     Extra keyword arguments (``device``, ``leaf_size``, ``show_progress``, ``return_engine``, ``comm``) are additions;

@@ -178,6 +178,28 @@ int dots_set_params(const dots_ctx_t *c, const double *host_params, void *stream
  * Synchronises the stream.  Slot meaning per condition is documented in dots_socp_b200/solver.py.   */
 int dots_kkt_sums(const dots_ctx_t *c, int which, double *host_out, void *stream);
 
+/* ---- setup (row f1): numeric factorisation of the small fronts (n <= dots_front_nmax()) of one tree level, one block
+ * per (node, time mode); replaces the per-mode SuperLU factorisations of utils/laplacian_inverse_socp.py:34-41 for the
+ * ~93 % of the separator-tree nodes near the leaves.  Large fronts: batched dense library calls (nested.py).        */
+typedef struct dots_front_args {
+    const int32_t *nodes;          /* [n_launch] node ids of this launch                                    */
+    int32_t n_modes, m_pad;
+    const int32_t *nd_off, *nd_s, *nd_b, *nd_child;
+    const int64_t *nd_panel, *nd_front, *nd_upd;
+    const int32_t *parent_pos;     /* [sum b] front row in the PARENT of every boundary row of a node        */
+    const int64_t *u_ptr;          /* [n_nodes] device address of the node's update matrix [b][b][m_pad]     */
+    const int64_t *a_ptr;          /* [V+1] CSR row pointers of K in the elimination ordering               */
+    const int32_t *a_pos;          /* [nnz] front position (in the row owner's front) of every entry or -1  */
+    const double  *a_val;          /* [nnz]                                                                  */
+    const double  *mass;           /* [V]                                                                    */
+    const double  *shifts;         /* [n_modes]                                                              */
+    double *panels, *panels_t;
+    int32_t pin_node, reserved;
+    double pin_value;
+} dots_front_args_t;
+int dots_factor_small_fronts(const dots_front_args_t *a, int n_launch, int max_front, void *stream);
+int dots_front_nmax(void);
+
 /* ---- operator-level entry points on the internal layout (rows a5, a6, a7, a8) ---------------------- */
 int dots_phi_rhs(const dots_ctx_t *c, void *stream);                       /* -> c->rhs                */
 int dots_time_transform(const dots_ctx_t *c, int inverse, void *stream);   /* rhs -> hat / hat -> phi   */

@@ -227,3 +227,27 @@ def test_large_problem_properties():
     nrm = np.sqrt(ops.M_oneT.dot(corner.T).T + st["z_end"] ** 2)
     assert (nrm <= st["z_fst"] * (1 + 1e-12) + 1e-12).all()
     assert np.isfinite(st["phi"]).all()
+
+
+@pytest.mark.parametrize("example,leaf,n_time", [("icosphere3", 8, 7), ("icosphere5", 24, 31), ("plane8", 6, 6)])
+def test_setup_factorisation_kernel_matches_library_path_row_f1(example, leaf, n_time):
+    """Hand-written small-front kernel + library large fronts == all-library batched factorisation (both layouts)."""
+    from dots_socp_b200 import nested, surface, capi
+    from dots_socp_b200.engine import time_basis
+    geo, _ = synth.example(example)
+    v, t = geo["vertices"], geo["triangles"]
+    K = surface.stiffness_matrix(v, t)
+    mass = surface.incident_area_sum(v.shape[0], t, surface.triangle_areas(v, t)) / 3.0
+    sym = nested.analyse(v, K, leaf_size=leaf)
+    _, lam = time_basis(n_time)
+    m_pad = 8 if n_time + 1 <= 8 else 32
+    dev = torch.device("cuda:0")
+    ref, ref_t = nested.factor_batched_device(sym, K, mass, -lam, m_pad, dev, transposed=True)
+    stats = {}
+    got, got_t = nested.factor_hybrid_device(sym, K, mass, -lam, m_pad, dev, capi.load(),
+                                             lambda: torch.cuda.current_stream(dev).cuda_stream, stats=stats)
+    torch.cuda.synchronize()
+    assert stats["small_fronts"] > 0
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() / scale < 1e-11
+    assert (got_t - ref_t).abs().max().item() / scale < 1e-11

@@ -124,3 +124,26 @@ def test_transposed_panel_copy_is_column_major_view_of_the_same_entries():
             col_off = j * (s + b) - j * (j - 1) // 2
             got = pt[p0 + col_off:p0 + col_off + (s + b - j)]
             assert np.array_equal(got, P[j:, j])
+
+
+def test_front_maps_agree_with_the_per_node_search():
+    geo, _ = synth.example("icosphere3")
+    v, t = geo["vertices"], geo["triangles"]
+    K = surface.stiffness_matrix(v, t)
+    sym = nested.analyse(v, K, leaf_size=12)
+    Kp = K[sym.perm][:, sym.perm].tocsr()
+    Kp.sort_indices()
+    a_pos, parent_pos = nested.front_maps(sym, Kp)
+    for i in range(sym.n_nodes):
+        s, b, lo, f0 = int(sym.s[i]), int(sym.b[i]), int(sym.off[i]), int(sym.front_off[i])
+        rows = sym.front_idx[f0:f0 + s + b]
+        q0, q1 = Kp.indptr[lo], Kp.indptr[lo + s]
+        cols = Kp.indices[q0:q1]
+        want = np.where(cols >= lo, np.searchsorted(rows, cols), -1)
+        assert np.array_equal(a_pos[q0:q1], want)
+        for slot in range(2):
+            k = int(sym.child[i, slot])
+            if k >= 0 and sym.b[k]:
+                cp = sym.child_pos[slot, f0:f0 + s + b]
+                pp = parent_pos[sym.upd_off[k]:sym.upd_off[k + 1]]
+                assert np.array_equal(cp[pp], np.arange(sym.b[k]))
