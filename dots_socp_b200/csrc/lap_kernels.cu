@@ -99,10 +99,21 @@ __device__ __forceinline__ size_t panel_row_off(int row, int s)
     return (row < s) ? (size_t)row * (row + 1) / 2 : (size_t)s * (s + 1) / 2 + (size_t)(row - s) * s;
 }
 
+// optional profiling: first thread of the first block records %globaltimer at kernel start (tools/level_times.py)
+__device__ __forceinline__ void sweep_stamp(const dots_ctx_t &c, int idx)
+{
+    if (c.phase_clock && idx >= 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        c.phase_clock[idx] = t;
+    }
+}
+
 // Gather step of the forward sweep, one tree level: r_S = hat_S + (children's updates landing on S), in place.
 // Block = one item (node, first S row, n rows) of the level's gather list (leaves have no children: no items).
-__global__ void __launch_bounds__(256) k_sweep_gather(dots_ctx_t c, int item0)
+__global__ void __launch_bounds__(256) k_sweep_gather(dots_ctx_t c, int item0, int stamp)
 {
+    sweep_stamp(c, stamp);
     const int M = c.m_pad;
     const int *it = c.lvn_nodes + 3 * (size_t)(item0 + blockIdx.x);
     const int node = it[0], j0 = it[1], nj = it[2];
@@ -144,14 +155,23 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) 
 // demand loads mostly see L2 latency instead of DRAM latency (ncu before: >80 % long_scoreboard).
 // ML = modes of this rank (8, 16, 32, 64, 96, 128).  ML >= 32: lane = mode (+32 per register); ML < 32: a warp covers
 // G = 32/ML consecutive entries at once (lane = entry-in-group * ML + mode) and folds the groups with shuffles.
-template <int ML, int WPR, int DIR>
-__global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_run(dots_ctx_t c, int item0)
+// FG (forward only): the block folds the children's updates into r_S itself and keeps r_S in shared memory (levels
+// whose separators have <= SWEEP_FG_SMAX rows), which removes the separate gather launch of the level.
+#define SWEEP_FG_SMAX 64
+template <int ML, int WPR, int DIR, bool FG>
+__global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_run(dots_ctx_t c, int item0, int stamp)
 {
+    sweep_stamp(c, stamp);
+    extern __shared__ double rsm[];                    // [s][M] staged r_S (FG only)
     constexpr int M = ML;
     constexpr int MP = (ML >= 32) ? ML / 32 : 1;
     constexpr int G = (ML >= 32) ? 1 : 32 / ML;
     constexpr int LSTRIDE = (ML >= 32) ? 32 : 0;       // register m of a lane is mode lane + 32 m (only ML >= 32)
     constexpr int ROWS = SWEEP_WARPS / WPR;
+    // measured: two outputs per warp or 8-deep unrolling cost more in occupancy (32-48 -> 90-114 registers) than they
+    // gain in loads in flight, so one output at a time and 4 entries in flight (profiles/README.md)
+    constexpr int NR = 1;                              // outputs a warp works on at a time
+    constexpr int UN = 4;                              // entries per output in flight
     __shared__ double red[(WPR > 1) ? SWEEP_WARPS * M : 1];
     const int *it = (DIR == 0 ? c.lvl_items : c.lvb_items) + 3 * (size_t)(item0 + blockIdx.x);
     const int node = it[0], o0 = it[1], n_o = it[2];
@@ -179,82 +199,106 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_run(dots_ctx_t c, int i
             if (len > 0) l2_prefetch_bulk(panel + out_off(o) * M, (uint32_t)len * M * 8u);
         }
     };
-    prefetch(o0 + rslot);
-    prefetch(o0 + ROWS + rslot);
+#pragma unroll
+    for (int k = 0; k < 2 * NR; ++k) prefetch(o0 + k * ROWS + rslot);
 
-    for (int base = o0; base <= last; base += ROWS) {
-        const int o = base + rslot;
-        const bool valid = o <= last;
-        prefetch(o + 2 * ROWS);
-        double acc[MP];
+    if (FG) {                                          // r_S = hat_S + children's updates landing on S
+        const int ncol = min(s, last + 1);
+        for (int i = threadIdx.x; i < ncol * M; i += SWEEP_THREADS) {
+            const int j = i / M, m = i - j * M;
+            double r = c.hat[(size_t)(off + j) * M + m];
+            const int a = cp0[j], b = cp1[j];
+            if (u0 && a >= 0) r += u0[(size_t)a * M + m];
+            if (u1 && b >= 0) r += u1[(size_t)b * M + m];
+            rsm[i] = r;
+        }
+        __syncthreads();
+    }
+
+    for (int base = o0; base <= last; base += ROWS * NR) {
+        int o[NR], len[NR];
+        const double *pr[NR];
+        int lenmax = 0;
 #pragma unroll
-        for (int m = 0; m < MP; ++m) acc[m] = 0.0;
-        if (valid) {
-            const int len = out_len(o);
-            const double *pr = panel + out_off(o) * M + lane;
-            auto vptr = [&](int e) -> const double * {
-                if (DIR == 0) return c.hat + (size_t)(off + e) * M + lane;
-                const int row = o + e;
-                return (row < s ? c.ywork + (size_t)(off + row) * M : c.hat + (size_t)fidx[row] * M) + lane;
-            };
-            int e = e_first;
-            for (; e + 3 * estep < len; e += 4 * estep) {
-                double p[4][MP], r[4][MP];
+        for (int q = 0; q < NR; ++q) {
+            o[q] = base + q * ROWS + rslot;
+            len[q] = (o[q] <= last) ? out_len(o[q]) : 0;
+            pr[q] = panel + ((o[q] <= last) ? out_off(o[q]) : 0) * M + lane;
+            lenmax = max(lenmax, len[q]);
+            prefetch(o[q] + 2 * NR * ROWS);
+        }
+        double acc[NR][MP];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const double *vp = vptr(e + u * estep);
+        for (int q = 0; q < NR; ++q)
+#pragma unroll
+            for (int m = 0; m < MP; ++m) acc[q][m] = 0.0;
+        auto vptr = [&](int q, int e) -> const double * {
+            if (DIR == 0) return (FG ? rsm + (size_t)e * M : c.hat + (size_t)(off + e) * M) + lane;
+            const int row = o[q] + e;
+            return (row < s ? c.ywork + (size_t)(off + row) * M : c.hat + (size_t)fidx[row] * M) + lane;
+        };
+        for (int e = e_first; e < lenmax; e += UN * estep) {
+            double p[NR][UN][MP], r[NR][UN][MP];
+#pragma unroll
+            for (int u = 0; u < UN; ++u)
+#pragma unroll
+                for (int q = 0; q < NR; ++q) {
+                    const int ee = e + u * estep;
+                    const bool on = ee < len[q];
+                    const double *vp = on ? vptr(q, ee) : nullptr;
 #pragma unroll
                     for (int m = 0; m < MP; ++m) {
-                        p[u][m] = __ldcs(pr + (size_t)(e + u * estep) * M + LSTRIDE * m);
-                        r[u][m] = vp[LSTRIDE * m];
+                        p[q][u][m] = on ? __ldcs(pr[q] + (size_t)ee * M + LSTRIDE * m) : 0.0;
+                        r[q][u][m] = on ? vp[LSTRIDE * m] : 0.0;
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < UN; ++u)
 #pragma unroll
-                    for (int m = 0; m < MP; ++m) acc[m] += p[u][m] * r[u][m];
-            }
-            for (; e < len; e += estep) {
-                const double *vp = vptr(e);
+                for (int q = 0; q < NR; ++q)
 #pragma unroll
-                for (int m = 0; m < MP; ++m) acc[m] += __ldcs(pr + (size_t)e * M + LSTRIDE * m) * vp[LSTRIDE * m];
-            }
+                    for (int m = 0; m < MP; ++m) acc[q][m] += p[q][u][m] * r[q][u][m];
         }
-        if (G > 1) {                                           // fold the entry slots of the warp (fixed order)
 #pragma unroll
-            for (int o2 = ML; o2 < 32; o2 <<= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o2);
-        }
-        const bool writer = (G > 1) ? (grp == 0) : true;
-        if (WPR > 1) {
-            __syncthreads();
+        for (int q = 0; q < NR; ++q) {
+            const bool valid = o[q] <= last;
+            if (G > 1) {                                       // fold the entry slots of the warp (fixed order)
 #pragma unroll
-            for (int m = 0; m < MP; ++m) if (writer) red[warp * M + LSTRIDE * m + lane] = acc[m];
-            __syncthreads();
-            if (cslot == 0) {
+                for (int o2 = ML; o2 < 32; o2 <<= 1) acc[q][0] += __shfl_xor_sync(0xffffffffu, acc[q][0], o2);
+            }
+            const bool writer = (G > 1) ? (grp == 0) : true;
+            if (WPR > 1) {
+                __syncthreads();
 #pragma unroll
-                for (int m = 0; m < MP; ++m) {
-                    double v = 0.0;
+                for (int m = 0; m < MP; ++m) if (writer) red[warp * M + LSTRIDE * m + lane] = acc[q][m];
+                __syncthreads();
+                if (cslot == 0) {
 #pragma unroll
-                    for (int w = 0; w < WPR; ++w) v += red[(rslot * WPR + w) * M + LSTRIDE * m + lane];
-                    acc[m] = v;
+                    for (int m = 0; m < MP; ++m) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int w = 0; w < WPR; ++w) v += red[(rslot * WPR + w) * M + LSTRIDE * m + lane];
+                        acc[q][m] = v;
+                    }
                 }
             }
-        }
-        if (valid && cslot == 0 && writer) {
-            if (DIR == 1) {
+            if (valid && cslot == 0 && writer) {
+                const int oo = o[q];
+                if (DIR == 1) {
 #pragma unroll
-                for (int m = 0; m < MP; ++m) c.hat[(size_t)(off + o) * M + LSTRIDE * m + lane] = -acc[m];
-            } else if (o < s) {
+                    for (int m = 0; m < MP; ++m) c.hat[(size_t)(off + oo) * M + LSTRIDE * m + lane] = -acc[q][m];
+                } else if (oo < s) {
 #pragma unroll
-                for (int m = 0; m < MP; ++m) c.ywork[(size_t)(off + o) * M + LSTRIDE * m + lane] = acc[m];
-            } else if (o - s < b_rows) {
-                const int a = cp0[o], b = cp1[o];
+                    for (int m = 0; m < MP; ++m) c.ywork[(size_t)(off + oo) * M + LSTRIDE * m + lane] = acc[q][m];
+                } else if (oo - s < b_rows) {
+                    const int a = cp0[oo], b = cp1[oo];
 #pragma unroll
-                for (int m = 0; m < MP; ++m) {
-                    double val = 0.0;
-                    if (u0 && a >= 0) val += u0[(size_t)a * M + LSTRIDE * m + lane];
-                    if (u1 && b >= 0) val += u1[(size_t)b * M + LSTRIDE * m + lane];
-                    myupd[(size_t)(o - s) * M + LSTRIDE * m + lane] = val - acc[m];
+                    for (int m = 0; m < MP; ++m) {
+                        double val = 0.0;
+                        if (u0 && a >= 0) val += u0[(size_t)a * M + LSTRIDE * m + lane];
+                        if (u1 && b >= 0) val += u1[(size_t)b * M + LSTRIDE * m + lane];
+                        myupd[(size_t)(oo - s) * M + LSTRIDE * m + lane] = val - acc[q][m];
+                    }
                 }
             }
         }
@@ -263,13 +307,28 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_run(dots_ctx_t c, int i
 
 // ------------------------------------------------------------------------------------------------
 template <int ML, int DIR>
-static int launch_level(const dots_ctx_t *c, int wpr, int i0, int n, cudaStream_t st)
+static int launch_level(const dots_ctx_t *c, int wpr_code, int i0, int n, int stamp, cudaStream_t st)
 {
-    switch (wpr) {
-    case 1: k_sweep_run<ML, 1, DIR><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
-    case 2: k_sweep_run<ML, 2, DIR><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
-    case 4: k_sweep_run<ML, 4, DIR><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
-    default: k_sweep_run<ML, 8, DIR><<<n, SWEEP_THREADS, 0, st>>>(*c, i0); break;
+    const bool fuse = (DIR == 0) && (wpr_code & 16);
+    const size_t smem = fuse ? (size_t)SWEEP_FG_SMAX * ML * sizeof(double) : 0;
+    if (fuse) {
+        static bool configured = false;
+        if (!configured && smem > 48 * 1024) {
+            DOTS_CUDA(cudaFuncSetAttribute(k_sweep_run<ML, 1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DOTS_CUDA(cudaFuncSetAttribute(k_sweep_run<ML, 2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        switch (wpr_code & 15) {
+        case 1: k_sweep_run<ML, 1, 0, true><<<n, SWEEP_THREADS, smem, st>>>(*c, i0, stamp); break;
+        default: k_sweep_run<ML, 2, 0, true><<<n, SWEEP_THREADS, smem, st>>>(*c, i0, stamp); break;
+        }
+    } else {
+        switch (wpr_code & 15) {
+        case 1: k_sweep_run<ML, 1, DIR, false><<<n, SWEEP_THREADS, 0, st>>>(*c, i0, stamp); break;
+        case 2: k_sweep_run<ML, 2, DIR, false><<<n, SWEEP_THREADS, 0, st>>>(*c, i0, stamp); break;
+        case 4: k_sweep_run<ML, 4, DIR, false><<<n, SWEEP_THREADS, 0, st>>>(*c, i0, stamp); break;
+        default: k_sweep_run<ML, 8, DIR, false><<<n, SWEEP_THREADS, 0, st>>>(*c, i0, stamp); break;
+        }
     }
     DOTS_LAUNCH_CHECK();
     return 0;
@@ -280,15 +339,18 @@ static int launch_sweeps(const dots_ctx_t *c, cudaStream_t st)
 {
     for (int lv = 0; lv < c->n_levels; ++lv) {
         const int g0 = c->h_lvn_ptr[lv], gn = c->h_lvn_ptr[lv + 1] - g0;
-        if (lv > 0 && gn > 0) { k_sweep_gather<<<gn, 256, 0, st>>>(*c, g0); DOTS_LAUNCH_CHECK(); }
+        // stamps: slot lv = start of forward level lv (its gather when there is one), slot L + k = start of the k-th backward level
+        const bool fused = (c->h_lvl_wpr[lv] & 16) != 0;      // the level's blocks fold the children's updates themselves
+        const bool gather = lv > 0 && gn > 0 && !fused;
+        if (gather) { k_sweep_gather<<<gn, 256, 0, st>>>(*c, g0, lv); DOTS_LAUNCH_CHECK(); }
         const int i0 = c->h_lvl_ptr[lv], n = c->h_lvl_ptr[lv + 1] - i0;
         if (n <= 0) continue;
-        if (int e = launch_level<ML, 0>(c, c->h_lvl_wpr[lv], i0, n, st)) return e;
+        if (int e = launch_level<ML, 0>(c, c->h_lvl_wpr[lv], i0, n, gather ? -1 : lv, st)) return e;
     }
     for (int lv = c->n_levels - 1; lv >= 0; --lv) {
         const int i0 = c->h_lvb_ptr[lv], n = c->h_lvb_ptr[lv + 1] - i0;
         if (n <= 0) continue;
-        if (int e = launch_level<ML, 1>(c, c->h_lvb_cw[lv], i0, n, st)) return e;
+        if (int e = launch_level<ML, 1>(c, c->h_lvb_cw[lv], i0, n, 2 * c->n_levels - 1 - lv, st)) return e;
     }
     return 0;
 }

@@ -62,16 +62,18 @@ def _sweep_items(sym: nested.Symbolic, n_sm: int, m_pad: int):
         col_eff = float(((s_l / 2 + b_l) * work).sum() / work.sum())
         wpr, rb = pick(s_eff, int((s_l + b_l).sum()))
         cw, cb = pick(col_eff, int(s_l.sum()))
+        has_kids = bool((sym.child[nodes] >= 0).any())
+        fuse = has_kids and wpr <= 2 and int(s_l.max()) <= 64 and os.environ.get("DOTS_FUSE_GATHER", "1") == "1"
         for nd in nodes:
             nrow, ncol = int(sym.s[nd] + sym.b[nd]), int(sym.s[nd])
             fwd += [(int(nd), r0, min(rb, nrow - r0)) for r0 in range(0, nrow, rb)]
             bwd += [(int(nd), c0, min(cb, ncol - c0)) for c0 in range(0, ncol, cb)]
-            if (sym.child[nd] >= 0).any():
+            if (sym.child[nd] >= 0).any() and not fuse:
                 nodes_flat += [(int(nd), j0, min(32, ncol - j0)) for j0 in range(0, ncol, 32)]
         node_ptr.append(len(nodes_flat))
         fwd_ptr.append(len(fwd))
         bwd_ptr.append(len(bwd))
-        wprs.append(wpr)
+        wprs.append(wpr + (16 if fuse else 0))
         cws.append(cw)
     as32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32).reshape(-1, 3)) if a else np.zeros((1, 3), np.int32)
     i32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32))

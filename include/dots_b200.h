@@ -93,7 +93,8 @@ typedef struct dots_ctx {
     const int32_t *h_lvl_ptr;  /* HOST copies of lvl_ptr / lvb_ptr (grid sizing of the per-level launches) */
     const int32_t *h_lvb_ptr;
     const int32_t *h_lvn_ptr;  /* HOST [n_levels+1] ranges into lvn_nodes                             */
-    const int32_t *h_lvl_wpr;  /* HOST [n_levels] warps sharing one panel row in the forward sweep (1,2,4,8) */
+    const int32_t *h_lvl_wpr;  /* HOST [n_levels] warps sharing one panel row in the forward sweep (1,2,4,8); +16: the level's
+                                  blocks fold the children's updates into r_S themselves (no separate gather launch) */
     const int32_t *h_lvb_cw;   /* HOST [n_levels] warps sharing one panel column in the backward sweep (1,2,4,8) */
     int64_t front_total;       /* sum(s+b)                                                            */
 
