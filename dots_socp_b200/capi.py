@@ -51,7 +51,7 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB
+    return os.environ.get("DOTS_LIB", _build.LIB)            # DOTS_LIB: A/B-test an alternative build of the same sources
 
 
 def load(build_if_missing: bool = True):
@@ -60,7 +60,7 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = lib_path()
-    if build_if_missing and _build.needs_build():
+    if build_if_missing and "DOTS_LIB" not in os.environ and _build.needs_build():
         try:
             _build.build()
         except Exception as exc:                      # no nvcc on the box: use the shipped .so if there is one

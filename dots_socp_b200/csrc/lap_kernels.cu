@@ -158,8 +158,11 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) 
 // FG (forward only): the block folds the children's updates into r_S itself and keeps r_S in shared memory (levels
 // whose separators have <= SWEEP_FG_SMAX rows), which removes the separate gather launch of the level.
 #define SWEEP_FG_SMAX 64
+#ifndef SWEEP_MIN_BLOCKS
+#define SWEEP_MIN_BLOCKS 1
+#endif
 template <int ML, int WPR, int DIR, bool FG>
-__global__ void __launch_bounds__(SWEEP_THREADS) k_sweep_run(dots_ctx_t c, int item0, int stamp)
+__global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS) k_sweep_run(dots_ctx_t c, int item0, int stamp)
 {
     sweep_stamp(c, stamp);
     extern __shared__ double rsm[];                    // [s][M] staged r_S (FG only)
