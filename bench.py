@@ -260,15 +260,16 @@ def run_own(args):
     part, comm, tt = eng.part, eng.comm, eng.t
     steps_fn = [
         lambda: capi.check(lib.dots_phi_rhs(ctxp, stream)),
-        lambda: comm.all_gather_into(tt["rhs"], tt["rhs"][part.rank * part.chunk:(part.rank + 1) * part.chunk]),
+        lambda: (eng.fence() if eng.peers else
+                 comm.all_gather_into(tt["rhs"], tt["rhs"][part.rank * part.chunk:(part.rank + 1) * part.chunk])),
         lambda: capi.check(lib.dots_time_transform(ctxp, 0, stream)),
         lambda: capi.check(lib.dots_mode_solves(ctxp, stream)),
         lambda: comm.all_gather_into(tt["hat_all"], tt["hat"]),
         lambda: capi.check(lib.dots_time_transform(ctxp, 1, stream)),
         lambda: capi.check(lib.dots_step_vertex(ctxp, stream)),
-        lambda: eng.exchange_vertex_halo(),
+        lambda: eng.exchange_vertex_halo(pushed=True),
         lambda: capi.check(lib.dots_step_tri(ctxp, 0, stream)),
-        lambda: eng.exchange_corner_halo(),
+        lambda: eng.exchange_corner_halo(fence=False),
     ]
     n_probe = min(args.steps, 20)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(n_probe)]
@@ -328,7 +329,10 @@ def run_own(args):
                              "working set fits in L2 (small config): numbers are launch/latency bound"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": args.steps * eng.launches_per_iteration(),
             "graph": ("cuda graph (one launch per iteration)" if world == 1 else
-                      ("torch CUDA graph incl. NCCL ops" if eng.use_sharded_graphs else f"eager ({eng.graph_error})")),
+                      ("torch CUDA graph incl. NCCL ops" if eng.use_sharded_graphs else "eager launches")),
+            "exchange": ("single GPU" if world == 1 else
+                         ("peer-memory stores (NVLink) + one-element all-reduce fences; NCCL all_gather for the solutions"
+                          if eng.peers else f"NCCL all_gather + isend/irecv ({eng.peer_error})")),
             "roofline": roofline}
     if rank == 0:
         if world == 1 and not args.no_cpu:

@@ -44,7 +44,12 @@ __global__ void __launch_bounds__(256) k_phi_rhs(dots_ctx_t c)
     for (int q = c.vc_ptr[v], qe = c.vc_ptr[v + 1]; q < qe; ++q) divx += cd[c.vc_idx[q]];
     const double bnd = (t == 0) ? c.bnd0[v] : ((t == nT) ? c.bnd1[v] : 0.0);
     const size_t o = (size_t)t * V + v;
-    c.rhs[o] = divt + divx - bnd - eps * av * c.phi[o];
+    const double val = divt + divx - bnd - eps * av * c.phi[o];
+    if (c.peer_rhs[0]) {                              // peer memory: the slab lands in every rank's rhs buffer directly
+        for (int p = 0; p < c.n_ranks; ++p) c.peer_rhs[p][o] = val;
+    } else {
+        c.rhs[o] = val;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -83,12 +88,19 @@ __global__ void __launch_bounds__(256) k_vertex(dots_ctx_t c)
     const double An = (1.0 / c2) * memo_a + (c1 / c2) * (ze + be - zf - bf);                  // :1062
     const double lc = (cong * r / (1. + cong * r)) * (memo_a - An);                           // :1065
 
+    const double mun = mu0 + tau * (dtphi - An - lc);                                         // :718
     c.lam[i] = lam;
     c.z_fst[i] = zf;
     c.z_end[i] = ze;
     c.A[i] = An;
     c.lam_c[i] = lc;
-    c.mu[i] = mu0 + tau * (dtphi - An - lc);                                                  // :718
+    c.mu[i] = mun;
+    if (c.peer_vertex[0] && t == min(c.lvl_end, nT) - 1) {      // last owned step: halo rows of the next rank (peer memory)
+        c.peer_vertex[0][v] = lam;
+        c.peer_vertex[1][v] = An;
+        c.peer_vertex[2][v] = lc;
+        c.peer_vertex[3][v] = mun;
+    }
     c.b_fst[i] = bf + tau * (zf + s * An - d);                                                // :720
     c.b_end[i] = be + tau * (ze - s * An - d);                                                // :722
 }
@@ -213,6 +225,7 @@ __global__ void __launch_bounds__(128, 4) k_tri(dots_ctx_t c)
                     }
                 }
                 cn[(sd * 3 + k) * T] = acc;
+                if (sd == 1 && c.peer_corner && tau == c.lvl_begin && has) c.peer_corner[k * T + f] = acc;   // halo of the previous rank
             }
         }
         double *cd = c.corner_div + (size_t)tau * 3 * T + f;
@@ -378,6 +391,7 @@ __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c)
                         }
                     }
                     cn[(sd * 3 + k) * T] = acc;
+                    if (sd == 1 && c.peer_corner && tau == c.lvl_begin && has) c.peer_corner[k * T + f] = acc;   // halo of the previous rank
                 }
             }
             double *cd = c.corner_div + (size_t)tau * 3 * T + f;

@@ -23,6 +23,20 @@ extern "C" const char *dots_last_error(void) { return g_err; }
 extern "C" int dots_abi_version(void) { return DOTS_ABI_VERSION; }
 extern "C" int dots_ctx_sizeof(void) { return (int)sizeof(dots_ctx_t); }
 
+// Let kernels of the CURRENT device dereference memory of `peer_device` (CUDA IPC mappings of other ranks' buffers).
+extern "C" int dots_enable_peer(int peer_device)
+{
+    int me = -1, can = 0;
+    DOTS_CUDA(cudaGetDevice(&me));
+    if (me == peer_device) return 0;
+    DOTS_CUDA(cudaDeviceCanAccessPeer(&can, me, peer_device));
+    if (!can) { dots_set_error("device %d cannot access device %d", me, peer_device); return DOTS_ERR_BAD_ARG; }
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) { dots_set_error("cudaDeviceEnablePeerAccess(%d) -> %s", peer_device, cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
 #define KKT_THREADS 256
 
 // ---- vertex-side sums: slots 0..3 ------------------------------------------------------------------

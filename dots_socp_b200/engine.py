@@ -270,6 +270,10 @@ class Engine:
         self.use_sharded_graphs = os.environ.get("DOTS_SHARDED_GRAPHS", "0") == "1"
         self._tgraphs, self._tgraph_warm, self.graph_error = {}, {}, None
         self.launches = 0
+        self.peers = False
+        self.peer_error = None
+        if self.comm.enabled and os.environ.get("DOTS_PEER", "0") == "1" and part.world <= 8:
+            self._setup_peers()
         self._push_params()
         torch.cuda.synchronize(dev)
         tm["upload"] = time.perf_counter() - t0
@@ -299,11 +303,68 @@ class Engine:
     def _call(self, fn, *args):
         capi.check(getattr(self.lib, fn)(self._ctxp, *args, self.stream), fn)
 
+    # ------------------------------------------------------------------ peer memory (NVLink stores instead of NCCL copies)
+    def _setup_peers(self):
+        """Map the neighbours' halo rows and every rank's rhs buffer into this process (CUDA IPC through torch's tensor
+        sharing), so that k_vertex / k_tri / k_phi_rhs store their boundary data straight into the consumers' memory.
+        Any failure leaves the NCCL exchanges in place."""
+        try:
+            from torch.multiprocessing.reductions import reduce_tensor
+            part, comm, ctx = self.part, self.comm, self.ctx
+            mine = {n: reduce_tensor(self.slab[n].data) for n in ("lam", "A", "lam_c", "mu", "corner_nrm")}
+            mine["rhs"] = reduce_tensor(self.t["rhs"])
+            everyone = [None] * part.world
+            comm.dist.all_gather_object(everyone, mine, group=comm.group)
+            self._peer_keep = []
+
+            def open_(rank, name):
+                fn, args = everyone[rank][name]
+                ten = fn(*args)
+                self._peer_keep.append(ten)
+                torch.cuda.set_device(self.device)
+                capi.check(self.lib.dots_enable_peer(int(ten.device.index)), "dots_enable_peer")   # me -> owner of `ten`
+                return ten
+
+            if part.rank + 1 < part.world:
+                for i, n in enumerate(("lam", "A", "lam_c", "mu")):
+                    ctx.peer_vertex[i] = open_(part.rank + 1, n)[0].data_ptr()        # row 0 = its step lvl_begin-1
+            if part.rank > 0:
+                ctx.peer_corner = open_(part.rank - 1, "corner_nrm")[-1][1].data_ptr()   # its halo level lvl_end, side 1
+            for r in range(part.world):
+                ctx.peer_rhs[r] = self.t["rhs"].data_ptr() if r == part.rank else open_(r, "rhs").data_ptr()
+            self._fence_t = torch.zeros(1, dtype=torch.float64, device=self.device)
+            ok = torch.ones(1, dtype=torch.float64, device=self.device)
+            comm.dist.all_reduce(ok, op=comm.dist.ReduceOp.MIN, group=comm.group)
+            self.peers = bool(ok.item() == 1.0)
+        except Exception as exc:                                   # pragma: no cover - depends on the node's IPC support
+            self.peer_error = repr(exc)
+            self.peers = False
+            try:
+                bad = torch.zeros(1, dtype=torch.float64, device=self.device)
+                self.comm.dist.all_reduce(bad, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
+            except Exception:
+                pass
+        if not self.peers:
+            ctx = self.ctx
+            for i in range(4):
+                ctx.peer_vertex[i] = None
+            ctx.peer_corner = None
+            for r in range(8):
+                ctx.peer_rhs[r] = None
+
+    def fence(self):
+        """Cross-rank, stream-ordered fence: a one-element all-reduce completes on a rank only after every rank's
+        preceding kernels (and their peer stores) have finished."""
+        self.comm.dist.all_reduce(self._fence_t, group=self.comm.group)
+
     # ------------------------------------------------------------------ halo exchanges (no-ops on one rank)
-    def exchange_vertex_halo(self):
-        """(lam, A, lam_c, mu) of the last owned step -> step lvl_begin-1 of the next rank."""
+    def exchange_vertex_halo(self, pushed=False):
+        """(lam, A, lam_c, mu) of the last owned step -> step lvl_begin-1 of the next rank.  ``pushed``: the producing
+        kernel already stored them through peer memory, only the fence is needed."""
         if not self.comm.enabled:
             return
+        if pushed and self.peers:
+            return self.fence()
         part, sl = self.part, self.slab
         send = None
         if part.rank + 1 < part.world and part.n_steps > 0:
@@ -314,10 +375,14 @@ class Engine:
             for i, n in enumerate(("lam", "A", "lam_c", "mu")):
                 sl[n].level(part.lvl_begin - 1).copy_(recv[i])
 
-    def exchange_corner_halo(self):
-        """side-1 corner norms of the first owned level -> level lvl_end of the previous rank."""
+    def exchange_corner_halo(self, fence=True):
+        """side-1 corner norms of the first owned level -> level lvl_end of the previous rank (k_tri stores them through
+        peer memory when that is set up; then only a fence is left, and inside the iteration not even that: the fence
+        after the next k_phi_rhs orders them before their only reader, k_vertex)."""
         if not self.comm.enabled:
             return
+        if self.peers:
+            return self.fence() if fence else None
         part, sl = self.part, self.slab
         send = sl["corner_nrm"].level(part.lvl_begin)[1].contiguous() if part.rank > 0 else None
         recv = self._halo_c if part.rank + 1 < part.world else None
@@ -369,15 +434,18 @@ class Engine:
         """One iteration across ranks: the same kernels on this rank's slab / modes + the exchanges of dist.py."""
         part, comm, t = self.part, self.comm, self.t
         self._call("dots_phi_rhs")                                                     # own levels of rhs
-        comm.all_gather_into(t["rhs"], t["rhs"][part.rank * part.chunk:(part.rank + 1) * part.chunk])
+        if self.peers:
+            self.fence()                                                               # slabs were stored into every rank's rhs
+        else:
+            comm.all_gather_into(t["rhs"], t["rhs"][part.rank * part.chunk:(part.rank + 1) * part.chunk])
         self._call("dots_time_transform", 0)                                           # all levels -> own modes
         self._call("dots_mode_solves")
         comm.all_gather_into(t["hat_all"], t["hat"])
         self._call("dots_time_transform", 1)                                           # all modes -> own levels (+halo)
         self._call("dots_step_vertex")
-        self.exchange_vertex_halo()
+        self.exchange_vertex_halo(pushed=True)
         self._call("dots_step_tri", int(write_z))
-        self.exchange_corner_halo()
+        self.exchange_corner_halo(fence=False)
 
     def _iterate_sharded_graphed(self, write_z):
         """Replay the sharded iteration (kernels + NCCL collectives) from a torch CUDA graph; the first two calls of each

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DOTS_ABI_VERSION 5
+#define DOTS_ABI_VERSION 6
 
 /* scalar block read by the kernels from device memory (so CUDA graphs stay valid across penalty updates) */
 enum {
@@ -133,9 +133,18 @@ typedef struct dots_ctx {
     int32_t sweep_grid;        /* blocks of the persistent kernel (0 = 2 per SM)                       */
     int32_t reserved0;
     uint64_t *phase_clock;     /* optional [2*n_levels+1]: %globaltimer (ns) at the start and after each sweep phase */
+
+    /* ---- peer memory (multi-GPU, optional; all NULL = exchanges go through the host-side collectives) ----
+     * Pointers into OTHER ranks' device memory (CUDA IPC mappings over NVLink).  When set, the producing kernels store
+     * the neighbour halos / the rhs slab straight into the consumers' buffers, and the host only issues a tiny
+     * stream-ordered all-reduce as the cross-rank fence (dist.py).                                                */
+    double *peer_vertex[4];    /* next rank's halo rows (step lvl_end-1 there = its lvl_begin-1) of lam, A, lam_c, mu  */
+    double *peer_corner;       /* previous rank's corner_nrm halo level (its lvl_end = my lvl_begin), side 1: [3][T]   */
+    double *peer_rhs[8];       /* every rank's rhs buffer (own included) when n_ranks <= 8                             */
 } dots_ctx_t;
 
 /* ------------------------------------------------------------------------------------------------ */
+int  dots_enable_peer(int peer_device);         /* cudaDeviceEnablePeerAccess(current -> peer), idempotent */
 int  dots_abi_version(void);
 int  dots_ctx_sizeof(void);                      /* sizeof(dots_ctx_t): the binding checks its mirror  */
 const char *dots_last_error(void);
