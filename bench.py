@@ -264,7 +264,7 @@ def run_own(args):
                  comm.all_gather_into(tt["rhs"], tt["rhs"][part.rank * part.chunk:(part.rank + 1) * part.chunk])),
         lambda: capi.check(lib.dots_time_transform(ctxp, 0, stream)),
         lambda: capi.check(lib.dots_mode_solves(ctxp, stream)),
-        lambda: comm.all_gather_into(tt["hat_all"], tt["hat"]),
+        lambda: (eng.fence() if eng.peers else comm.all_gather_into(tt["hat_all"], tt["hat"])),
         lambda: capi.check(lib.dots_time_transform(ctxp, 1, stream)),
         lambda: capi.check(lib.dots_step_vertex(ctxp, stream)),
         lambda: eng.exchange_vertex_halo(pushed=True),
@@ -331,7 +331,7 @@ def run_own(args):
             "graph": ("cuda graph (one launch per iteration)" if world == 1 else
                       ("torch CUDA graph incl. NCCL ops" if eng.use_sharded_graphs else "eager launches")),
             "exchange": ("single GPU" if world == 1 else
-                         ("peer-memory stores (NVLink) + one-element all-reduce fences; NCCL all_gather for the solutions"
+                         ("peer memory over NVLink (stores for the rhs slabs and halos, loads for the solutions) + one-element all-reduce fences"
                           if eng.peers else f"NCCL all_gather + isend/irecv ({eng.peer_error})")),
             "roofline": roofline}
     if rank == 0:

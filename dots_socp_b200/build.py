@@ -32,7 +32,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("DOTS_NVCC_EXTRA", "").split()
-    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-o", LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -9,7 +9,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 P_R, P_S, P_D, P_CONG, P_TAU, P_EPS, P_COUNT = 0, 1, 2, 3, 4, 5, 8
 
 _i32p, _i64p, _f64p = C.c_void_p, C.c_void_p, C.c_void_p      # raw device/host addresses
@@ -32,7 +32,7 @@ class DotsCtx(C.Structure):
             "rhs", "hat", "hat_all", "ywork", "upd", "red_part", "red_out")]
         + [("red_blocks", C.c_int32), ("sweep_mode", C.c_int32), ("sweep_grid", C.c_int32), ("reserved0", C.c_int32),
            ("phase_clock", C.c_void_p), ("peer_vertex", C.c_void_p * 4), ("peer_corner", C.c_void_p),
-           ("peer_rhs", C.c_void_p * 8)]
+           ("peer_rhs", C.c_void_p * 8), ("peer_hat", C.c_void_p * 8)]
     )
 
 
@@ -84,6 +84,7 @@ def load(build_if_missing: bool = True):
         "dots_mode_solves": (ctxp, vp), "dots_grad_space": (ctxp, vp, vp, vp), "dots_div_space": (ctxp, vp, vp, vp),
         "dots_graph_create": (ctxp, i, vp, C.POINTER(vp)), "dots_graph_launch": (vp, vp), "dots_graph_destroy": (vp,),
         "dots_factor_small_fronts": (C.POINTER(FrontArgs), i, i, vp), "dots_front_nmax": (), "dots_enable_peer": (i,),
+        "dots_ipc_export": (vp, vp, C.POINTER(C.c_ulonglong)), "dots_ipc_import": (vp, C.c_ulonglong, C.POINTER(vp)),
     }
     for name, args in protos.items():
         fn = getattr(lib, name)
@@ -96,7 +97,7 @@ EXPORTS = ("dots_abi_version", "dots_ctx_sizeof", "dots_last_error", "dots_step_
            "dots_step_tri", "dots_iterate", "dots_refresh_corner_terms", "dots_scale_dual", "dots_scale_z",
            "dots_set_params", "dots_kkt_sums", "dots_phi_rhs", "dots_time_transform", "dots_mode_solves",
            "dots_grad_space", "dots_div_space", "dots_graph_create", "dots_graph_launch", "dots_graph_destroy",
-           "dots_factor_small_fronts", "dots_front_nmax", "dots_enable_peer")
+           "dots_factor_small_fronts", "dots_front_nmax", "dots_enable_peer", "dots_ipc_export", "dots_ipc_import")
 
 
 def check(code: int, what: str = ""):

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <dlfcn.h>
 
 static thread_local char g_err[512] = "";
 void dots_set_error(const char *fmt, ...)
@@ -34,6 +35,38 @@ extern "C" int dots_enable_peer(int peer_device)
     cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
     if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
     if (e != cudaSuccess) { dots_set_error("cudaDeviceEnablePeerAccess(%d) -> %s", peer_device, cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+// CUDA IPC export / import of a device buffer (peer-memory exchange between the ranks of one node).
+// export: handle of the allocation that contains `dev_ptr` + the byte offset of `dev_ptr` inside it.
+extern "C" int dots_ipc_export(const void *dev_ptr, void *handle_out_64, unsigned long long *offset_out)
+{
+    // the driver entry point is resolved at run time so that the library itself does not link against libcuda
+    typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+    static range_fn get_range = nullptr;
+    if (!get_range) {
+        void *drv = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (drv) get_range = (range_fn)dlsym(drv, "cuMemGetAddressRange_v2");
+        if (!get_range) { dots_set_error("cuMemGetAddressRange_v2 not available"); return DOTS_ERR_BAD_ARG; }
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (get_range(&base, &size, (unsigned long long)dev_ptr) != 0) { dots_set_error("cuMemGetAddressRange failed"); return DOTS_ERR_BAD_ARG; }
+    cudaIpcMemHandle_t h;
+    DOTS_CUDA(cudaIpcGetMemHandle(&h, (void *)base));
+    memcpy(handle_out_64, &h, sizeof(h));
+    *offset_out = (unsigned long long)dev_ptr - base;
+    return 0;
+}
+// import in the CURRENT device's context (lazy peer access), so kernels of this device may dereference the result
+extern "C" int dots_ipc_import(const void *handle_64, unsigned long long offset, void **dev_ptr_out)
+{
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_64, sizeof(h));
+    void *base = nullptr;
+    DOTS_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr_out = (char *)base + offset;
     return 0;
 }
 

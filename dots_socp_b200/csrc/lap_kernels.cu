@@ -64,7 +64,10 @@ __global__ void __launch_bounds__(256) k_time_mma(dots_ctx_t c, int n_tiles)
                     } else {
                         const int vv = i / K, p = i - vv * K;
                         const int rk = p / M, pos = p - rk * M;     // gathered layout [rank][v][m_pad]
-                        if (v0 + vv < V) val[u] = c.hat_all[((size_t)rk * V + v0 + vv) * M + pos];
+                        if (v0 + vv < V) {
+                            val[u] = c.peer_hat[0] ? c.peer_hat[rk][(size_t)(v0 + vv) * M + pos]      // peer memory (NVLink loads)
+                                                   : c.hat_all[((size_t)rk * V + v0 + vv) * M + pos];
+                        }
                     }
                 }
             }

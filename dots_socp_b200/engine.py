@@ -272,7 +272,7 @@ class Engine:
         self.launches = 0
         self.peers = False
         self.peer_error = None
-        if self.comm.enabled and os.environ.get("DOTS_PEER", "0") == "1" and part.world <= 8:
+        if self.comm.enabled and os.environ.get("DOTS_PEER", "1") == "1" and part.world <= 8:
             self._setup_peers()
         self._push_params()
         torch.cuda.synchronize(dev)
@@ -309,29 +309,41 @@ class Engine:
         sharing), so that k_vertex / k_tri / k_phi_rhs store their boundary data straight into the consumers' memory.
         Any failure leaves the NCCL exchanges in place."""
         try:
-            from torch.multiprocessing.reductions import reduce_tensor
             part, comm, ctx = self.part, self.comm, self.ctx
-            mine = {n: reduce_tensor(self.slab[n].data) for n in ("lam", "A", "lam_c", "mu", "corner_nrm")}
-            mine["rhs"] = reduce_tensor(self.t["rhs"])
+            torch.cuda.set_device(self.device)
+
+            def export(ten):
+                handle, off = C.create_string_buffer(64), C.c_ulonglong(0)
+                capi.check(self.lib.dots_ipc_export(ten.data_ptr(), handle, C.byref(off)), "dots_ipc_export")
+                return bytes(handle.raw), int(off.value), self.device.index
+
+            mine = {n: export(self.slab[n].data) for n in ("lam", "A", "lam_c", "mu", "corner_nrm")}
+            mine["rhs"] = export(self.t["rhs"])
+            mine["hat"] = export(self.t["hat"])
             everyone = [None] * part.world
             comm.dist.all_gather_object(everyone, mine, group=comm.group)
-            self._peer_keep = []
+            self._ipc_cache = {}
 
             def open_(rank, name):
-                fn, args = everyone[rank][name]
-                ten = fn(*args)
-                self._peer_keep.append(ten)
-                torch.cuda.set_device(self.device)
-                capi.check(self.lib.dots_enable_peer(int(ten.device.index)), "dots_enable_peer")   # me -> owner of `ten`
-                return ten
+                handle, off, dev_index = everyone[rank][name]
+                if handle not in self._ipc_cache:               # one mapping per exporting allocation
+                    capi.check(self.lib.dots_enable_peer(int(dev_index)), "dots_enable_peer")
+                    base = C.c_void_p()
+                    capi.check(self.lib.dots_ipc_import(handle, 0, C.byref(base)), "dots_ipc_import")
+                    self._ipc_cache[handle] = base.value
+                return self._ipc_cache[handle] + off
 
+            V, T = self.V, self.T
             if part.rank + 1 < part.world:
                 for i, n in enumerate(("lam", "A", "lam_c", "mu")):
-                    ctx.peer_vertex[i] = open_(part.rank + 1, n)[0].data_ptr()        # row 0 = its step lvl_begin-1
+                    ctx.peer_vertex[i] = open_(part.rank + 1, n)                      # row 0 = its step lvl_begin-1
             if part.rank > 0:
-                ctx.peer_corner = open_(part.rank - 1, "corner_nrm")[-1][1].data_ptr()   # its halo level lvl_end, side 1
+                prev = dd.partition(self.nT, part.rank - 1, part.world)
+                halo_elems = (prev.n_levels * 2 + 1) * 3 * T                          # its halo level lvl_end, side 1
+                ctx.peer_corner = open_(part.rank - 1, "corner_nrm") + halo_elems * 8
             for r in range(part.world):
-                ctx.peer_rhs[r] = self.t["rhs"].data_ptr() if r == part.rank else open_(r, "rhs").data_ptr()
+                ctx.peer_rhs[r] = self.t["rhs"].data_ptr() if r == part.rank else open_(r, "rhs")
+                ctx.peer_hat[r] = self.t["hat"].data_ptr() if r == part.rank else open_(r, "hat")
             self._fence_t = torch.zeros(1, dtype=torch.float64, device=self.device)
             ok = torch.ones(1, dtype=torch.float64, device=self.device)
             comm.dist.all_reduce(ok, op=comm.dist.ReduceOp.MIN, group=comm.group)
@@ -351,6 +363,7 @@ class Engine:
             ctx.peer_corner = None
             for r in range(8):
                 ctx.peer_rhs[r] = None
+                ctx.peer_hat[r] = None
 
     def fence(self):
         """Cross-rank, stream-ordered fence: a one-element all-reduce completes on a rank only after every rank's
@@ -440,7 +453,10 @@ class Engine:
             comm.all_gather_into(t["rhs"], t["rhs"][part.rank * part.chunk:(part.rank + 1) * part.chunk])
         self._call("dots_time_transform", 0)                                           # all levels -> own modes
         self._call("dots_mode_solves")
-        comm.all_gather_into(t["hat_all"], t["hat"])
+        if self.peers:
+            self.fence()                                                               # the inverse transform reads the peers' `hat`
+        else:
+            comm.all_gather_into(t["hat_all"], t["hat"])
         self._call("dots_time_transform", 1)                                           # all modes -> own levels (+halo)
         self._call("dots_step_vertex")
         self.exchange_vertex_halo(pushed=True)

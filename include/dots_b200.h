@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DOTS_ABI_VERSION 6
+#define DOTS_ABI_VERSION 7
 
 /* scalar block read by the kernels from device memory (so CUDA graphs stay valid across penalty updates) */
 enum {
@@ -141,10 +141,15 @@ typedef struct dots_ctx {
     double *peer_vertex[4];    /* next rank's halo rows (step lvl_end-1 there = its lvl_begin-1) of lam, A, lam_c, mu  */
     double *peer_corner;       /* previous rank's corner_nrm halo level (its lvl_end = my lvl_begin), side 1: [3][T]   */
     double *peer_rhs[8];       /* every rank's rhs buffer (own included) when n_ranks <= 8                             */
+    const double *peer_hat[8]; /* every rank's solution buffer `hat` (own included): the inverse transform reads the other
+                                  ranks' modes straight from their memory instead of from a gathered copy             */
 } dots_ctx_t;
 
 /* ------------------------------------------------------------------------------------------------ */
 int  dots_enable_peer(int peer_device);         /* cudaDeviceEnablePeerAccess(current -> peer), idempotent */
+/* CUDA IPC hand-over of a device buffer between the ranks of one node (64-byte handle + offset inside the allocation) */
+int  dots_ipc_export(const void *dev_ptr, void *handle_out_64, unsigned long long *offset_out);
+int  dots_ipc_import(const void *handle_64, unsigned long long offset, void **dev_ptr_out);
 int  dots_abi_version(void);
 int  dots_ctx_sizeof(void);                      /* sizeof(dots_ctx_t): the binding checks its mirror  */
 const char *dots_last_error(void);
