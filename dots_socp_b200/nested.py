@@ -431,7 +431,7 @@ def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shif
     for lv, nodes in enumerate(levels):
         b_l = sym.b[nodes].astype(np.int64)
         offs = np.concatenate([[0], np.cumsum(b_l * b_l)])
-        buf = torch.empty((max(1, int(offs[-1])), m_pad), dtype=torch.float64, device=device)
+        buf = torch.zeros((max(1, int(offs[-1])), m_pad), dtype=torch.float64, device=device)
         level_buf[lv] = buf
         for nd, o0, bb in zip(nodes, offs[:-1], b_l):
             if bb:

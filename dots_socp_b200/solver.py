@@ -151,6 +151,8 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
         errs = lazy.collect()                                                             # :739-740
         org = [e[0] for e in errs]
         sec = [e[1] for e in errs]
+        if any(v is not None and v != v for v in org):
+            raise FloatingPointError(f"non-finite KKT residual at iteration {it}: {org} (device state is corrupt)")
         if will_check:
             torch.cuda.current_stream(eng.device).synchronize()
             hist.add_time(STEP_TAG, ev_a.elapsed_time(ev_b) * 1e-3)

@@ -67,6 +67,9 @@ def test_sharded_solver_matches_single_gpu_and_reference(tmp_path, golden, name,
     eng.adjust_penalty(1.35)
     eng.iterate(5, write_z=True)
     ref = eng.get_state()
+    bad_multi = [k for k in ref if not np.isfinite(got["st_" + k]).all()]
+    bad_single = [k for k, v in ref.items() if not np.isfinite(v).all()]
+    assert not bad_multi and not bad_single, f"non-finite state: sharded run {bad_multi}, single-GPU run {bad_single}"
     for k, v in ref.items():
         a = got["st_" + k]
         if k == "phi":
