@@ -50,21 +50,34 @@ __global__ void __launch_bounds__(256) k_time_mma(dots_ctx_t c, int n_tiles)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int v0 = tile * TT_VT;
         __syncthreads();
-        if (DIR == 0) {
-            for (int i = tid; i < K * TT_VT; i += 256) {
-                const int p = i / TT_VT, vv = i - p * TT_VT;
-                As[vv * lda + p] = (p < nt1 && v0 + vv < V) ? c.rhs[(size_t)p * V + v0 + vv] : 0.0;
-            }
-        } else {
-            for (int i = tid; i < TT_VT * K; i += 256) {
-                const int vv = i / K, p = i - vv * K;
-                const int rk = p / M, pos = p - rk * M;     // gathered layout [rank][v][m_pad]
-                double val = 0.0;
-                if (v0 + vv < V) {
-                    val = c.peer_hat[0] ? c.peer_hat[rk][(size_t)(v0 + vv) * M + pos]              // peer memory (NVLink loads)
-                                        : c.hat_all[((size_t)rk * V + v0 + vv) * M + pos];
+        // tile load in batches of 8 independent global loads per thread (all in flight before the first smem store)
+        for (int i0 = tid; i0 < K * TT_VT; i0 += 256 * 8) {
+            double val[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * 256;
+                val[u] = 0.0;
+                if (i < K * TT_VT) {
+                    if (DIR == 0) {
+                        const int p = i / TT_VT, vv = i - p * TT_VT;
+                        if (p < nt1 && v0 + vv < V) val[u] = c.rhs[(size_t)p * V + v0 + vv];
+                    } else {
+                        const int vv = i / K, p = i - vv * K;
+                        const int rk = p / M, pos = p - rk * M;     // gathered layout [rank][v][m_pad]
+                        if (v0 + vv < V) {
+                            val[u] = c.peer_hat[0] ? c.peer_hat[rk][(size_t)(v0 + vv) * M + pos]      // peer memory (NVLink loads)
+                                                   : c.hat_all[((size_t)rk * V + v0 + vv) * M + pos];
+                        }
+                    }
                 }
-                As[vv * lda + p] = val;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * 256;
+                if (i < K * TT_VT) {
+                    if (DIR == 0) { const int p = i / TT_VT, vv = i - p * TT_VT; As[vv * lda + p] = val[u]; }
+                    else { const int vv = i / K, p = i - vv * K; As[vv * lda + p] = val[u]; }
+                }
             }
         }
         __syncthreads();
