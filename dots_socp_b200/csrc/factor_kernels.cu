@@ -50,8 +50,11 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front_small(dots_front_args_t
         }
     }
     __syncthreads();
-    for (int r = tid; r < s; r += FRONT_THREADS) F[r * ld + r] += shift * a.mass[off + r];
-    if (tid == 0 && node == a.pin_node && shift == 0.0 && s > 0) F[(s - 1) * ld + s - 1] += a.pin_value;
+    // the pin of the singular mode goes through the SAME thread that owns the last diagonal entry: a second thread
+    // updating F[s-1][s-1] here raced with it (lost update -> zero pivot -> NaN in mode 0 on small meshes)
+    const bool pinned = node == a.pin_node && shift == 0.0;
+    for (int r = tid; r < s; r += FRONT_THREADS)
+        F[r * ld + r] += shift * a.mass[off + r] + ((pinned && r == s - 1) ? a.pin_value : 0.0);
     __syncthreads();
     // ---- extend-add the children's update matrices
     for (int slot = 0; slot < 2; ++slot) {
