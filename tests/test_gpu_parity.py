@@ -251,3 +251,25 @@ def test_setup_factorisation_kernel_matches_library_path_row_f1(example, leaf, n
     scale = ref.abs().max().item()
     assert (got - ref).abs().max().item() / scale < 1e-11
     assert (got_t - ref_t).abs().max().item() / scale < 1e-11
+
+
+def test_small_root_front_is_pinned_deterministically():
+    """Meshes whose ROOT separator front fits the small-front kernel (<= 96 rows): the singular time mode must be
+    pinned by exactly one thread (regression test for a lost-update race that produced NaN in mode 0)."""
+    from dots_socp_b200 import nested, surface, capi
+    from dots_socp_b200.engine import time_basis
+    geo, _ = synth.example("icosphere3")
+    v, t = geo["vertices"], geo["triangles"]
+    K = surface.stiffness_matrix(v, t)
+    mass = surface.incident_area_sum(v.shape[0], t, surface.triangle_areas(v, t)) / 3.0
+    sym = nested.analyse(v, K, leaf_size=8)
+    assert int(sym.s[-1] + sym.b[-1]) <= capi.load().dots_front_nmax()
+    _, lam = time_basis(31)
+    dev = torch.device("cuda:0")
+    first = None
+    for _ in range(25):
+        p, _pt = nested.factor_hybrid_device(sym, K, mass, -lam, 32, dev, capi.load(),
+                                             lambda: torch.cuda.current_stream(dev).cuda_stream)
+        assert torch.isfinite(p).all()
+        first = p if first is None else first
+        assert torch.equal(p, first)
