@@ -63,10 +63,14 @@ __global__ void __launch_bounds__(256) k_time_mma(dots_ctx_t c, int n_tiles)
                         if (p < nt1 && v0 + vv < V) val[u] = c.rhs[(size_t)p * V + v0 + vv];
                     } else {
                         const int vv = i / K, p = i - vv * K;
-                        const int rk = p / M, pos = p - rk * M;     // gathered layout [rank][v][m_pad]
                         if (v0 + vv < V) {
-                            val[u] = c.peer_hat[0] ? c.peer_hat[rk][(size_t)(v0 + vv) * M + pos]      // peer memory (NVLink loads)
-                                                   : c.hat_all[((size_t)rk * V + v0 + vv) * M + pos];
+                            if (c.n_ranks == 1) {                   // K == M: the tile is a contiguous run of `hat`
+                                val[u] = c.hat[(size_t)(v0 + vv) * M + p];
+                            } else {
+                                const int rk = p / M, pos = p - rk * M;     // gathered layout [rank][v][m_pad]
+                                val[u] = c.peer_hat[0] ? c.peer_hat[rk][(size_t)(v0 + vv) * M + pos]      // peer memory (NVLink loads)
+                                                       : c.hat_all[((size_t)rk * V + v0 + vv) * M + pos];
+                            }
                         }
                     }
                 }

@@ -655,6 +655,27 @@ class Engine:
         names = names or (STATE_VERTEX + STATE_TRI + STATE_CORNER)
         return {n: self.from_internal(n).cpu().numpy() for n in names}
 
+    def _download(self, ten):
+        """Device tensor -> numpy through a pinned staging buffer (about 2x the pageable rate for the 0.5 GB fields)."""
+        host = torch.empty(ten.shape, dtype=ten.dtype, pin_memory=True)
+        host.copy_(ten, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host.numpy()
+
+    def dot_solution(self, geometry, centred):
+        """The DOT-unit solution of utils/type.py:48-65 (mu * area_v / 3, E * area_f) and, if ``centred``, the time-centred
+        mu of socp/solver_decorator.py:32-34, formed on the device so that only the final mu and E cross PCIe."""
+        dev = self.device
+        av = torch.as_tensor(np.asarray(geometry["area_vertices"], dtype=np.float64), device=dev)[None, :] / 3.0
+        af = torch.as_tensor(np.asarray(geometry["area_triangles"], dtype=np.float64), device=dev)[None, :, None]
+        mu = (self.from_internal("mu") * self.r) * av
+        if centred:
+            mu0 = torch.as_tensor(np.asarray(geometry["mu0"], dtype=np.float64), device=dev)[None, :]
+            mu1 = torch.as_tensor(np.asarray(geometry["mu1"], dtype=np.float64), device=dev)[None, :]
+            mu = torch.cat([mu0, 0.5 * (mu[:-1] + mu[1:]), mu1], dim=0)
+        E = (self.from_internal("E") * self.r) * af
+        return dict(mu=self._download(mu), E=self._download(E))
+
     def solution(self, keys=None):
         """Un-scaled solution dict with the reference's keys and layouts (:397-405, :855-869).
 

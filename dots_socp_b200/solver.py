@@ -78,13 +78,15 @@ def _warm_start(eng: Engine, init):
 def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8), tol=1e-4, tau=1.90,
                 is_palm=False, is_multi_threads=True, is_z_scaling=True, is_constant_scaling=False,
                 check_kkt_step_by_step=False, init_solution=None, tol_checkpoints=None, time_limit=1000,
-                device=None, leaf_size=16, show_progress=False, return_engine=False, comm=None, solution_keys=None):
+                device=None, leaf_size=16, show_progress=False, return_engine=False, comm=None, solution_keys=None,
+                dot_units=None):
     """B200 implementation of ``dot_surface_socp.socp.solver_socp.solver_socp``.
 
     Extra keyword arguments (``device``, ``leaf_size``, ``show_progress``, ``return_engine``, ``comm``) are additions;
     with torch.distributed initialised (one process per GPU) the problem is sharded over the ranks of ``comm``
     (default: the world group) and every rank returns the full solution; ``solution_keys`` limits which of the twelve
-    solution arrays are converted and copied to the host (default: all, as the reference returns them);
+    solution arrays are converted and copied to the host (default: all, as the reference returns them); ``dot_units``
+    ("staggered" / "centred", set by ``solver_raw`` / ``solver``) returns the DOT-unit ``mu``, ``E`` formed on the device;
     ``is_multi_threads`` is accepted and ignored (the two reference threads become stream order).
     ``is_palm=True`` and ``is_constant_scaling=True`` are solver-only knobs that the reference's CLI /
     interface cannot reach (interface.py:275-284); they are not built and raise."""
@@ -192,7 +194,10 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
     hist.kkt_seconds = kkt_seconds
     hist.evaluations = list(lazy.evaluations)
     hist.gpu_launches = eng.launches
-    solution = eng.solution(solution_keys)                                                # :845, :855-869
+    if dot_units is None:
+        solution = eng.solution(solution_keys)                                            # :845, :855-869
+    else:                                                  # decorators' translate / centring done on the device
+        solution = eng.dot_solution(geometry, centred=(dot_units == "centred"))
     solution["checkpoints"] = checkpoints if checkpoints else None
     cong_norm = (f"{np.linalg.norm(solution['lambda_c'] - congestion * solution['mu']):.2f}"
                  if "lambda_c" in solution and "mu" in solution else "n/a")
@@ -222,24 +227,35 @@ def _centre_in_time(sol, mu0, mu1):
     sol["mu"] = np.concatenate([mu0[None, :], mid, mu1[None, :]], axis=0)
 
 
-def solver_raw(n_time, geometry, **kwargs):
-    """DOT-unit solution on the staggered time grid (reference name ``dot_solver_socp``).
+def _dot_checkpoints(sol, geometry, centred):
+    """Checkpoints (few, small) keep the host path of utils/type.py:54-63 / solver_decorator.py:50-52."""
+    cps = sol.get("checkpoints")
+    if not cps:
+        sol.pop("checkpoints", None)
+        return
+    av = np.asarray(geometry["area_vertices"])[None, :] / 3.0
+    af = np.asarray(geometry["area_triangles"])[None, :, None]
+    out = [dict(mu=c["mu"] * av, E=c["E"] * af, iteration=c["iteration"], time=c["time"], kkt=c["kkt"]) for c in cps]
+    if centred:
+        for c in out:
+            _centre_in_time(c, np.asarray(geometry["mu0"]), np.asarray(geometry["mu1"]))
+    sol["checkpoints"] = out
 
-    Only ``mu`` and ``E`` (what the DOT solution consists of, utils/type.py:40-65) leave the device."""
-    kwargs.setdefault("solution_keys", ("mu", "E"))
-    res = solver_socp(n_time, geometry, **kwargs)
-    return (translate_solution_socp_to_dot(res[0], geometry),) + tuple(res[1:])
+
+def solver_raw(n_time, geometry, **kwargs):
+    """DOT-unit solution on the staggered time grid (reference name ``dot_solver_socp``): solver_socp followed by
+    translate_solution_socp_to_dot (socp/solver_decorator.py:10-26), the translation running on the device."""
+    res = solver_socp(n_time, geometry, dot_units="staggered", **kwargs)
+    _dot_checkpoints(res[0], geometry, centred=False)
+    return res
 
 
 def solver(n_time, geometry, **kwargs):
-    """DOT-unit solution on the time-centred grid incl. mu0 / mu1 (reference name ``dot_solver_socp_center``)."""
-    res = solver_raw(n_time, geometry, **kwargs)
-    sol = res[0]
-    mu0, mu1 = np.asarray(geometry["mu0"]), np.asarray(geometry["mu1"])
-    _centre_in_time(sol, mu0, mu1)
-    for c in sol.get("checkpoints") or []:
-        _centre_in_time(c, mu0, mu1)
-    return res if len(res) > 2 else (sol, res[1])
+    """DOT-unit solution on the time-centred grid incl. mu0 / mu1 (reference name ``dot_solver_socp_center``,
+    socp/solver_decorator.py:29-54)."""
+    res = solver_socp(n_time, geometry, dot_units="centred", **kwargs)
+    _dot_checkpoints(res[0], geometry, centred=True)
+    return res
 
 
 solver_raw.__name__ = "dot_solver_socp"

@@ -209,6 +209,14 @@ def test_drop_in_decorators_and_checkpoints():
     assert sol["checkpoints"] and sol["checkpoints"][0]["mu"].shape == (8, V)
     with pytest.raises(ValueError):
         b200.solver_socp(7, geo, tol=1e-3, tol_checkpoints=[1e-4])
+    # the device-side translation of solver / solver_raw equals the reference decorators applied on the host
+    from dots_socp_b200.solver import translate_solution_socp_to_dot
+    full, _ = b200.solver_socp(7, geo, tol=1e-3, nit=400, leaf_size=8)
+    raw, _ = b200.solver_raw(7, geo, tol=1e-3, nit=400, leaf_size=8)
+    host = translate_solution_socp_to_dot(full, geo)
+    assert rel(raw["mu"], host["mu"]) < 1e-13 and rel(raw["E"], host["E"]) < 1e-13
+    mid = 0.5 * (host["mu"][:-1] + host["mu"][1:])
+    assert rel(sol["mu"][1:-1], mid) < 1e-13 and rel(sol["E"], host["E"]) < 1e-13
 
 
 def test_large_problem_properties():
