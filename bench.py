@@ -85,7 +85,7 @@ def kernel_bytes(V, T, nT, m_pad, sym):
     rhs = 8 * (3 * a + (nT + 1) * 3 * T + 2 * V + c + V) + 4 * (V + 1 + 3 * T)
     ttr = 8 * (c + V * m_pad) * 2
     sweeps = 8 * m_pad * (2 * sym.panel_entries + 6 * V + 3 * int(sym.upd_off[-1]))
-    return {"k_tri": tri, "k_vertex": vert, "k_phi_rhs": rhs, "k_time_fwd+k_time_bwd": ttr, "k_sweep_fwd+k_sweep_bwd": sweeps}
+    return {"k_tri_tma": tri, "k_vertex": vert, "k_phi_rhs": rhs, "k_time_mma": ttr, "k_sweep_run+k_sweep_gather": sweeps}
 
 
 class ClockSampler:
@@ -255,7 +255,7 @@ def run_own(args):
     value = 1e3 / ms_per_step
 
     # ---- per-kernel-group durations, measured live (second pass, events between the step calls) ------
-    names = ["k_phi_rhs", "comm:all_gather(rhs)", "k_time_fwd", "k_sweep_fwd+k_sweep_bwd", "comm:all_gather(hat)", "k_time_bwd",
+    names = ["k_phi_rhs", "comm:all_gather(rhs)", "k_time_fwd", "k_sweep_run+k_sweep_gather", "comm:all_gather(hat)", "k_time_bwd",
              "k_vertex", "comm:halo(vertex)", "k_tri", "comm:halo(corner)"]
     part, comm, tt = eng.part, eng.comm, eng.t
     steps_fn = [
@@ -286,8 +286,8 @@ def run_own(args):
         tmax = torch.tensor([raw[n] for n in names], device="cuda", dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         raw = {n: float(v) for n, v in zip(names, tmax.tolist())}
-    groups = {"k_phi_rhs": raw["k_phi_rhs"], "k_time_fwd+k_time_bwd": raw["k_time_fwd"] + raw["k_time_bwd"],
-              "k_sweep_fwd+k_sweep_bwd": raw["k_sweep_fwd+k_sweep_bwd"], "k_vertex": raw["k_vertex"], "k_tri": raw["k_tri"]}
+    groups = {"k_phi_rhs": raw["k_phi_rhs"], "k_time_mma": raw["k_time_fwd"] + raw["k_time_bwd"],
+              "k_sweep_run+k_sweep_gather": raw["k_sweep_run+k_sweep_gather"], "k_vertex": raw["k_vertex"], "k_tri_tma": raw["k_tri"]}
     comm_ms = {n: round(raw[n], 4) for n in names if n.startswith("comm:")} if world > 1 else {}
     peak, peak_src = peaks()
     kb = {k: v / world for k, v in kernel_bytes(V, T, n_time, n_time + 1, eng.sym).items()}     # per GPU
