@@ -48,6 +48,8 @@ WORKLOADS = {
     "icosphere6_nt63": ("icosphere6", 63, 0.0, "icosphere4"),
     "knots5class_nt31_c01": ("knot", 31, 0.1, "knot"),
     "knots5class_nt31": ("knot", 31, 0.0, "knot"),
+    "knots5class_nt63": ("knot", 63, 0.0, "knot"),                 # BASELINE configs[2]: time-direction scaling
+    "knots5class_nt127": ("knot", 127, 0.0, "knot"),
     "icosphere3_nt31": ("icosphere3", 31, 0.0, "icosphere3"),
 }
 

@@ -664,7 +664,8 @@ class Engine:
 
     def dot_solution(self, geometry, centred):
         """The DOT-unit solution of utils/type.py:48-65 (mu * area_v / 3, E * area_f) and, if ``centred``, the time-centred
-        mu of socp/solver_decorator.py:32-34, formed on the device so that only the final mu and E cross PCIe."""
+        mu of socp/solver_decorator.py:32-34, formed on the device so that only the final mu and E cross PCIe.  The mass
+        diagnostics the caller prints (interface.py:313-314) come along as ``diagnostics`` (2 x (nT [+1]) doubles)."""
         dev = self.device
         av = torch.as_tensor(np.asarray(geometry["area_vertices"], dtype=np.float64), device=dev)[None, :] / 3.0
         af = torch.as_tensor(np.asarray(geometry["area_triangles"], dtype=np.float64), device=dev)[None, :, None]
@@ -674,7 +675,13 @@ class Engine:
             mu1 = torch.as_tensor(np.asarray(geometry["mu1"], dtype=np.float64), device=dev)[None, :]
             mu = torch.cat([mu0, 0.5 * (mu[:-1] + mu[1:]), mu1], dim=0)
         E = (self.from_internal("E") * self.r) * af
-        return dict(mu=self._download(mu), E=self._download(E))
+        # utils/evaluate_solution.py:7-45 on the device: per-layer mass and per-layer negative mass of the returned mu
+        layers = torch.stack([mu.sum(dim=1), torch.where(mu < 0, mu, torch.zeros_like(mu)).sum(dim=1)]).cpu().numpy()
+        n = layers.shape[1]
+        diagnostics = dict(mass_time_layers=layers[0], negative_mass_time_layers=layers[1],
+                           mass_conservation=float(np.linalg.norm(layers[0] - 1.0) / np.sqrt(n)),
+                           negative_mass=float(np.linalg.norm(layers[1]) / np.sqrt(n)))
+        return dict(mu=self._download(mu), E=self._download(E), diagnostics=diagnostics)
 
     def solution(self, keys=None):
         """Un-scaled solution dict with the reference's keys and layouts (:397-405, :855-869).

@@ -109,6 +109,38 @@ def hex_plane(n: int):
     return verts, np.concatenate(tris, axis=0).astype(np.int64)
 
 
+def torus(n_u: int = 100, n_v: int = 40, big_r: float = 1.0, small_r: float = 0.35):
+    """Closed torus, V = n_u * n_v, T = 2V (stand-in for the reference's genus-1 example ``ring``)."""
+    return knot_tube(p=1, q=0, big_r=big_r, amp=0.0, n_u=n_u, n_v=n_v, tube_r=small_r)
+
+
+def deformed_sphere(level: int, axes=(1.0, 1.0, 1.0), amp: float = 0.0, freq: int = 3):
+    """Icosphere pushed to an ellipsoid with semi-axes ``axes`` and a smooth radial ripple ``1 + amp*sin*sin*cos``:
+    closed genus-0 stand-ins of the bundled scanned models (airplane, armadillo, hand, bunny) at matching sizes."""
+    v, t = icosphere(level)
+    rad = 1.0 + amp * np.sin(freq * np.pi * v[:, 0]) * np.sin(freq * np.pi * v[:, 1]) * np.cos(freq * np.pi * v[:, 2])
+    return v * rad[:, None] * np.asarray(axes, dtype=np.float64)[None, :], t
+
+
+def punctured_sphere(level: int, z_cut: float = 0.8):
+    """Icosphere with the polar cap z > z_cut removed (one boundary loop; stand-in for ``punctured_ball``)."""
+    v, t = icosphere(level)
+    keep_t = (v[t][:, :, 2] <= z_cut).all(axis=1)
+    t = t[keep_t]
+    used = np.zeros(v.shape[0], dtype=bool)
+    used[t.reshape(-1)] = True
+    new_id = np.cumsum(used) - 1
+    return v[used], new_id[t]
+
+
+def hills(n: int = 60, amp: float = 0.15):
+    """Height field over the hexagonal plane grid (open surface with boundary; stand-in for ``hills``)."""
+    v, t = hex_plane(n)
+    v = v.copy()
+    v[:, 2] = amp * (np.sin(3 * np.pi * v[:, 0]) * np.sin(2 * np.pi * v[:, 1]) + 0.5 * np.cos(5 * np.pi * v[:, 0] * v[:, 1]))
+    return v, t
+
+
 # ----------------------------------------------------------------------------- densities
 def _bump_mass(vertices, area_vertices, centres, width, cutoff=None):
     rho = np.zeros(vertices.shape[0])
@@ -132,6 +164,16 @@ def gaussian_bump_masses(vertices, area_vertices, seed: int = 0, width: float = 
     scale = np.abs(vertices).max()
     return (_bump_mass(vertices, area_vertices, c0 * scale, width),
             _bump_mass(vertices, area_vertices, c1 * scale, width))
+
+
+def vertex_bump_masses(vertices, area_vertices, seed: int = 0, rel_width: float = 0.02):
+    """One bump for mu0, two for mu1, centred AT mesh vertices picked by default_rng(seed) (so they sit on the surface
+    whatever its shape); width = rel_width * (bounding-box diagonal)^2."""
+    rng = np.random.default_rng(seed)
+    ids = rng.choice(vertices.shape[0], size=3, replace=False)
+    width = rel_width * float(((vertices.max(axis=0) - vertices.min(axis=0)) ** 2).sum())
+    return (_bump_mass(vertices, area_vertices, vertices[ids[:1]], width),
+            _bump_mass(vertices, area_vertices, vertices[ids[1:]], width))
 
 
 def knot_masses(vertices, area_vertices, ids=(2786, 1232, 406)):
@@ -166,6 +208,8 @@ def make_geometry(vertices, triangles, mu0=None, mu1=None, masses="gaussian", se
             mu0, mu1 = knot_masses(vertices, area_v_sum)
         elif masses == "plane":
             mu0, mu1 = plane_masses(vertices, area_v_sum)
+        elif masses == "vertex":
+            mu0, mu1 = vertex_bump_masses(vertices, area_v_sum, seed)
         else:
             raise ValueError(f"unknown masses recipe {masses!r}")
     return dict(vertices=np.ascontiguousarray(vertices, dtype=np.float64),

@@ -68,6 +68,9 @@ CASES = {
     "refplane20_nt15": ("@reference:plane:20", {}, 15, dict(tol=1e-3, nit=1000), (0, 9), False),
     "knots5class_nt31_c0": ("knot", {}, 31, dict(tol=1e-3, nit=1000), (), False),
     "knots5class_nt31_c01": ("knot", {}, 31, dict(tol=1e-3, nit=1000, congestion=0.1), (), False),
+    # BASELINE.json configs[2]: the same surface at nT = 63 and nT = 127 (time-direction scaling)
+    "knots5class_nt63_c0": ("knot", {}, 63, dict(tol=1e-3, nit=2000), (), False),
+    "knots5class_nt127_c0": ("knot", {}, 127, dict(tol=1e-3, nit=2000), (), False),
 }
 
 
@@ -115,5 +118,42 @@ def main(only=None):
               f"-> {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+
+
+def exact_study_fixture():
+    """``refplane20_exact.npz``: the reference's analytic transport on ``plane --n_space=20 --ntime=15`` (centred grid,
+    data/load_example.py:153-200) and its error functional (utils/evaluate_solution.py:47-69) evaluated on the DOT-unit,
+    time-centred solution of the ``refplane20_nt15`` fixture (socp/solver_decorator.py:29-54, utils/type.py:48-65)."""
+    refshim.load()
+    cwd = os.getcwd()
+    os.chdir(refshim.REFERENCE_ROOT)
+    try:
+        from dot_surface_socp.data.load_example import load_example, load_exact_transportation
+        from dot_surface_socp.utils.evaluate_solution import (check_mass_conservation, check_negative_mass,
+                                                              compare_with_exact_transportation)
+        from dot_surface_socp.socp.data_preprocessing import normalize_geometry
+        _, raw_geo, _ = load_example(example_name="plane", kwargs_generating_mesh={"n": 20})
+        _, exact = load_exact_transportation(t_array=np.linspace(0.0, 1.0, 16), example_name="plane",
+                                             kwargs_generating_mesh={"n": 20})
+        norm_geo, _ = normalize_geometry(raw_geo)
+    finally:
+        os.chdir(cwd)
+    fx = np.load(os.path.join(HERE, "refplane20_nt15.npz"))
+    mu = fx["sol_mu"] * (norm_geo["area_vertices"][None, :] / 3.0)
+    mu = np.concatenate([norm_geo["mu0"][None], 0.5 * (mu[:-1] + mu[1:]), norm_geo["mu1"][None]], axis=0)
+    err = compare_with_exact_transportation(mu=mu, mu_exact=exact, geometry=raw_geo, verbose=False)
+    neg, neg_layers = check_negative_mass(mu, verbose=False)
+    path = os.path.join(HERE, "refplane20_exact.npz")
+    np.savez_compressed(path, exact=exact, mu_centred=mu, l1=err["l1"], l2=err["l2"], linf=err["linf"],
+                        mass_violation=check_mass_conservation(mu, verbose=False), negative_mass=neg,
+                        negative_layers=neg_layers, raw_area_vertices=raw_geo["area_vertices"])
+    print(f"refplane20_exact: l1={err['l1']:.6e} l2={err['l2']:.6e} linf={err['linf']:.6e} -> {os.path.getsize(path) / 1e3:.0f} kB")
+
+
 if __name__ == "__main__":
-    main(sys.argv[1:])
+    if sys.argv[1:] == ["refplane20_exact"]:
+        exact_study_fixture()
+    else:
+        main(sys.argv[1:])
+        if not sys.argv[1:]:
+            exact_study_fixture()

@@ -63,7 +63,8 @@ def compare_states(alm, eng, tol, label=""):
 
 # ---------------------------------------------------------------------------------------------- operators
 @pytest.mark.parametrize("example,n_time,leaf", [("icosphere2", 7, 8), ("plane8", 6, 6), ("icosphere3", 31, 16),
-                                                 ("icosphere2", 40, 8)])
+                                                 ("icosphere2", 40, 8),
+                                                 ("icosphere2", 95, 8), ("icosphere3", 127, 16)])   # 96 / 128 time modes
 def test_laplacian_inverse_rows_a7_a8(example, n_time, leaf):
     """rhs assembly, time transform, per-mode solves, inverse transform vs the oracle's SuperLU path."""
     geo, alm, eng = make_pair(example, n_time, congestion=0.05, leaf=leaf)
@@ -140,7 +141,7 @@ def test_fused_step_rows_a1_a4(congestion):
 # ---------------------------------------------------------------------------------------------- iterates
 @pytest.mark.parametrize("example,n_time,congestion,exkw", [
     ("icosphere2", 7, 0.0, {}), ("icosphere2", 7, 0.1, {}), ("plane8", 6, 0.0, {}),
-    ("knot", 8, 0.05, dict(n_u=40, n_v=6)), ("icosphere3", 31, 0.0, {})])
+    ("knot", 8, 0.05, dict(n_u=40, n_v=6)), ("icosphere3", 31, 0.0, {}), ("icosphere2", 127, 0.0, {})])
 def test_iterates_match_oracle(example, n_time, congestion, exkw):
     geo, alm, eng = make_pair(example, n_time, congestion=congestion, **exkw)
     done = 0
@@ -175,6 +176,7 @@ def test_kkt_and_objective_rows_a9_a11():
 @pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005",
                                   "ico2_nt15_tol1e-4", "ico3_nt31_c0", "ico3_nt31_c01",
                                   "knots5class_nt31_c0", "knots5class_nt31_c01",        # BASELINE configs[0], [1]
+                                  "knots5class_nt63_c0",                                # BASELINE configs[2]
                                   "ico2_nt7_stepwise", "refplane20_nt15"])
 def test_solver_matches_reference_fixture(golden, name):
     """Through the public solver_socp: iteration count, KKT schedule (which residual on which iteration), penalty
@@ -217,6 +219,38 @@ def test_drop_in_decorators_and_checkpoints():
     assert rel(raw["mu"], host["mu"]) < 1e-13 and rel(raw["E"], host["E"]) < 1e-13
     mid = 0.5 * (host["mu"][:-1] + host["mu"][1:])
     assert rel(sol["mu"][1:-1], mid) < 1e-13 and rel(sol["E"], host["E"]) < 1e-13
+    # mass diagnostics formed on the device (row f2) == utils/evaluate_solution.py:7-45 applied to the returned mu
+    from dots_socp_b200 import replication as rep
+    for s_ in (sol, raw):
+        d = s_["diagnostics"]
+        assert d["mass_time_layers"].shape == (s_["mu"].shape[0],)
+        assert d["mass_conservation"] == pytest.approx(rep.mass_conservation(s_["mu"], verbose=False), rel=1e-9, abs=1e-15)
+        neg, neg_layers = rep.negative_mass(s_["mu"], verbose=False)
+        assert d["negative_mass"] == pytest.approx(neg, rel=1e-9, abs=1e-18)
+        assert np.allclose(d["negative_mass_time_layers"], neg_layers, rtol=1e-9, atol=1e-18)
+
+
+def test_replication_flow_reproduces_the_reference_plane_run_row_f4(golden):
+    """The caller's flow (run_dot_surface_versus_exact, interface.py:386-480) around the plug-in on the reference's own
+    ``plane --n_space=20 --ntime=15`` example: iteration count, de-scaled cost, centred DOT-unit mu and the error against
+    the analytic transport equal what the unmodified reference produced (fixtures refplane20_nt15 / refplane20_exact)."""
+    import os
+    from conftest import GOLDEN_DIR
+    from dots_socp_b200 import replication as rep
+    z, _, n_time, kw = golden("refplane20_nt15")
+    ex = np.load(os.path.join(GOLDEN_DIR, "refplane20_exact.npz"))
+    opts = rep.options(example="plane", n_space=20, ntime=n_time, tol=kw["tol"], nit=kw["nit"], checkpoints=[1e-1, 1e-2])
+    sol, geo, hist, err, cps = rep.run_versus_exact(opts, solver=b200.solver)
+    assert int(hist.kkt_iteration[-1]) == int(z["iterations"])
+    scale = float(z["scale_factor"])
+    assert hist.history["Transportation cost"][-1] == pytest.approx(float(z["cost"]) / scale ** 2, rel=1e-6)
+    assert rel(sol["mu"], ex["mu_centred"]) < 1e-6
+    for k in ("l1", "l2", "linf"):
+        assert err[k] == pytest.approx(float(ex[k]), rel=1e-5)
+    assert rep.mass_conservation(sol["mu"], verbose=False) == pytest.approx(float(ex["mass_violation"]), rel=1e-4, abs=1e-9)
+    assert [c["kkt_error"] <= t for c, t in zip(cps, (1e-1, 1e-2))] == [True, True]
+    assert cps[0]["iteration"] < cps[1]["iteration"] <= int(z["iterations"])
+    assert cps[1]["error"]["l2"] < cps[0]["error"]["l2"]
 
 
 def test_large_problem_properties():
