@@ -683,6 +683,12 @@ class Engine:
                            negative_mass=float(np.linalg.norm(layers[1]) / np.sqrt(n)))
         return dict(mu=self._download(mu), E=self._download(E), diagnostics=diagnostics)
 
+    def congestion_norm(self):
+        """``||lambda_c - congestion * mu||_2`` of the un-scaled solution (the solver's closing log line,
+        socp/solver_socp.py:846-853), formed on the device; a norm does not care about the vertex ordering."""
+        diff = self.full("lam_c") - self.cong * self.r * self.full("mu")
+        return float(torch.linalg.vector_norm(diff))
+
     def solution(self, keys=None):
         """Un-scaled solution dict with the reference's keys and layouts (:397-405, :855-869).
 

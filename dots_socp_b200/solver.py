@@ -198,10 +198,8 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
     else:                                                  # decorators' translate / centring done on the device
         solution = eng.dot_solution(geometry, centred=(dot_units == "centred"))
     solution["checkpoints"] = checkpoints if checkpoints else None
-    cong_norm = (f"{np.linalg.norm(solution['lambda_c'] - congestion * solution['mu']):.2f}"
-                 if "lambda_c" in solution and "mu" in solution else "n/a")
     logging.log(LOG_INFO, "---- Overview of solution ".ljust(42, "-") + "\n"
-                f"Congestion norm: {cong_norm}\n"
+                f"Congestion norm: {eng.congestion_norm():.2f}\n"
                 f"Number of iterations: {it}\nIteration time: {hist.running_time:.2f}")
     if return_engine:
         return solution, hist, eng

@@ -68,6 +68,9 @@ CASES = {
     "refplane20_nt15": ("@reference:plane:20", {}, 15, dict(tol=1e-3, nit=1000), (0, 9), False),
     "knots5class_nt31_c0": ("knot", {}, 31, dict(tol=1e-3, nit=1000), (), False),
     "knots5class_nt31_c01": ("knot", {}, 31, dict(tol=1e-3, nit=1000, congestion=0.1), (), False),
+    # edge of the time grid: a single time step (two time levels / modes) and two steps, smallest closed mesh (V = 42)
+    "ico1_nt1_c005": ("icosphere1", {}, 1, dict(tol=1e-3, nit=500, congestion=0.05), (0, 4), True),
+    "ico1_nt2_c0": ("icosphere1", {}, 2, dict(tol=1e-3, nit=500), (0, 4), True),
     # BASELINE.json configs[2]: the same surface at nT = 63 and nT = 127 (time-direction scaling)
     "knots5class_nt63_c0": ("knot", {}, 63, dict(tol=1e-3, nit=2000), (), False),
     "knots5class_nt127_c0": ("knot", {}, 127, dict(tol=1e-3, nit=2000), (), False),

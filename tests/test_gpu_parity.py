@@ -176,8 +176,9 @@ def test_kkt_and_objective_rows_a9_a11():
 @pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005",
                                   "ico2_nt15_tol1e-4", "ico3_nt31_c0", "ico3_nt31_c01",
                                   "knots5class_nt31_c0", "knots5class_nt31_c01",        # BASELINE configs[0], [1]
-                                  "knots5class_nt63_c0",                                # BASELINE configs[2]
-                                  "ico2_nt7_stepwise", "refplane20_nt15"])
+                                  "knots5class_nt63_c0", "knots5class_nt127_c0",        # BASELINE configs[2]
+                                  "ico2_nt7_stepwise", "refplane20_nt15",
+                                  "ico1_nt1_c005", "ico1_nt2_c0"])                      # smallest time grids
 def test_solver_matches_reference_fixture(golden, name):
     """Through the public solver_socp: iteration count, KKT schedule (which residual on which iteration), penalty
     path, transport cost and the returned mu against the fixtures generated by the unmodified reference."""

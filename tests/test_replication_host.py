@@ -153,3 +153,22 @@ def test_option_validation_follows_the_reference_caller(kw, msg):
         rep.run_example(rep.options(example="ring", **kw), solver=_fake_solver)
     with pytest.raises(TypeError):
         rep.run_example(rep.options(example="ring"), solver=3)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+def test_written_off_file_is_read_identically_by_the_reference_reader(tmp_path):
+    import sys
+    sys.path.insert(0, GOLDEN_DIR)
+    import refshim
+    refshim.load()
+    from dot_surface_socp.data.util import read_mesh_off
+    v, t = rep.synth.hills(12)
+    path = tmp_path / "hills.off"
+    rep.write_off(path, v, t)
+    rv, rt, re_ = read_mesh_off(str(path))
+    mv, mt, me = rep.read_off(path)
+    np.testing.assert_array_equal(rv, v)
+    np.testing.assert_array_equal(rt, t)
+    np.testing.assert_array_equal(mv, rv)
+    np.testing.assert_array_equal(mt, rt)
+    np.testing.assert_array_equal(me, re_)
