@@ -18,6 +18,13 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _with_areas(geo):
+    """The fixtures store only vertices / triangles / masses; the DOT-unit decorators also need the GeometryData areas."""
+    from dots_socp_b200 import surface
+    af = surface.triangle_areas(geo["vertices"], geo["triangles"])
+    return dict(geo, area_triangles=af, area_vertices=surface.incident_area_sum(geo["vertices"].shape[0], geo["triangles"], af))
+
+
 def _worker(rank, world, port, name, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -42,9 +49,12 @@ def _worker(rank, world, port, name, out_dir):
         cost = eng.objective()
         # (2) full solve through the public API
         sol, hist = b200.solver_socp(n_time, geo, leaf_size=8, **kw)
+        # (3) the DOT-unit plug-in (device-side translation, centring and mass diagnostics) on the sharded state
+        dot, _ = b200.solver(n_time, _with_areas(geo), leaf_size=8, **kw)
         if rank == 0:
             np.savez(os.path.join(out_dir, "multi.npz"), kkt=np.array(kk), cost=np.array(cost), iters=int(hist.kkt_iteration[-1]),
-                     rows=hist.kkt_errors, sol_mu=sol["mu"], sol_z_mid=sol["z_mid"], **{"st_" + k: v for k, v in st.items()})
+                     rows=hist.kkt_errors, sol_mu=sol["mu"], sol_z_mid=sol["z_mid"], dot_mu=dot["mu"], dot_E=dot["E"],
+                     dot_mass=dot["diagnostics"]["mass_time_layers"], **{"st_" + k: v for k, v in st.items()})
     finally:
         dist.destroy_process_group()
 
@@ -84,3 +94,9 @@ def test_sharded_solver_matches_single_gpu_and_reference(tmp_path, golden, name,
     m = ~np.isnan(z["kkt_rows"])
     assert np.allclose(got["rows"][m], z["kkt_rows"][m], rtol=1e-6, atol=1e-12)
     assert np.abs(got["sol_mu"] - z["sol_mu"]).max() / np.abs(z["sol_mu"]).max() < 1e-6
+    # DOT-unit hand-off: sharded == single GPU
+    import dots_socp_b200 as b200
+    dot, _ = b200.solver(n_time, _with_areas(geo), leaf_size=8, **kw)
+    assert np.abs(got["dot_mu"] - dot["mu"]).max() / np.abs(dot["mu"]).max() < 1e-8
+    assert np.abs(got["dot_E"] - dot["E"]).max() / np.abs(dot["E"]).max() < 1e-8
+    assert np.allclose(got["dot_mass"], dot["mu"].sum(axis=1), rtol=1e-12)
