@@ -8,6 +8,7 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 from dots_socp_b200 import nested, surface, synth
+from host_multifrontal import factor_batched
 
 
 def panel_rows(sym, panels, i):
@@ -64,7 +65,7 @@ def test_batched_factor_solves_all_modes(example, leaf):
     n_time = 7
     k = np.arange(n_time + 1)
     shifts = 4.0 * n_time ** 2 * np.sin(np.pi * k / (2 * (n_time + 1))) ** 2
-    panels = nested.factor_batched(sym, K, mass, shifts, m_pad=8)
+    panels = factor_batched(sym, K, mass, shifts, m_pad=8)
     rng = np.random.default_rng(0)
     rhs_old = rng.standard_normal((v.shape[0], 8))
     rhs_old[:, 0] -= rhs_old[:, 0].mean()                  # compatible rhs for the singular mode
@@ -99,7 +100,7 @@ def test_device_factorisation_matches_host_version():
     mass = surface.incident_area_sum(v.shape[0], t, surface.triangle_areas(v, t)) / 3.0
     sym = nested.analyse(v, K, leaf_size=8)
     shifts = np.array([0.0, 3.0, 11.0, 40.0, 170.0])
-    a = nested.factor_batched(sym, K, mass, shifts, m_pad=32)
+    a = factor_batched(sym, K, mass, shifts, m_pad=32)
     b = nested.factor_batched_device(sym, K, mass, shifts, m_pad=32, device="cpu").numpy()
     assert a.shape == b.shape
     assert np.abs(a - b).max() / np.abs(a).max() < 1e-12
