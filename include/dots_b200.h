@@ -25,7 +25,8 @@
  *         corner fields   b_mid, z_mid [tau][side][k][xyz][f]       (reference: (nT, 2, 3, T, 3) indexed
  *                         [t][s][k][f][xyz] with tau = t + s, side = s; the slots (tau=0, side=1) and
  *                         (tau=nT, side=0) do not exist in the reference and stay zero)
- *     The host side (dots_socp_b200/layout.py) converts between the reference layout and this one.
+ *     The host side (dots_socp_b200/engine.py: to_internal / from_internal) converts between the reference
+ *     layout and this one.
  */
 #ifndef DOTS_B200_H
 #define DOTS_B200_H
@@ -190,7 +191,8 @@ int dots_set_params(const dots_ctx_t *c, const double *host_params, void *stream
 
 /* ---- residuals (rows a9-a11).  Writes the raw weighted sums (un-normalised, un-rooted) of KKT condition
  * `which` (0..6, order of solver_socp.py:591-639) or of the objective (which = 7) into host_out[8].
- * Synchronises the stream.  Slot meaning per condition is documented in dots_socp_b200/solver.py.   */
+ * Synchronises the stream.  Slot meaning per condition: csrc/kkt_kernels.cu (k_kkt_vertex / k_kkt_tri) and
+ * dots_socp_b200/engine.py (Engine.kkt, which forms the relative residuals of solver_socp.py:433-559 from them). */
 int dots_kkt_sums(const dots_ctx_t *c, int which, double *host_out, void *stream);
 
 /* ---- setup (row f1): numeric factorisation of the small fronts (n <= dots_front_nmax()) of one tree level, one block
