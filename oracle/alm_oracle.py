@@ -358,7 +358,7 @@ class OracleALM:
     """State + one ALM iteration, written against MeshOps.  Default-flag semantics of ``solver_socp``."""
 
     def __init__(self, n_time, geometry, congestion=0.0, eps=0.0, tau=1.9, is_palm=False, is_z_scaling=True,
-                 ops: MeshOps | None = None):
+                 ops: MeshOps | None = None, init_solution=None):
         self.ops = ops or MeshOps(n_time, geometry, eps=eps)
         o = self.ops
         nT, V, T = o.nT, o.V, o.T
@@ -373,6 +373,16 @@ class OracleALM:
         self.B, self.E = z((nT + 1, T, 3)), z((nT + 1, T, 3))
         self.z_fst, self.z_end, self.b_fst, self.b_end = z((nT, V)), z((nT, V)), z((nT, V)), z((nT, V))
         self.z_mid, self.b_mid = z((nT, 2, 3, T, 3)), z((nT, 2, 3, T, 3))
+        if init_solution:                                                          # :239-250 (r = 1 here)
+            g = lambda k, default: np.array(init_solution[k], dtype=np.float64, copy=True) if k in init_solution else default()
+            self.phi = g("phi", lambda: self.phi)
+            self.A = g("A", lambda: grad_time(o.dt, self.phi))
+            self.B = g("B", lambda: grad_space(o.G, self.phi))
+            self.lam_c = g("lambda_c", lambda: self.lam_c)
+            self.z_fst, self.z_end, self.z_mid = g("z_fst", lambda: self.z_fst), g("z_end", lambda: self.z_end), g("z_mid", lambda: self.z_mid)
+            self.b_fst, self.b_end, self.b_mid = g("beta_fst", lambda: self.b_fst), g("beta_end", lambda: self.b_end), g("beta_mid", lambda: self.b_mid)
+            self.mu = g("mu", lambda: self.b_fst - self.b_end)
+            self.E = g("E", lambda: -decouple_adjoint(self.b_mid, 1.0))
         self.Bd_new = z((nT, 2, 3, T, 3))       # memo_z_mid (:262, :717)
         self.dt_phi = np.array(0.0) if not is_palm else grad_time(o.dt, self.phi)  # :253-257
         self.dx_phi = np.array(0.0) if not is_palm else grad_space(o.G, self.phi)
@@ -508,12 +518,12 @@ class OracleALM:
 
 
 def solve(n_time, geometry, congestion=0.0, nit=1000, eps=0.0, tol=1e-4, tau=1.9, is_palm=False,
-          is_z_scaling=True, time_limit=1000, trace=None, ops=None, check_kkt_step_by_step=False):
+          is_z_scaling=True, time_limit=1000, trace=None, ops=None, check_kkt_step_by_step=False, init_solution=None):
     """The reference's outer loop (:565-871) around OracleALM.  Returns (solution, info).
 
     ``info``: iterations (= last 0-based index, what the reference prints), kkt rows (nan = not
     evaluated), r per iteration, costs.  ``trace(it, alm)`` is called after every iteration."""
-    alm = OracleALM(n_time, geometry, congestion, eps, tau, is_palm, is_z_scaling, ops=ops)
+    alm = OracleALM(n_time, geometry, congestion, eps, tau, is_palm, is_z_scaling, ops=ops, init_solution=init_solution)
     t0 = time.perf_counter()
     prim_gap = 1.0 + 1.0 * np.exp(-100 * congestion)                                       # :568
     lazy = LazyKKT([(lambda i=i: alm.kkt(i)) for i in range(7)], tol)

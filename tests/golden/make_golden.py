@@ -71,6 +71,10 @@ CASES = {
     # edge of the time grid: a single time step (two time levels / modes) and two steps, smallest closed mesh (V = 42)
     "ico1_nt1_c005": ("icosphere1", {}, 1, dict(tol=1e-3, nit=500, congestion=0.05), (0, 4), True),
     "ico1_nt2_c0": ("icosphere1", {}, 2, dict(tol=1e-3, nit=500), (0, 4), True),
+    # eps > 0: regularised Laplacian (rhs term -eps*area*phi, shift lambda - eps; solver_socp.py:976-986, laplacian_inverse_socp.py:37)
+    "ico2_nt7_eps1e-2": ("icosphere2", {}, 7, dict(tol=1e-3, nit=1000, eps=1e-2, congestion=0.05), (0, 4, 49), False),
+    # time limit already exceeded at the first check: one iteration, full KKT row, un-converged solution returned (:725-731, :804)
+    "ico2_nt7_tl0": ("icosphere2", {}, 7, dict(tol=1e-3, nit=1000, time_limit=0.0), (0,), True),
     # BASELINE.json configs[2]: the same surface at nT = 63 and nT = 127 (time-direction scaling)
     "knots5class_nt63_c0": ("knot", {}, 63, dict(tol=1e-3, nit=2000), (), False),
     "knots5class_nt127_c0": ("knot", {}, 127, dict(tol=1e-3, nit=2000), (), False),
@@ -153,10 +157,39 @@ def exact_study_fixture():
     print(f"refplane20_exact: l1={err['l1']:.6e} l2={err['l2']:.6e} linf={err['linf']:.6e} -> {os.path.getsize(path) / 1e3:.0f} kB")
 
 
+def warm_start_fixture():
+    """``ico2_nt7_warm.npz``: ``init_solution`` (socp/solver_socp.py:239-250).  A coarse reference solve (tol 1e-2) provides
+    the start; the reference is then restarted (tol 1e-3) from (a) the full solution dict and (b) a partial dict
+    (phi, beta_fst, beta_end, beta_mid only: A, B, mu, E take their defaults)."""
+    geo, scale = synth.example("icosphere2")
+    kw = dict(congestion=0.05, nit=1000)
+    sol0, hist0, _, _ = run_reference(geo, 7, (), tol=1e-2, **kw)
+    full = {k: np.array(sol0[k], copy=True) for k in STATE}
+    part = {k: np.array(sol0[k], copy=True) for k in ("phi", "beta_fst", "beta_end", "beta_mid")}
+    out = dict(vertices=geo["vertices"], triangles=geo["triangles"], mu0=geo["mu0"], mu1=geo["mu1"], n_time=7,
+               scale_factor=scale, kw_keys=np.array(list(kw) + ["tol"]), kw_vals=np.array([float(v) for v in kw.values()] + [1e-3]),
+               coarse_iterations=int(hist0.kkt_iteration[-1]))
+    for k, v in full.items():
+        out["init_" + k] = v
+    for tag, init in (("full", full), ("part", part)):
+        sol, hist, _, _ = run_reference(geo, 7, (), tol=1e-3, init_solution={k: v.copy() for k, v in init.items()}, **kw)
+        out[tag + "_iterations"] = int(hist.kkt_iteration[-1])
+        out[tag + "_kkt_rows"] = hist.kkt_errors
+        out[tag + "_cost"] = hist.history["Transportation cost"][-1]
+        out[tag + "_mu"] = sol["mu"]
+        out[tag + "_phi_grad_t"] = np.diff(sol["phi"], axis=0)
+        out[tag + "_beta_mid"] = sol["beta_mid"]
+        print(f"ico2_nt7_warm[{tag}]: iterations={out[tag + '_iterations']} cost={out[tag + '_cost']:.12e}")
+    path = os.path.join(HERE, "ico2_nt7_warm.npz")
+    np.savez_compressed(path, **out)
+    print(f"ico2_nt7_warm: coarse iterations={out['coarse_iterations']} -> {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+EXTRA = {"refplane20_exact": exact_study_fixture, "ico2_nt7_warm": warm_start_fixture}
+
 if __name__ == "__main__":
-    if sys.argv[1:] == ["refplane20_exact"]:
-        exact_study_fixture()
-    else:
-        main(sys.argv[1:])
-        if not sys.argv[1:]:
-            exact_study_fixture()
+    names = sys.argv[1:]
+    main([n for n in names if n not in EXTRA] or (None if not names else ["-"]))
+    for n, fn in EXTRA.items():
+        if not names or n in names:
+            fn()

@@ -178,7 +178,9 @@ def test_kkt_and_objective_rows_a9_a11():
                                   "knots5class_nt31_c0", "knots5class_nt31_c01",        # BASELINE configs[0], [1]
                                   "knots5class_nt63_c0", "knots5class_nt127_c0",        # BASELINE configs[2]
                                   "ico2_nt7_stepwise", "refplane20_nt15",
-                                  "ico1_nt1_c005", "ico1_nt2_c0"])                      # smallest time grids
+                                  "ico1_nt1_c005", "ico1_nt2_c0",                       # smallest time grids
+                                  "ico2_nt7_eps1e-2",                                   # regularised Laplacian (eps > 0)
+                                  "ico2_nt7_tl0"])                                      # time limit hit on the first iteration
 def test_solver_matches_reference_fixture(golden, name):
     """Through the public solver_socp: iteration count, KKT schedule (which residual on which iteration), penalty
     path, transport cost and the returned mu against the fixtures generated by the unmodified reference."""
@@ -200,6 +202,23 @@ def test_solver_matches_reference_fixture(golden, name):
     if "sol_z_mid" in z:
         for key in ("A", "B", "lambda_c", "E", "z_fst", "z_mid", "z_end", "beta_fst", "beta_mid", "beta_end"):
             assert rel(sol[key], z["sol_" + key]) < 1e-6, key
+
+
+@pytest.mark.parametrize("tag,keys", [("full", None), ("part", ("phi", "beta_fst", "beta_end", "beta_mid"))])
+def test_warm_start_matches_reference_fixture(golden, tag, keys):
+    """``init_solution`` (solver_socp.py:239-250): restart from a coarse reference solution, all keys or a subset."""
+    z, geo, n_time, kw = golden("ico2_nt7_warm")
+    init = {k[5:]: z[k] for k in z.files if k.startswith("init_") and (keys is None or k[5:] in keys)}
+    sol, hist = b200.solver_socp(n_time, geo, leaf_size=8, init_solution=init, **kw)
+    assert int(hist.kkt_iteration[-1]) == int(z[tag + "_iterations"])
+    ref_rows = z[tag + "_kkt_rows"]
+    assert np.array_equal(np.isnan(hist.kkt_errors), np.isnan(ref_rows))
+    m = ~np.isnan(ref_rows)
+    assert np.allclose(hist.kkt_errors[m], ref_rows[m], rtol=1e-6, atol=1e-12)
+    assert hist.history["Transportation cost"][-1] == pytest.approx(float(z[tag + "_cost"]), rel=1e-6)
+    assert rel(sol["mu"], z[tag + "_mu"]) < 1e-6
+    assert rel(sol["beta_mid"], z[tag + "_beta_mid"]) < 1e-6
+    assert rel(np.diff(sol["phi"], axis=0), z[tag + "_phi_grad_t"]) < 1e-6
 
 
 def test_drop_in_decorators_and_checkpoints():

@@ -20,7 +20,8 @@ def phi_mod_const(phi):
 
 
 @pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005",
-                                  "ico2_nt7_stepwise", "refplane20_nt15", "ico1_nt1_c005", "ico1_nt2_c0"])
+                                  "ico2_nt7_stepwise", "refplane20_nt15", "ico1_nt1_c005", "ico1_nt2_c0",
+                                  "ico2_nt7_eps1e-2", "ico2_nt7_tl0"])
 def test_iterates_match_reference(golden, name):
     z, geo, n_time, kw = golden(name)
     snap_its = [int(i) for i in z["snap_its"]]
@@ -108,3 +109,16 @@ def test_operator_identities():
     L2 = ops.D @ (ops.G.multiply(W[:, None])).tocsr()
     assert abs(L2 - ops.L).max() < 1e-13
     assert abs(ops.L @ np.ones(ops.V)).max() < 1e-12
+
+
+@pytest.mark.parametrize("tag,keys", [("full", None), ("part", ("phi", "beta_fst", "beta_end", "beta_mid"))])
+def test_warm_start_matches_reference(golden, tag, keys):
+    """``init_solution`` (solver_socp.py:239-250): restart from a coarse reference solution, all keys or a subset
+    (the missing ones take the reference's defaults)."""
+    z, geo, n_time, kw = golden("ico2_nt7_warm")
+    init = {k[5:]: z[k] for k in z.files if k.startswith("init_") and (keys is None or k[5:] in keys)}
+    sol, info = orc.solve(n_time, geo, init_solution=init, **kw)
+    assert info["iterations"] == int(z[tag + "_iterations"])
+    assert info["cost"] == pytest.approx(float(z[tag + "_cost"]), rel=1e-8)
+    assert rel_err(sol["mu"], z[tag + "_mu"]) < 1e-7
+    assert rel_err(sol["beta_mid"], z[tag + "_beta_mid"]) < 1e-7
