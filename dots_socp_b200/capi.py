@@ -9,7 +9,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 P_R, P_S, P_D, P_CONG, P_TAU, P_EPS, P_COUNT = 0, 1, 2, 3, 4, 5, 8
 
 _i32p, _i64p, _f64p = C.c_void_p, C.c_void_p, C.c_void_p      # raw device/host addresses
@@ -86,6 +86,11 @@ def load(build_if_missing: bool = True):
         "dots_factor_small_fronts": (C.POINTER(FrontArgs), i, i, vp), "dots_front_nmax": (), "dots_enable_peer": (i,),
         "dots_ipc_export": (vp, vp, C.POINTER(C.c_ulonglong)), "dots_ipc_import": (vp, C.c_ulonglong, C.POINTER(vp)),
     }
+    i64 = C.c_int64
+    protos.update({
+        "dots_order_create": (i64, vp, vp, vp, i64, C.POINTER(vp)), "dots_order_sizes": (vp, C.POINTER(i64), C.POINTER(i64)),
+        "dots_order_export": (vp,) * 9, "dots_order_destroy": (vp,),
+    })
     for name, args in protos.items():
         fn = getattr(lib, name)
         fn.argtypes, fn.restype = list(args), C.c_int
@@ -97,7 +102,8 @@ EXPORTS = ("dots_abi_version", "dots_ctx_sizeof", "dots_last_error", "dots_step_
            "dots_step_tri", "dots_iterate", "dots_refresh_corner_terms", "dots_scale_dual", "dots_scale_z",
            "dots_set_params", "dots_kkt_sums", "dots_phi_rhs", "dots_time_transform", "dots_mode_solves",
            "dots_grad_space", "dots_div_space", "dots_graph_create", "dots_graph_launch", "dots_graph_destroy",
-           "dots_factor_small_fronts", "dots_front_nmax", "dots_enable_peer", "dots_ipc_export", "dots_ipc_import")
+           "dots_factor_small_fronts", "dots_front_nmax", "dots_enable_peer", "dots_ipc_export", "dots_ipc_import",
+           "dots_order_create", "dots_order_sizes", "dots_order_export", "dots_order_destroy")
 
 
 def check(code: int, what: str = ""):

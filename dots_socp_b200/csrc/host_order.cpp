@@ -1,0 +1,250 @@
+// Host-side setup (row f1): nested-dissection ordering + symbolic multifrontal structure of the surface Laplacian.
+//
+// The reference hands each of its nT+1 shifted Laplacians to SuperLU, which orders and analyses every one of them
+// separately (utils/laplacian_inverse_socp.py:34-41).  Here ONE ordering / symbolic analysis serves all time modes
+// (dots_socp_b200/nested.py explains the structure); this file is the native version of nested.dissect + nested.symbolic
+// (a Python loop over ~18 000 tree nodes at V = 164k took 1 s of the 2.4 s setup).  It reproduces the Python reference
+// implementation decision for decision (same split axis, same stable order, same tie breaks), so both produce the same
+// permutation and the same front structure bit for bit (tests/test_nested_host.py checks that).
+//
+// Plain C++, no CUDA: geometric recursive bisection with vertex separators, then boundary sets by a post-order sweep.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <new>
+#include <numeric>
+#include <utility>
+#include <vector>
+
+#include "../../include/dots_b200.h"
+
+void dots_set_error(const char *fmt, ...);
+
+namespace {
+
+struct TreeNode {
+    std::vector<int64_t> own;   // old vertex ids eliminated by this node, in elimination order
+    int kid[2] = {-1, -1};
+    int n_kids = 0;
+};
+
+}  // namespace
+
+struct dots_order {
+    int64_t n = 0;
+    std::vector<int64_t> perm, s, b, level, parent, child, front_idx, child_pos;
+    int64_t n_nodes = 0, front_total = 0;
+};
+
+namespace {
+
+// nested.dissect: split along the longest bounding-box axis at the median (stable order), take as separator the smaller
+// of the two one-sided vertex frontiers, recurse on what is left of the halves until a part has <= leaf_size vertices.
+void dissect(int64_t n, const double *xyz, const int64_t *indptr, const int64_t *indices, int64_t leaf_size,
+             std::vector<TreeNode> &nodes) {
+    std::vector<int8_t> side((size_t)n, -1);
+    struct Frame { int node; std::vector<int64_t> verts; };
+    std::vector<Frame> stack;
+    nodes.emplace_back();
+    {
+        std::vector<int64_t> all((size_t)n);
+        std::iota(all.begin(), all.end(), (int64_t)0);
+        stack.push_back({0, std::move(all)});
+    }
+    std::vector<int64_t> left, right;
+    std::vector<std::pair<double, int64_t>> keyed;
+    std::vector<char> fl, fr;
+    while (!stack.empty()) {
+        Frame fr_ = std::move(stack.back());
+        stack.pop_back();
+        const int me = fr_.node;
+        std::vector<int64_t> &verts = fr_.verts;
+        const int64_t m = (int64_t)verts.size();
+        if (m <= leaf_size) { nodes[me].own = std::move(verts); continue; }
+        double lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) lo[a] = hi[a] = xyz[3 * verts[0] + a];
+        for (int64_t i = 1; i < m; ++i)
+            for (int a = 0; a < 3; ++a) {
+                const double x = xyz[3 * verts[i] + a];
+                if (x < lo[a]) lo[a] = x;
+                if (x > hi[a]) hi[a] = x;
+            }
+        int axis = 0;
+        for (int a = 1; a < 3; ++a)
+            if (hi[a] - lo[a] > hi[axis] - lo[axis]) axis = a;                 // first maximum wins, like np.argmax
+        keyed.resize((size_t)m);                                               // (coordinate, vertex) pairs: the sort then
+        for (int64_t i = 0; i < m; ++i) keyed[i] = {xyz[3 * verts[i] + axis], verts[i]};   // runs over contiguous memory
+        std::stable_sort(keyed.begin(), keyed.end(),
+                         [](const std::pair<double, int64_t> &p, const std::pair<double, int64_t> &q) { return p.first < q.first; });
+        const int64_t half = m / 2;
+        left.resize((size_t)half);
+        right.resize((size_t)(m - half));
+        for (int64_t i = 0; i < half; ++i) { left[i] = keyed[i].second; side[left[i]] = 0; }
+        for (int64_t i = half; i < m; ++i) { right[i - half] = keyed[i].second; side[right[i - half]] = 1; }
+        auto frontier = [&](const std::vector<int64_t> &part, int8_t other, std::vector<char> &mask) {
+            int64_t cnt = 0;
+            mask.assign(part.size(), 0);
+            for (size_t i = 0; i < part.size(); ++i) {
+                const int64_t v = part[i];
+                for (int64_t q = indptr[v]; q < indptr[v + 1]; ++q)
+                    if (side[indices[q]] == other) { mask[i] = 1; ++cnt; break; }
+            }
+            return cnt;
+        };
+        const int64_t nl = frontier(left, 1, fl), nr = frontier(right, 0, fr);
+        std::vector<int64_t> sep, keep;
+        auto split = [&](std::vector<int64_t> &part, const std::vector<char> &mask) {
+            keep.clear();
+            for (size_t i = 0; i < part.size(); ++i) (mask[i] ? sep : keep).push_back(part[i]);
+            part.swap(keep);
+        };
+        if (nl <= nr) split(left, fl); else split(right, fr);
+        for (int64_t i = 0; i < m; ++i) side[verts[i]] = -1;
+        nodes[me].own = std::move(sep);
+        for (std::vector<int64_t> *part : {&left, &right}) {
+            if (part->empty()) continue;
+            const int kid = (int)nodes.size();
+            nodes.emplace_back();
+            nodes[me].kid[nodes[me].n_kids++] = kid;
+            stack.push_back({kid, *part});
+        }
+    }
+}
+
+// nested.symbolic: post-order numbering, boundary sets B(i) = (neighbours of S(i) and children's boundaries) beyond the
+// node's own block, front row lists and the child -> parent row maps.
+void symbolic(int64_t n, const int64_t *indptr, const int64_t *indices, const std::vector<TreeNode> &nodes, dots_order &o) {
+    std::vector<int> post;
+    post.reserve(nodes.size());
+    {
+        std::vector<std::pair<int, bool>> st;
+        st.push_back({0, false});
+        while (!st.empty()) {
+            auto [nd, seen] = st.back();
+            st.pop_back();
+            if (seen) { post.push_back(nd); continue; }
+            st.push_back({nd, true});
+            for (int k = nodes[nd].n_kids - 1; k >= 0; --k) st.push_back({nodes[nd].kid[k], false});
+        }
+    }
+    const int64_t N = (int64_t)post.size();
+    std::vector<int64_t> id_of(nodes.size());
+    for (int64_t i = 0; i < N; ++i) id_of[post[i]] = i;
+    o.n = n;
+    o.n_nodes = N;
+    o.perm.clear();
+    o.perm.reserve((size_t)n);
+    o.s.assign(N, 0); o.b.assign(N, 0); o.level.assign(N, 0); o.parent.assign(N, -1); o.child.assign(2 * N, -1);
+    std::vector<int64_t> off(N + 1, 0);
+    for (int64_t i = 0; i < N; ++i) {
+        const TreeNode &nd = nodes[post[i]];
+        o.s[i] = (int64_t)nd.own.size();
+        off[i + 1] = off[i] + o.s[i];
+        o.perm.insert(o.perm.end(), nd.own.begin(), nd.own.end());
+        for (int slot = 0; slot < nd.n_kids; ++slot) {
+            const int64_t k = id_of[nd.kid[slot]];
+            o.parent[k] = i;
+            o.child[2 * i + slot] = k;
+            o.level[i] = std::max(o.level[i], o.level[k] + 1);
+        }
+    }
+    std::vector<int64_t> iperm((size_t)n);
+    for (int64_t i = 0; i < n; ++i) iperm[o.perm[i]] = i;
+    std::vector<std::vector<int64_t>> bset(N);
+    std::vector<int64_t> cand;
+    for (int64_t i = 0; i < N; ++i) {                                  // post-order: children are ready
+        const int64_t hi = off[i + 1];
+        cand.clear();
+        for (int64_t r = off[i]; r < hi; ++r) {
+            const int64_t v = o.perm[r];
+            for (int64_t q = indptr[v]; q < indptr[v + 1]; ++q) {
+                const int64_t w = iperm[indices[q]];
+                if (w >= hi) cand.push_back(w);
+            }
+        }
+        for (int slot = 0; slot < 2; ++slot) {
+            const int64_t k = o.child[2 * i + slot];
+            if (k < 0) continue;
+            for (int64_t w : bset[k])
+                if (w >= hi) cand.push_back(w);
+        }
+        std::sort(cand.begin(), cand.end());
+        cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+        bset[i] = cand;
+        o.b[i] = (int64_t)cand.size();
+    }
+    std::vector<int64_t> front_off(N + 1, 0);
+    for (int64_t i = 0; i < N; ++i) front_off[i + 1] = front_off[i] + o.s[i] + o.b[i];
+    o.front_total = front_off[N];
+    o.front_idx.assign((size_t)o.front_total, 0);
+    o.child_pos.assign((size_t)(2 * o.front_total), -1);
+    for (int64_t i = 0; i < N; ++i) {
+        int64_t *rows = o.front_idx.data() + front_off[i];
+        const int64_t nf = o.s[i] + o.b[i];
+        for (int64_t r = 0; r < o.s[i]; ++r) rows[r] = off[i] + r;
+        std::copy(bset[i].begin(), bset[i].end(), rows + o.s[i]);
+        for (int slot = 0; slot < 2; ++slot) {
+            const int64_t k = o.child[2 * i + slot];
+            if (k < 0 || o.b[k] == 0) continue;
+            int64_t *cp = o.child_pos.data() + (size_t)slot * o.front_total + front_off[i];
+            for (int64_t j = 0; j < o.b[k]; ++j) {
+                const int64_t *hit = std::lower_bound(rows, rows + nf, bset[k][j]);
+                cp[hit - rows] = j;                                     // the child's boundary always embeds in the parent's front
+            }
+        }
+        if (o.child[2 * i] >= 0) std::vector<int64_t>().swap(bset[o.child[2 * i]]);
+        if (o.child[2 * i + 1] >= 0) std::vector<int64_t>().swap(bset[o.child[2 * i + 1]]);
+    }
+}
+
+}  // namespace
+
+extern "C" int dots_order_create(int64_t n_vert, const double *vertices, const int64_t *adj_ptr, const int64_t *adj_idx,
+                                 int64_t leaf_size, dots_order_t **out) {
+    if (!out || !vertices || !adj_ptr || !adj_idx || n_vert <= 0 || leaf_size < 1) {
+        dots_set_error("dots_order_create: bad argument (n_vert=%lld, leaf_size=%lld)", (long long)n_vert, (long long)leaf_size);
+        return -1;
+    }
+    *out = nullptr;
+    try {
+        dots_order *o = new dots_order();
+        std::vector<TreeNode> nodes;
+        dissect(n_vert, vertices, adj_ptr, adj_idx, leaf_size, nodes);
+        symbolic(n_vert, adj_ptr, adj_idx, nodes, *o);
+        if ((int64_t)o->perm.size() != n_vert) {
+            const long long covered = (long long)o->perm.size();
+            delete o;
+            dots_set_error("dots_order_create: dissection covered %lld of %lld vertices", covered, (long long)n_vert);
+            return -1;
+        }
+        *out = o;
+    } catch (const std::bad_alloc &) {
+        dots_set_error("dots_order_create: out of host memory");
+        return -1;
+    }
+    return 0;
+}
+
+extern "C" int dots_order_sizes(const dots_order_t *o, int64_t *n_nodes, int64_t *front_total) {
+    if (!o || !n_nodes || !front_total) { dots_set_error("dots_order_sizes: null argument"); return -1; }
+    *n_nodes = o->n_nodes;
+    *front_total = o->front_total;
+    return 0;
+}
+
+extern "C" int dots_order_export(const dots_order_t *o, int64_t *perm, int64_t *s, int64_t *b, int64_t *level, int64_t *parent,
+                                 int64_t *child, int64_t *front_idx, int64_t *child_pos) {
+    if (!o || !perm || !s || !b || !level || !parent || !child || !front_idx || !child_pos) {
+        dots_set_error("dots_order_export: null argument");
+        return -1;
+    }
+    auto put = [](int64_t *dst, const std::vector<int64_t> &src) { if (!src.empty()) std::memcpy(dst, src.data(), src.size() * sizeof(int64_t)); };
+    put(perm, o->perm); put(s, o->s); put(b, o->b); put(level, o->level); put(parent, o->parent); put(child, o->child);
+    put(front_idx, o->front_idx); put(child_pos, o->child_pos);
+    return 0;
+}
+
+extern "C" int dots_order_destroy(dots_order_t *o) {
+    delete o;
+    return 0;
+}

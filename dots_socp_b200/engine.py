@@ -138,7 +138,7 @@ class Engine:
 
         # ---- ordering + batched factorisation (this rank's time modes only) -------------------------
         t0 = time.perf_counter()
-        sym = nested.analyse(v, K, leaf_size=leaf_size)
+        sym = nested.analyse_native(self.lib, v, K, leaf_size=leaf_size)               # C++ (csrc/host_order.cpp)
         self.sym = sym
         self.perm_v = sym.perm                                                          # new -> old
         tri_new = sym.iperm[tri_old]                                                    # (T,3) in new vertex ids

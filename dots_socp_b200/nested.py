@@ -185,11 +185,52 @@ def symbolic(root: _Node, adj: sp.csr_matrix) -> Symbolic:
                     panel_off=panel_off, upd_off=upd_off)
 
 
-def analyse(vertices: np.ndarray, K: sp.csr_matrix, leaf_size: int = 24) -> Symbolic:
+def _pattern(K: sp.csr_matrix) -> sp.csr_matrix:
     adj = K.copy().tocsr()
     adj.setdiag(0)
     adj.eliminate_zeros()
+    return adj
+
+
+def analyse(vertices: np.ndarray, K: sp.csr_matrix, leaf_size: int = 24) -> Symbolic:
+    """Ordering + symbolic structure, plain numpy (the readable statement of the algorithm and the checker of
+    ``analyse_native``, which is what the engine calls)."""
+    adj = _pattern(K)
     return symbolic(dissect(np.asarray(vertices, dtype=np.float64), adj, leaf_size), adj)
+
+
+def analyse_native(lib, vertices: np.ndarray, K: sp.csr_matrix, leaf_size: int = 24) -> Symbolic:
+    """Same result as ``analyse`` (bit for bit) from the C++ implementation in libdots_b200.so
+    (csrc/host_order.cpp, ``dots_order_*`` of include/dots_b200.h): ~20x faster at V = 164k."""
+    import ctypes as C
+    from . import capi
+    adj = _pattern(K)
+    n = adj.shape[0]
+    xyz = np.ascontiguousarray(vertices, dtype=np.float64)
+    if xyz.shape != (n, 3):
+        raise ValueError(f"vertices must be ({n}, 3), got {xyz.shape}")
+    ptr = np.ascontiguousarray(adj.indptr, dtype=np.int64)
+    idx = np.ascontiguousarray(adj.indices, dtype=np.int64)
+    handle = C.c_void_p()
+    capi.check(lib.dots_order_create(n, xyz.ctypes.data, ptr.ctypes.data, idx.ctypes.data, int(leaf_size), C.byref(handle)),
+               "dots_order_create")
+    try:
+        n_nodes, front_total = C.c_int64(), C.c_int64()
+        capi.check(lib.dots_order_sizes(handle, C.byref(n_nodes), C.byref(front_total)), "dots_order_sizes")
+        n_nodes, front_total = n_nodes.value, front_total.value
+        i64 = lambda *shape: np.empty(shape, dtype=np.int64)
+        perm, s, b, level, parent = i64(n), i64(n_nodes), i64(n_nodes), i64(n_nodes), i64(n_nodes)
+        child, front_idx, child_pos = i64(n_nodes, 2), i64(front_total), i64(2, front_total)
+        capi.check(lib.dots_order_export(handle, *(a.ctypes.data for a in (perm, s, b, level, parent, child, front_idx, child_pos))),
+                   "dots_order_export")
+    finally:
+        lib.dots_order_destroy(handle)
+    iperm = np.empty(n, dtype=np.int64)
+    iperm[perm] = np.arange(n)
+    cum = lambda a: np.concatenate([[0], np.cumsum(a)]).astype(np.int64)
+    return Symbolic(n=n, perm=perm, iperm=iperm, n_nodes=int(n_nodes), off=cum(s)[:-1], s=s, b=b, level=level, parent=parent,
+                    child=child, front_off=cum(s + b), front_idx=front_idx, child_pos=child_pos,
+                    panel_off=cum(s * (s + 1) // 2 + b * s), upd_off=cum(b))
 
 
 # ----------------------------------------------------------------------------- level schedule for the kernels

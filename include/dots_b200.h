@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DOTS_ABI_VERSION 7
+#define DOTS_ABI_VERSION 8
 
 /* scalar block read by the kernels from device memory (so CUDA graphs stay valid across penalty updates) */
 enum {
@@ -216,6 +216,22 @@ typedef struct dots_front_args {
 } dots_front_args_t;
 int dots_factor_small_fronts(const dots_front_args_t *a, int n_launch, int max_front, void *stream);
 int dots_front_nmax(void);
+
+/* ---- setup (row f1), host side: ONE nested-dissection ordering + symbolic multifrontal analysis shared by all time
+ * modes (the reference lets SuperLU order and analyse each of its nT+1 matrices, utils/laplacian_inverse_socp.py:34-41).
+ * HOST pointers, no CUDA.  vertices [V][3]; adj_ptr [V+1] / adj_idx: CSR pattern of the Laplacian WITHOUT the diagonal.
+ * dots_order_export fills caller-allocated int64 arrays: perm [V] (new -> old vertex), s / b / level / parent [n_nodes]
+ * (|S|, |B|, tree level with leaves = 0, parent node or -1; nodes in post-order), child [n_nodes][2] (-1 = none),
+ * front_idx [front_total] (rows of every front: S rows then B rows, new vertex ids ascending) and
+ * child_pos [2][front_total] (row of child slot's update vector that feeds this front row, or -1).
+ * Semantics and tie breaks are those of dots_socp_b200/nested.py (dissect, symbolic): identical output.            */
+typedef struct dots_order dots_order_t;
+int dots_order_create(int64_t n_vert, const double *vertices, const int64_t *adj_ptr, const int64_t *adj_idx,
+                      int64_t leaf_size, dots_order_t **out);
+int dots_order_sizes(const dots_order_t *o, int64_t *n_nodes, int64_t *front_total);
+int dots_order_export(const dots_order_t *o, int64_t *perm, int64_t *s, int64_t *b, int64_t *level, int64_t *parent,
+                      int64_t *child, int64_t *front_idx, int64_t *child_pos);
+int dots_order_destroy(dots_order_t *o);
 
 /* ---- operator-level entry points on the internal layout (rows a5, a6, a7, a8) ---------------------- */
 int dots_phi_rhs(const dots_ctx_t *c, void *stream);                       /* -> c->rhs                */

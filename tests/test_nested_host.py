@@ -148,3 +148,42 @@ def test_front_maps_agree_with_the_per_node_search():
                 cp = sym.child_pos[slot, f0:f0 + s + b]
                 pp = parent_pos[sym.upd_off[k]:sym.upd_off[k + 1]]
                 assert np.array_equal(cp[pp], np.arange(sym.b[k]))
+
+
+def _same_symbolic(a, b):
+    import dataclasses
+    for f in dataclasses.fields(a):
+        x, y = getattr(a, f.name), getattr(b, f.name)
+        if isinstance(x, np.ndarray):
+            assert x.dtype == y.dtype and x.shape == y.shape and np.array_equal(x, y), f.name
+        else:
+            assert x == y, f.name
+
+
+@pytest.mark.parametrize("example,leaf", [("icosphere1", 8), ("icosphere2", 8), ("icosphere3", 16), ("icosphere5", 24),
+                                          ("plane8", 6), ("plane20", 8), ("knot", 16), ("icosphere4", 1)])
+def test_native_ordering_is_identical_to_the_python_statement(example, leaf):
+    """csrc/host_order.cpp (what the engine calls) against nested.dissect + nested.symbolic: same permutation, same
+    separator tree, same front rows and child maps, bit for bit - so everything downstream sees the same inputs."""
+    from dots_socp_b200 import capi
+    geo, _ = synth.example(example)
+    K = surface.stiffness_matrix(geo["vertices"], geo["triangles"])
+    _same_symbolic(nested.analyse(geo["vertices"], K, leaf_size=leaf),
+                   nested.analyse_native(capi.load(), geo["vertices"], K, leaf_size=leaf))
+
+
+def test_native_ordering_on_open_and_higher_genus_surfaces():
+    from dots_socp_b200 import capi
+    for v, t in (synth.hills(24), synth.punctured_sphere(3), synth.torus(40, 12), synth.knot_tube(p=2, q=3, n_u=90, n_v=8)):
+        K = surface.stiffness_matrix(v, t)
+        _same_symbolic(nested.analyse(v, K, leaf_size=12), nested.analyse_native(capi.load(), v, K, leaf_size=12))
+
+
+def test_native_ordering_rejects_bad_arguments():
+    from dots_socp_b200 import capi
+    geo, _ = synth.example("icosphere1")
+    K = surface.stiffness_matrix(geo["vertices"], geo["triangles"])
+    with pytest.raises(capi.DotsError, match="leaf_size"):
+        nested.analyse_native(capi.load(), geo["vertices"], K, leaf_size=0)
+    with pytest.raises(ValueError):
+        nested.analyse_native(capi.load(), geo["vertices"][:, :2], K, leaf_size=8)
