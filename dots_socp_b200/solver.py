@@ -21,7 +21,7 @@ import time
 import numpy as np
 import torch
 
-from .engine import Engine, REF_KEYS
+from .engine import Engine
 from .history import RunHistory, LOG_KKT, LOG_SCALING, LOG_INFO
 from .schedule import LazyResidualCheck, PenaltySchedule, max_or_none
 

@@ -3,7 +3,6 @@ the stand-in ``plane`` reproduces the reference's example bit for bit, the analy
 diagnostics agree with values produced by the reference (fixture ``refplane20_exact``, tests/golden/make_golden.py), the
 OFF writer round-trips through the reference's dialect, and a run's log parses into the replication table."""
 import logging
-from types import SimpleNamespace
 
 import os
 

@@ -4,7 +4,6 @@
   which iteration, penalty path, stopping iteration);
 * cross-checked against the oracle's independent restatement on random residual streams;
 * and, when /root/reference is present (build container only), against the reference's own classes."""
-import math
 import os
 
 import numpy as np
