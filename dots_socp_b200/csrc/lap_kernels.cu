@@ -381,11 +381,13 @@ static int launch_sweeps(const dots_ctx_t *c, cudaStream_t st)
 }
 
 int dots_mode_solves_persistent(const dots_ctx_t *c, void *stream);   // sweep_tma.cu
+int dots_mode_solves_tile(const dots_ctx_t *c, void *stream);         // sweep_tile.cu (experimental)
 
 extern "C" int dots_mode_solves(const dots_ctx_t *c, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
     if (c->sweep_mode == 1) return dots_mode_solves_persistent(c, stream);
+    if (c->sweep_mode == 2) return dots_mode_solves_tile(c, stream);
     cudaStream_t st = (cudaStream_t)stream;
     switch (c->m_pad) {
     case 8: return launch_sweeps<8>(c, st);

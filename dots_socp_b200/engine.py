@@ -105,6 +105,37 @@ def _sweep_items_persistent(sym: nested.Symbolic, n_blocks: int):
                 node_ptr=i32([0] * (n_lv + 1)), nodes=np.zeros((1, 3), np.int32), wpr=i32([1] * n_lv), cw=i32([1] * n_lv))
 
 
+def _sweep_items_tile(sym: nested.Symbolic, n_sm: int):
+    """Work items (node, first output, n outputs) of the experimental tile-streamed sweep (csrc/sweep_tile.cu,
+    ``sweep_mode=2``): a block walks its item in groups of 8 outputs (one warp per output), so items are multiples of 8
+    outputs long - up to 32 where the level has enough outputs to still give every SM ~6 blocks."""
+    fwd_ptr, bwd_ptr, fwd, bwd = [0], [0], [], []
+
+    def cut(total, n_per_node):
+        groups = int(min(4, max(1, total // (8 * 6 * n_sm))))
+        out = []
+        for nd, n in n_per_node:
+            if n <= 0:
+                continue
+            n_items = -(-n // (8 * groups))
+            per = 8 * -(-(-(-n // n_items)) // 8)                       # even split, rounded up to whole groups
+            out += [(int(nd), o0, min(per, n - o0)) for o0 in range(0, n, per)]
+        return out
+
+    for nodes in nested.level_schedule(sym):
+        rows = [(nd, int(sym.s[nd] + sym.b[nd])) for nd in nodes]
+        cols = [(nd, int(sym.s[nd])) for nd in nodes]
+        fwd += cut(sum(n for _, n in rows), rows)
+        bwd += cut(sum(n for _, n in cols), cols)
+        fwd_ptr.append(len(fwd))
+        bwd_ptr.append(len(bwd))
+    as32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32).reshape(-1, 3)) if a else np.zeros((1, 3), np.int32)
+    i32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32))
+    n_lv = len(fwd_ptr) - 1
+    return dict(fwd_ptr=i32(fwd_ptr), fwd_items=as32(fwd), bwd_ptr=i32(bwd_ptr), bwd_items=as32(bwd),
+                node_ptr=i32([0] * (n_lv + 1)), nodes=np.zeros((1, 3), np.int32), wpr=i32([1] * n_lv), cw=i32([1] * n_lv))
+
+
 class Engine:
     """One rank's share of the problem.  ``comm`` (dist.Comm) spans the ranks; None / single rank = whole problem."""
 
@@ -182,7 +213,10 @@ class Engine:
         vc_ptr, vc_tri, vc_corner = surface.corner_adjacency(V, tri_new)
         qf, qb, n_phi_out = dd.transform_matrices(Q, part)
         self.sweep_grid = 2 * self.n_sm if self.m_pad <= 96 else self.n_sm
+        if self.sweep_mode in (1, 2) and self.m_pad < 32:
+            raise capi.DotsError(f"sweep_mode={self.sweep_mode} (experimental) needs >= 32 time modes per rank, got {self.m_pad}")
         plan = (_sweep_items_persistent(sym, self.sweep_grid) if self.sweep_mode == 1
+                else _sweep_items_tile(sym, self.n_sm) if self.sweep_mode == 2
                 else _sweep_items(sym, self.n_sm, self.m_pad))
         self.plan = plan                                                                 # host arrays stay alive
         fwd_ptr, fwd_items, bwd_ptr, bwd_items = plan["fwd_ptr"], plan["fwd_items"], plan["bwd_ptr"], plan["bwd_items"]

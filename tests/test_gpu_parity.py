@@ -335,3 +335,26 @@ def test_small_root_front_is_pinned_deterministically():
         assert torch.isfinite(p).all()
         first = p if first is None else first
         assert torch.equal(p, first)
+
+
+# ---------------------------------------------------------------------------------------------- experimental sweeps
+@pytest.mark.skipif(__import__("os").environ.get("DOTS_TEST_EXPERIMENTAL") != "1",
+                    reason="opt-in: sweep_mode 1 (persistent) / 2 (tile-streamed, not yet run on hardware); "
+                           "set DOTS_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("example,n_time,leaf", [("icosphere3", 31, 16), ("icosphere2", 40, 8), ("icosphere5", 63, 16),
+                                                 ("icosphere3", 127, 16)])
+def test_experimental_sweep_modes_match_the_default_path(mode, example, n_time, leaf):
+    """Same iterates as the default per-level sweep (different summation order inside a front: 1e-10)."""
+    geo, _ = synth.example(example)
+    ref = Engine(n_time, geo, congestion=0.05, leaf_size=leaf)
+    alt = Engine(n_time, geo, congestion=0.05, leaf_size=leaf, sweep_mode=mode)
+    for eng in (ref, alt):
+        eng.scale_z(2.0)
+        eng.iterate(6, write_z=True)
+    a, b = ref.get_state(), alt.get_state()
+    for k in a:
+        x, y = a[k], b[k]
+        if k == "phi":
+            x, y = x - x.mean(), y - y.mean()
+        assert rel(y, x) < 1e-10, (mode, k, rel(y, x))

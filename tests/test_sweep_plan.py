@@ -71,3 +71,20 @@ def test_children_sit_on_strictly_lower_levels():
         for k in sym.child[n]:
             if k >= 0:
                 assert sym.level[k] < sym.level[n]
+
+
+@pytest.mark.parametrize("example,leaf,n_sm", [("icosphere3", 16, 148), ("icosphere5", 16, 148), ("knot", 16, 148), ("plane8", 6, 4)])
+def test_tile_plan_covers_every_output_once_in_whole_groups(example, leaf, n_sm):
+    """Plan of the experimental tile-streamed sweep (sweep_mode=2): exact cover, items start on their node's output 0 + k*per
+    and every item but a node's last one is a multiple of 8 outputs long."""
+    sym = _sym(example, leaf)
+    plan = engine._sweep_items_tile(sym, n_sm)
+    for lv, nodes in enumerate(nested.level_schedule(sym)):
+        for key_ptr, key_items, lens in (("fwd_ptr", "fwd_items", {int(n): int(sym.s[n] + sym.b[n]) for n in nodes}),
+                                         ("bwd_ptr", "bwd_items", {int(n): int(sym.s[n]) for n in nodes})):
+            items = plan[key_items][plan[key_ptr][lv]:plan[key_ptr][lv + 1]]
+            seen = _coverage(items, lens)
+            assert all((c == 1).all() for c in seen.values())
+            assert {int(n) for n in items[:, 0]} == {n for n, ln in lens.items() if ln > 0}
+            for nd, o0, cnt in items:
+                assert cnt <= 32 and (cnt % 8 == 0 or o0 + cnt == lens[int(nd)])
