@@ -8,19 +8,22 @@
 //     output's dot product is accumulated by one warp in a fixed order (no cross-warp combine, deterministic);
 //   * the input index (columns of the row-major panel in the forward sweep, rows of the column-major copy in the
 //     backward sweep) is cut into chunks of C = 512 / M entries; the 8 outputs' segments of one chunk form a 2-D tile of
-//     <= 32 KB that thread 0 streams with 8 bulk async copies (cp.async.bulk, one mbarrier per stage) into a 3-stage
+//     <= 32 KB that the producer streams with 8 bulk async copies (cp.async.bulk, one mbarrier per stage) into a 3-stage
 //     shared-memory ring, running 3 tiles ahead of the math.  Bytes in flight per SM = 2 blocks x 3 x 32 KB, independent
 //     of occupancy and registers (k_sweep_run: ~48 KB requested, ~half of it in flight, 66 % of the HBM peak);
 //   * the chunk of the input vector (r_S with the children's updates folded in / -[y_S ; xt_B]) is fetched one step ahead
 //     into registers and double-buffered in shared memory; it is shared by the 8 outputs of the tile;
+//   * a ninth warp is the producer: after the per-tile barrier it refills the freed stage while the math warps are already
+//     on the next tile, so the address arithmetic of the 8 copies is off the critical path;
 //   * one __syncthreads per tile.  The persistent variant (sweep_tma.cu) paid that per <= 16 KB (row, chunk) segment and a
 //     single-thread address walk on top, which is why it lost.
 //
 // The children's updates are folded while staging r_S, so no k_sweep_gather launches are needed.
 #include "common.cuh"
 
-#define ST_THREADS 256
-#define ST_WARPS 8
+#define ST_WARPS 8                          // math warps: one output each
+#define ST_MATH (32 * ST_WARPS)
+#define ST_THREADS (ST_MATH + 32)           // + one producer warp (its lane 0 issues the bulk copies)
 #define ST_STAGES 3
 
 __host__ __device__ __forceinline__ int st_chunk(int M) { return 512 / M; }          // 16, 8, 5, 4 for M = 32, 64, 96, 128
@@ -87,12 +90,13 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_sweep_tile(dots_ctx_t c, int 
 {
     constexpr int M = 32 * MP;
     constexpr int C = 512 / M;
-    constexpr int VPT = (C * M + ST_THREADS - 1) / ST_THREADS;            // input-vector elements per thread and chunk
+    constexpr int VPT = (C * M + ST_MATH - 1) / ST_MATH;                  // input-vector elements per math thread and chunk
     extern __shared__ __align__(128) unsigned char smraw[];
     double *ring = reinterpret_cast<double *>(smraw);                     // [ST_STAGES][8][C][M]
     double *vec = ring + (size_t)ST_STAGES * ST_WARPS * C * M;            // [2][C][M]
     uint64_t *full = reinterpret_cast<uint64_t *>(vec + (size_t)2 * C * M);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool math = warp < ST_WARPS, producer = tid == ST_MATH;
 
     const int *it = (DIR == 0 ? c.lvl_items : c.lvb_items) + 3 * (size_t)(item0 + blockIdx.x);
     const int node = it[0], o0 = it[1], n_o = it[2];
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_sweep_tile(dots_ctx_t c, int 
     }
     __syncthreads();
 
-    // producer (thread 0): one stage = the segments of the group's outputs that fall into the chunk
+    // producer (lane 0 of the ninth warp): one stage = the segments of the group's outputs that fall into the chunk
     auto issue = [&](const StCursor &k, int slot) {
         uint32_t total = 0;
         const int first = o0 + ST_WARPS * k.g;
@@ -142,10 +146,10 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_sweep_tile(dots_ctx_t c, int 
     auto vec_fetch = [&](int cb, int cb_end, double (&reg)[VPT]) {
 #pragma unroll
         for (int k = 0; k < VPT; ++k) {
-            const int i = tid + k * ST_THREADS;
+            const int i = tid + k * ST_MATH;
             const int jj = i / M, m = i - jj * M, j = cb + jj;
             double v = 0.0;
-            if (i < C * M && j < cb_end) {
+            if (math && i < C * M && j < cb_end) {
                 if (DIR == 0) {
                     v = c.hat[(size_t)(off + j) * M + m];
                     const int a = cp0[j], bb = cp1[j];
@@ -161,8 +165,8 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_sweep_tile(dots_ctx_t c, int 
     auto vec_store = [&](int buf, const double (&reg)[VPT]) {
 #pragma unroll
         for (int k = 0; k < VPT; ++k) {
-            const int i = tid + k * ST_THREADS;
-            if (i < C * M) vec[(size_t)buf * C * M + i] = reg[k];
+            const int i = tid + k * ST_MATH;
+            if (math && i < C * M) vec[(size_t)buf * C * M + i] = reg[k];
         }
     };
 
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_sweep_tile(dots_ctx_t c, int 
     if (!st_first<DIR>(cur, o0, n_o, s, b, C)) return;                   // empty item (never produced by the plan)
     prod = cur;
     bool prod_ok = true;
-    if (tid == 0) {
+    if (producer) {
         for (int i = 0; i < ST_STAGES && prod_ok; ++i) {
             issue(prod, i);
             prod_ok = st_next<DIR>(prod, o0, n_o, s, b, C);
@@ -190,9 +194,9 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_sweep_tile(dots_ctx_t c, int 
         StCursor nxt = cur;
         more = st_next<DIR>(nxt, o0, n_o, s, b, C);
         if (more) vec_fetch(nxt.cb, nxt.cb_end, reg);                    // next chunk's input vector: loads in flight during the math
-        mbar_wait(&full[slot], (step / ST_STAGES) & 1);
         const int o = o0 + ST_WARPS * cur.g + warp;
-        if (o < o0 + n_o) {
+        if (math && o < o0 + n_o) {
+            mbar_wait(&full[slot], (step / ST_STAGES) & 1);
             int lo, hi;
             st_span<DIR>(o, s, b, lo, hi);
             const int e_lo = max(lo, cur.cb), ne = min(hi, cur.cb + C) - e_lo;
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_sweep_tile(dots_ctx_t c, int 
         }
         if (more) vec_store(buf ^ 1, reg);
         __syncthreads();                                                 // ring[slot] and vec[buf] are free, vec[buf^1] is visible
-        if (tid == 0 && prod_ok) {
+        if (producer && prod_ok) {
             issue(prod, slot);
             prod_ok = st_next<DIR>(prod, o0, n_o, s, b, C);
         }
