@@ -40,6 +40,19 @@ def time_basis(n_time: int):
     return Q, lam
 
 
+def _cut(nodes, lengths, step):
+    """Work items (node, first output, n outputs <= step) covering ``lengths[i]`` outputs of ``nodes[i]``, node by node."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    n_items = -(-lengths // step)
+    total = int(n_items.sum())
+    if total == 0:
+        return np.zeros((0, 3), dtype=np.int32)
+    owner = np.repeat(np.arange(len(nodes)), n_items)
+    first = (np.arange(total) - np.repeat(np.cumsum(n_items) - n_items, n_items)) * step
+    count = np.minimum(step, lengths[owner] - first)
+    return np.stack([np.asarray(nodes, dtype=np.int64)[owner], first, count], axis=1).astype(np.int32)
+
+
 def _sweep_items(sym: nested.Symbolic, n_sm: int, m_pad: int):
     """Per-level launch plan of the two sweeps (one launch per level and direction).
 
@@ -47,7 +60,7 @@ def _sweep_items(sym: nested.Symbolic, n_sm: int, m_pad: int):
     column-major copy) in the backward sweep.  ``wpr`` warps share one output: 1 for the short runs of the leaf
     fronts, up to 8 for the long runs of the top separators, so every level exposes >= ~8 blocks per SM whenever it
     has the outputs for it."""
-    fwd_ptr, bwd_ptr, node_ptr, fwd, bwd, nodes_flat, wprs, cws = [0], [0], [0], [], [], [], [], []
+    fwd_ptr, bwd_ptr, node_ptr, fwd, bwd, gather, wprs, cws = [0], [0], [0], [], [], [], [], []
 
     def pick(len_eff, total):
         wpr = 1 if len_eff < 32 else 2 if len_eff < 96 else 4 if len_eff < 256 else 8
@@ -55,6 +68,7 @@ def _sweep_items(sym: nested.Symbolic, n_sm: int, m_pad: int):
         passes = int(min(8, max(1, total // (per_pass * 8 * n_sm))))
         return wpr, per_pass * passes
 
+    has_child = (sym.child >= 0).any(axis=1)
     for nodes in nested.level_schedule(sym):
         s_l, b_l = sym.s[nodes].astype(np.int64), sym.b[nodes].astype(np.int64)
         work = np.maximum(1, s_l * (s_l + 1) // 2 + s_l * b_l)
@@ -62,23 +76,22 @@ def _sweep_items(sym: nested.Symbolic, n_sm: int, m_pad: int):
         col_eff = float(((s_l / 2 + b_l) * work).sum() / work.sum())
         wpr, rb = pick(s_eff, int((s_l + b_l).sum()))
         cw, cb = pick(col_eff, int(s_l.sum()))
-        has_kids = bool((sym.child[nodes] >= 0).any())
-        fuse = has_kids and wpr <= 2 and int(s_l.max()) <= 64 and os.environ.get("DOTS_FUSE_GATHER", "1") == "1"
-        for nd in nodes:
-            nrow, ncol = int(sym.s[nd] + sym.b[nd]), int(sym.s[nd])
-            fwd += [(int(nd), r0, min(rb, nrow - r0)) for r0 in range(0, nrow, rb)]
-            bwd += [(int(nd), c0, min(cb, ncol - c0)) for c0 in range(0, ncol, cb)]
-            if (sym.child[nd] >= 0).any() and not fuse:
-                nodes_flat += [(int(nd), j0, min(32, ncol - j0)) for j0 in range(0, ncol, 32)]
-        node_ptr.append(len(nodes_flat))
-        fwd_ptr.append(len(fwd))
-        bwd_ptr.append(len(bwd))
+        kids = has_child[nodes]
+        fuse = bool(kids.any()) and wpr <= 2 and int(s_l.max()) <= 64 and os.environ.get("DOTS_FUSE_GATHER", "1") == "1"
+        fwd.append(_cut(nodes, s_l + b_l, rb))
+        bwd.append(_cut(nodes, s_l, cb))
+        if not fuse:
+            gather.append(_cut(nodes[kids], s_l[kids], 32))
+        fwd_ptr.append(fwd_ptr[-1] + len(fwd[-1]))
+        bwd_ptr.append(bwd_ptr[-1] + len(bwd[-1]))
+        node_ptr.append(node_ptr[-1] + (len(gather[-1]) if not fuse else 0))
         wprs.append(wpr + (16 if fuse else 0))
         cws.append(cw)
-    as32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32).reshape(-1, 3)) if a else np.zeros((1, 3), np.int32)
+    cat = lambda parts: (np.ascontiguousarray(np.concatenate(parts, axis=0)) if sum(len(p) for p in parts)
+                         else np.zeros((1, 3), np.int32))
     i32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32))
-    return dict(fwd_ptr=i32(fwd_ptr), fwd_items=as32(fwd), bwd_ptr=i32(bwd_ptr), bwd_items=as32(bwd),
-                node_ptr=i32(node_ptr), nodes=as32(nodes_flat), wpr=i32(wprs), cw=i32(cws))
+    return dict(fwd_ptr=i32(fwd_ptr), fwd_items=cat(fwd), bwd_ptr=i32(bwd_ptr), bwd_items=cat(bwd),
+                node_ptr=i32(node_ptr), nodes=cat(gather), wpr=i32(wprs), cw=i32(cws))
 
 
 def _sweep_items_persistent(sym: nested.Symbolic, n_blocks: int):
