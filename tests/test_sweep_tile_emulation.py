@@ -34,17 +34,21 @@ def group_range(d, o0, n_o, g, s, b, C):               # st_group_range
     return (0, min(lastq + 1, s)) if d == 0 else ((first // C) * C, s + b)
 
 
-def steps(d, o0, n_o, s, b, C):                        # st_first / st_next
-    g = 0
+def steps(d, o0, n_o, s, b, C):                        # st_first / st_next, statement by statement
+    rng = group_range(d, o0, n_o, 0, s, b, C)          # st_first: the first step exists even if its chunk range is empty
+    if rng is None:                                     # (a node with an empty separator still has to forward its
+        return                                          #  children's updates: one step without data per output group)
+    g, (cb, cb_end) = 0, rng
     while True:
+        yield g, cb, cb_end
+        cb += C                                         # st_next
+        if cb < cb_end:
+            continue
+        g += 1
         rng = group_range(d, o0, n_o, g, s, b, C)
         if rng is None:
             return
         cb, cb_end = rng
-        while cb < cb_end:
-            yield g, cb, cb_end
-            cb += C
-        g += 1
 
 
 def run_item(d, sym, item, panels, panels_t, hat, ywork, upd, M, C):
@@ -127,7 +131,8 @@ def run_item(d, sym, item, panels, panels_t, hat, ywork, upd, M, C):
     assert not np.isnan(acc).any()
 
 
-@pytest.mark.parametrize("example,leaf,n_sm", [("icosphere2", 8, 148), ("plane8", 6, 2), ("knot_small", 12, 4)])
+@pytest.mark.parametrize("example,leaf,n_sm", [("icosphere2", 8, 148), ("plane8", 6, 2), ("knot_small", 12, 4),
+                                               ("knot", 16, 148)])          # the last one has an empty separator (s = 0, b > 0)
 def test_tile_sweep_walk_solves_every_mode(example, leaf, n_sm):
     if example == "knot_small":
         v, t = synth.knot_tube(n_u=40, n_v=6)
@@ -139,6 +144,8 @@ def test_tile_sweep_walk_solves_every_mode(example, leaf, n_sm):
     M = 32
     shifts = np.concatenate([[0.0], np.linspace(0.3, 40.0, M - 1)])
     sym = nested.analyse(v, K, leaf_size=leaf)
+    if example == "knot":
+        assert ((sym.s == 0) & (sym.b > 0)).any()
     p, pt = nested.factor_batched_device(sym, K, mass, shifts, m_pad=M, device="cpu", transposed=True)
     panels, panels_t = p.numpy(), pt.numpy()
     plan = engine._sweep_items_tile(sym, n_sm)
