@@ -387,7 +387,7 @@ extern "C" int dots_mode_solves(const dots_ctx_t *c, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
     if (c->sweep_mode == 1) return dots_mode_solves_persistent(c, stream);
-    if (c->sweep_mode == 2) return dots_mode_solves_tile(c, stream);
+    if (c->sweep_mode == 2 || c->sweep_mode == 3) return dots_mode_solves_tile(c, stream);
     cudaStream_t st = (cudaStream_t)stream;
     switch (c->m_pad) {
     case 8: return launch_sweeps<8>(c, st);

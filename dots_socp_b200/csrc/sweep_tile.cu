@@ -1,4 +1,4 @@
-// EXPERIMENTAL (sweep_mode = 2, off by default, NOT yet run on hardware - written at the end of round 1 from the analysis in
+// EXPERIMENTAL (sweep_mode = 2, or 3 = the same with programmatic dependent launch; off by default, NOT yet run on hardware - written at the end of round 1 from the analysis in
 // DESIGN.md section 8; validate with DOTS_TEST_EXPERIMENTAL=1 before use).
 //
 // Tile-streamed form of the batched multifrontal sweeps (row a8; reference utils/laplacian_inverse_socp.py:58-59).
@@ -85,9 +85,14 @@ __device__ __forceinline__ bool st_next(StCursor &k, int o0, int n_o, int s, int
     return true;
 }
 
-template <int MP, int DIR>
+// PDL (sweep_mode = 3): the launches of consecutive tree levels are chained with programmatic dependent launch.  A block
+// lets the next level start as soon as it runs (griddepcontrol.launch_dependents) and, because the factor panels are
+// read-only, streams its first ST_STAGES tiles BEFORE it waits for the previous level (griddepcontrol.wait): the tail of
+// one level overlaps the first loads of the next instead of an idle launch boundary.
+template <int MP, int DIR, bool PDL>
 __global__ void __launch_bounds__(ST_THREADS, 2) k_sweep_tile(dots_ctx_t c, int item0)
 {
+    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     constexpr int M = 32 * MP;
     constexpr int C = 512 / M;
     constexpr int VPT = (C * M + ST_MATH - 1) / ST_MATH;                  // input-vector elements per math thread and chunk
@@ -180,6 +185,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_sweep_tile(dots_ctx_t c, int 
             prod_ok = st_next<DIR>(prod, o0, n_o, s, b, C);
         }
     }
+    if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");           // everything below reads the previous level's output
     double reg[VPT];
     vec_fetch(cur.cb, cur.cb_end, reg);
     vec_store(0, reg);
@@ -238,7 +244,29 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_sweep_tile(dots_ctx_t c, int 
     }
 }
 
-template <int MP>
+template <int MP, int DIR, bool PDL>
+static int launch_tile_level(const dots_ctx_t *c, int i0, int n, size_t smem, cudaStream_t st)
+{
+    if (!PDL) {
+        k_sweep_tile<MP, DIR, false><<<n, ST_THREADS, smem, st>>>(*c, i0);
+        DOTS_LAUNCH_CHECK();
+        return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n);
+    cfg.blockDim = dim3(ST_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_tile<MP, DIR, true>, *c, i0));
+    return 0;
+}
+
+template <int MP, bool PDL>
 static int launch_tile(const dots_ctx_t *c, cudaStream_t st)
 {
     constexpr int M = 32 * MP;
@@ -246,21 +274,19 @@ static int launch_tile(const dots_ctx_t *c, cudaStream_t st)
     const size_t smem = ((size_t)ST_STAGES * ST_WARPS * C * M + (size_t)2 * C * M) * sizeof(double) + 64;
     static bool configured = false;
     if (!configured) {
-        DOTS_CUDA(cudaFuncSetAttribute(k_sweep_tile<MP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        DOTS_CUDA(cudaFuncSetAttribute(k_sweep_tile<MP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DOTS_CUDA(cudaFuncSetAttribute(k_sweep_tile<MP, 0, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DOTS_CUDA(cudaFuncSetAttribute(k_sweep_tile<MP, 1, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     for (int lv = 0; lv < c->n_levels; ++lv) {
         const int i0 = c->h_lvl_ptr[lv], n = c->h_lvl_ptr[lv + 1] - i0;
         if (n <= 0) continue;
-        k_sweep_tile<MP, 0><<<n, ST_THREADS, smem, st>>>(*c, i0);
-        DOTS_LAUNCH_CHECK();
+        if (int e = launch_tile_level<MP, 0, PDL>(c, i0, n, smem, st)) return e;
     }
     for (int lv = c->n_levels - 1; lv >= 0; --lv) {
         const int i0 = c->h_lvb_ptr[lv], n = c->h_lvb_ptr[lv + 1] - i0;
         if (n <= 0) continue;
-        k_sweep_tile<MP, 1><<<n, ST_THREADS, smem, st>>>(*c, i0);
-        DOTS_LAUNCH_CHECK();
+        if (int e = launch_tile_level<MP, 1, PDL>(c, i0, n, smem, st)) return e;
     }
     return 0;
 }
@@ -269,11 +295,12 @@ int dots_mode_solves_tile(const dots_ctx_t *c, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (c->m_pad % 32) { dots_set_error("tile sweep needs m_pad >= 32 (got %d)", c->m_pad); return DOTS_ERR_BAD_ARG; }
+    const bool pdl = c->sweep_mode == 3;
     switch (c->m_pad / 32) {
-    case 1: return launch_tile<1>(c, st);
-    case 2: return launch_tile<2>(c, st);
-    case 3: return launch_tile<3>(c, st);
-    case 4: return launch_tile<4>(c, st);
+    case 1: return pdl ? launch_tile<1, true>(c, st) : launch_tile<1, false>(c, st);
+    case 2: return pdl ? launch_tile<2, true>(c, st) : launch_tile<2, false>(c, st);
+    case 3: return pdl ? launch_tile<3, true>(c, st) : launch_tile<3, false>(c, st);
+    case 4: return pdl ? launch_tile<4, true>(c, st) : launch_tile<4, false>(c, st);
     }
     dots_set_error("m_pad=%d unsupported", c->m_pad);
     return DOTS_ERR_BAD_ARG;

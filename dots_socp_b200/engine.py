@@ -226,10 +226,10 @@ class Engine:
         vc_ptr, vc_tri, vc_corner = surface.corner_adjacency(V, tri_new)
         qf, qb, n_phi_out = dd.transform_matrices(Q, part)
         self.sweep_grid = 2 * self.n_sm if self.m_pad <= 96 else self.n_sm
-        if self.sweep_mode in (1, 2) and self.m_pad < 32:
+        if self.sweep_mode in (1, 2, 3) and self.m_pad < 32:
             raise capi.DotsError(f"sweep_mode={self.sweep_mode} (experimental) needs >= 32 time modes per rank, got {self.m_pad}")
         plan = (_sweep_items_persistent(sym, self.sweep_grid) if self.sweep_mode == 1
-                else _sweep_items_tile(sym, self.n_sm) if self.sweep_mode == 2
+                else _sweep_items_tile(sym, self.n_sm) if self.sweep_mode in (2, 3)
                 else _sweep_items(sym, self.n_sm, self.m_pad))
         self.plan = plan                                                                 # host arrays stay alive
         fwd_ptr, fwd_items, bwd_ptr, bwd_items = plan["fwd_ptr"], plan["fwd_items"], plan["bwd_ptr"], plan["bwd_items"]

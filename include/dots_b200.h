@@ -131,7 +131,8 @@ typedef struct dots_ctx {
     double *red_out;           /* [8] reduced sums (device)                                           */
     int32_t red_blocks;
     int32_t sweep_mode;        /* 0: one launch per tree level and direction; 1: persistent TMA-fed cooperative kernel;
-                                  2: per-level launches streaming 2-D panel tiles through a TMA ring (experimental) */
+                                  2: per-level launches streaming 2-D panel tiles through a TMA ring; 3: the same, levels chained
+                                  with programmatic dependent launch (2, 3: experimental) */
     int32_t sweep_grid;        /* blocks of the persistent kernel (0 = 2 per SM)                       */
     int32_t reserved0;
     uint64_t *phase_clock;     /* optional [2*n_levels+1]: %globaltimer (ns) at the start and after each sweep phase */

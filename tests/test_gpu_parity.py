@@ -339,9 +339,9 @@ def test_small_root_front_is_pinned_deterministically():
 
 # ---------------------------------------------------------------------------------------------- experimental sweeps
 @pytest.mark.skipif(__import__("os").environ.get("DOTS_TEST_EXPERIMENTAL") != "1",
-                    reason="opt-in: sweep_mode 1 (persistent) / 2 (tile-streamed, not yet run on hardware); "
+                    reason="opt-in: sweep_mode 1 (persistent) / 2, 3 (tile-streamed, not yet run on hardware); "
                            "set DOTS_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("example,n_time,leaf", [("icosphere3", 31, 16), ("icosphere2", 40, 8), ("icosphere5", 63, 16),
                                                  ("icosphere3", 127, 16)])
 def test_experimental_sweep_modes_match_the_default_path(mode, example, n_time, leaf):
