@@ -1,0 +1,178 @@
+"""The host control flow of the product's ``solver_socp`` (dots_socp_b200/solver.py) on the CPU.
+
+On a GPU box that loop drives ``engine.Engine`` (CUDA kernels).  Here the engine is replaced by a test double with the
+same interface whose arithmetic is the CPU oracle (oracle/alm_oracle.py - test infrastructure, allowed in tests/ only), so
+everything ELSE the loop owns is exercised without a GPU and compared with the fixtures of the unmodified reference:
+lazy KKT scheduling (which residual on which iteration), penalty path, z rescale, stopping, time limit, step-by-step mode,
+tolerance checkpoints, warm start wiring, history rows, solution hand-off (SOCP units and DOT units)."""
+import importlib
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import alm_oracle as orc
+
+solver_mod = importlib.import_module("dots_socp_b200.solver")
+
+E2O = dict(phi="phi", A="A", B="B", lam_c="lam_c", mu="mu", E="E", z_fst="z_fst", z_mid="z_mid", z_end="z_end",
+           b_fst="b_fst", b_mid="b_mid", b_end="b_end")
+
+
+class OracleEngine:
+    """``engine.Engine``'s public surface, reference layout inside, numpy arithmetic from the oracle."""
+
+    def __init__(self, n_time, geometry, congestion=0.0, eps=0.0, tau=1.9, device=None, leaf_size=16, comm=None, **_):
+        self.alm = orc.OracleALM(n_time, geometry, congestion=congestion, eps=eps, tau=tau, is_z_scaling=False)
+        o = self.alm.ops
+        self.nT, self.V, self.T, self.dt = o.nT, o.V, o.T, o.dt
+        self.cong = congestion
+        self.device = torch.device("cpu")
+        self.timings = {"setup_total": 0.0}
+        self.launches = 0
+        self.z_valid = False
+        self.calls = []
+
+    r = property(lambda self: self.alm.r)
+
+    def scale_z(self, f):
+        self.alm.scale_z(f)
+
+    def adjust_penalty(self, f):
+        self.alm.adjust_penalty(f)
+
+    def iterate(self, n=1, write_z=False):
+        for _ in range(n):
+            self.alm.iterate()
+        self.z_valid = bool(write_z)
+        self.calls.append(bool(write_z))
+
+    def kkt(self, i):
+        if i == 1:
+            assert self.z_valid, "KKT #1 requested on an iteration that did not store z_mid"
+        return self.alm.kkt(i)
+
+    def objective(self):
+        return self.alm.objective()
+
+    def from_internal(self, name):
+        return torch.from_numpy(np.array(getattr(self.alm, E2O[name]), copy=True))
+
+    def set_state(self, **arrays):
+        for name, val in arrays.items():
+            setattr(self.alm, E2O[name], np.array(torch.as_tensor(val).numpy(), dtype=np.float64, copy=True))
+
+    def grad_space_into(self, src, dst):
+        assert (src, dst) == ("phi", "B")
+        self.alm.B = orc.grad_space(self.alm.ops.G, self.alm.phi)
+
+    def E_from_beta(self, scale):
+        self.alm.E = -orc.decouple_adjoint(self.alm.b_mid, scale)
+
+    def refresh(self):
+        pass
+
+    def solution(self, keys=None):
+        sol = self.alm.solution()
+        return sol if keys is None else {k: sol[k] for k in keys}
+
+    def dot_solution(self, geometry, centred):
+        av = np.asarray(geometry["area_vertices"])[None, :] / 3.0
+        mu = (self.alm.mu * self.alm.r) * av
+        if centred:
+            mu = np.concatenate([geometry["mu0"][None], 0.5 * (mu[:-1] + mu[1:]), geometry["mu1"][None]], axis=0)
+        return dict(mu=mu, E=(self.alm.E * self.alm.r) * np.asarray(geometry["area_triangles"])[None, :, None])
+
+    def congestion_norm(self):
+        return float(np.linalg.norm(self.alm.lam_c - self.cong * self.alm.r * self.alm.mu))
+
+
+class _Event:
+    def __init__(self, enable_timing=False):
+        pass
+
+    def record(self):
+        pass
+
+    def elapsed_time(self, other):
+        return 0.0
+
+
+class _TorchShim:
+    """Real torch, except the CUDA events / stream the loop uses for its timers."""
+    cuda = SimpleNamespace(Event=_Event, current_stream=lambda dev=None: SimpleNamespace(synchronize=lambda: None))
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+
+@pytest.fixture
+def cpu_loop(monkeypatch):
+    made = []
+
+    def factory(*a, **kw):
+        made.append(OracleEngine(*a, **kw))
+        return made[-1]
+
+    monkeypatch.setattr(solver_mod, "Engine", factory)
+    monkeypatch.setattr(solver_mod, "torch", _TorchShim())
+    return made
+
+
+@pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005", "ico2_nt15_tol1e-4",
+                                  "ico2_nt7_stepwise", "ico1_nt1_c005", "ico1_nt2_c0", "ico2_nt7_eps1e-2", "ico2_nt7_tl0"])
+def test_loop_reproduces_reference_runs(cpu_loop, golden, name):
+    z, geo, n_time, kw = golden(name)
+    sol, hist = solver_mod.solver_socp(n_time, geo, **kw)
+    assert int(hist.kkt_iteration[-1]) == int(z["iterations"])
+    ref_rows = z["kkt_rows"]
+    assert hist.kkt_errors.shape == ref_rows.shape
+    assert np.array_equal(np.isnan(hist.kkt_errors), np.isnan(ref_rows))              # same residual on the same iteration
+    m = ~np.isnan(ref_rows)
+    assert np.allclose(hist.kkt_errors[m], ref_rows[m], rtol=1e-6, atol=1e-12)
+    assert hist.history["Transportation cost"][-1] == pytest.approx(float(z["cost"]), rel=1e-8)
+    if kw.get("check_kkt_step_by_step"):
+        assert np.allclose(hist.history["Transportation cost"], z["cost_history"], rtol=1e-8)
+    assert np.abs(sol["mu"] - z["sol_mu"]).max() <= 1e-7 * np.abs(z["sol_mu"]).max()
+    eng = cpu_loop[-1]
+    # z_mid is only materialised on iterations that check (or may check) KKT #1; most iterations must not ask for it
+    if not kw.get("check_kkt_step_by_step") and len(eng.calls) > 50:
+        assert 0 < sum(eng.calls) < 0.8 * len(eng.calls)
+
+
+@pytest.mark.parametrize("tag,keys", [("full", None), ("part", ("phi", "beta_fst", "beta_end", "beta_mid"))])
+def test_loop_warm_start_wiring(cpu_loop, golden, tag, keys):
+    z, geo, n_time, kw = golden("ico2_nt7_warm")
+    init = {k[5:]: z[k] for k in z.files if k.startswith("init_") and (keys is None or k[5:] in keys)}
+    sol, hist = solver_mod.solver_socp(n_time, geo, init_solution=init, **kw)
+    assert int(hist.kkt_iteration[-1]) == int(z[tag + "_iterations"])
+    assert hist.history["Transportation cost"][-1] == pytest.approx(float(z[tag + "_cost"]), rel=1e-8)
+    assert np.abs(sol["mu"] - z[tag + "_mu"]).max() <= 1e-7 * np.abs(z[tag + "_mu"]).max()
+
+
+def test_loop_checkpoints_and_dot_units(cpu_loop, golden):
+    from dots_socp_b200 import surface
+    z, geo, n_time, kw = golden("ico2_nt7_c01")
+    af = surface.triangle_areas(geo["vertices"], geo["triangles"])
+    geo = dict(geo, area_triangles=af, area_vertices=surface.incident_area_sum(geo["vertices"].shape[0], geo["triangles"], af))
+    sol, hist = solver_mod.solver(n_time, geo, tol_checkpoints=[1e-1, 1e-2], **kw)
+    assert int(hist.kkt_iteration[-1]) == int(z["iterations"])                         # checkpoints do not perturb the run
+    av = geo["area_vertices"][None, :] / 3.0
+    mid = z["sol_mu"] * av
+    assert np.allclose(sol["mu"][1:-1], 0.5 * (mid[:-1] + mid[1:]), rtol=1e-7, atol=1e-14)
+    assert np.array_equal(sol["mu"][0], geo["mu0"]) and np.array_equal(sol["mu"][-1], geo["mu1"])
+    cps = sol["checkpoints"]
+    assert len(cps) == 2 and cps[0]["iteration"] < cps[1]["iteration"] <= int(z["iterations"])
+    for cp, level in zip(cps, (1e-1, 1e-2)):
+        assert cp["mu"].shape == sol["mu"].shape and cp["E"].shape == sol["E"].shape
+        assert max(k for k in cp["kkt"] if k is not None) <= level
+    raw, _ = solver_mod.solver_raw(n_time, geo, **kw)
+    assert np.allclose(raw["mu"], mid, rtol=1e-7, atol=1e-14)
+
+
+def test_loop_raises_on_non_finite_residual(cpu_loop, golden, monkeypatch):
+    z, geo, n_time, kw = golden("ico2_nt7_c0")
+    monkeypatch.setattr(OracleEngine, "kkt", lambda self, i: [float("nan"), float("nan")])
+    with pytest.raises(FloatingPointError, match="non-finite KKT residual"):
+        solver_mod.solver_socp(n_time, geo, **kw)
