@@ -185,7 +185,39 @@ def warm_start_fixture():
     print(f"ico2_nt7_warm: coarse iterations={out['coarse_iterations']} -> {os.path.getsize(path) / 1e6:.2f} MB")
 
 
-EXTRA = {"refplane20_exact": exact_study_fixture, "ico2_nt7_warm": warm_start_fixture}
+def plugin_fixture():
+    """``ico2_nt7_plugin.npz``: the reference's own plug-in callables ``solver`` (dot_solver_socp_center) and ``solver_raw``
+    (socp/solver_decorator.py:10-72) on a geometry with areas, with tolerance checkpoints (solver_socp.py:790-801):
+    DOT-unit mu / E on the centred and on the staggered grid, and every checkpoint's iteration, kkt row, mu, E."""
+    from dots_socp_b200 import surface
+    refshim.load()
+    from dot_surface_socp.socp.solver_decorator import solver as ref_solver, solver_raw as ref_raw
+    geo, scale = synth.example("icosphere2")
+    assert "area_vertices" in geo and "area_triangles" in geo
+    kw = dict(tol=1e-3, nit=1000, congestion=0.1)
+    cps = [1e-1, 1e-2]
+    cwd = os.getcwd()
+    try:
+        sol_c, hist = ref_solver(7, geo, tol_checkpoints=list(cps), **kw)
+        sol_r, _ = ref_raw(7, geo, **kw)
+    finally:
+        os.chdir(cwd)
+    out = dict(vertices=geo["vertices"], triangles=geo["triangles"], mu0=geo["mu0"], mu1=geo["mu1"], n_time=7,
+               scale_factor=scale, kw_keys=np.array(list(kw)), kw_vals=np.array([float(v) for v in kw.values()]),
+               area_vertices=geo["area_vertices"], area_triangles=geo["area_triangles"], tol_checkpoints=np.array(cps),
+               iterations=int(hist.kkt_iteration[-1]), centre_mu=sol_c["mu"], centre_E=sol_c["E"],
+               raw_mu=sol_r["mu"], raw_E=sol_r["E"], n_checkpoints=len(sol_c["checkpoints"]))
+    for i, cp in enumerate(sol_c["checkpoints"]):
+        out[f"cp{i}_mu"], out[f"cp{i}_E"] = cp["mu"], cp["E"]
+        out[f"cp{i}_iteration"] = int(cp["iteration"])
+        out[f"cp{i}_kkt"] = np.array([np.nan if k is None else float(k) for k in cp["kkt"]])
+    path = os.path.join(HERE, "ico2_nt7_plugin.npz")
+    np.savez_compressed(path, **out)
+    print(f"ico2_nt7_plugin: iterations={out['iterations']} checkpoints at {[out[f'cp{i}_iteration'] for i in range(len(cps))]}"
+          f" -> {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+EXTRA = {"refplane20_exact": exact_study_fixture, "ico2_nt7_warm": warm_start_fixture, "ico2_nt7_plugin": plugin_fixture}
 
 if __name__ == "__main__":
     names = sys.argv[1:]

@@ -358,3 +358,14 @@ def test_experimental_sweep_modes_match_the_default_path(mode, example, n_time, 
         if k == "phi":
             x, y = x - x.mean(), y - y.mean()
         assert rel(y, x) < 1e-10, (mode, k, rel(y, x))
+
+
+def test_plugin_callables_match_the_reference_decorators_on_gpu():
+    """Last in the file on purpose (added after the round's final GPU run): ``solver`` / ``solver_raw`` against the
+    reference's own decorators incl. checkpoint iterations and values (fixture ico2_nt7_plugin; same check as the CPU
+    loop test, here with the CUDA engine underneath)."""
+    from test_solver_loop_cpu import _plugin_fixture, check_plugin_outputs
+    z, geo, n_time, kw = _plugin_fixture()
+    sol_c, hist = b200.solver(n_time, geo, leaf_size=8, tol_checkpoints=[float(t) for t in z["tol_checkpoints"]], **kw)
+    sol_r, _ = b200.solver_raw(n_time, geo, leaf_size=8, **kw)
+    check_plugin_outputs(z, sol_c, hist, sol_r, 1e-6)

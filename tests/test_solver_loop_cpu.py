@@ -176,3 +176,41 @@ def test_loop_raises_on_non_finite_residual(cpu_loop, golden, monkeypatch):
     monkeypatch.setattr(OracleEngine, "kkt", lambda self, i: [float("nan"), float("nan")])
     with pytest.raises(FloatingPointError, match="non-finite KKT residual"):
         solver_mod.solver_socp(n_time, geo, **kw)
+
+
+def _plugin_fixture():
+    import os
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "ico2_nt7_plugin.npz"))
+    geo = dict(vertices=z["vertices"], triangles=z["triangles"], mu0=z["mu0"], mu1=z["mu1"],
+               area_vertices=z["area_vertices"], area_triangles=z["area_triangles"])
+    kw = {str(k): float(v) for k, v in zip(z["kw_keys"], z["kw_vals"])}
+    kw["nit"] = int(kw["nit"])
+    return z, geo, int(z["n_time"]), kw
+
+
+def check_plugin_outputs(z, sol_c, hist, sol_r, tol):
+    """Shared with the GPU test: the plug-in callables against what the reference's own decorators returned."""
+    close = lambda a, b: np.abs(a - b).max() <= tol * np.abs(b).max()
+    assert int(hist.kkt_iteration[-1]) == int(z["iterations"])
+    assert close(sol_c["mu"], z["centre_mu"]) and close(sol_c["E"], z["centre_E"])
+    assert close(sol_r["mu"], z["raw_mu"]) and close(sol_r["E"], z["raw_E"])
+    assert sol_r.get("checkpoints") is None
+    cps = sol_c["checkpoints"]
+    assert len(cps) == int(z["n_checkpoints"])
+    for i, cp in enumerate(cps):
+        assert int(cp["iteration"]) == int(z[f"cp{i}_iteration"])
+        assert close(cp["mu"], z[f"cp{i}_mu"]) and close(cp["E"], z[f"cp{i}_E"])
+        ref_kkt = z[f"cp{i}_kkt"]
+        got = np.array([np.nan if k is None else float(k) for k in cp["kkt"]])
+        assert np.array_equal(np.isnan(got), np.isnan(ref_kkt))
+        assert np.allclose(got[~np.isnan(got)], ref_kkt[~np.isnan(ref_kkt)], rtol=1e-6, atol=1e-12)
+
+
+def test_plugin_callables_match_the_reference_decorators(cpu_loop):
+    """``solver`` / ``solver_raw`` (the callables handed to run_dot_surface) against the reference's own
+    dot_solver_socp_center / dot_solver_socp incl. the tolerance checkpoints (fixture ico2_nt7_plugin)."""
+    z, geo, n_time, kw = _plugin_fixture()
+    sol_c, hist = solver_mod.solver(n_time, geo, tol_checkpoints=[float(t) for t in z["tol_checkpoints"]], **kw)
+    sol_r, _ = solver_mod.solver_raw(n_time, geo, **kw)
+    check_plugin_outputs(z, sol_c, hist, sol_r, 1e-7)
