@@ -75,6 +75,8 @@ CASES = {
     "ico2_nt7_eps1e-2": ("icosphere2", {}, 7, dict(tol=1e-3, nit=1000, eps=1e-2, congestion=0.05), (0, 4, 49), False),
     # time limit already exceeded at the first check: one iteration, full KKT row, un-converged solution returned (:725-731, :804)
     "ico2_nt7_tl0": ("icosphere2", {}, 7, dict(tol=1e-3, nit=1000, time_limit=0.0), (0,), True),
+    # iteration cap reached before convergence: the last iteration is fully checked and returned (:656, :826-871)
+    "ico2_nt7_nit20": ("icosphere2", {}, 7, dict(tol=1e-6, nit=20, congestion=0.05), (0, 19), True),
     # BASELINE.json configs[2]: the same surface at nT = 63 and nT = 127 (time-direction scaling)
     "knots5class_nt63_c0": ("knot", {}, 63, dict(tol=1e-3, nit=2000), (), False),
     "knots5class_nt127_c0": ("knot", {}, 127, dict(tol=1e-3, nit=2000), (), False),

@@ -121,7 +121,8 @@ def cpu_loop(monkeypatch):
 
 
 @pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005", "ico2_nt15_tol1e-4",
-                                  "ico2_nt7_stepwise", "ico1_nt1_c005", "ico1_nt2_c0", "ico2_nt7_eps1e-2", "ico2_nt7_tl0"])
+                                  "ico2_nt7_stepwise", "ico1_nt1_c005", "ico1_nt2_c0", "ico2_nt7_eps1e-2", "ico2_nt7_tl0",
+                                  "ico2_nt7_nit20"])
 def test_loop_reproduces_reference_runs(cpu_loop, golden, name):
     z, geo, n_time, kw = golden(name)
     sol, hist = solver_mod.solver_socp(n_time, geo, **kw)
