@@ -543,6 +543,28 @@ class Engine:
         except Exception:
             pass
 
+    def step_q0(self):
+        """``is_palm=True`` only (solver_socp.py:668-672): the q / lambda solve that opens an iteration, from the gradients
+        of the current phi and the current z, beta, mu, E (``palm.q_lambda_step``), followed by a refresh of the corner
+        terms the fused kernels derive from (B, E, beta_mid).  Needs z_mid of the previous iteration (write_z=True)."""
+        from . import palm
+        if self.comm.enabled:
+            raise NotImplementedError("is_palm is not available on the sharded (multi-GPU) path")
+        if not self.z_valid:
+            raise capi.DotsError("is_palm needs z_mid of the previous iteration: call iterate(..., write_z=True)")
+        nT, sl = self.nT, self.slab
+        dx_phi = torch.empty((nT + 1, 3, self.T), dtype=torch.float64, device=self.device)
+        capi.check(self.lib.dots_grad_space(self._ctxp, sl["phi"].base_ptr, dx_phi.data_ptr(), self.stream), "dots_grad_space")
+        A, lam_c, B = palm.q_lambda_step(
+            self.dt, self.s, self.cong, self.r, sl["phi"].levels(0, nT + 1), dx_phi, sl["mu"].levels(0, nT),
+            sl["E"].levels(0, nT + 1), sl["z_fst"].levels(0, nT), sl["z_end"].levels(0, nT), sl["z_mid"].levels(0, nT + 1),
+            sl["b_fst"].levels(0, nT), sl["b_end"].levels(0, nT), sl["b_mid"].levels(0, nT + 1))
+        sl["A"].levels(0, nT).copy_(A)
+        sl["lam_c"].levels(0, nT).copy_(lam_c)
+        sl["B"].levels(0, nT + 1).copy_(B)
+        self.refresh()
+        self.launches += 2
+
     def adjust_penalty(self, f):                                                         # :367-371
         self.r *= f
         self._push_params()

@@ -16,6 +16,7 @@ in between are enqueued back to back.
 from __future__ import annotations
 
 import logging
+import os
 import time
 
 import numpy as np
@@ -87,10 +88,15 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
     solution arrays are converted and copied to the host (default: all, as the reference returns them); ``dot_units``
     ("staggered" / "centred", set by ``solver_raw`` / ``solver``) returns the DOT-unit ``mu``, ``E`` formed on the device;
     ``is_multi_threads`` is accepted and ignored (the two reference threads become stream order).
-    ``is_palm=True`` and ``is_constant_scaling=True`` are solver-only knobs that the reference's CLI /
-    interface cannot reach (interface.py:275-284); they are not built and raise."""
-    if is_palm or is_constant_scaling:
-        raise NotImplementedError("is_palm / is_constant_scaling are not part of the B200 hot path (see DESIGN.md)")
+    ``is_palm=True`` and ``is_constant_scaling=True`` are solver-only knobs that the reference's CLI / interface cannot
+    reach (interface.py:275-284).  ``is_palm`` is served outside the fused kernels (``Engine.step_q0``: whole-array
+    device operations before every fused iteration, single GPU only) and stays behind ``DOTS_EXPERIMENTAL=1`` until it
+    has been validated on hardware; ``is_constant_scaling`` is not built and raises."""
+    if is_constant_scaling:
+        raise NotImplementedError("is_constant_scaling is not part of the B200 hot path (see DESIGN.md)")
+    if is_palm and os.environ.get("DOTS_EXPERIMENTAL") != "1":
+        raise NotImplementedError("is_palm: the extra q/lambda step (Engine.step_q0) is written and checked on the CPU but has "
+                                  "not run on a GPU yet; set DOTS_EXPERIMENTAL=1 to use it (see DESIGN.md)")
     logging.basicConfig(level=LOG_INFO, format="%(message)s")
     tol_checkpoints = _validate_checkpoints(tol_checkpoints, tol)
     checkpoints = []
@@ -137,7 +143,9 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
         if adjust:
             lazy.restart_ticks()                                                          # :735-736
         will_check = check_kkt_step_by_step or lazy.will_fire(required) or it == nit - 1
-        eng.iterate(1, write_z=will_check)                                                # Steps 1-3, :674-722
+        if is_palm:
+            eng.step_q0()                                                                 # Step 0, :668-672
+        eng.iterate(1, write_z=will_check or is_palm)                                     # Steps 1-3, :674-722
         pending = True
 
         cost = lagr = None

@@ -22,8 +22,9 @@ def load_golden(name):
     kw = {str(k): float(v) for k, v in zip(z["kw_keys"], z["kw_vals"])}
     if "nit" in kw:
         kw["nit"] = int(kw["nit"])
-    if "check_kkt_step_by_step" in kw:
-        kw["check_kkt_step_by_step"] = bool(kw["check_kkt_step_by_step"])
+    for flag in ("check_kkt_step_by_step", "is_palm"):
+        if flag in kw:
+            kw[flag] = bool(kw[flag])
     return z, geo, int(z["n_time"]), kw
 
 

@@ -77,6 +77,8 @@ CASES = {
     "ico2_nt7_tl0": ("icosphere2", {}, 7, dict(tol=1e-3, nit=1000, time_limit=0.0), (0,), True),
     # iteration cap reached before convergence: the last iteration is fully checked and returned (:656, :826-871)
     "ico2_nt7_nit20": ("icosphere2", {}, 7, dict(tol=1e-6, nit=20, congestion=0.05), (0, 19), True),
+    # is_palm=True (solver-only knob, solver_socp.py:668-672): an extra q / lambda solve opens every iteration
+    "ico2_nt7_palm": ("icosphere2", {}, 7, dict(tol=1e-3, nit=1000, congestion=0.05, is_palm=1.0), (0, 1, 4, 49), False),
     # BASELINE.json configs[2]: the same surface at nT = 63 and nT = 127 (time-direction scaling)
     "knots5class_nt63_c0": ("knot", {}, 63, dict(tol=1e-3, nit=2000), (), False),
     "knots5class_nt127_c0": ("knot", {}, 127, dict(tol=1e-3, nit=2000), (), False),

@@ -364,6 +364,13 @@ def test_experimental_sweep_modes_match_the_default_path(mode, example, n_time, 
         assert rel(y, x) < 1e-10, (mode, k, rel(y, x))
 
 
+@pytest.mark.skipif(__import__("os").environ.get("DOTS_TEST_EXPERIMENTAL") != "1",
+                    reason="opt-in: Engine.step_q0 (is_palm) has not run on hardware yet; set DOTS_TEST_EXPERIMENTAL=1")
+def test_is_palm_matches_reference_fixture(golden, monkeypatch):
+    monkeypatch.setenv("DOTS_EXPERIMENTAL", "1")
+    _check_against_fixture(golden, "ico2_nt7_palm")
+
+
 def test_plugin_callables_match_the_reference_decorators_on_gpu():
     """Last in the file on purpose (added after the round's final GPU run): ``solver`` / ``solver_raw`` against the
     reference's own decorators incl. checkpoint iterations and values (fixture ico2_nt7_plugin; same check as the CPU

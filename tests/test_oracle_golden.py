@@ -21,7 +21,7 @@ def phi_mod_const(phi):
 
 @pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005",
                                   "ico2_nt7_stepwise", "refplane20_nt15", "ico1_nt1_c005", "ico1_nt2_c0",
-                                  "ico2_nt7_eps1e-2", "ico2_nt7_tl0", "ico2_nt7_nit20"])
+                                  "ico2_nt7_eps1e-2", "ico2_nt7_tl0", "ico2_nt7_nit20", "ico2_nt7_palm"])
 def test_iterates_match_reference(golden, name):
     z, geo, n_time, kw = golden(name)
     snap_its = [int(i) for i in z["snap_its"]]

@@ -21,10 +21,12 @@ def geo():
     return synth.example("icosphere1")[0]
 
 
-@pytest.mark.parametrize("kw", [dict(is_palm=True), dict(is_constant_scaling=True)])
-def test_unbuilt_knobs_raise_before_any_work(geo, kw):
+def test_unbuilt_knobs_raise_before_any_work(geo, monkeypatch):
     with pytest.raises(NotImplementedError):
-        b200.solver_socp(3, geo, **kw)
+        b200.solver_socp(3, geo, is_constant_scaling=True)
+    monkeypatch.delenv("DOTS_EXPERIMENTAL", raising=False)
+    with pytest.raises(NotImplementedError, match="DOTS_EXPERIMENTAL=1"):        # written, not yet validated on a GPU
+        b200.solver_socp(3, geo, is_palm=True)
 
 
 @pytest.mark.parametrize("cps,msg", [([], "non-empty list"), ((1e-2,), "non-empty list"), ([1.5], "between 0 and 1"),

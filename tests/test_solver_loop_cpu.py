@@ -31,7 +31,7 @@ class OracleEngine:
         self.device = torch.device("cpu")
         self.timings = {"setup_total": 0.0}
         self.launches = 0
-        self.z_valid = False
+        self.z_valid = True                              # z_mid = 0 is the true initial z_mid (engine.py does the same)
         self.calls = []
 
     r = property(lambda self: self.alm.r)
@@ -41,6 +41,13 @@ class OracleEngine:
 
     def adjust_penalty(self, f):
         self.alm.adjust_penalty(f)
+
+    def step_q0(self):                                   # is_palm: Step 0 from the gradients of the current phi
+        assert self.z_valid, "Step 0 needs z_mid of the previous iteration"
+        self.alm.dt_phi = orc.grad_time(self.alm.ops.dt, self.alm.phi)
+        self.alm.dx_phi = orc.grad_space(self.alm.ops.G, self.alm.phi)
+        self.alm.step_q()
+        self.calls_q0 = getattr(self, "calls_q0", 0) + 1
 
     def iterate(self, n=1, write_z=False):
         for _ in range(n):
@@ -117,12 +124,13 @@ def cpu_loop(monkeypatch):
 
     monkeypatch.setattr(solver_mod, "Engine", factory)
     monkeypatch.setattr(solver_mod, "torch", _TorchShim())
+    monkeypatch.setenv("DOTS_EXPERIMENTAL", "1")          # is_palm is gated until its engine step has run on hardware
     return made
 
 
 @pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005", "ico2_nt15_tol1e-4",
                                   "ico2_nt7_stepwise", "ico1_nt1_c005", "ico1_nt2_c0", "ico2_nt7_eps1e-2", "ico2_nt7_tl0",
-                                  "ico2_nt7_nit20"])
+                                  "ico2_nt7_nit20", "ico2_nt7_palm"])
 def test_loop_reproduces_reference_runs(cpu_loop, golden, name):
     z, geo, n_time, kw = golden(name)
     sol, hist = solver_mod.solver_socp(n_time, geo, **kw)
@@ -138,7 +146,9 @@ def test_loop_reproduces_reference_runs(cpu_loop, golden, name):
     assert np.abs(sol["mu"] - z["sol_mu"]).max() <= 1e-7 * np.abs(z["sol_mu"]).max()
     eng = cpu_loop[-1]
     # z_mid is only materialised on iterations that check (or may check) KKT #1; most iterations must not ask for it
-    if not kw.get("check_kkt_step_by_step") and len(eng.calls) > 50:
+    if kw.get("is_palm"):
+        assert eng.calls_q0 == len(eng.calls) and all(eng.calls)       # Step 0 before every iteration, z_mid always stored
+    elif not kw.get("check_kkt_step_by_step") and len(eng.calls) > 50:
         assert 0 < sum(eng.calls) < 0.8 * len(eng.calls)
 
 
