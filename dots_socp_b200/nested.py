@@ -360,7 +360,7 @@ def front_maps(sym: Symbolic, Kp: sp.csr_matrix):
 
 
 def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shifts: np.ndarray, m_pad: int, device, lib,
-                         stream_fn, stats: dict | None = None):
+                         stream_fn, stats: dict | None = None, front_nmax: int | None = None):
     """Numeric factorisation on the GPU, level by level: small fronts by the hand-written ``k_front_small`` kernel (one
     block per node and mode), the few large fronts near the root by batched dense torch.linalg calls.  Returns
     (panels, panels_t), both (panel_entries, m_pad) on ``device``."""
@@ -369,7 +369,7 @@ def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shif
     from . import capi
 
     n_modes = int(len(shifts))
-    nmax = int(lib.dots_front_nmax())
+    nmax = int(lib.dots_front_nmax()) if front_nmax is None else int(front_nmax)   # 0: every front through the library path
     Kp = K[sym.perm][:, sym.perm].tocsr()
     Kp.sort_indices()
     a_pos, parent_pos = front_maps(sym, Kp)
@@ -398,6 +398,17 @@ def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shif
     tril_cache, triu_cache = {}, {}
     dev_i64 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int64), device=device)
     n_small = n_large = 0
+    # Index data of the library path, uploaded ONCE (a host->device copy per large front used to cost more than its algebra):
+    # the CSR entries whose column lies inside their owner's front ("kept"), as (row inside the owner's S block, front
+    # position, value), in CSR order; kept_ptr[v] = number of kept entries in the rows before vertex v.
+    row_of = np.repeat(np.arange(sym.n), np.diff(Kp.indptr))
+    kept = a_pos >= 0
+    kept_ptr = np.concatenate([[0], np.cumsum(np.bincount(row_of[kept], minlength=sym.n))]).astype(np.int64)
+    node_of = np.repeat(np.arange(sym.n_nodes), sym.s)
+    kept_r = dev_i64((row_of - sym.off[node_of[row_of]])[kept])
+    kept_c = dev_i64(a_pos[kept])
+    kept_v = torch.as_tensor(np.ascontiguousarray(Kp.data[kept], dtype=np.float64), device=device)
+    parent_pos64 = dev_i64(parent_pos)
 
     args = capi.FrontArgs()
     args.n_modes, args.m_pad = n_modes, m_pad
@@ -433,11 +444,8 @@ def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shif
             nf, lo, f0 = s + b, int(sym.off[i]), int(sym.front_off[i])
             F = torch.zeros((n_modes, nf, nf), dtype=torch.float64, device=device)
             if s:
-                q0, q1 = int(Kp.indptr[lo]), int(Kp.indptr[lo + s])
-                r = np.repeat(np.arange(s), np.diff(Kp.indptr[lo:lo + s + 1]))
-                c, v = a_pos[q0:q1], Kp.data[q0:q1]
-                keep = c >= 0
-                rt, ct, vt = dev_i64(r[keep]), dev_i64(c[keep]), torch.as_tensor(v[keep], device=device)
+                k0, k1 = int(kept_ptr[lo]), int(kept_ptr[lo + s])        # this node's kept CSR entries, in CSR order
+                rt, ct, vt = kept_r[k0:k1], kept_c[k0:k1], kept_v[k0:k1]
                 F[:, rt, ct] = vt
                 F[:, ct, rt] = vt
                 d = torch.arange(s, device=device)
@@ -448,7 +456,7 @@ def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shif
             for slot in range(2):
                 k = int(sym.child[i, slot])
                 if k >= 0 and sym.b[k]:
-                    pp = dev_i64(parent_pos[int(sym.upd_off[k]):int(sym.upd_off[k + 1])])
+                    pp = parent_pos64[int(sym.upd_off[k]):int(sym.upd_off[k + 1])]
                     F[:, pp[:, None], pp[None, :]] += u_view[k][:, :, :n_modes].permute(2, 0, 1)
             if s == 0:
                 if b:
