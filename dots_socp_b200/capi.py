@@ -9,7 +9,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 P_R, P_S, P_D, P_CONG, P_TAU, P_EPS, P_COUNT = 0, 1, 2, 3, 4, 5, 8
 
 _i32p, _i64p, _f64p = C.c_void_p, C.c_void_p, C.c_void_p      # raw device/host addresses
@@ -33,6 +33,9 @@ class DotsCtx(C.Structure):
         + [("red_blocks", C.c_int32), ("sweep_mode", C.c_int32), ("sweep_grid", C.c_int32), ("reserved0", C.c_int32),
            ("phase_clock", C.c_void_p), ("peer_vertex", C.c_void_p * 4), ("peer_corner", C.c_void_p),
            ("peer_rhs", C.c_void_p * 8), ("peer_hat", C.c_void_p * 8)]
+        + [(n, C.c_void_p) for n in ("rt_fwd", "rt_bwd", "h_rt_fwd_ptr", "h_rt_bwd_ptr", "h_rt_fwd_wpr", "h_rt_bwd_wpr",
+                                     "bidx", "gptr", "gidx", "gverts", "h_gv_ptr")]
+        + [("ring_stages", C.c_int32), ("ring_pdl", C.c_int32)]
     )
 
 

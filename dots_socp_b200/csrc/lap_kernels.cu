@@ -380,14 +380,13 @@ static int launch_sweeps(const dots_ctx_t *c, cudaStream_t st)
     return 0;
 }
 
-int dots_mode_solves_persistent(const dots_ctx_t *c, void *stream);   // sweep_tma.cu
-int dots_mode_solves_tile(const dots_ctx_t *c, void *stream);         // sweep_tile.cu (experimental)
+int dots_mode_solves_ring(const dots_ctx_t *c, void *stream);         // sweep_ring.cu
 
 extern "C" int dots_mode_solves(const dots_ctx_t *c, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
-    if (c->sweep_mode == 1) return dots_mode_solves_persistent(c, stream);
-    if (c->sweep_mode == 2 || c->sweep_mode == 3) return dots_mode_solves_tile(c, stream);
+    if (c->sweep_mode == 4) return dots_mode_solves_ring(c, stream);
+    if (c->sweep_mode != 0) { dots_set_error("sweep_mode=%d unsupported (0 or 4)", c->sweep_mode); return DOTS_ERR_BAD_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     switch (c->m_pad) {
     case 8: return launch_sweeps<8>(c, st);

@@ -1,0 +1,389 @@
+// Ring-streamed batched multifrontal sweeps (sweep_mode 4; row a8, reference utils/laplacian_inverse_socp.py:58-59:
+// the nT+1 per-mode solves  x_a = (L + (lambda_a - eps) M)^-1 b_a ).
+//
+// Same factor data as k_sweep_run (lap_kernels.cu): per separator-tree node a solve-ready panel
+// P = [inv(L11) ; L21 inv(L11)], `[row][col][mode]` (forward) and its column-major copy (backward), mode fastest.
+// What changes is how the panels reach the SMs and how the children's updates are passed on:
+//
+//  * every WARP owns a small shared-memory ring (ring_stages x 4 KB) that its lane 0 feeds with 1-D bulk async copies
+//    (cp.async.bulk + mbarrier, SASS UBLKCP / SYNCS).  A warp's work is one contiguous run of panel bytes, so the copies
+//    are full 4 KB pieces regardless of where the (short) panel rows begin and end, the bytes in flight per SM
+//    (2 blocks x 8 warps x (stages-1) x 4 KB) no longer depend on registers, and warps never wait for each other:
+//    there is no block-wide barrier in the contiguous kernel (k_sweep_run at the headline size: 31-35 % warps active,
+//    60-80 % long_scoreboard, 0.61-0.67 of the HBM peak);
+//  * the vector operand (r_S forward, [y_S ; x_B] backward) of a stage is fetched into registers before the warp waits
+//    for the stage's mbarrier, so its (L1 / L2) latency overlaps the wait;
+//  * "pull" extend-add: a node stores only ITS OWN contribution  -(L21 inv(L11)) r_S  to its boundary rows (`upd`, producer
+//    order).  Before a level is swept, k_ring_gather adds to every vertex of that level the contributions of ALL its
+//    descendants (fixed order: gidx lists them in post-order), in place in `hat`.  The pass-through gather at the end of
+//    every boundary row of k_sweep_run (two dependent loads per 4-20 streamed entries on the lower levels) is gone;
+//  * outputs whose run is long (top of the tree) are shared by WPR warps as contiguous pieces and combined in a fixed
+//    order through shared memory (k_ring_split);
+//  * optionally (ring_pdl) the level launches are chained with programmatic dependent launch: a block streams its first
+//    panel stages (read-only data) before griddepcontrol.wait, so the tail of one level overlaps the ramp-up of the next.
+//
+// Needs m_pad % 32 == 0 and Z = [hat | ywork] in one allocation (bidx addresses both).
+#include "common.cuh"
+
+#define SR_WARPS 8
+#define SR_THREADS (32 * SR_WARPS)
+#define SR_STAGE_BYTES 4096
+
+__device__ __forceinline__ size_t sr_row_off(int row, int s)             // row-major panel: entries before row `row`
+{
+    return (row < s) ? (size_t)row * (row + 1) / 2 : (size_t)s * (s + 1) / 2 + (size_t)(row - s) * s;
+}
+__device__ __forceinline__ size_t sr_col_off(int col, int s, int b)      // column-major copy: entries before column `col`
+{
+    return (size_t)col * (s + b) - (size_t)col * (col - 1) / 2;
+}
+// range [lo, hi) of the shared index (panel column, forward / panel row, backward) an output runs over
+template <int DIR> __device__ __forceinline__ int sr_lo(int o) { return DIR == 0 ? 0 : o; }
+template <int DIR> __device__ __forceinline__ int sr_hi(int o, int s, int b) { return DIR == 0 ? min(o + 1, s) : s + b; }
+
+template <int ML, int DIR>
+__device__ __forceinline__ void sr_flush(const dots_ctx_t &c, const dots_ring_task_t &t, int o, const double (&acc)[ML / 32], int lane)
+{
+    constexpr int MP = ML / 32;
+    double *dst;
+    double sign;
+    if (DIR == 1) { dst = c.hat + (size_t)(t.off + o) * ML; sign = -1.0; }                 // x_S = -P^T [y_S ; x_B]
+    else if (o < t.s) { dst = c.ywork + (size_t)(t.off + o) * ML; sign = 1.0; }            // y_S = inv(L11) r_S
+    else { dst = c.upd + (size_t)(t.ubase + o - t.s) * ML; sign = -1.0; }                  // own contribution to boundary row o - s
+#pragma unroll
+    for (int m = 0; m < MP; ++m) dst[lane + 32 * m] = sign * acc[m];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Contiguous tasks: one warp streams the outputs [oa, oa + n_out) of a node, i.e. n_ent consecutive panel entries.
+template <int ML, int DIR, bool PDL>
+__global__ void __launch_bounds__(SR_THREADS, 2) k_ring_run(dots_ctx_t c, int task0, int task_end)
+{
+    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    constexpr int MP = ML / 32;
+    constexpr int EC = SR_STAGE_BYTES / (8 * ML);                        // panel entries per stage: 16, 8, 5, 4
+    extern __shared__ __align__(128) unsigned char sr_smem[];
+    const int nst = c.ring_stages;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *ring = reinterpret_cast<double *>(sr_smem) + (size_t)warp * nst * EC * ML;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sr_smem + (size_t)SR_WARPS * nst * EC * ML * 8) + warp * nst;
+    const int ti = task0 + blockIdx.x * SR_WARPS + warp;
+    if (ti >= task_end) return;                                          // warps are independent: no block barrier below
+    if (lane == 0) {
+        for (int i = 0; i < nst; ++i) mbar_init(&bar[i], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    const dots_ring_task_t t = (DIR == 0 ? c.rt_fwd : c.rt_bwd)[ti];
+    const double *src = (DIR == 0 ? c.panels : c.panels_t) + (size_t)t.pbase * ML;
+    const int n_ent = t.n_ent, n_stage = (n_ent + EC - 1) / EC;
+    const int s = t.s, b = t.b;
+
+    auto issue = [&](int k, int slot) {                                  // lane 0: stage k of the run -> ring slot
+        const uint32_t bytes = (uint32_t)min(EC, n_ent - k * EC) * (uint32_t)(ML * 8);
+        mbar_expect_tx(&bar[slot], bytes);
+        tma_load_1d(ring + (size_t)slot * EC * ML, src + (size_t)k * EC * ML, bytes, &bar[slot]);
+    };
+    if (lane == 0) {
+        for (int k = 0; k < nst && k < n_stage; ++k) issue(k, k);        // the panels are read-only: stream before the wait
+    }
+    if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");          // below: data written by the previous launches
+
+    const double *z = c.hat + lane;                                      // Z = [hat | ywork]
+    const int32_t *bi = c.bidx + t.fbase;
+    int o = t.oa, x = sr_lo<DIR>(o), hi = sr_hi<DIR>(o, s, b);
+    double acc[MP];
+#pragma unroll
+    for (int m = 0; m < MP; ++m) acc[m] = 0.0;
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int k = 0; k < n_stage; ++k) {
+        const int ne = min(EC, n_ent - k * EC);
+        // vector operand of the stage's entries (walks over output boundaries like the math below)
+        double rv[EC][MP];
+        {
+            int row[EC];
+            int o2 = o, x2 = x, hi2 = hi;
+#pragma unroll
+            for (int e = 0; e < EC; ++e) {
+                row[e] = 0;
+                if (e < ne) {
+                    row[e] = (DIR == 0) ? t.off + x2 : bi[x2];
+                    if (++x2 == hi2) { ++o2; x2 = sr_lo<DIR>(o2); hi2 = sr_hi<DIR>(o2, s, b); }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < EC; ++e) {
+#pragma unroll
+                for (int m = 0; m < MP; ++m) rv[e][m] = (e < ne) ? z[(size_t)row[e] * ML + 32 * m] : 0.0;
+            }
+        }
+        mbar_wait(&bar[slot], phase);
+        const double *sp = ring + (size_t)slot * EC * ML + lane;
+#pragma unroll
+        for (int e = 0; e < EC; ++e) {
+            if (e < ne) {
+#pragma unroll
+                for (int m = 0; m < MP; ++m) acc[m] += sp[e * ML + 32 * m] * rv[e][m];
+                if (++x == hi) {
+                    sr_flush<ML, DIR>(c, t, o, acc, lane);
+#pragma unroll
+                    for (int m = 0; m < MP; ++m) acc[m] = 0.0;
+                    ++o; x = sr_lo<DIR>(o); hi = sr_hi<DIR>(o, s, b);
+                }
+            }
+        }
+        __syncwarp();                                                    // every lane is done reading the slot
+        if (lane == 0 && k + nst < n_stage) issue(k + nst, slot);
+        if (++slot == nst) { slot = 0; phase ^= 1u; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Split items: block = (node, outputs [oa, oa + n_out)); ROWS = 8 / WPR outputs per pass, the run of an output is cut into
+// WPR contiguous pieces (one per warp), partial sums combined in warp order through shared memory.  A warp's ring runs
+// ahead across the passes.
+template <int ML, int WPR, int DIR, bool PDL>
+__global__ void __launch_bounds__(SR_THREADS, 2) k_ring_split(dots_ctx_t c, int item0)
+{
+    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    constexpr int MP = ML / 32;
+    constexpr int EC = SR_STAGE_BYTES / (8 * ML);
+    constexpr int ROWS = SR_WARPS / WPR;
+    extern __shared__ __align__(128) unsigned char sr_smem[];
+    const int nst = c.ring_stages;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *ring = reinterpret_cast<double *>(sr_smem) + (size_t)warp * nst * EC * ML;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sr_smem + (size_t)SR_WARPS * nst * EC * ML * 8) + warp * nst;
+    double *red = reinterpret_cast<double *>(sr_smem + (size_t)SR_WARPS * nst * (EC * ML * 8 + 8));     // [SR_WARPS][ML]
+    if (lane == 0) {
+        for (int i = 0; i < nst; ++i) mbar_init(&bar[i], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    const dots_ring_task_t t = (DIR == 0 ? c.rt_fwd : c.rt_bwd)[item0 + blockIdx.x];
+    const double *pan = (DIR == 0 ? c.panels : c.panels_t) + (size_t)t.pbase * ML;
+    const int s = t.s, b = t.b, last = t.oa + t.n_out - 1;
+    const int npass = (t.n_out + ROWS - 1) / ROWS;
+    const int rslot = warp / WPR, cslot = warp % WPR;
+
+    // this warp's piece [xa, xb) of the output it shares in pass `pass`
+    auto piece = [&](int pass, int &o, int &xa, int &xb) -> bool {
+        o = t.oa + pass * ROWS + rslot;
+        if (o > last) return false;
+        const int lo = sr_lo<DIR>(o), hi = sr_hi<DIR>(o, s, b);
+        const int plen = ((hi - lo + WPR - 1) / WPR + EC - 1) / EC * EC;
+        xa = lo + cslot * plen;
+        xb = min(hi, xa + plen);
+        return xa < xb;
+    };
+    // producer cursor: the next chunk to issue is [px, min(px + EC, pxb)) of output po (pass pp)
+    int pp = -1, po = 0, px = 0, pxb = 0;
+    auto prod_next = [&]() -> bool {
+        px += EC;
+        while (px >= pxb) {
+            if (++pp >= npass) return false;
+            if (!piece(pp, po, px, pxb)) px = pxb = 0;
+        }
+        return true;
+    };
+    auto issue = [&](int slot) {                                         // lane 0
+        const uint32_t bytes = (uint32_t)min(EC, pxb - px) * (uint32_t)(ML * 8);
+        const size_t ent = (DIR == 0 ? sr_row_off(po, s) : sr_col_off(po, s, b)) + (size_t)(px - sr_lo<DIR>(po));
+        mbar_expect_tx(&bar[slot], bytes);
+        tma_load_1d(ring + (size_t)slot * EC * ML, pan + ent * ML, bytes, &bar[slot]);
+    };
+    bool pvalid = prod_next();
+    for (int i = 0; i < nst && pvalid; ++i) {
+        if (lane == 0) issue(i);
+        pvalid = prod_next();
+    }
+    if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    const double *z = c.hat + lane;
+    const int32_t *bi = c.bidx + t.fbase;
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int pass = 0; pass < npass; ++pass) {
+        int o, xa, xb;
+        const bool mine = piece(pass, o, xa, xb);
+        double acc[MP];
+#pragma unroll
+        for (int m = 0; m < MP; ++m) acc[m] = 0.0;
+        if (mine) {
+            for (int x = xa; x < xb; x += EC) {
+                const int ne = min(EC, xb - x);
+                double rv[EC][MP];
+                int row[EC];
+#pragma unroll
+                for (int e = 0; e < EC; ++e) row[e] = (e < ne) ? ((DIR == 0) ? t.off + x + e : bi[x + e]) : 0;
+#pragma unroll
+                for (int e = 0; e < EC; ++e) {
+#pragma unroll
+                    for (int m = 0; m < MP; ++m) rv[e][m] = (e < ne) ? z[(size_t)row[e] * ML + 32 * m] : 0.0;
+                }
+                mbar_wait(&bar[slot], phase);
+                const double *sp = ring + (size_t)slot * EC * ML + lane;
+#pragma unroll
+                for (int e = 0; e < EC; ++e) {
+                    if (e < ne) {
+#pragma unroll
+                        for (int m = 0; m < MP; ++m) acc[m] += sp[e * ML + 32 * m] * rv[e][m];
+                    }
+                }
+                __syncwarp();
+                if (pvalid) {
+                    if (lane == 0) issue(slot);
+                    pvalid = prod_next();
+                }
+                if (++slot == nst) { slot = 0; phase ^= 1u; }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MP; ++m) red[warp * ML + lane + 32 * m] = acc[m];
+        __syncthreads();
+        if (cslot == 0 && o <= last) {
+#pragma unroll
+            for (int m = 0; m < MP; ++m) {
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) v += red[(rslot * WPR + w) * ML + lane + 32 * m];
+                acc[m] = v;
+            }
+            sr_flush<ML, DIR>(c, t, o, acc, lane);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// r_S of one tree level, in place in `hat`:  hat[v] += sum of the descendants' contributions landing on v.
+template <int ML, bool PDL>
+__global__ void __launch_bounds__(256) k_ring_gather(dots_ctx_t c, int v0, int v_end)
+{
+    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    constexpr int VPB = 256 / ML;                                        // vertices per block: 8, 4, 2, 2
+    const int vs = threadIdx.x / ML, m = threadIdx.x - vs * ML;
+    const int i = v0 + blockIdx.x * VPB + vs;
+    const bool on = vs < VPB && i < v_end;
+    int v = 0, g0 = 0, g1 = 0;
+    if (on) { v = c.gverts[i]; g0 = c.gptr[v]; g1 = c.gptr[v + 1]; }     // structure: constant, safe before the wait
+    if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!on) return;
+    double *h = c.hat + (size_t)v * ML + m;
+    double r = *h;
+    int g = g0;
+    for (; g + 4 <= g1; g += 4) {
+        const int i0 = c.gidx[g], i1 = c.gidx[g + 1], i2 = c.gidx[g + 2], i3 = c.gidx[g + 3];
+        const double a0 = c.upd[(size_t)i0 * ML + m], a1 = c.upd[(size_t)i1 * ML + m];
+        const double a2 = c.upd[(size_t)i2 * ML + m], a3 = c.upd[(size_t)i3 * ML + m];
+        r += a0; r += a1; r += a2; r += a3;
+    }
+    for (; g < g1; ++g) r += c.upd[(size_t)c.gidx[g] * ML + m];
+    *h = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename... Args>
+static int sr_launch(void (*kern)(Args...), int grid, int threads, size_t smem, cudaStream_t st, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    DOTS_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+    return 0;
+}
+
+static size_t sr_smem_bytes(int ML, int nst, bool split)
+{
+    const int EC = SR_STAGE_BYTES / (8 * ML);
+    return (size_t)SR_WARPS * nst * ((size_t)EC * ML * 8 + 8) + (split ? (size_t)SR_WARPS * ML * 8 : 0) + 16;
+}
+
+template <int ML, bool PDL>
+static int sr_configure(int nst)
+{
+    // the opt-in is per device and per function: keyed by (device, stages) so that a second engine on another GPU of the
+    // same process configures its own copy
+    static int done[64] = {0};
+    int dev = 0;
+    DOTS_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && done[dev] == nst) return 0;
+    const int run = (int)sr_smem_bytes(ML, nst, false), split = (int)sr_smem_bytes(ML, nst, true);
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_run<ML, 0, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, run));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_run<ML, 1, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, run));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 2, 0, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 4, 0, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 8, 0, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 2, 1, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 4, 1, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 8, 1, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    if (dev >= 0 && dev < 64) done[dev] = nst;
+    return 0;
+}
+
+template <int ML, int DIR, bool PDL>
+static int sr_level(const dots_ctx_t *c, int lv, bool chain, cudaStream_t st)
+{
+    const int32_t *ptr = DIR == 0 ? c->h_rt_fwd_ptr : c->h_rt_bwd_ptr;
+    const int wpr = (DIR == 0 ? c->h_rt_fwd_wpr : c->h_rt_bwd_wpr)[lv];
+    const int i0 = ptr[lv], n = ptr[lv + 1] - i0;
+    if (n <= 0) return 0;
+    const int nst = c->ring_stages;
+    if (wpr == 1) return sr_launch(k_ring_run<ML, DIR, PDL>, ceil_div(n, SR_WARPS), SR_THREADS, sr_smem_bytes(ML, nst, false), st, chain, *c, i0, i0 + n);
+    const size_t smem = sr_smem_bytes(ML, nst, true);
+    switch (wpr) {
+    case 2: return sr_launch(k_ring_split<ML, 2, DIR, PDL>, n, SR_THREADS, smem, st, chain, *c, i0);
+    case 4: return sr_launch(k_ring_split<ML, 4, DIR, PDL>, n, SR_THREADS, smem, st, chain, *c, i0);
+    case 8: return sr_launch(k_ring_split<ML, 8, DIR, PDL>, n, SR_THREADS, smem, st, chain, *c, i0);
+    }
+    dots_set_error("ring sweep: wpr=%d unsupported", wpr);
+    return DOTS_ERR_BAD_ARG;
+}
+
+template <int ML, bool PDL>
+static int sr_sweeps(const dots_ctx_t *c, cudaStream_t st)
+{
+    if (int e = sr_configure<ML, PDL>(c->ring_stages)) return e;
+    bool chain = false;                                                   // the first launch waits for the transform normally
+    for (int lv = 0; lv < c->n_levels; ++lv) {
+        const int g0 = c->h_gv_ptr[lv], gn = c->h_gv_ptr[lv + 1] - g0;
+        if (gn > 0) {
+            if (int e = sr_launch(k_ring_gather<ML, PDL>, ceil_div(gn, 256 / ML), 256, 0, st, PDL && chain, *c, g0, g0 + gn)) return e;
+            chain = true;
+        }
+        const int n = c->h_rt_fwd_ptr[lv + 1] - c->h_rt_fwd_ptr[lv];
+        if (int e = sr_level<ML, 0, PDL>(c, lv, PDL && chain, st)) return e;
+        if (n > 0) chain = true;
+    }
+    for (int lv = c->n_levels - 1; lv >= 0; --lv) {
+        const int n = c->h_rt_bwd_ptr[lv + 1] - c->h_rt_bwd_ptr[lv];
+        if (int e = sr_level<ML, 1, PDL>(c, lv, PDL && chain, st)) return e;
+        if (n > 0) chain = true;
+    }
+    return 0;
+}
+
+int dots_mode_solves_ring(const dots_ctx_t *c, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c->m_pad % 32 || c->m_pad > 128) { dots_set_error("ring sweeps need m_pad in {32, 64, 96, 128} (got %d)", c->m_pad); return DOTS_ERR_BAD_ARG; }
+    if (c->ywork != c->hat + (size_t)c->n_vert * c->m_pad) { dots_set_error("ring sweeps need ywork == hat + n_vert * m_pad"); return DOTS_ERR_BAD_ARG; }
+    if (c->ring_stages < 2 || c->ring_stages > 6) { dots_set_error("ring_stages=%d outside 2..6", c->ring_stages); return DOTS_ERR_BAD_ARG; }
+    if (!c->rt_fwd || !c->rt_bwd || !c->bidx || !c->gptr || !c->gidx) { dots_set_error("ring sweep plan missing from the context"); return DOTS_ERR_BAD_ARG; }
+    const bool pdl = c->ring_pdl != 0;
+    switch (c->m_pad) {
+    case 32: return pdl ? sr_sweeps<32, true>(c, st) : sr_sweeps<32, false>(c, st);
+    case 64: return pdl ? sr_sweeps<64, true>(c, st) : sr_sweeps<64, false>(c, st);
+    case 96: return pdl ? sr_sweeps<96, true>(c, st) : sr_sweeps<96, false>(c, st);
+    case 128: return pdl ? sr_sweeps<128, true>(c, st) : sr_sweeps<128, false>(c, st);
+    }
+    return DOTS_ERR_BAD_ARG;
+}

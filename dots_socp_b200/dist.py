@@ -64,13 +64,13 @@ class Partition:
         return [(r * self.chunk, min(n, (r + 1) * self.chunk)) for r in range(self.world)]
 
 
-def partition(n_time: int, rank: int = 0, world: int = 1) -> Partition:
+def partition(n_time: int, rank: int = 0, world: int = 1, min_pad: int = 0) -> Partition:
     n = n_time + 1
     chunk = -(-n // world)
     lo, hi = rank * chunk, min(n, (rank + 1) * chunk)
     if (world - 1) * chunk >= n:
         raise ValueError(f"{world} ranks cannot each own a time level of {n} levels")
-    return Partition(n_time, rank, world, chunk, lo, hi, pad_modes(chunk))
+    return Partition(n_time, rank, world, chunk, lo, hi, max(pad_modes(chunk), int(min_pad)))
 
 
 def transform_matrices(Q: np.ndarray, part: Partition):
@@ -144,6 +144,14 @@ class Comm:
         for r in range(1, self.world):
             total += parts[r]
         return total
+
+    def any_true(self, flag: bool, device) -> bool:
+        """Logical OR of a host flag over the ranks (every rank gets the same answer)."""
+        if not self.enabled:
+            return bool(flag)
+        t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device=device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return bool(t.item() > 0.0)
 
     def barrier(self):
         if self.enabled:

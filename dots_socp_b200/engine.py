@@ -16,7 +16,7 @@ import time
 import numpy as np
 import torch
 
-from . import capi, nested, surface
+from . import capi, nested, ring_plan, surface
 from . import dist as dd
 
 STATE_VERTEX = ("phi", "A", "lam_c", "mu", "z_fst", "z_end", "b_fst", "b_end")
@@ -94,61 +94,6 @@ def _sweep_items(sym: nested.Symbolic, n_sm: int, m_pad: int):
                 node_ptr=i32(node_ptr), nodes=cat(gather), wpr=i32(wprs), cw=i32(cws))
 
 
-def _sweep_items_persistent(sym: nested.Symbolic, n_blocks: int):
-    """Work items (node, first output, n outputs <= 8) of the persistent TMA-fed sweep kernel, per level.
-
-    n outputs is chosen per level so that the level has about one item per resident block when it is small (the
-    top separators) and 8 outputs per item when it is large (the leaves)."""
-    fwd_ptr, bwd_ptr, fwd, bwd = [0], [0], [], []
-    for nodes in nested.level_schedule(sym):
-        rows_total = int((sym.s[nodes] + sym.b[nodes]).sum())
-        cols_total = int(sym.s[nodes].sum())
-        rb = int(min(8, max(1, rows_total // n_blocks)))
-        cb = int(min(8, max(1, cols_total // n_blocks)))
-        for nd in nodes:
-            nrow, ncol = int(sym.s[nd] + sym.b[nd]), int(sym.s[nd])
-            fwd += [(int(nd), r0, min(rb, nrow - r0)) for r0 in range(0, nrow, rb)]
-            bwd += [(int(nd), c0, min(cb, ncol - c0)) for c0 in range(0, ncol, cb)]
-        fwd_ptr.append(len(fwd))
-        bwd_ptr.append(len(bwd))
-    as32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32).reshape(-1, 3)) if a else np.zeros((1, 3), np.int32)
-    i32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32))
-    n_lv = len(fwd_ptr) - 1
-    return dict(fwd_ptr=i32(fwd_ptr), fwd_items=as32(fwd), bwd_ptr=i32(bwd_ptr), bwd_items=as32(bwd),
-                node_ptr=i32([0] * (n_lv + 1)), nodes=np.zeros((1, 3), np.int32), wpr=i32([1] * n_lv), cw=i32([1] * n_lv))
-
-
-def _sweep_items_tile(sym: nested.Symbolic, n_sm: int):
-    """Work items (node, first output, n outputs) of the experimental tile-streamed sweep (csrc/sweep_tile.cu,
-    ``sweep_mode=2``): a block walks its item in groups of 8 outputs (one warp per output), so items are multiples of 8
-    outputs long - up to 32 where the level has enough outputs to still give every SM ~6 blocks."""
-    fwd_ptr, bwd_ptr, fwd, bwd = [0], [0], [], []
-
-    def cut(total, n_per_node):
-        groups = int(min(4, max(1, total // (8 * 6 * n_sm))))
-        out = []
-        for nd, n in n_per_node:
-            if n <= 0:
-                continue
-            n_items = -(-n // (8 * groups))
-            per = 8 * -(-(-(-n // n_items)) // 8)                       # even split, rounded up to whole groups
-            out += [(int(nd), o0, min(per, n - o0)) for o0 in range(0, n, per)]
-        return out
-
-    for nodes in nested.level_schedule(sym):
-        rows = [(nd, int(sym.s[nd] + sym.b[nd])) for nd in nodes]
-        cols = [(nd, int(sym.s[nd])) for nd in nodes]
-        fwd += cut(sum(n for _, n in rows), rows)
-        bwd += cut(sum(n for _, n in cols), cols)
-        fwd_ptr.append(len(fwd))
-        bwd_ptr.append(len(bwd))
-    as32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32).reshape(-1, 3)) if a else np.zeros((1, 3), np.int32)
-    i32 = lambda a: np.ascontiguousarray(np.array(a, dtype=np.int32))
-    n_lv = len(fwd_ptr) - 1
-    return dict(fwd_ptr=i32(fwd_ptr), fwd_items=as32(fwd), bwd_ptr=i32(bwd_ptr), bwd_items=as32(bwd),
-                node_ptr=i32([0] * (n_lv + 1)), nodes=np.zeros((1, 3), np.int32), wpr=i32([1] * n_lv), cw=i32([1] * n_lv))
-
-
 class Engine:
     """One rank's share of the problem.  ``comm`` (dist.Comm) spans the ranks; None / single rank = whole problem."""
 
@@ -167,8 +112,19 @@ class Engine:
         tri_old = np.ascontiguousarray(geometry["triangles"]).astype(np.int64)
         self.nT, self.V, self.T = int(n_time), v.shape[0], tri_old.shape[0]
         nT, V, T = self.nT, self.V, self.T
-        self.part = dd.partition(nT, self.comm.rank, self.comm.world)
+        if sweep_mode is None:
+            sweep_mode = int(os.environ.get("DOTS_SWEEP_MODE", "-1"))
+        # ring-streamed sweeps (mode 4) need whole warps of modes: a single rank pads small time grids up to 32 modes
+        # (identity padding, a few KB); mode-sharded ranks with fewer than 32 modes keep the register-staged kernel (mode 0)
+        min_pad = 32 if (self.comm.world == 1 and sweep_mode in (-1, 4)) else 0
+        self.part = dd.partition(nT, self.comm.rank, self.comm.world, min_pad=min_pad)
         part = self.part
+        if sweep_mode == -1:
+            sweep_mode = 4 if part.m_pad % 32 == 0 else 0
+        if sweep_mode not in (0, 4):
+            raise capi.DotsError(f"sweep_mode={sweep_mode} unsupported (0: k_sweep_run, 4: ring-streamed)")
+        if sweep_mode == 4 and part.m_pad % 32:
+            raise capi.DotsError(f"sweep_mode=4 needs a multiple of 32 time modes per rank, got {part.m_pad}")
         self.dt = 1.0 / nT
         self.cong, self.tau, self.eps = float(congestion), float(tau), float(eps)
         self.m_pad = part.m_pad
@@ -193,8 +149,6 @@ class Engine:
         Q, lam_t = time_basis(nT)
         self.Q, self.lam_t = Q, lam_t
         shifts = (-lam_t + self.eps)[part.lvl_begin:part.lvl_end]   # (L + (lam - eps) M) = -(K + (|lam| + eps) M)   (laplacian_inverse_socp.py:37-38)
-        if sweep_mode is None:
-            sweep_mode = int(os.environ.get("DOTS_SWEEP_MODE", "0"))
         self.sweep_mode = int(sweep_mode)
         self.factor_stats = {}
         if os.environ.get("DOTS_FACTOR", "hybrid") == "library":
@@ -225,13 +179,17 @@ class Engine:
         diag = np.sqrt(area_f_n[None, :] / area_v_n[tri_new.T])                          # (3,T)  solver_socp.py:172-180
         vc_ptr, vc_tri, vc_corner = surface.corner_adjacency(V, tri_new)
         qf, qb, n_phi_out = dd.transform_matrices(Q, part)
-        self.sweep_grid = 2 * self.n_sm if self.m_pad <= 96 else self.n_sm
-        if self.sweep_mode in (1, 2, 3) and self.m_pad < 32:
-            raise capi.DotsError(f"sweep_mode={self.sweep_mode} (experimental) needs >= 32 time modes per rank, got {self.m_pad}")
-        plan = (_sweep_items_persistent(sym, self.sweep_grid) if self.sweep_mode == 1
-                else _sweep_items_tile(sym, self.n_sm) if self.sweep_mode in (2, 3)
-                else _sweep_items(sym, self.n_sm, self.m_pad))
+        self.sweep_grid = 0
+        plan = _sweep_items(sym, self.n_sm, self.m_pad)
         self.plan = plan                                                                 # host arrays stay alive
+        env_kb = lambda name, default: int(float(os.environ.get(name, default)) * 1024)
+        self.ring = None
+        if self.sweep_mode == 4:
+            self.ring = ring_plan.build(
+                sym, self.n_sm, self.m_pad, split_bytes=env_kb("DOTS_RING_SPLIT_KB", 96),
+                tasks_per_sm=int(os.environ.get("DOTS_RING_TASKS_PER_SM", 64)),
+                task_bytes=(env_kb("DOTS_RING_TASK_MIN_KB", 16), env_kb("DOTS_RING_TASK_MAX_KB", 96)),
+                wpr_max=int(os.environ.get("DOTS_RING_WPR_MAX", 8)))
         fwd_ptr, fwd_items, bwd_ptr, bwd_items = plan["fwd_ptr"], plan["fwd_items"], plan["bwd_ptr"], plan["bwd_items"]
         self._h_fwd_ptr, self._h_bwd_ptr = fwd_ptr, bwd_ptr
 
@@ -263,6 +221,19 @@ class Engine:
         ctx.h_lvb_cw = plan["cw"].ctypes.data
         ctx.front_total = int(sym.front_off[-1])
         ctx.sweep_mode, ctx.sweep_grid = self.sweep_mode, self.sweep_grid
+        if self.ring is not None:
+            rp = self.ring
+            for name in ("rt_fwd", "rt_bwd"):
+                ten = torch.from_numpy(rp[name].view(np.uint8).reshape(-1).copy()).to(dev)
+                self._keep[name] = ten
+                setattr(ctx, name, ten.data_ptr())
+            for name in ("bidx", "gptr", "gidx", "gverts"):
+                setattr(ctx, name, up("ring_" + name, rp[name], np.int32).data_ptr())
+            ctx.h_rt_fwd_ptr, ctx.h_rt_bwd_ptr = rp["fwd_ptr"].ctypes.data, rp["bwd_ptr"].ctypes.data
+            ctx.h_rt_fwd_wpr, ctx.h_rt_bwd_wpr = rp["fwd_wpr"].ctypes.data, rp["bwd_wpr"].ctypes.data
+            ctx.h_gv_ptr = rp["gv_ptr"].ctypes.data
+            ctx.ring_stages = int(os.environ.get("DOTS_RING_STAGES", 3))
+            ctx.ring_pdl = int(os.environ.get("DOTS_RING_PDL", 0))
         self._keep["phase_clock"] = torch.zeros(2 * sym.n_levels + 1, dtype=torch.int64, device=dev)
         if os.environ.get("DOTS_PHASE_CLOCK"):
             ctx.phase_clock = self._keep["phase_clock"].data_ptr()
@@ -279,10 +250,12 @@ class Engine:
             setattr(ctx, name, st_.base_ptr)
         z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)
         self.red_blocks = self.n_sm * 4
-        hat_local = z(V, self.m_pad)
+        z_all = z(2 * V, self.m_pad)                     # Z = [hat | ywork]: one allocation, the ring sweeps index both halves
+        hat_local = z_all[:V]
+        self._keep["z_all"] = z_all
         self.t = dict(params=z(capi.P_COUNT), bnd0=z(V), bnd1=z(V), rhs=z(part.world * part.chunk, V),
                       hat=hat_local, hat_all=hat_local if part.world == 1 else z(part.world, V, self.m_pad),
-                      ywork=z(V, self.m_pad), upd=z(max(1, int(sym.upd_off[-1])), self.m_pad),
+                      ywork=z_all[V:], upd=z(max(1, int(sym.upd_off[-1])), self.m_pad),
                       red_part=z(self.red_blocks, 8), red_out=z(8))
         for k, ten in self.t.items():
             setattr(ctx, k, ten.data_ptr())
@@ -301,6 +274,7 @@ class Engine:
         b0, b1 = -mu0 / (self.r * self.dt), mu1 / (self.r * self.dt)
         self.t["bnd0"].copy_(torch.from_numpy(b0))
         self.t["bnd1"].copy_(torch.from_numpy(b1))
+        self._bnd_init = (self.t["bnd0"].clone(), self.t["bnd1"].clone())
         self.norm_bnd = self.r * self.dt * math.sqrt((np.sum((b0 / area_v_n) ** 2 * area_v_n)
                                                       + np.sum((b1 / area_v_n) ** 2 * area_v_n)) / (nT + 1))
         self.area_mesh = float(np.sum(area_f))
@@ -340,8 +314,8 @@ class Engine:
 
     def launches_per_iteration(self):
         """Kernel launches of one iteration: rhs, 2 transforms, the sweep launches, vertex, triangle."""
-        if self.sweep_mode == 1:
-            return 6
+        if self.sweep_mode == 4:
+            return 5 + ring_plan.launches(self.ring)
         n_f = int(np.count_nonzero(np.diff(self._h_fwd_ptr)))
         n_b = int(np.count_nonzero(np.diff(self._h_bwd_ptr)))
         n_g = int(np.count_nonzero(np.diff(self.plan["node_ptr"])[1:]))
@@ -581,6 +555,52 @@ class Engine:
         self.exchange_vertex_halo()
         self.refresh()
         self.launches += 8
+
+    def reset_state(self):
+        """Back to the state solver_socp starts from (socp/solver_socp.py:239-270: all arrays zero, r = 1, unscaled z)."""
+        for st_ in self.slab.values():
+            st_.data.zero_()
+        self.r, self.s, self.d = 1.0, 1.0, 1.0
+        self.norm_d = math.sqrt(2 * self.area_mesh)
+        self.t["bnd0"].copy_(self._bnd_init[0])
+        self.t["bnd1"].copy_(self._bnd_init[1])
+        self.z_valid = True
+        self._push_params()
+        self.refresh()
+
+    def phi_residual(self):
+        """Residual of the space-time operator for the CURRENT phi against the CURRENT rhs, per time mode:
+        ``max |Q^T (div_t(area_v grad_t phi) + D(area_f G phi) - rhs)| / max |Q^T rhs|`` (eps = 0; the operator the reference
+        inverts in utils/laplacian_inverse_socp.py:52-61), formed with the stand-alone operator kernels dots_grad_space /
+        dots_div_space (rows a5, a6) and whole-array device arithmetic.  Single GPU.  Returns a numpy array (nT + 1)."""
+        if self.comm.enabled:
+            raise NotImplementedError("phi_residual is a single-GPU diagnostic")
+        nT, V, T, dev = self.nT, self.V, self.T, self.device
+        phi = self.slab["phi"].levels(0, nT + 1)
+        g = torch.empty((nT + 1, 3, T), dtype=torch.float64, device=dev)
+        capi.check(self.lib.dots_grad_space(self._ctxp, self.slab["phi"].base_ptr, g.data_ptr(), self.stream), "dots_grad_space")
+        g *= self._keep["area_f"][None, None, :]
+        lap = torch.empty((nT + 1, V), dtype=torch.float64, device=dev)
+        capi.check(self.lib.dots_div_space(self._ctxp, g.data_ptr(), lap.data_ptr(), self.stream), "dots_div_space")
+        m = (phi[1:] - phi[:-1]) / self.dt * self._keep["area_v"][None, :]
+        lap[0] += m[0] / self.dt
+        lap[1:-1] += (m[1:] - m[:-1]) / self.dt
+        lap[-1] -= m[-1] / self.dt
+        q = torch.as_tensor(self.Q, device=dev)
+        rhs = self.t["rhs"][:nT + 1]
+        res, den = q.T @ (lap - rhs), q.T @ rhs
+        self.launches += 2
+        return (res.abs().amax(dim=1) / den.abs().amax(dim=1).clamp_min(1e-300)).cpu().numpy()
+
+    def state_checksums(self):
+        """A few order-independent sums of the iterate (for cross-run / cross-rank-count parity records)."""
+        out = {}
+        for name in ("mu", "A", "B", "E"):
+            x = self.full(name)
+            out[name] = [float(x.sum()), float((x * x).sum())]
+        g = torch.diff(self.full("phi"), dim=0)
+        out["dt_phi"] = [float(g.sum()), float((g * g).sum())]
+        return out
 
     def set_scalars(self, r=None, s=None, d=None, norm_d=None):
         """Overwrite the driver scalars (tests / warm starts) and push them to the device."""

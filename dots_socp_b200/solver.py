@@ -125,6 +125,7 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev_a.record()
     pending = False                                  # GPU work enqueued since ev_a
+    time_up, synced = False, False
     kkt_seconds = 0.0
     start = time.perf_counter()                                                           # :655
     for it in range(nit):                                                                 # :656
@@ -137,7 +138,12 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
                 eng.scale_z(f)
         # The wall-clock limit is sampled before the step is enqueued (the reference samples it after
         # its synchronous steps, :725): the decision whether z_mid must be stored has to precede the launch.
-        time_up = (time.perf_counter() - start) > time_limit
+        # On the sharded path the ranks must take the same branch (it feeds the KKT collectives and the break), so the
+        # flag is agreed with an all-reduce, and only on iterations that follow a host synchronisation anyway.
+        if not eng.comm.enabled:
+            time_up = (time.perf_counter() - start) > time_limit
+        elif it == 0 or synced:
+            time_up = eng.comm.any_true((time.perf_counter() - start) > time_limit, eng.device)
         adjust = sched.due(it) or time_up                                                 # :726
         required = list(PRIM_SET + DUAL_SET) if adjust else None                          # :728-731
         if adjust:
@@ -162,6 +168,7 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
         sec = [e[1] for e in errs]
         if any(v is not None and v != v for v in org):
             raise FloatingPointError(f"non-finite KKT residual at iteration {it}: {org} (device state is corrupt)")
+        synced = bool(will_check)
         if will_check:
             torch.cuda.current_stream(eng.device).synchronize()
             hist.add_time(STEP_TAG, ev_a.elapsed_time(ev_b) * 1e-3)

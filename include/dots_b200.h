@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DOTS_ABI_VERSION 8
+#define DOTS_ABI_VERSION 9
 
 /* scalar block read by the kernels from device memory (so CUDA graphs stay valid across penalty updates) */
 enum {
@@ -49,6 +49,24 @@ enum {
     DOTS_P_EPS,          /* Laplacian regularisation eps   (:30)                                      */
     DOTS_P_COUNT = 8
 };
+
+/* Work item of the ring-streamed sweeps (sweep_mode 4, csrc/sweep_ring.cu).  "Output" = a panel row in the forward
+ * sweep, a panel column (of the column-major copy) in the backward sweep.
+ *   contiguous task (one warp): the outputs [oa, oa + n_out) of one node, whose n_ent panel entries form ONE contiguous
+ *                               run starting at entry pbase of panels / panels_t;
+ *   split item (one block)    : the outputs [oa, oa + n_out) of one node whose runs are long enough to be shared by several
+ *                               warps; pbase = the node's panel base, n_ent unused.                                        */
+typedef struct dots_ring_task {
+    int64_t pbase;
+    int32_t n_ent;
+    int32_t oa;
+    int32_t n_out;
+    int32_t s, b;              /* |S|, |B| of the node                                                 */
+    int32_t off;               /* first vertex owned by the node                                       */
+    int32_t ubase;             /* first row of the node's contribution block in `upd`                  */
+    int32_t fbase;             /* first row of the node's front in `bidx`                              */
+    int32_t pad[2];
+} dots_ring_task_t;
 
 /* Problem description + device storage.  Filled by the host side once; passed to every call. */
 typedef struct dots_ctx {
@@ -130,10 +148,9 @@ typedef struct dots_ctx {
     double *red_part;          /* [red_blocks][8] block partial sums                                  */
     double *red_out;           /* [8] reduced sums (device)                                           */
     int32_t red_blocks;
-    int32_t sweep_mode;        /* 0: one launch per tree level and direction; 1: persistent TMA-fed cooperative kernel;
-                                  2: per-level launches streaming 2-D panel tiles through a TMA ring; 3: the same, levels chained
-                                  with programmatic dependent launch (2, 3: experimental) */
-    int32_t sweep_grid;        /* blocks of the persistent kernel (0 = 2 per SM)                       */
+    int32_t sweep_mode;        /* 0: k_sweep_run, register-staged loads (any m_pad); 4: ring-streamed sweeps, every warp feeds its
+                                  own shared-memory ring with bulk async copies (m_pad a multiple of 32)                        */
+    int32_t sweep_grid;        /* unused (kept for layout stability)                                   */
     int32_t reserved0;
     uint64_t *phase_clock;     /* optional [2*n_levels+1]: %globaltimer (ns) at the start and after each sweep phase */
 
@@ -146,6 +163,21 @@ typedef struct dots_ctx {
     double *peer_rhs[8];       /* every rank's rhs buffer (own included) when n_ranks <= 8                             */
     const double *peer_hat[8]; /* every rank's solution buffer `hat` (own included): the inverse transform reads the other
                                   ranks' modes straight from their memory instead of from a gathered copy             */
+
+    /* ---- ring-streamed sweeps (sweep_mode 4).  Needs ywork == hat + n_vert*m_pad (one allocation Z = [hat | ywork]). ---- */
+    const dots_ring_task_t *rt_fwd, *rt_bwd;    /* device task arrays, grouped by tree level                              */
+    const int32_t *h_rt_fwd_ptr, *h_rt_bwd_ptr; /* HOST [n_levels+1] ranges into rt_fwd / rt_bwd                           */
+    const int32_t *h_rt_fwd_wpr, *h_rt_bwd_wpr; /* HOST [n_levels] 1: contiguous warp tasks; 2, 4, 8: split items, that many
+                                                   warps share one output                                                  */
+    const int32_t *bidx;       /* [front_total] row of Z read by the backward sweep for every front row: n_vert + vertex for
+                                  the S rows (y in ywork), vertex for the B rows (x of the ancestors in hat)               */
+    const int32_t *gptr;       /* [V+1] ranges into gidx: the contributions landing on vertex v                           */
+    const int32_t *gidx;       /* [sum b] rows of `upd` (producer order: nd_upd[node] + boundary row), grouped by the vertex
+                                  they land on, producers in post-order (fixed summation order)                           */
+    const int32_t *gverts;     /* vertices that receive contributions, grouped by the tree level of their owner node      */
+    const int32_t *h_gv_ptr;   /* HOST [n_levels+1] ranges into gverts                                                    */
+    int32_t ring_stages;       /* shared-memory stages per warp (2..6)                                                    */
+    int32_t ring_pdl;          /* 1: chain the level launches with programmatic dependent launch                          */
 } dots_ctx_t;
 
 /* ------------------------------------------------------------------------------------------------ */

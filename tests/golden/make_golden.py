@@ -82,6 +82,8 @@ CASES = {
     # BASELINE.json configs[2]: the same surface at nT = 63 and nT = 127 (time-direction scaling)
     "knots5class_nt63_c0": ("knot", {}, 63, dict(tol=1e-3, nit=2000), (), False),
     "knots5class_nt127_c0": ("knot", {}, 127, dict(tol=1e-3, nit=2000), (), False),
+    # >= 10k vertices: fronts beyond the small-front factorisation kernel and split sweep items (round 2; ~10 min of reference time)
+    "ico5_nt31_c0": ("icosphere5", {}, 31, dict(tol=1e-3, nit=1000), (), False),
 }
 
 

@@ -180,7 +180,8 @@ def test_kkt_and_objective_rows_a9_a11():
                                   "ico2_nt7_stepwise", "refplane20_nt15",
                                   "ico1_nt1_c005", "ico1_nt2_c0",                       # smallest time grids
                                   "ico2_nt7_eps1e-2",                                   # regularised Laplacian (eps > 0)
-                                  "ico2_nt7_tl0"])                                      # time limit hit on the first iteration
+                                  "ico2_nt7_tl0",                                       # time limit hit on the first iteration
+                                  "ico5_nt31_c0"])                                      # 10 242 vertices: large fronts, split sweep items
 def test_solver_matches_reference_fixture(golden, name):
     """Through the public solver_socp: iteration count, KKT schedule (which residual on which iteration), penalty
     path, transport cost and the returned mu against the fixtures generated by the unmodified reference."""
@@ -277,9 +278,21 @@ def test_replication_flow_reproduces_the_reference_plane_run_row_f4(golden):
     assert cps[1]["error"]["l2"] < cps[0]["error"]["l2"]
 
 
+def operator_residual_per_mode(ops, n_time, phi, rhs):
+    """max-norm of  div_t(area_v grad_t phi) + D(area_f G phi) - rhs  per time mode, relative to the mode's rhs
+    (space-time operator of socp/solver_socp.py:976-986 / utils/laplacian_inverse_socp.py:52-61, oracle's sparse G / D)."""
+    from dots_socp_b200.engine import time_basis
+    lap = orc.div_time(ops.dt, ops.area_v[None] * orc.grad_time(ops.dt, phi)) \
+        + orc.div_space(ops.D, ops.area_f[None, :, None] * orc.grad_space(ops.G, phi))
+    Q, _ = time_basis(n_time)
+    res_hat, rhs_hat = Q.T @ (lap - rhs), Q.T @ rhs
+    return np.abs(res_hat).max(axis=1) / np.maximum(np.abs(rhs_hat).max(axis=1), 1e-300)
+
+
 def test_large_problem_properties():
     """Full-size style check (size-independent properties): solve residual of the space-time operator and
     feasibility of the cone projection on a 10k-vertex icosphere with nT=63."""
+    from dots_socp_b200 import capi
     geo, _ = synth.example("icosphere5")
     n_time = 63
     eng = Engine(n_time, geo, leaf_size=24)
@@ -293,11 +306,105 @@ def test_large_problem_properties():
     nrm = np.sqrt(ops.M_oneT.dot(corner.T).T + st["z_end"] ** 2)
     assert (nrm <= st["z_fst"] * (1 + 1e-12) + 1e-12).all()
     assert np.isfinite(st["phi"]).all()
+    # the phi-step of the NEXT iteration: residual of the space-time operator against the rhs it was solved for
+    capi.check(eng.lib.dots_step_phi(eng._ctxp, eng.stream))
+    rhs = eng.from_internal("rhs", eng.t["rhs"][:n_time + 1]).cpu().numpy()
+    phi = eng.from_internal("phi").cpu().numpy()
+    assert operator_residual_per_mode(ops, n_time, phi, rhs).max() < 1e-9
 
 
-@pytest.mark.parametrize("example,leaf,n_time", [("icosphere3", 8, 7), ("icosphere5", 24, 31), ("plane8", 6, 6)])
-def test_setup_factorisation_kernel_matches_library_path_row_f1(example, leaf, n_time):
-    """Hand-written small-front kernel + library large fronts == all-library batched factorisation (both layouts)."""
+# ---------------------------------------------------------------------------------------------- headline code path
+@pytest.mark.parametrize("example", ["icosphere6", "icosphere7"])
+def test_headline_laplacian_solve_residual(example):
+    """The bench configuration itself (icosphere level 7 x nT = 63, leaf 16: fronts up to 1 277 rows, split sweep items with
+    2 / 4 / 8 warps per output, the large-front factorisation) and the level below it: after 3 real iterations the phi-step
+    is checked against the oracle's sparse space-time operator, per time mode.  No CPU factorisation is needed, so
+    this runs at the full size in seconds."""
+    from dots_socp_b200 import capi
+    n_time = 63
+    geo, _ = synth.example(example)
+    eng = Engine(n_time, geo, leaf_size=16)
+    eng.scale_z(2.0)
+    eng.iterate(3)
+    capi.check(eng.lib.dots_step_phi(eng._ctxp, eng.stream))
+    rhs = eng.from_internal("rhs", eng.t["rhs"][:n_time + 1]).cpu().numpy()
+    phi = eng.from_internal("phi").cpu().numpy()
+    assert np.isfinite(phi).all()
+    ops = orc.MeshOps(n_time, geo, build_inverse=False)
+    res = operator_residual_per_mode(ops, n_time, phi, rhs)
+    assert res.max() < 1e-9, res
+    if eng.sweep_mode == 4:                         # the plan really contains the split kernels this test is meant to cover
+        assert {int(w) for w in eng.ring["fwd_wpr"]} | {int(w) for w in eng.ring["bwd_wpr"]} >= {1, 2, 4}
+
+
+@pytest.mark.parametrize("example,iters", [("icosphere5", (1, 2, 5)), ("icosphere6", (1, 2))])
+def test_headline_size_iterates_match_oracle(example, iters):
+    """Per-iterate parity (1e-8) at nT = 63 on the 10k- and 41k-vertex icospheres: the oracle factorises its 64 modes with
+    SuperLU on all host cores (seconds / about a minute)."""
+    import os
+    n_time = 63
+    geo, _ = synth.example(example)
+    ops = orc.MeshOps(n_time, geo, n_threads=os.cpu_count() or 1)
+    alm = orc.OracleALM(n_time, geo, ops=ops)
+    eng = Engine(n_time, geo, leaf_size=16)
+    eng.scale_z(2.0)
+    done = 0
+    for k in iters:
+        for _ in range(k - done):
+            alm.iterate()
+        eng.iterate(k - done, write_z=True)
+        done = k
+        compare_states(alm, eng, 1e-8, f"{example} nT={n_time} k={k}")
+
+
+@pytest.mark.parametrize("mode", [0, 4])
+@pytest.mark.parametrize("example,n_time,leaf", [("icosphere3", 31, 16), ("icosphere2", 40, 8), ("icosphere3", 95, 16),
+                                                 ("icosphere4", 127, 16)])
+def test_both_sweep_kernels_match_the_sparse_solve(mode, example, n_time, leaf):
+    """dots_mode_solves alone, both implementations (0: k_sweep_run, 4: ring-streamed), 32 / 64 / 96 / 128 modes, against
+    scipy's sparse LU of the same shifted matrices (utils/laplacian_inverse_socp.py:34-41,58-59)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from dots_socp_b200 import capi, surface
+    geo, _ = synth.example(example)
+    eng = Engine(n_time, geo, leaf_size=leaf, sweep_mode=mode)
+    rng = np.random.default_rng(17)
+    rhs = rng.standard_normal((eng.V, eng.m_pad))
+    eng.t["hat"].copy_(torch.from_numpy(rhs))
+    capi.check(eng.lib.dots_mode_solves(eng._ctxp, eng.stream))
+    x = eng.t["hat"].cpu().numpy()
+    K = surface.stiffness_matrix(geo["vertices"], geo["triangles"])
+    Kp = K[eng.perm_v][:, eng.perm_v].tocsc()
+    M = sp.diags(eng.area_v_new)
+    for m in range(1, n_time + 1, max(1, n_time // 6)):            # mode 0 is singular (pinned): covered through phi elsewhere
+        ref = -spla.spsolve(Kp + (-eng.lam_t[m] + eng.eps) * M, rhs[:, m])
+        assert rel(x[:, m], ref) < 1e-10, (m, rel(x[:, m], ref))
+
+
+@pytest.mark.parametrize("stages,pdl", [(2, 0), (4, 1), (3, 1)])
+def test_ring_sweep_variants_match(monkeypatch, stages, pdl):
+    """Ring depth and programmatic dependent launch change scheduling only: bit-identical iterates."""
+    geo, _ = synth.example("icosphere4")
+    outs = []
+    for st_, pd in ((3, 0), (stages, pdl)):
+        monkeypatch.setenv("DOTS_RING_STAGES", str(st_))
+        monkeypatch.setenv("DOTS_RING_PDL", str(pd))
+        monkeypatch.setenv("DOTS_RING_SPLIT_KB", "24")               # small mesh: force split items too
+        eng = Engine(63, geo, leaf_size=16, sweep_mode=4)
+        eng.scale_z(2.0)
+        eng.iterate(5, write_z=True)
+        outs.append(eng.get_state(("phi", "mu", "B")))
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+@pytest.mark.parametrize("example,leaf,n_time", [("icosphere3", 8, 7), ("icosphere5", 24, 31), ("plane8", 6, 6), ("icosphere5", 16, 63)])
+def test_setup_factorisation_matches_numpy_multifrontal_row_f1(example, leaf, n_time):
+    """GPU setup factorisation (hand-written front kernels) against the independent numpy multifrontal checker
+    (tests/host_multifrontal.py: numpy Cholesky / inverse per front), both panel layouts; plus a solve through the panels
+    against scipy's sparse LU (what the reference factorises with, utils/laplacian_inverse_socp.py:34-41)."""
+    import host_multifrontal as hm
+    from ring_emulation import transpose_panels
     from dots_socp_b200 import nested, surface, capi
     from dots_socp_b200.engine import time_basis
     geo, _ = synth.example(example)
@@ -306,17 +413,25 @@ def test_setup_factorisation_kernel_matches_library_path_row_f1(example, leaf, n
     mass = surface.incident_area_sum(v.shape[0], t, surface.triangle_areas(v, t)) / 3.0
     sym = nested.analyse(v, K, leaf_size=leaf)
     _, lam = time_basis(n_time)
-    m_pad = 8 if n_time + 1 <= 8 else 32
+    shifts = -lam
+    m_pad = 8 if n_time + 1 <= 8 else (32 if n_time + 1 <= 32 else 64)
     dev = torch.device("cuda:0")
-    ref, ref_t = nested.factor_batched_device(sym, K, mass, -lam, m_pad, dev, transposed=True)
     stats = {}
-    got, got_t = nested.factor_hybrid_device(sym, K, mass, -lam, m_pad, dev, capi.load(),
+    got, got_t = nested.factor_hybrid_device(sym, K, mass, shifts, m_pad, dev, capi.load(),
                                              lambda: torch.cuda.current_stream(dev).cuda_stream, stats=stats)
     torch.cuda.synchronize()
     assert stats["small_fronts"] > 0
-    scale = ref.abs().max().item()
-    assert (got - ref).abs().max().item() / scale < 1e-11
-    assert (got_t - ref_t).abs().max().item() / scale < 1e-11
+    ref = hm.factor_batched(sym, K, mass, shifts, m_pad=m_pad)
+    ref_t = transpose_panels(sym, ref)
+    got, got_t = got.cpu().numpy(), got_t.cpu().numpy()
+    # node by node, relative to the node's largest entry (mode 0 is pinned: its panels are O(1 / pin) in some nodes)
+    for name, a, b in (("panels", got, ref), ("panels_t", got_t, ref_t)):
+        for i in range(sym.n_nodes):
+            p0, p1 = int(sym.panel_off[i]), int(sym.panel_off[i + 1])
+            if p1 > p0:
+                scale = np.abs(b[p0:p1]).max(axis=0)
+                err = (np.abs(a[p0:p1] - b[p0:p1]).max(axis=0) / np.maximum(scale, 1e-300)).max()
+                assert err < 1e-9, (name, i, int(sym.s[i]), int(sym.b[i]), err)
 
 
 def test_small_root_front_is_pinned_deterministically():
@@ -339,29 +454,6 @@ def test_small_root_front_is_pinned_deterministically():
         assert torch.isfinite(p).all()
         first = p if first is None else first
         assert torch.equal(p, first)
-
-
-# ---------------------------------------------------------------------------------------------- experimental sweeps
-@pytest.mark.skipif(__import__("os").environ.get("DOTS_TEST_EXPERIMENTAL") != "1",
-                    reason="opt-in: sweep_mode 1 (persistent) / 2, 3 (tile-streamed, not yet run on hardware); "
-                           "set DOTS_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("mode", [1, 2, 3])
-@pytest.mark.parametrize("example,n_time,leaf", [("icosphere3", 31, 16), ("icosphere2", 40, 8), ("icosphere5", 63, 16),
-                                                 ("icosphere3", 127, 16)])
-def test_experimental_sweep_modes_match_the_default_path(mode, example, n_time, leaf):
-    """Same iterates as the default per-level sweep (different summation order inside a front: 1e-10)."""
-    geo, _ = synth.example(example)
-    ref = Engine(n_time, geo, congestion=0.05, leaf_size=leaf)
-    alt = Engine(n_time, geo, congestion=0.05, leaf_size=leaf, sweep_mode=mode)
-    for eng in (ref, alt):
-        eng.scale_z(2.0)
-        eng.iterate(6, write_z=True)
-    a, b = ref.get_state(), alt.get_state()
-    for k in a:
-        x, y = a[k], b[k]
-        if k == "phi":
-            x, y = x - x.mean(), y - y.mean()
-        assert rel(y, x) < 1e-10, (mode, k, rel(y, x))
 
 
 @pytest.mark.skipif(__import__("os").environ.get("DOTS_TEST_EXPERIMENTAL") != "1",

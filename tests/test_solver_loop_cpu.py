@@ -33,6 +33,8 @@ class OracleEngine:
         self.launches = 0
         self.z_valid = True                              # z_mid = 0 is the true initial z_mid (engine.py does the same)
         self.calls = []
+        from dots_socp_b200 import dist as dd
+        self.comm = dd.Comm()                            # single rank
 
     r = property(lambda self: self.alm.r)
 

@@ -1,4 +1,5 @@
-"""Host-side invariants of the per-level launch plan of the batched sweeps (dots_socp_b200/engine.py:_sweep_items).
+"""Host-side invariants of the launch plans of the batched sweeps (dots_socp_b200/engine.py:_sweep_items for k_sweep_run,
+dots_socp_b200/ring_plan.py for the ring-streamed kernels of csrc/sweep_ring.cu).
 
 The kernels trust the plan blindly: every panel row (forward) and every panel column (backward) must be covered by
 exactly one work item, a level may only contain nodes of that level, and the fused child gather may only be selected
@@ -6,7 +7,7 @@ where the forward block's shared-memory staging fits.  These are checked here wi
 import numpy as np
 import pytest
 
-from dots_socp_b200 import engine, nested, surface, synth
+from dots_socp_b200 import engine, nested, ring_plan, surface, synth
 
 
 def _sym(example, leaf):
@@ -73,18 +74,98 @@ def test_children_sit_on_strictly_lower_levels():
                 assert sym.level[k] < sym.level[n]
 
 
-@pytest.mark.parametrize("example,leaf,n_sm", [("icosphere3", 16, 148), ("icosphere5", 16, 148), ("knot", 16, 148), ("plane8", 6, 4)])
-def test_tile_plan_covers_every_output_once_in_whole_groups(example, leaf, n_sm):
-    """Plan of the experimental tile-streamed sweep (sweep_mode=2): exact cover, items start on their node's output 0 + k*per
-    and every item but a node's last one is a multiple of 8 outputs long."""
+# ------------------------------------------------------------------------------------------------ ring plan (sweep_mode 4)
+RING_CASES = [("icosphere3", 16, 32, 148, {}), ("icosphere4", 16, 64, 148, {}), ("knot", 16, 128, 148, {}),
+              ("plane8", 6, 96, 4, {}),
+              # tiny thresholds: every kind of item (many short tasks, split outputs with 2 / 4 / 8 warps) on a small mesh
+              ("icosphere3", 8, 64, 2, dict(split_bytes=2048, task_bytes=(512, 2048))),
+              ("icosphere2", 8, 32, 2, dict(split_bytes=1024, task_bytes=(256, 1024), wpr_max=4))]
+
+
+@pytest.mark.parametrize("example,leaf,m_pad,n_sm,kw", RING_CASES)
+def test_ring_plan_streams_every_panel_entry_exactly_once(example, leaf, m_pad, n_sm, kw):
+    """Contiguous tasks: their entry runs tile each node's panel exactly, start and end on output boundaries and carry the
+    node data the kernel reads.  Split items: every output of the node is in exactly one item."""
     sym = _sym(example, leaf)
-    plan = engine._sweep_items_tile(sym, n_sm)
-    for lv, nodes in enumerate(nested.level_schedule(sym)):
-        for key_ptr, key_items, lens in (("fwd_ptr", "fwd_items", {int(n): int(sym.s[n] + sym.b[n]) for n in nodes}),
-                                         ("bwd_ptr", "bwd_items", {int(n): int(sym.s[n]) for n in nodes})):
-            items = plan[key_items][plan[key_ptr][lv]:plan[key_ptr][lv + 1]]
-            seen = _coverage(items, lens)
-            assert all((c == 1).all() for c in seen.values())
-            assert {int(n) for n in items[:, 0]} == {n for n, ln in lens.items() if ln > 0}
-            for nd, o0, cnt in items:
-                assert cnt <= 32 and (cnt % 8 == 0 or o0 + cnt == lens[int(nd)])
+    plan = ring_plan.build(sym, n_sm, m_pad, **kw)
+    levels = nested.level_schedule(sym)
+    assert len(plan["fwd_ptr"]) == len(plan["bwd_ptr"]) == len(plan["gv_ptr"]) == len(levels) + 1
+    for lv, nodes in enumerate(levels):
+        for d, forward in (("fwd", True), ("bwd", False)):
+            items = plan["rt_" + d][plan[d + "_ptr"][lv]:plan[d + "_ptr"][lv + 1]]
+            wpr = int(plan[d + "_wpr"][lv])
+            assert wpr in (1, 2, 4, 8)
+            live = [int(n) for n in nodes if sym.s[n] > 0]
+            by_node = {n: [] for n in live}
+            for t in items:
+                nd = int(np.searchsorted(sym.off, t["off"], side="right") - 1)
+                while sym.s[nd] == 0:                                    # empty separators share their offset with a neighbour
+                    nd -= 1
+                assert nd in by_node, "item of a node from another level"
+                assert (t["s"], t["b"], t["ubase"], t["fbase"]) == (sym.s[nd], sym.b[nd], sym.upd_off[nd], sym.front_off[nd])
+                by_node[nd].append(t)
+            for nd, ts in by_node.items():
+                s, b = int(sym.s[nd]), int(sym.b[nd])
+                n_out = s + b if forward else s
+                row_off = lambda o: (o * (o + 1) // 2 if o < s else s * (s + 1) // 2 + (o - s) * s) if forward else (o * (s + b) - o * (o - 1) // 2)
+                nxt = 0
+                for t in ts:
+                    assert t["oa"] == nxt and t["n_out"] >= 1
+                    nxt = int(t["oa"] + t["n_out"])
+                    if wpr == 1:
+                        assert t["pbase"] == sym.panel_off[nd] + row_off(int(t["oa"]))
+                        assert t["n_ent"] == row_off(nxt) - row_off(int(t["oa"])) > 0
+                    else:
+                        assert t["pbase"] == sym.panel_off[nd]
+                assert nxt == n_out
+
+
+@pytest.mark.parametrize("example,leaf", [("icosphere3", 8), ("knot", 16), ("plane8", 6)])
+def test_pull_lists_route_every_boundary_row_to_its_vertex_once(example, leaf):
+    sym = _sym(example, leaf)
+    plan = ring_plan.build(sym, 148, 64)
+    gptr, gidx = plan["gptr"], plan["gidx"]
+    total = int(sym.upd_off[-1])
+    live_rows = np.repeat(sym.s > 0, sym.b)
+    assert gptr[-1] == live_rows.sum() and gptr[0] == 0
+    assert sorted(gidx[:gptr[-1]].tolist()) == np.nonzero(live_rows)[0].tolist()         # every live row exactly once
+    row_node = np.repeat(np.arange(sym.n_nodes), sym.b)
+    for v in range(sym.n):
+        rows = gidx[gptr[v]:gptr[v + 1]]
+        prod = row_node[rows]
+        assert (np.diff(prod) > 0).all()                                                # producers in post-order
+        for r, nd in zip(rows, prod):
+            assert sym.front_idx[sym.front_off[nd] + sym.s[nd] + (r - sym.upd_off[nd])] == v
+    # gverts: level by level exactly the vertices with a non-empty list
+    node_of = np.repeat(np.arange(sym.n_nodes), sym.s)
+    for lv in range(sym.n_levels):
+        gv = plan["gverts"][plan["gv_ptr"][lv]:plan["gv_ptr"][lv + 1]]
+        want = [v for v in range(sym.n) if sym.level[node_of[v]] == lv and gptr[v + 1] > gptr[v]]
+        assert gv.tolist() == want
+    assert total == 0 or plan["bidx"].max() < 2 * sym.n
+
+
+@pytest.mark.parametrize("example,leaf,m_pad,n_sm,kw", RING_CASES[:1] + RING_CASES[4:])
+def test_ring_plan_reproduces_the_sparse_solve(example, leaf, m_pad, n_sm, kw):
+    """The numpy statement of the ring kernels (tests/ring_emulation.py), run on this plan with panels from the numpy
+    multifrontal checker, solves (K + shift M) x = -rhs for every mode."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    import host_multifrontal as hm
+    from ring_emulation import emulate, transpose_panels
+    geo, _ = synth.example(example)
+    v, tri = geo["vertices"], geo["triangles"]
+    K = surface.stiffness_matrix(v, tri)
+    area_f = surface.triangle_areas(v, tri)
+    mass = surface.incident_area_sum(v.shape[0], tri, area_f) / 3.0
+    sym = nested.analyse(v, K, leaf_size=leaf)
+    shifts = np.array([0.7, 31.0, 900.0])
+    panels = hm.factor_batched(sym, K, mass, shifts)
+    plan = ring_plan.build(sym, n_sm, m_pad, **kw)
+    rng = np.random.default_rng(11)
+    rhs = rng.standard_normal((sym.n, shifts.size))
+    x = emulate(sym, plan, panels, transpose_panels(sym, panels), rhs)
+    Kp = K[sym.perm][:, sym.perm].tocsc()
+    for m, sh in enumerate(shifts):
+        ref = -spla.spsolve(Kp + sh * sp.diags(mass[sym.perm]), rhs[:, m])
+        assert np.abs(x[:, m] - ref).max() <= 1e-10 * np.abs(ref).max()
