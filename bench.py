@@ -20,8 +20,17 @@ Own arm (default)
   roofline : the dominant kernel's unique bytes per launch / its mean duration measured live with CUDA events.
   cpu_baseline : the oracle port (numpy/scipy restatement of the reference) on a bounded sample, host cores.
 
-Reference arm (--impl reference): the oracle port on the host cores (the reference is pure Python and its
-tree does not travel to the GPU box), same metric/unit/config, bounded sample.
+  parity   : measured on the bench workload before the timed region: residual of the phi-solve per time mode
+             (space-time operator applied with the stand-alone operator kernels) after 3 iterations, and checksums of the
+             iterate compared with the single-GPU record in profiles/.
+  secondary: the knots_5-class configurations of BASELINE.json (configs[0..2]): ms per iteration and iterations to
+             tol 1e-3, checked against the counts of the unmodified reference (fixtures).
+
+Reference arm (--impl reference): the oracle port (the reference is pure Python and its tree does not travel to the
+GPU box) on the host cores, ON THE CONFIGURATION IT PRINTS: all nT+1 modes of the full-size mesh are factorised with
+SuperLU (threaded over the modes), then ALM iterations are timed; `steps` is the number of iterations actually timed
+(bounded by --ref-seconds), nothing is extrapolated.  NCCL_DEBUG is left as the caller set it: the JSON line is the
+last line on stdout.
 """
 from __future__ import annotations
 
@@ -35,8 +44,6 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("DOTS_KEEP_NCCL_DEBUG"):
-    os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its banner on stdout; stdout carries exactly one JSON line
 
 import numpy as np
 
@@ -86,8 +93,11 @@ def kernel_bytes(V, T, nT, m_pad, sym):
     vert = 8 * (c + (nT + 1) * 6 * T - 2 * 3 * T + 4 * a + 8 * a + V) + 4 * (V + 1 + 3 * T)
     rhs = 8 * (3 * a + (nT + 1) * 3 * T + 2 * V + c + V) + 4 * (V + 1 + 3 * T)
     ttr = 8 * (c + V * m_pad) * 2
-    sweeps = 8 * m_pad * (2 * sym.panel_entries + 6 * V + 3 * int(sym.upd_off[-1]))
-    return {"k_tri_tma": tri, "k_vertex": vert, "k_phi_rhs": rhs, "k_time_mma": ttr, "k_sweep_run+k_sweep_gather": sweeps}
+    # SURVEY 8(d), strictly: the solve pass reads and writes the (nT+1) x V vector once (2c) and streams the factor twice (F);
+    # the y / update vectors the two sweeps exchange (3c + 2 * update rows) are counted apart
+    sweeps = 8 * m_pad * (2 * sym.panel_entries + 2 * V)
+    return {"k_tri_tma": tri, "k_vertex": vert, "k_phi_rhs": rhs, "k_time_mma": ttr, "sweeps": sweeps,
+            "sweeps_incl_work_vectors": sweeps + 8 * m_pad * (3 * V + 2 * int(sym.upd_off[-1]))}
 
 
 class ClockSampler:
@@ -142,7 +152,8 @@ class ClockSampler:
 
 
 def cpu_sample(workload, steps=3, warmup=1, threads=None):
-    """Oracle port on the host cores: `steps` ALM iterations on the sample mesh, scaled to the workload's size."""
+    """cpu_baseline of the own arm: oracle port on the host cores, `steps` ALM iterations on a SMALLER sample mesh of the
+    same family (bounded to ~10-30 s of CPU work), scaled linearly in V to the workload's size and labelled as such."""
     from dots_socp_b200 import synth
     from oracle import alm_oracle as orc
     ex, n_time, cong, sample_ex = WORKLOADS[workload]
@@ -162,7 +173,8 @@ def cpu_sample(workload, steps=3, warmup=1, threads=None):
     dt = (time.perf_counter() - t0) / steps
     v_s = geo["vertices"].shape[0]
     scale = v_s / full_v
-    return dict(value=(1.0 / dt) * scale, unit=UNIT, cores=threads, kind="port",
+    return dict(value=(1.0 / dt) * scale, unit=UNIT, cores=threads, kind="port, threaded", extrapolated=scale != 1.0,
+                sample_value=1.0 / dt, sample_workload=f"{sample_ex}_nt{n_time}",
                 sample=(f"oracle port (numpy + SuperLU, per-mode solves on {threads} threads, Laplacian || projection), {steps} ALM "
                         f"iterations on {sample_ex} (V={v_s}) x nT={n_time}: {dt * 1e3:.0f} ms/iteration, scaled by V_sample/V = "
                         f"{scale:.4f} (linear in V: favours the CPU, its sparse LU solves grow faster than V)"),
@@ -170,20 +182,142 @@ def cpu_sample(workload, steps=3, warmup=1, threads=None):
 
 
 def run_reference(args):
+    """The CPU implementation of the path on the configuration it prints (no extrapolation): threaded SuperLU factorisation
+    of all modes of the full-size mesh (setup, reported), then ALM iterations of the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_sample(args.workload, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
-    ex, n_time, cong, sample_ex = WORKLOADS[args.workload]
+    from dots_socp_b200 import synth
+    from oracle import alm_oracle as orc
+    workload, fallback = args.workload, None
+    need_gb = {"icosphere7_nt63": 110.0, "icosphere6_nt63": 28.0}.get(workload, 0.0)   # SuperLU L+U of all modes + oracle state
+    try:
+        import psutil
+        avail_gb = psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        avail_gb = float("inf")
+    if avail_gb < need_gb and workload == "icosphere7_nt63":
+        fallback = (f"{workload} needs ~{need_gb:.0f} GB of host memory for the {WORKLOADS[workload][1] + 1} SuperLU factors, "
+                    f"{avail_gb:.0f} GB available: measured on icosphere6_nt63 instead (the own arm reports the same workload "
+                    f"under secondary.icosphere6_nt63)")
+        workload = "icosphere6_nt63"
+    ex, n_time, cong, _ = WORKLOADS[workload]
+    threads = os.cpu_count() or 1
+    geo, _ = synth.example(ex)
+    V, T = geo["vertices"].shape[0], geo["triangles"].shape[0]
+    t0 = time.perf_counter()
+    ops = orc.MeshOps(n_time, geo, n_threads=threads)
+    setup = time.perf_counter() - t0
+    alm = orc.OracleALM(n_time, geo, congestion=cong, ops=ops)
+    alm.two_threads = True
+    t0 = time.perf_counter()
+    alm.iterate()                                                  # first iteration: also sizes the time budget
+    first = time.perf_counter() - t0
+    warm = max(0, min(args.warmup, 2) - 1) if first * 3 < args.ref_seconds else 0
+    for _ in range(warm):
+        alm.iterate()
+    steps = int(max(1, min(args.steps, (args.ref_seconds - first * (1 + warm)) // max(first, 1e-9))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        alm.iterate()
+    dt = (time.perf_counter() - t0) / steps
+    cb = dict(value=1.0 / dt, unit=UNIT, cores=threads, kind="port, threaded", extrapolated=False,
+              sample=(f"oracle port (numpy + SuperLU; per-mode solves on {threads} threads, Laplacian || projection as in the "
+                      f"reference's is_multi_threads) on the full workload {workload} (V={V}, nT={n_time}): {steps} ALM "
+                      f"iterations timed after {1 + warm} warm-up, {dt * 1e3:.0f} ms/iteration; factorisation of the {n_time + 1} "
+                      f"modes (setup, not in the value): {setup:.1f} s"),
+              setup_s=setup, steps_measured=steps, steps_requested=args.steps)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "n_vertices": FULL_SIZE.get(ex, (None, None))[0],
-                       "n_triangles": FULL_SIZE.get(ex, (None, None))[1], "n_time": n_time, "congestion": cong, "tol": 1e-3,
-                       "time_modes": n_time + 1},
+            "steps": steps, "warmup": 1 + warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "same_config": fallback is None,
+            "extrapolated": False, "fallback": fallback,
+            "config": {"workload": workload, "n_vertices": V, "n_triangles": T, "n_time": n_time, "congestion": cong,
+                       "tol": 1e-3, "time_modes": n_time + 1},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+
+
+PARITY_RECORD = os.path.join(ROOT, "profiles", "r2_parity_record.json")
+SECONDARY = {   # workload -> iterations to tol 1e-3 of the unmodified reference (tests/golden/knots5class_*.npz); None: no reference run
+    "knots5class_nt31": 741, "knots5class_nt31_c01": 208, "knots5class_nt63": 678, "knots5class_nt127": 614,
+    "icosphere6_nt63": None}     # the size the reference arm falls back to when the host cannot hold the level-7 factors
+
+
+def parity_block(eng, workload, world):
+    """3 iterations from the start state on the bench workload: phi-solve residual per time mode (single GPU) and checksums
+    of the iterate, compared (rtol 1e-9) with the single-GPU record kept under profiles/."""
+    import torch
+    eng.reset_state()
+    eng.scale_z(2.0)
+    eng.iterate(3)
+    out = {"iterations": 3}
+    if world == 1:
+        from dots_socp_b200 import capi
+        capi.check(eng.lib.dots_step_phi(eng._ctxp, eng.stream), "dots_step_phi")
+        res = eng.phi_residual()
+        out["phi_solve_residual_max_over_modes"] = float(res.max())
+        out["phi_solve_residual_ok"] = bool(np.isfinite(res).all() and res.max() < 1e-9)
+    sums = eng.state_checksums()
+    out["state_checksums"] = sums
+    key = workload
+    rec = {}
+    if os.path.exists(PARITY_RECORD):
+        with open(PARITY_RECORD) as f:
+            rec = json.load(f)
+    if key in rec:
+        worst = 0.0
+        for name, (a, b) in rec[key]["state_checksums"].items():
+            for x, y in zip((a, b), sums[name]):
+                worst = max(worst, abs(x - y) / max(abs(x), 1e-300))
+        out["checksums_vs_single_gpu_record"] = worst
+        out["checksums_ok"] = bool(worst < 1e-9)
+    else:
+        out["checksums_vs_single_gpu_record"] = None
+    ok = out.get("phi_solve_residual_ok", True) and out.get("checksums_ok", True)
+    pinned = ("phi_solve_residual_ok" in out) or ("checksums_ok" in out)
+    out["status"] = ("green" if ok else "MISMATCH") if pinned else "unpinned"
+    torch.cuda.synchronize()
+    return out
+
+
+def secondary_block(args):
+    """BASELINE configs[0..2] (knots_5-class stand-in): iterations to tol 1e-3 through the public solver and ms per
+    iteration of the resident loop (CUDA events, `steps` iterations); the working set fits in L2, so an L2 flush (a 256 MB
+    fill) runs between the timed batches."""
+    import torch
+    import dots_socp_b200 as b200
+    from dots_socp_b200 import synth
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for name, want in SECONDARY.items():
+        ex, n_time, cong, _ = WORKLOADS[name]
+        geo, _ = synth.example(ex)
+        sol, hist, eng = b200.solver(n_time, geo, congestion=cong, tol=1e-3, nit=3000, return_engine=True, leaf_size=args.leaf)
+        iters = int(hist.kkt_iteration[-1]) + 1
+        for _ in range(5):
+            eng.iterate(1)
+        times = []
+        for _ in range(5):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(50):
+                eng.iterate(1)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) / 50)
+        ms = float(np.median(times))
+        V, T = geo["vertices"].shape[0], geo["triangles"].shape[0]
+        kb = kernel_bytes(V, T, n_time, eng.m_pad, eng.sym)
+        fused = sum(v for k, v in kb.items() if k != "sweeps") 
+        out[name] = {"ms_per_step": round(ms, 5), "iterations_to_tol": iters, "reference_iterations": want,
+                     "iterations_match": (iters == want) if want is not None else None, "time_to_tol_s": round(float(hist.running_time), 4),
+                     "fused_bytes": fused, "frac_hbm_peak": round(fused / ms / 1e6 / peaks()[0], 4),
+                     "launches_per_iteration": eng.launches_per_iteration()}
+        eng.close()
+        del eng, sol
+    return out
 
 
 def run_own(args):
@@ -231,6 +365,9 @@ def run_own(args):
            "value_incl_setup": iters / wall, "transport_cost": float(hist.history["Transportation cost"][-1]) / scale ** 2,
            "kkt_evaluations": hist.evaluations, "converged": bool(np.nanmax(hist.kkt_errors[-1]) < 1e-3)}
 
+    # ---- parity on the bench workload itself, before the timed region -------------------------------
+    parity = parity_block(eng, args.workload, world)
+
     # ---- device-resident timed region ----------------------------------------------------------------
     lib, ctxp = eng.lib, eng._ctxp
     stream = eng.stream
@@ -260,7 +397,8 @@ def run_own(args):
     value = 1e3 / ms_per_step
 
     # ---- per-kernel-group durations, measured live (second pass, events between the step calls) ------
-    names = ["k_phi_rhs", "comm:all_gather(rhs)", "k_time_fwd", "k_sweep_run+k_sweep_gather", "comm:all_gather(hat)", "k_time_bwd",
+    sweep_name = "k_ring_run+k_ring_split+k_ring_gather" if eng.sweep_mode == 4 else "k_sweep_run+k_sweep_gather"
+    names = ["k_phi_rhs", "comm:all_gather(rhs)", "k_time_fwd", sweep_name, "comm:all_gather(hat)", "k_time_bwd",
              "k_vertex", "comm:halo(vertex)", "k_tri", "comm:halo(corner)"]
     part, comm, tt = eng.part, eng.comm, eng.t
     steps_fn = [
@@ -292,10 +430,13 @@ def run_own(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         raw = {n: float(v) for n, v in zip(names, tmax.tolist())}
     groups = {"k_phi_rhs": raw["k_phi_rhs"], "k_time_mma": raw["k_time_fwd"] + raw["k_time_bwd"],
-              "k_sweep_run+k_sweep_gather": raw["k_sweep_run+k_sweep_gather"], "k_vertex": raw["k_vertex"], "k_tri_tma": raw["k_tri"]}
+              sweep_name: raw[sweep_name], "k_vertex": raw["k_vertex"], "k_tri_tma": raw["k_tri"]}
     comm_ms = {n: round(raw[n], 4) for n in names if n.startswith("comm:")} if world > 1 else {}
     peak, peak_src = peaks()
-    kb = {k: v / world for k, v in kernel_bytes(V, T, n_time, n_time + 1, eng.sym).items()}     # per GPU
+    kb_all = kernel_bytes(V, T, n_time, n_time + 1, eng.sym)
+    sweeps_incl = kb_all.pop("sweeps_incl_work_vectors") / world
+    kb_all[sweep_name] = kb_all.pop("sweeps")
+    kb = {k: v / world for k, v in kb_all.items()}                                               # per GPU
     kernels = {}
     for name, t_ms in groups.items():
         kernels[name] = {"ms": round(t_ms, 4), "bytes": kb[name], "gbs": round(kb[name] / t_ms / 1e6, 1),
@@ -312,7 +453,10 @@ def run_own(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": traffic if world == 1 else None, "peak_source": peak_src,
                 "bytes_per_launch": kb[dom], "ms_per_launch": kernels[dom]["ms"], "kernels": kernels,
-                "per_gpu": True, "comm_ms": comm_ms}
+                "per_gpu": True, "comm_ms": comm_ms,
+                "bytes_definition": ("sweeps: SURVEY 8(d) strictly, 8 M (2 panel entries + 2 V) = factor streamed twice + the "
+                                     "solve's vector read and written once; with the y / update work vectors of the two sweeps: "
+                                     f"{sweeps_incl:.4g} B per launch")}
     ref_bytes = reference_bytes_per_iteration(V, T, n_time, eng.sym.panel_entries, n_time + 1)
     own_bytes = sum(kb.values()) * world
     roofline["iteration"] = {
@@ -338,13 +482,22 @@ def run_own(args):
             "exchange": ("single GPU" if world == 1 else
                          ("peer memory over NVLink (stores for the rhs slabs and halos, loads for the solutions) + one-element all-reduce fences"
                           if eng.peers else f"NCCL all_gather + isend/irecv ({eng.peer_error})")),
-            "roofline": roofline}
+            "roofline": roofline, "parity": parity, "sweep_mode": eng.sweep_mode}
+    eng.close()
+    del eng, sol
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_secondary and args.workload == "icosphere7_nt63":
+        line["secondary"] = secondary_block(args)
     if rank == 0:
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_sample(args.workload)
-        print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
+    return
 
 
 def main():
@@ -357,6 +510,9 @@ def main():
     ap.add_argument("--e2e-nit", type=int, default=1000, dest="e2e_nit")
     ap.add_argument("--leaf", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--no-secondary", action="store_true", dest="no_secondary")
+    ap.add_argument("--ref-seconds", type=float, default=150.0, dest="ref_seconds",
+                    help="reference arm: wall-clock budget of the timed ALM iterations")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -498,11 +498,14 @@ extern "C" int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
     if (c->n_tri % 2 == 0) {                               // 16-byte aligned planes: TMA-staged kernel
-        static bool configured = false;
-        if (!configured) {
+        static bool configured[64] = {false};                  // per device (a second engine on another GPU of the process)
+        int dev = 0;
+        DOTS_CUDA(cudaGetDevice(&dev));
+        dev = (dev >= 0 && dev < 64) ? dev : 0;
+        if (!configured[dev]) {
             DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM));
             DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM));
-            configured = true;
+            configured[dev] = true;
         }
         dim3 grid(ceil_div(c->n_tri, TRI_TILE), ceil_div(c->lvl_end - c->lvl_begin, TRI_TMA_TCH));
         if (write_z) k_tri_tma<1><<<grid, TRI_TILE, TRI_TMA_SMEM, (cudaStream_t)stream>>>(*c);

@@ -337,11 +337,15 @@ static int launch_level(const dots_ctx_t *c, int wpr_code, int i0, int n, int st
     const bool fuse = (DIR == 0) && (wpr_code & 16);
     const size_t smem = fuse ? (size_t)SWEEP_FG_SMAX * ML * sizeof(double) : 0;
     if (fuse) {
-        static bool configured = false;
-        if (!configured && smem > 48 * 1024) {
+        // dynamic r_S staging + the static combine buffer of the WPR = 2 instantiation must fit: opt in whenever the sum can
+        // exceed the 48 KB default (ML = 96: 48 KB + 6 KB), once per device
+        static bool configured[64] = {false};
+        int dev = 0;
+        DOTS_CUDA(cudaGetDevice(&dev));
+        if (smem + (size_t)SWEEP_WARPS * ML * sizeof(double) > 48 * 1024 && dev >= 0 && dev < 64 && !configured[dev]) {
             DOTS_CUDA(cudaFuncSetAttribute(k_sweep_run<ML, 1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             DOTS_CUDA(cudaFuncSetAttribute(k_sweep_run<ML, 2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
+            configured[dev] = true;
         }
         switch (wpr_code & 15) {
         case 1: k_sweep_run<ML, 1, 0, true><<<n, SWEEP_THREADS, smem, st>>>(*c, i0, stamp); break;
@@ -413,11 +417,14 @@ extern "C" int dots_time_transform(const dots_ctx_t *c, int inverse, void *strea
     // the tile loads of different blocks; the single-GPU B (36-140 KB) is loaded once per persistent block instead
     const bool small_b = (size_t)K * N * sizeof(double) <= 16 * 1024;
     const int grid = (small_b || n_tiles < c->n_sm * per_sm) ? n_tiles : c->n_sm * per_sm;
-    static size_t configured[2] = {0, 0};
-    if (smem > 48 * 1024 && smem > configured[inverse ? 1 : 0]) {
+    static size_t configured[64][2] = {{0, 0}};                    // per device: the attribute belongs to the device's copy of the function
+    int dev = 0;
+    DOTS_CUDA(cudaGetDevice(&dev));
+    dev = (dev >= 0 && dev < 64) ? dev : 0;
+    if (smem > 48 * 1024 && smem > configured[dev][inverse ? 1 : 0]) {
         if (inverse) DOTS_CUDA(cudaFuncSetAttribute(k_time_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else DOTS_CUDA(cudaFuncSetAttribute(k_time_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[inverse ? 1 : 0] = smem;
+        configured[dev][inverse ? 1 : 0] = smem;
     }
     if (inverse) k_time_mma<1><<<grid, 256, smem, st>>>(*c, n_tiles);
     else k_time_mma<0><<<grid, 256, smem, st>>>(*c, n_tiles);

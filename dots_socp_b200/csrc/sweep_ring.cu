@@ -55,13 +55,33 @@ __device__ __forceinline__ void sr_flush(const dots_ctx_t &c, const dots_ring_ta
 }
 
 // ------------------------------------------------------------------------------------------------
+// Vector operand of up to EC consecutive entries of ONE output piece [x, x + ne): rows of Z.
+template <int ML, int DIR, int EC>
+__device__ __forceinline__ void sr_fetch_vec(double (&rv)[EC][ML / 32], const double *z, const int32_t *bi, int off, int x, int ne)
+{
+    constexpr int MP = ML / 32;
+    int row[EC];
+#pragma unroll
+    for (int e = 0; e < EC; ++e) row[e] = (e < ne) ? ((DIR == 0) ? off + x + e : bi[x + e]) : 0;
+#pragma unroll
+    for (int e = 0; e < EC; ++e) {
+#pragma unroll
+        for (int m = 0; m < MP; ++m) rv[e][m] = (e < ne) ? z[(size_t)row[e] * ML + 32 * m] : 0.0;
+    }
+}
+
 // Contiguous tasks: one warp streams the outputs [oa, oa + n_out) of a node, i.e. n_ent consecutive panel entries.
-template <int ML, int DIR, bool PDL>
+// SB = bytes per ring stage.  The vector operand of stage k + 1 is requested before the math of stage k (SR_VEC_PIPE), so a
+// whole stage period hides its L1 / L2 latency.
+#ifndef SR_VEC_PIPE
+#define SR_VEC_PIPE 1
+#endif
+template <int ML, int DIR, int SB>
 __global__ void __launch_bounds__(SR_THREADS, 2) k_ring_run(dots_ctx_t c, int task0, int task_end)
 {
-    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // no-ops unless launched as a programmatic dependent
     constexpr int MP = ML / 32;
-    constexpr int EC = SR_STAGE_BYTES / (8 * ML);                        // panel entries per stage: 16, 8, 5, 4
+    constexpr int EC = SB / (8 * ML);                                    // panel entries per stage
     extern __shared__ __align__(128) unsigned char sr_smem[];
     const int nst = c.ring_stages;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -87,36 +107,51 @@ __global__ void __launch_bounds__(SR_THREADS, 2) k_ring_run(dots_ctx_t c, int ta
     if (lane == 0) {
         for (int k = 0; k < nst && k < n_stage; ++k) issue(k, k);        // the panels are read-only: stream before the wait
     }
-    if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");          // below: data written by the previous launches
+    asm volatile("griddepcontrol.wait;" ::: "memory");                   // below: data written by the previous launches
 
     const double *z = c.hat + lane;                                      // Z = [hat | ywork]
     const int32_t *bi = c.bidx + t.fbase;
+    // vector operand of a stage's entries: walks over the output boundaries exactly like the math below
+    int vo = t.oa, vx = sr_lo<DIR>(vo), vhi = sr_hi<DIR>(vo, s, b);
+    auto fetch = [&](double (&rv)[EC][MP], int k) {
+        const int ne = min(EC, n_ent - k * EC);
+        int row[EC];
+#pragma unroll
+        for (int e = 0; e < EC; ++e) {
+            row[e] = 0;
+            if (e < ne) {
+                row[e] = (DIR == 0) ? t.off + vx : bi[vx];
+#ifdef SR_DEBUG_VEC0
+                row[e] = 0;                                              // timing experiment only: no vector traffic, wrong results
+#endif
+                if (++vx == vhi) { ++vo; vx = sr_lo<DIR>(vo); vhi = sr_hi<DIR>(vo, s, b); }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < EC; ++e) {
+#pragma unroll
+            for (int m = 0; m < MP; ++m) rv[e][m] = (e < ne) ? z[(size_t)row[e] * ML + 32 * m] : 0.0;
+        }
+    };
     int o = t.oa, x = sr_lo<DIR>(o), hi = sr_hi<DIR>(o, s, b);
     double acc[MP];
 #pragma unroll
     for (int m = 0; m < MP; ++m) acc[m] = 0.0;
     int slot = 0;
     uint32_t phase = 0;
+    double rvn[EC][MP];
+    if (SR_VEC_PIPE) fetch(rvn, 0);
     for (int k = 0; k < n_stage; ++k) {
         const int ne = min(EC, n_ent - k * EC);
-        // vector operand of the stage's entries (walks over output boundaries like the math below)
         double rv[EC][MP];
-        {
-            int row[EC];
-            int o2 = o, x2 = x, hi2 = hi;
+        if (SR_VEC_PIPE) {
 #pragma unroll
-            for (int e = 0; e < EC; ++e) {
-                row[e] = 0;
-                if (e < ne) {
-                    row[e] = (DIR == 0) ? t.off + x2 : bi[x2];
-                    if (++x2 == hi2) { ++o2; x2 = sr_lo<DIR>(o2); hi2 = sr_hi<DIR>(o2, s, b); }
-                }
-            }
+            for (int e = 0; e < EC; ++e)
 #pragma unroll
-            for (int e = 0; e < EC; ++e) {
-#pragma unroll
-                for (int m = 0; m < MP; ++m) rv[e][m] = (e < ne) ? z[(size_t)row[e] * ML + 32 * m] : 0.0;
-            }
+                for (int m = 0; m < MP; ++m) rv[e][m] = rvn[e][m];
+            fetch(rvn, k + 1);                                           // requested now, used one stage later
+        } else {
+            fetch(rv, k);
         }
         mbar_wait(&bar[slot], phase);
         const double *sp = ring + (size_t)slot * EC * ML + lane;
@@ -141,14 +176,15 @@ __global__ void __launch_bounds__(SR_THREADS, 2) k_ring_run(dots_ctx_t c, int ta
 
 // ------------------------------------------------------------------------------------------------
 // Split items: block = (node, outputs [oa, oa + n_out)); ROWS = 8 / WPR outputs per pass, the run of an output is cut into
-// WPR contiguous pieces (one per warp), partial sums combined in warp order through shared memory.  A warp's ring runs
-// ahead across the passes.
-template <int ML, int WPR, int DIR, bool PDL>
+// WPR contiguous pieces (one per warp), partial sums combined in warp order through shared memory.  A warp's chunk
+// sequence runs over all passes of the item; three cursors walk it: the bulk copies (ring_stages chunks ahead), the vector
+// operand (one chunk ahead) and the math.
+template <int ML, int WPR, int DIR, int SB>
 __global__ void __launch_bounds__(SR_THREADS, 2) k_ring_split(dots_ctx_t c, int item0)
 {
-    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     constexpr int MP = ML / 32;
-    constexpr int EC = SR_STAGE_BYTES / (8 * ML);
+    constexpr int EC = SB / (8 * ML);
     constexpr int ROWS = SR_WARPS / WPR;
     extern __shared__ __align__(128) unsigned char sr_smem[];
     const int nst = c.ring_stages;
@@ -167,81 +203,88 @@ __global__ void __launch_bounds__(SR_THREADS, 2) k_ring_split(dots_ctx_t c, int 
     const int npass = (t.n_out + ROWS - 1) / ROWS;
     const int rslot = warp / WPR, cslot = warp % WPR;
 
+    struct Cur { int pass, o, x, xb; };                                  // chunk [x, min(x + EC, xb)) of output o in pass `pass`
     // this warp's piece [xa, xb) of the output it shares in pass `pass`
-    auto piece = [&](int pass, int &o, int &xa, int &xb) -> bool {
-        o = t.oa + pass * ROWS + rslot;
-        if (o > last) return false;
-        const int lo = sr_lo<DIR>(o), hi = sr_hi<DIR>(o, s, b);
+    auto piece = [&](Cur &q) -> bool {
+        q.o = t.oa + q.pass * ROWS + rslot;
+        if (q.o > last) return false;
+        const int lo = sr_lo<DIR>(q.o), hi = sr_hi<DIR>(q.o, s, b);
         const int plen = ((hi - lo + WPR - 1) / WPR + EC - 1) / EC * EC;
-        xa = lo + cslot * plen;
-        xb = min(hi, xa + plen);
-        return xa < xb;
+        q.x = lo + cslot * plen;
+        q.xb = min(hi, q.x + plen);
+        return q.x < q.xb;
     };
-    // producer cursor: the next chunk to issue is [px, min(px + EC, pxb)) of output po (pass pp)
-    int pp = -1, po = 0, px = 0, pxb = 0;
-    auto prod_next = [&]() -> bool {
-        px += EC;
-        while (px >= pxb) {
-            if (++pp >= npass) return false;
-            if (!piece(pp, po, px, pxb)) px = pxb = 0;
+    auto next = [&](Cur &q) -> bool {                                    // advance to the warp's next chunk; false: no more
+        q.x += EC;
+        while (q.x >= q.xb) {
+            if (++q.pass >= npass) return false;
+            if (!piece(q)) q.x = q.xb = 0;
         }
         return true;
     };
-    auto issue = [&](int slot) {                                         // lane 0
-        const uint32_t bytes = (uint32_t)min(EC, pxb - px) * (uint32_t)(ML * 8);
-        const size_t ent = (DIR == 0 ? sr_row_off(po, s) : sr_col_off(po, s, b)) + (size_t)(px - sr_lo<DIR>(po));
+    auto issue = [&](const Cur &q, int slot) {                           // lane 0
+        const uint32_t bytes = (uint32_t)min(EC, q.xb - q.x) * (uint32_t)(ML * 8);
+        const size_t ent = (DIR == 0 ? sr_row_off(q.o, s) : sr_col_off(q.o, s, b)) + (size_t)(q.x - sr_lo<DIR>(q.o));
         mbar_expect_tx(&bar[slot], bytes);
         tma_load_1d(ring + (size_t)slot * EC * ML, pan + ent * ML, bytes, &bar[slot]);
     };
-    bool pvalid = prod_next();
+    Cur pc{-1, 0, 0, 0}, vc{-1, 0, 0, 0}, cc{-1, 0, 0, 0};
+    bool pvalid = next(pc), vvalid = next(vc), cvalid = next(cc);
     for (int i = 0; i < nst && pvalid; ++i) {
-        if (lane == 0) issue(i);
-        pvalid = prod_next();
+        if (lane == 0) issue(pc, i);
+        pvalid = next(pc);
     }
-    if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const double *z = c.hat + lane;
     const int32_t *bi = c.bidx + t.fbase;
     int slot = 0;
     uint32_t phase = 0;
+    double rvn[EC][MP];
+    if (SR_VEC_PIPE && vvalid) {
+        sr_fetch_vec<ML, DIR, EC>(rvn, z, bi, t.off, vc.x, min(EC, vc.xb - vc.x));
+        vvalid = next(vc);
+    }
     for (int pass = 0; pass < npass; ++pass) {
-        int o, xa, xb;
-        const bool mine = piece(pass, o, xa, xb);
         double acc[MP];
 #pragma unroll
         for (int m = 0; m < MP; ++m) acc[m] = 0.0;
-        if (mine) {
-            for (int x = xa; x < xb; x += EC) {
-                const int ne = min(EC, xb - x);
-                double rv[EC][MP];
-                int row[EC];
+        while (cvalid && cc.pass == pass) {
+            const int ne = min(EC, cc.xb - cc.x);
+            double rv[EC][MP];
+            if (SR_VEC_PIPE) {
 #pragma unroll
-                for (int e = 0; e < EC; ++e) row[e] = (e < ne) ? ((DIR == 0) ? t.off + x + e : bi[x + e]) : 0;
+                for (int e = 0; e < EC; ++e)
 #pragma unroll
-                for (int e = 0; e < EC; ++e) {
-#pragma unroll
-                    for (int m = 0; m < MP; ++m) rv[e][m] = (e < ne) ? z[(size_t)row[e] * ML + 32 * m] : 0.0;
+                    for (int m = 0; m < MP; ++m) rv[e][m] = rvn[e][m];
+                if (vvalid) {
+                    sr_fetch_vec<ML, DIR, EC>(rvn, z, bi, t.off, vc.x, min(EC, vc.xb - vc.x));
+                    vvalid = next(vc);
                 }
-                mbar_wait(&bar[slot], phase);
-                const double *sp = ring + (size_t)slot * EC * ML + lane;
-#pragma unroll
-                for (int e = 0; e < EC; ++e) {
-                    if (e < ne) {
-#pragma unroll
-                        for (int m = 0; m < MP; ++m) acc[m] += sp[e * ML + 32 * m] * rv[e][m];
-                    }
-                }
-                __syncwarp();
-                if (pvalid) {
-                    if (lane == 0) issue(slot);
-                    pvalid = prod_next();
-                }
-                if (++slot == nst) { slot = 0; phase ^= 1u; }
+            } else {
+                sr_fetch_vec<ML, DIR, EC>(rv, z, bi, t.off, cc.x, ne);
             }
+            mbar_wait(&bar[slot], phase);
+            const double *sp = ring + (size_t)slot * EC * ML + lane;
+#pragma unroll
+            for (int e = 0; e < EC; ++e) {
+                if (e < ne) {
+#pragma unroll
+                    for (int m = 0; m < MP; ++m) acc[m] += sp[e * ML + 32 * m] * rv[e][m];
+                }
+            }
+            __syncwarp();
+            if (pvalid) {
+                if (lane == 0) issue(pc, slot);
+                pvalid = next(pc);
+            }
+            if (++slot == nst) { slot = 0; phase ^= 1u; }
+            cvalid = next(cc);
         }
 #pragma unroll
         for (int m = 0; m < MP; ++m) red[warp * ML + lane + 32 * m] = acc[m];
         __syncthreads();
+        const int o = t.oa + pass * ROWS + rslot;
         if (cslot == 0 && o <= last) {
 #pragma unroll
             for (int m = 0; m < MP; ++m) {
@@ -258,17 +301,17 @@ __global__ void __launch_bounds__(SR_THREADS, 2) k_ring_split(dots_ctx_t c, int 
 
 // ------------------------------------------------------------------------------------------------
 // r_S of one tree level, in place in `hat`:  hat[v] += sum of the descendants' contributions landing on v.
-template <int ML, bool PDL>
+template <int ML>
 __global__ void __launch_bounds__(256) k_ring_gather(dots_ctx_t c, int v0, int v_end)
 {
-    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     constexpr int VPB = 256 / ML;                                        // vertices per block: 8, 4, 2, 2
     const int vs = threadIdx.x / ML, m = threadIdx.x - vs * ML;
     const int i = v0 + blockIdx.x * VPB + vs;
     const bool on = vs < VPB && i < v_end;
     int v = 0, g0 = 0, g1 = 0;
     if (on) { v = c.gverts[i]; g0 = c.gptr[v]; g1 = c.gptr[v + 1]; }     // structure: constant, safe before the wait
-    if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (!on) return;
     double *h = c.hat + (size_t)v * ML + m;
     double r = *h;
@@ -301,13 +344,13 @@ static int sr_launch(void (*kern)(Args...), int grid, int threads, size_t smem, 
     return 0;
 }
 
-static size_t sr_smem_bytes(int ML, int nst, bool split)
+static size_t sr_smem_bytes(int ML, int SB, int nst, bool split)
 {
-    const int EC = SR_STAGE_BYTES / (8 * ML);
+    const int EC = SB / (8 * ML);
     return (size_t)SR_WARPS * nst * ((size_t)EC * ML * 8 + 8) + (split ? (size_t)SR_WARPS * ML * 8 : 0) + 16;
 }
 
-template <int ML, bool PDL>
+template <int ML, int SB>
 static int sr_configure(int nst)
 {
     // the opt-in is per device and per function: keyed by (device, stages) so that a second engine on another GPU of the
@@ -316,20 +359,20 @@ static int sr_configure(int nst)
     int dev = 0;
     DOTS_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && done[dev] == nst) return 0;
-    const int run = (int)sr_smem_bytes(ML, nst, false), split = (int)sr_smem_bytes(ML, nst, true);
-    DOTS_CUDA(cudaFuncSetAttribute(k_ring_run<ML, 0, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, run));
-    DOTS_CUDA(cudaFuncSetAttribute(k_ring_run<ML, 1, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, run));
-    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 2, 0, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
-    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 4, 0, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
-    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 8, 0, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
-    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 2, 1, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
-    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 4, 1, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
-    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 8, 1, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    const int run = (int)sr_smem_bytes(ML, SB, nst, false), split = (int)sr_smem_bytes(ML, SB, nst, true);
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_run<ML, 0, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, run));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_run<ML, 1, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, run));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 2, 0, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 4, 0, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 8, 0, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 2, 1, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 4, 1, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 8, 1, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
     if (dev >= 0 && dev < 64) done[dev] = nst;
     return 0;
 }
 
-template <int ML, int DIR, bool PDL>
+template <int ML, int DIR, int SB>
 static int sr_level(const dots_ctx_t *c, int lv, bool chain, cudaStream_t st)
 {
     const int32_t *ptr = DIR == 0 ? c->h_rt_fwd_ptr : c->h_rt_bwd_ptr;
@@ -337,53 +380,102 @@ static int sr_level(const dots_ctx_t *c, int lv, bool chain, cudaStream_t st)
     const int i0 = ptr[lv], n = ptr[lv + 1] - i0;
     if (n <= 0) return 0;
     const int nst = c->ring_stages;
-    if (wpr == 1) return sr_launch(k_ring_run<ML, DIR, PDL>, ceil_div(n, SR_WARPS), SR_THREADS, sr_smem_bytes(ML, nst, false), st, chain, *c, i0, i0 + n);
-    const size_t smem = sr_smem_bytes(ML, nst, true);
+    if (wpr == 1) return sr_launch(k_ring_run<ML, DIR, SB>, ceil_div(n, SR_WARPS), SR_THREADS, sr_smem_bytes(ML, SB, nst, false), st, chain, *c, i0, i0 + n);
+    const size_t smem = sr_smem_bytes(ML, SB, nst, true);
     switch (wpr) {
-    case 2: return sr_launch(k_ring_split<ML, 2, DIR, PDL>, n, SR_THREADS, smem, st, chain, *c, i0);
-    case 4: return sr_launch(k_ring_split<ML, 4, DIR, PDL>, n, SR_THREADS, smem, st, chain, *c, i0);
-    case 8: return sr_launch(k_ring_split<ML, 8, DIR, PDL>, n, SR_THREADS, smem, st, chain, *c, i0);
+    case 2: return sr_launch(k_ring_split<ML, 2, DIR, SB>, n, SR_THREADS, smem, st, chain, *c, i0);
+    case 4: return sr_launch(k_ring_split<ML, 4, DIR, SB>, n, SR_THREADS, smem, st, chain, *c, i0);
+    case 8: return sr_launch(k_ring_split<ML, 8, DIR, SB>, n, SR_THREADS, smem, st, chain, *c, i0);
     }
     dots_set_error("ring sweep: wpr=%d unsupported", wpr);
     return DOTS_ERR_BAD_ARG;
 }
 
-template <int ML, bool PDL>
-static int sr_sweeps(const dots_ctx_t *c, cudaStream_t st)
+// `marks` (optional, profiling): an event is recorded before every launch and after the last one; tags[i] = level of launch
+// i, +1000 for a gather, +2000 for a backward level.
+struct sr_marks {
+    cudaEvent_t *ev;
+    int *tag;
+    int cap, n;
+};
+static int sr_mark(sr_marks *mk, int tag, cudaStream_t st)
 {
-    if (int e = sr_configure<ML, PDL>(c->ring_stages)) return e;
+    if (!mk || mk->n >= mk->cap) return 0;
+    DOTS_CUDA(cudaEventRecord(mk->ev[mk->n], st));
+    mk->tag[mk->n++] = tag;
+    return 0;
+}
+
+template <int ML, int SB>
+static int sr_sweeps(const dots_ctx_t *c, cudaStream_t st, sr_marks *mk)
+{
+    if (int e = sr_configure<ML, SB>(c->ring_stages)) return e;
+    const bool pdl = c->ring_pdl != 0;
     bool chain = false;                                                   // the first launch waits for the transform normally
     for (int lv = 0; lv < c->n_levels; ++lv) {
         const int g0 = c->h_gv_ptr[lv], gn = c->h_gv_ptr[lv + 1] - g0;
         if (gn > 0) {
-            if (int e = sr_launch(k_ring_gather<ML, PDL>, ceil_div(gn, 256 / ML), 256, 0, st, PDL && chain, *c, g0, g0 + gn)) return e;
+            if (int e = sr_mark(mk, 1000 + lv, st)) return e;
+            if (int e = sr_launch(k_ring_gather<ML>, ceil_div(gn, 256 / ML), 256, 0, st, pdl && chain, *c, g0, g0 + gn)) return e;
             chain = true;
         }
         const int n = c->h_rt_fwd_ptr[lv + 1] - c->h_rt_fwd_ptr[lv];
-        if (int e = sr_level<ML, 0, PDL>(c, lv, PDL && chain, st)) return e;
+        if (n > 0) { if (int e = sr_mark(mk, lv, st)) return e; }
+        if (int e = sr_level<ML, 0, SB>(c, lv, pdl && chain, st)) return e;
         if (n > 0) chain = true;
     }
     for (int lv = c->n_levels - 1; lv >= 0; --lv) {
         const int n = c->h_rt_bwd_ptr[lv + 1] - c->h_rt_bwd_ptr[lv];
-        if (int e = sr_level<ML, 1, PDL>(c, lv, PDL && chain, st)) return e;
+        if (n > 0) { if (int e = sr_mark(mk, 2000 + lv, st)) return e; }
+        if (int e = sr_level<ML, 1, SB>(c, lv, pdl && chain, st)) return e;
         if (n > 0) chain = true;
     }
-    return 0;
+    return sr_mark(mk, -1, st);
 }
 
-int dots_mode_solves_ring(const dots_ctx_t *c, void *stream)
+static int sr_dispatch(const dots_ctx_t *c, void *stream, sr_marks *mk)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (c->m_pad % 32 || c->m_pad > 128) { dots_set_error("ring sweeps need m_pad in {32, 64, 96, 128} (got %d)", c->m_pad); return DOTS_ERR_BAD_ARG; }
     if (c->ywork != c->hat + (size_t)c->n_vert * c->m_pad) { dots_set_error("ring sweeps need ywork == hat + n_vert * m_pad"); return DOTS_ERR_BAD_ARG; }
     if (c->ring_stages < 2 || c->ring_stages > 6) { dots_set_error("ring_stages=%d outside 2..6", c->ring_stages); return DOTS_ERR_BAD_ARG; }
     if (!c->rt_fwd || !c->rt_bwd || !c->bidx || !c->gptr || !c->gidx) { dots_set_error("ring sweep plan missing from the context"); return DOTS_ERR_BAD_ARG; }
-    const bool pdl = c->ring_pdl != 0;
+    const bool small = c->ring_stage_bytes == 2048;
+    if (!small && c->ring_stage_bytes != 4096) { dots_set_error("ring_stage_bytes=%d: 2048 or 4096", c->ring_stage_bytes); return DOTS_ERR_BAD_ARG; }
     switch (c->m_pad) {
-    case 32: return pdl ? sr_sweeps<32, true>(c, st) : sr_sweeps<32, false>(c, st);
-    case 64: return pdl ? sr_sweeps<64, true>(c, st) : sr_sweeps<64, false>(c, st);
-    case 96: return pdl ? sr_sweeps<96, true>(c, st) : sr_sweeps<96, false>(c, st);
-    case 128: return pdl ? sr_sweeps<128, true>(c, st) : sr_sweeps<128, false>(c, st);
+    case 32: return small ? sr_sweeps<32, 2048>(c, st, mk) : sr_sweeps<32, 4096>(c, st, mk);
+    case 64: return small ? sr_sweeps<64, 2048>(c, st, mk) : sr_sweeps<64, 4096>(c, st, mk);
+    case 96: return small ? sr_sweeps<96, 2048>(c, st, mk) : sr_sweeps<96, 4096>(c, st, mk);
+    case 128: return small ? sr_sweeps<128, 2048>(c, st, mk) : sr_sweeps<128, 4096>(c, st, mk);
     }
     return DOTS_ERR_BAD_ARG;
+}
+
+int dots_mode_solves_ring(const dots_ctx_t *c, void *stream) { return sr_dispatch(c, stream, nullptr); }
+
+// Profiling aid (tools/level_times.py): one pair of ring sweeps with a CUDA event between the launches.  ms_out[i] = time from
+// the start of launch i to the start of launch i + 1 (the end of the sweeps for the last one), tag_out[i] as in sr_marks.
+// Synchronises the stream.  Returns the number of launches in *n_out.
+extern "C" int dots_ring_level_times(const dots_ctx_t *c, void *stream, float *ms_out, int32_t *tag_out, int cap, int *n_out)
+{
+    if (int e = dots_check_ctx(c)) return e;
+    if (c->sweep_mode != 4 || cap < 2 || cap > 256) { dots_set_error("dots_ring_level_times: sweep_mode 4 and 2 <= cap <= 256"); return DOTS_ERR_BAD_ARG; }
+    cudaEvent_t ev[256];
+    int tag[256];
+    for (int i = 0; i < cap; ++i) DOTS_CUDA(cudaEventCreate(&ev[i]));
+    sr_marks mk{ev, tag, cap, 0};
+    int e = sr_dispatch(c, stream, &mk);
+    cudaError_t ce = cudaStreamSynchronize((cudaStream_t)stream);
+    int n = 0;
+    if (!e && ce == cudaSuccess) {
+        for (int i = 0; i + 1 < mk.n; ++i) {
+            if (cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]) != cudaSuccess) break;
+            tag_out[i] = tag[i];
+            n = i + 1;
+        }
+    }
+    for (int i = 0; i < cap; ++i) cudaEventDestroy(ev[i]);
+    if (n_out) *n_out = n;
+    if (!e && ce != cudaSuccess) { dots_set_error("dots_ring_level_times: %s", cudaGetErrorString(ce)); return (int)ce; }
+    return e;
 }

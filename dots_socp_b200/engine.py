@@ -234,6 +234,7 @@ class Engine:
             ctx.h_gv_ptr = rp["gv_ptr"].ctypes.data
             ctx.ring_stages = int(os.environ.get("DOTS_RING_STAGES", 3))
             ctx.ring_pdl = int(os.environ.get("DOTS_RING_PDL", 0))
+            ctx.ring_stage_bytes = int(os.environ.get("DOTS_RING_STAGE_BYTES", 4096))
         self._keep["phase_clock"] = torch.zeros(2 * sym.n_levels + 1, dtype=torch.int64, device=dev)
         if os.environ.get("DOTS_PHASE_CLOCK"):
             ctx.phase_clock = self._keep["phase_clock"].data_ptr()

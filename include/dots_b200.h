@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DOTS_ABI_VERSION 9
+#define DOTS_ABI_VERSION 10
 
 /* scalar block read by the kernels from device memory (so CUDA graphs stay valid across penalty updates) */
 enum {
@@ -178,6 +178,8 @@ typedef struct dots_ctx {
     const int32_t *h_gv_ptr;   /* HOST [n_levels+1] ranges into gverts                                                    */
     int32_t ring_stages;       /* shared-memory stages per warp (2..6)                                                    */
     int32_t ring_pdl;          /* 1: chain the level launches with programmatic dependent launch                          */
+    int32_t ring_stage_bytes;  /* bytes per ring stage: 2048 or 4096                                                      */
+    int32_t reserved2;
 } dots_ctx_t;
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -271,6 +273,9 @@ int dots_order_destroy(dots_order_t *o);
 int dots_phi_rhs(const dots_ctx_t *c, void *stream);                       /* -> c->rhs                */
 int dots_time_transform(const dots_ctx_t *c, int inverse, void *stream);   /* rhs -> hat / hat -> phi   */
 int dots_mode_solves(const dots_ctx_t *c, void *stream);                   /* hat <- (K+shift M)^-1 hat */
+/* profiling aid: one pair of ring sweeps (sweep_mode 4) with a CUDA event before every launch; ms_out[i] = start of launch i ->
+ * start of launch i+1, tag_out[i] = tree level (+1000: gather, +2000: backward).  Synchronises the stream.              */
+int dots_ring_level_times(const dots_ctx_t *c, void *stream, float *ms_out, int32_t *tag_out, int cap, int *n_out);
 int dots_grad_space(const dots_ctx_t *c, const double *phi, double *out, void *stream);  /* [nT+1][3][T] */
 int dots_div_space(const dots_ctx_t *c, const double *x, double *out, void *stream);     /* [nT+1][V]    */
 
