@@ -9,7 +9,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 P_R, P_S, P_D, P_CONG, P_TAU, P_EPS, P_COUNT = 0, 1, 2, 3, 4, 5, 8
 
 _i32p, _i64p, _f64p = C.c_void_p, C.c_void_p, C.c_void_p      # raw device/host addresses
@@ -34,7 +34,7 @@ class DotsCtx(C.Structure):
            ("phase_clock", C.c_void_p), ("peer_vertex", C.c_void_p * 4), ("peer_corner", C.c_void_p),
            ("peer_rhs", C.c_void_p * 8), ("peer_hat", C.c_void_p * 8)]
         + [(n, C.c_void_p) for n in ("rt_fwd", "rt_bwd", "h_rt_fwd_ptr", "h_rt_bwd_ptr", "h_rt_fwd_wpr", "h_rt_bwd_wpr",
-                                     "bidx", "gptr", "gidx", "gverts", "h_gv_ptr")]
+                                     "bidx", "erow_fwd", "erow_bwd", "gptr", "gidx", "gverts", "h_gv_ptr")]
         + [("ring_stages", C.c_int32), ("ring_pdl", C.c_int32), ("ring_stage_bytes", C.c_int32), ("reserved2", C.c_int32)]
     )
 
@@ -83,7 +83,7 @@ def load(build_if_missing: bool = True):
         "dots_step_phi": (ctxp, vp), "dots_step_vertex": (ctxp, vp), "dots_step_tri": (ctxp, i, vp),
         "dots_iterate": (ctxp, i, i, vp), "dots_refresh_corner_terms": (ctxp, vp),
         "dots_scale_dual": (ctxp, d, vp), "dots_scale_z": (ctxp, d, vp), "dots_set_params": (ctxp, vp, vp),
-        "dots_kkt_sums": (ctxp, i, vp, vp), "dots_phi_rhs": (ctxp, vp), "dots_time_transform": (ctxp, i, vp),
+        "dots_kkt_sums": (ctxp, i, vp, vp), "dots_kkt_sums_multi": (ctxp, C.c_uint, vp, vp), "dots_phi_rhs": (ctxp, vp), "dots_time_transform": (ctxp, i, vp),
         "dots_mode_solves": (ctxp, vp), "dots_grad_space": (ctxp, vp, vp, vp), "dots_div_space": (ctxp, vp, vp, vp),
         "dots_graph_create": (ctxp, i, vp, C.POINTER(vp)), "dots_graph_launch": (vp, vp), "dots_graph_destroy": (vp,),
         "dots_factor_small_fronts": (C.POINTER(FrontArgs), i, i, vp), "dots_front_nmax": (), "dots_enable_peer": (i,),
@@ -94,6 +94,7 @@ def load(build_if_missing: bool = True):
     protos.update({
         "dots_order_create": (i64, vp, vp, vp, i64, C.POINTER(vp)), "dots_order_sizes": (vp, C.POINTER(i64), C.POINTER(i64)),
         "dots_order_export": (vp,) * 9, "dots_order_destroy": (vp,),
+        "dots_ring_entry_rows": (i64,) + (vp,) * 8,
     })
     for name, args in protos.items():
         fn = getattr(lib, name)
@@ -104,10 +105,10 @@ def load(build_if_missing: bool = True):
 
 EXPORTS = ("dots_abi_version", "dots_ctx_sizeof", "dots_last_error", "dots_step_phi", "dots_step_vertex",
            "dots_step_tri", "dots_iterate", "dots_refresh_corner_terms", "dots_scale_dual", "dots_scale_z",
-           "dots_set_params", "dots_kkt_sums", "dots_phi_rhs", "dots_time_transform", "dots_mode_solves",
+           "dots_set_params", "dots_kkt_sums", "dots_kkt_sums_multi", "dots_phi_rhs", "dots_time_transform", "dots_mode_solves",
            "dots_grad_space", "dots_div_space", "dots_graph_create", "dots_graph_launch", "dots_graph_destroy",
            "dots_factor_small_fronts", "dots_front_nmax", "dots_enable_peer", "dots_ipc_export", "dots_ipc_import",
-           "dots_ring_level_times",
+           "dots_ring_level_times", "dots_ring_entry_rows",
            "dots_order_create", "dots_order_sizes", "dots_order_export", "dots_order_destroy")
 
 

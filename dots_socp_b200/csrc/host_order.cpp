@@ -248,3 +248,29 @@ extern "C" int dots_order_destroy(dots_order_t *o) {
     delete o;
     return 0;
 }
+
+// Per-entry operand rows of the ring-streamed sweeps (csrc/sweep_ring.cu): for every panel entry, in streaming order, the
+// row of Z = [hat | ywork] it is multiplied with; bit 31 marks the last entry of an output.
+//   forward  (row-major panel)       entry (row i, col j < min(i+1, s)):  off + j                 last: j == min(i+1, s) - 1
+//   backward (column-major copy)     entry (col j, row i in [j, s+b)):    bidx[front_off + i]     last: i == s + b - 1
+extern "C" int dots_ring_entry_rows(int64_t n_nodes, const int64_t *s, const int64_t *b, const int64_t *off, const int64_t *front_off,
+                                    const int64_t *panel_off, const int32_t *bidx, int32_t *rows_fwd, int32_t *rows_bwd)
+{
+    if (!s || !b || !off || !front_off || !panel_off || !bidx || !rows_fwd || !rows_bwd) { dots_set_error("dots_ring_entry_rows: null argument"); return -1; }
+    const int32_t LAST = (int32_t)0x80000000u;
+    for (int64_t nd = 0; nd < n_nodes; ++nd) {
+        const int64_t sn = s[nd], bn = b[nd], o = off[nd];
+        if (sn <= 0) continue;
+        int32_t *f = rows_fwd + panel_off[nd];
+        for (int64_t i = 0; i < sn + bn; ++i) {
+            const int64_t len = (i + 1 < sn) ? i + 1 : sn;
+            for (int64_t j = 0; j < len; ++j) *f++ = (int32_t)(o + j) | (j == len - 1 ? LAST : 0);
+        }
+        int32_t *t = rows_bwd + panel_off[nd];
+        const int32_t *bi = bidx + front_off[nd];
+        for (int64_t j = 0; j < sn; ++j)
+            for (int64_t i = j; i < sn + bn; ++i) *t++ = bi[i] | (i == sn + bn - 1 ? LAST : 0);
+        if (f - rows_fwd != panel_off[nd + 1] || t - rows_bwd != panel_off[nd + 1]) { dots_set_error("dots_ring_entry_rows: panel size mismatch at node %lld", (long long)nd); return -1; }
+    }
+    return 0;
+}

@@ -71,196 +71,248 @@ extern "C" int dots_ipc_import(const void *handle_64, unsigned long long offset,
 }
 
 #define KKT_THREADS 256
+#define KKT_CONDS 8            // 7 KKT conditions + the objective (which = 7)
 
-// ---- vertex-side sums: slots 0..3 ------------------------------------------------------------------
-__global__ void __launch_bounds__(KKT_THREADS) k_kkt_vertex(dots_ctx_t c, int which)
+// ---- vertex-side terms of condition W at (t, v): acc[0..3] += ...  (slots 0..3 of the condition's row) ---------------
+template <int W>
+__device__ __forceinline__ void kkt_vertex_terms(const dots_ctx_t &c, size_t i, int t, int v, double av, double r, double s, double d,
+                                                 double cong, double dt, double (&acc)[4])
 {
     const int V = c.n_vert, nT = c.n_time;
     const size_t T = (size_t)c.n_tri;
+    if (W != 2 && t >= nT) return;                                         // staggered arrays have nT steps; #2 lives on the nT+1 levels
+    if (W == 0) {                                                          // Prim(phi, q)  :433-450, :591-596
+        const double dtp = (c.phi[i + V] - c.phi[i]) / dt;
+        const double A = c.A[i], lc = c.lam_c[i];
+        const double res = dtp - A - lc;
+        acc[0] += res * res * av; acc[1] += dtp * dtp * av; acc[2] += A * A * av; acc[3] += lc * lc * av;
+    } else if (W == 1) {                                                   // Prim(q, z)    :452-464, :597-603
+        const double A = c.A[i];
+        const double r1 = c.z_fst[i] + s * A - d, r2 = c.z_end[i] - s * A - d;
+        acc[0] += r1 * r1 * av; acc[1] += r2 * r2 * av;
+    } else if (W == 2) {                                                   // Dual(alpha)   :466-482
+        double divt;
+        if (t == 0) divt = (c.mu[v] * av) / dt;
+        else if (t == nT) divt = -(c.mu[(size_t)(nT - 1) * V + v] * av) / dt;
+        else divt = (c.mu[(size_t)t * V + v] * av - c.mu[(size_t)(t - 1) * V + v] * av) / dt;
+        const double *Et = c.E + (size_t)t * 3 * T;
+        double divx = 0.0;
+        for (int q = c.vc_ptr[v], qe = c.vc_ptr[v + 1]; q < qe; ++q) {
+            const int cid = c.vc_idx[q];
+            const size_t k = cid / T, f = cid - k * T;
+            const double af = c.area_f[f];
+            divx += -(c.hat_grad[(k * 3 + 0) * T + f] * (Et[f] * af) + c.hat_grad[(k * 3 + 1) * T + f] * (Et[T + f] * af)
+                      + c.hat_grad[(k * 3 + 2) * T + f] * (Et[2 * T + f] * af));
+        }
+        const double bnd = (t == 0) ? c.bnd0[v] : ((t == nT) ? c.bnd1[v] : 0.0);
+        const double aux = (r * dt) * ((bnd + divt + divx) / av);
+        acc[0] += aux * aux * av;
+    } else if (W == 3) {                                                   // Dual(beta)    :484-503
+        const double mu = c.mu[i];
+        const double a1 = s * (c.b_end[i] - c.b_fst[i]);
+        const double sum = mu + a1;
+        acc[0] += mu * mu * av; acc[1] += a1 * a1 * av; acc[2] += sum * sum * av;
+    } else if (W == 4) {                                                   // Comp(rho, f(q)) :505-526
+        const double c3 = 1.0 / sqrt(3.0);
+        const double *B0 = c.B + (size_t)t * 3 * T, *B1 = B0 + 3 * T;
+        double q = 0.0;
+        for (int p = c.vc_ptr[v], pe = c.vc_ptr[v + 1]; p < pe; ++p) {
+            const int cid = c.vc_idx[p];
+            const size_t k = cid / T, f = cid - k * T;
+            double sq = 0.0;
+#pragma unroll
+            for (int x = 0; x < 3; ++x) { const double a = c3 * B0[x * T + f]; sq += a * a; }
+#pragma unroll
+            for (int x = 0; x < 3; ++x) { const double a = c3 * B1[x * T + f]; sq += a * a; }
+            q += c.area_f[f] * sq;
+        }
+        const double rho = r * c.mu[i];
+        const double aux = c.A[i] + .25 * (q / av);
+        double pos = aux + rho;
+        pos = (pos < 0.) ? 0. : pos;                                       // np.maximum(0., .) keeps NaN
+        const double res = pos - rho;
+        acc[0] += rho * rho * av; acc[1] += aux * aux * av; acc[2] += res * res * av;
+    } else if (W == 6) {                                                   // Comp(rho, cong.) :549-559
+        const double rho = r * c.mu[i], lc = c.lam_c[i];
+        const double res = cong * rho - lc;
+        acc[0] += rho * rho * av; acc[1] += lc * lc * av; acc[2] += res * res * av;
+    } else if (W == 7) {                                                   // objective :417-431
+        if (t == 0) acc[0] += c.phi[v] * (r * c.bnd0[v]);
+        if (t == nT - 1) acc[1] += c.phi[(size_t)nT * V + v] * (r * c.bnd1[v]);
+        const double lc = c.lam_c[i];
+        acc[2] += lc * lc * av;
+    }
+}
+
+// ---- triangle-side terms of condition W at (tau, f): slots 4..7 of the condition's row ------------------------------
+template <int W>
+__device__ __forceinline__ void kkt_tri_terms(const dots_ctx_t &c, int tau, size_t f, double af, double r, double s, double cs,
+                                              double (&acc)[4])
+{
+    const int V = c.n_vert, nT = c.n_time;
+    const size_t T = (size_t)c.n_tri;
+    const double *Bp = c.B + (size_t)tau * 3 * T + f;
+    if (W == 0) {                                                          // ||dx_phi - B||, ||dx_phi||, ||B||
+        const double *ph = c.phi + (size_t)tau * V;
+        const double p0 = ph[c.tri[f]], p1 = ph[c.tri[T + f]], p2 = ph[c.tri[2 * T + f]];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            const double dx = c.hat_grad[(0 * 3 + x) * T + f] * p0 + c.hat_grad[(1 * 3 + x) * T + f] * p1 + c.hat_grad[(2 * 3 + x) * T + f] * p2;
+            const double B = Bp[x * T], res = dx - B;
+            acc[0] += res * res * af; acc[1] += dx * dx * af; acc[2] += B * B * af;
+        }
+    } else if (W == 1) {                                                   // ||s (z_mid - Bd(B))||_dec  :599
+        const double *zm = c.z_mid + (size_t)tau * 18 * T + f;
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            if (sd == 0 ? tau >= nT : tau <= 0) continue;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    const double res = s * (zm[((sd * 3 + k) * 3 + x) * T] - cs * Bp[x * T]);
+                    acc[0] += res * res * af;
+                }
+        }
+    } else if (W == 3) {                                                   // ||E||, ||adj(b_mid)||, ||E + adj(b_mid)||
+        const double *bm = c.b_mid + (size_t)tau * 18 * T + f;
+        const double *Ep = c.E + (size_t)tau * 3 * T + f;
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            double a2 = 0.0;
+            if (tau < nT) a2 = cs * ((bm[(0 * 3 + x) * T] + bm[(1 * 3 + x) * T]) + bm[(2 * 3 + x) * T]);
+            if (tau > 0) {
+                const double s1 = cs * ((bm[(9 + 0 * 3 + x) * T] + bm[(9 + 1 * 3 + x) * T]) + bm[(9 + 2 * 3 + x) * T]);
+                a2 = (tau < nT) ? a2 + s1 : s1;
+            }
+            const double E = Ep[x * T], sum = E + a2;
+            acc[0] += E * E * af; acc[1] += a2 * a2 * af; acc[2] += sum * sum * af;
+        }
+    } else if (W == 5) {                                                   // Comp(m, rho o B) :528-547
+        double avg = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int v = c.tri[k * T + f];
+            const double cur = (tau < nT) ? r * c.mu[(size_t)tau * V + v] : 0.0;
+            const double prv = (tau > 0) ? r * c.mu[(size_t)(tau - 1) * V + v] : 0.0;
+            avg += (1.0 / 3.0) * (0.5 * cur + 0.5 * prv);                  // :961-974, :163-166
+        }
+        const double *Ep = c.E + (size_t)tau * 3 * T + f;
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            const double m = r * Ep[x * T], aux = avg * Bp[x * T], res = aux - m;
+            acc[0] += m * m * af; acc[1] += aux * aux * af; acc[2] += res * res * af;
+        }
+    }
+}
+
+// Fixed-order block reduction of the 4 partial sums of every condition in `mask`; row blockIdx.x of part[.][64].
+__device__ __forceinline__ void kkt_block_store(double (&acc)[KKT_CONDS][4], unsigned mask, double *part, int slot0)
+{
+    __shared__ double sm[KKT_THREADS / 32][KKT_CONDS * 4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int w = 0; w < KKT_CONDS; ++w) {
+        if (!(mask >> w & 1u)) continue;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double v = warp_sum(acc[w][k]);
+            if (lane == 0) sm[warp][w * 4 + k] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < KKT_CONDS * 4 && (mask >> (threadIdx.x >> 2) & 1u)) {
+        double v = 0.0;
+        for (int w = 0; w < KKT_THREADS / 32; ++w) v += sm[w][threadIdx.x];
+        part[(size_t)blockIdx.x * (KKT_CONDS * 8) + (threadIdx.x >> 2) * 8 + slot0 + (threadIdx.x & 3)] = v;
+    }
+}
+
+// One pass over the (time, vertex) pairs for ALL conditions in `mask`: shared operands (A, mu, lam_c, phi, ...) are loaded once.
+__global__ void __launch_bounds__(KKT_THREADS) k_kkt_vertex(dots_ctx_t c, unsigned mask)
+{
+    const int V = c.n_vert, nT = c.n_time;
     const double *prm = c.params;
     const double r = prm[DOTS_P_R], s = prm[DOTS_P_S], d = prm[DOTS_P_D], cong = prm[DOTS_P_CONG];
     const double dt = 1.0 / nT;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    // owned range: levels [lvl_begin, lvl_end) for the centred residual (#2), staggered steps otherwise
-    const int t_end = (which == 2) ? c.lvl_end : min(c.lvl_end, nT);
+    double acc[KKT_CONDS][4];
+#pragma unroll
+    for (int w = 0; w < KKT_CONDS; ++w)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[w][k] = 0.0;
+    // owned range: levels [lvl_begin, lvl_end) when the centred residual (#2) is wanted, staggered steps otherwise
+    const int t_end = (mask >> 2 & 1u) ? c.lvl_end : min(c.lvl_end, nT);
     const size_t i0 = (size_t)c.lvl_begin * V, n = (size_t)max(t_end, c.lvl_begin) * V;
     for (size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int t = (int)(i / V), v = (int)(i - (size_t)t * V);
         const double av = c.area_v[v];
-        switch (which) {
-        case 0: {                                                          // Prim(phi, q)  :433-450, :591-596
-            const double dtp = (c.phi[i + V] - c.phi[i]) / dt;
-            const double A = c.A[i], lc = c.lam_c[i];
-            const double res = dtp - A - lc;
-            acc[0] += res * res * av; acc[1] += dtp * dtp * av; acc[2] += A * A * av; acc[3] += lc * lc * av;
-        } break;
-        case 1: {                                                          // Prim(q, z)    :452-464, :597-603
-            const double A = c.A[i];
-            const double r1 = c.z_fst[i] + s * A - d, r2 = c.z_end[i] - s * A - d;
-            acc[0] += r1 * r1 * av; acc[1] += r2 * r2 * av;
-        } break;
-        case 2: {                                                          // Dual(alpha)   :466-482
-            double divt;
-            if (t == 0) divt = (c.mu[v] * av) / dt;
-            else if (t == nT) divt = -(c.mu[(size_t)(nT - 1) * V + v] * av) / dt;
-            else divt = (c.mu[(size_t)t * V + v] * av - c.mu[(size_t)(t - 1) * V + v] * av) / dt;
-            const double *Et = c.E + (size_t)t * 3 * T;
-            double divx = 0.0;
-            for (int q = c.vc_ptr[v], qe = c.vc_ptr[v + 1]; q < qe; ++q) {
-                const int cid = c.vc_idx[q];
-                const size_t k = cid / T, f = cid - k * T;
-                const double af = c.area_f[f];
-                divx += -(c.hat_grad[(k * 3 + 0) * T + f] * (Et[f] * af) + c.hat_grad[(k * 3 + 1) * T + f] * (Et[T + f] * af)
-                          + c.hat_grad[(k * 3 + 2) * T + f] * (Et[2 * T + f] * af));
-            }
-            const double bnd = (t == 0) ? c.bnd0[v] : ((t == nT) ? c.bnd1[v] : 0.0);
-            const double aux = (r * dt) * ((bnd + divt + divx) / av);
-            acc[0] += aux * aux * av;
-        } break;
-        case 3: {                                                          // Dual(beta)    :484-503
-            const double mu = c.mu[i];
-            const double a1 = s * (c.b_end[i] - c.b_fst[i]);
-            const double sum = mu + a1;
-            acc[0] += mu * mu * av; acc[1] += a1 * a1 * av; acc[2] += sum * sum * av;
-        } break;
-        case 4: {                                                          // Comp(rho, f(q)) :505-526
-            const double c3 = 1.0 / sqrt(3.0);
-            const double *B0 = c.B + (size_t)t * 3 * T, *B1 = B0 + 3 * T;
-            double q = 0.0;
-            for (int p = c.vc_ptr[v], pe = c.vc_ptr[v + 1]; p < pe; ++p) {
-                const int cid = c.vc_idx[p];
-                const size_t k = cid / T, f = cid - k * T;
-                double sq = 0.0;
-#pragma unroll
-                for (int x = 0; x < 3; ++x) { const double a = c3 * B0[x * T + f]; sq += a * a; }
-#pragma unroll
-                for (int x = 0; x < 3; ++x) { const double a = c3 * B1[x * T + f]; sq += a * a; }
-                q += c.area_f[f] * sq;
-            }
-            const double rho = r * c.mu[i];
-            const double aux = c.A[i] + .25 * (q / av);
-            double pos = aux + rho;
-            pos = (pos < 0.) ? 0. : pos;                                   // np.maximum(0., .) keeps NaN
-            const double res = pos - rho;
-            acc[0] += rho * rho * av; acc[1] += aux * aux * av; acc[2] += res * res * av;
-        } break;
-        case 6: {                                                          // Comp(rho, cong.) :549-559
-            const double rho = r * c.mu[i], lc = c.lam_c[i];
-            const double res = cong * rho - lc;
-            acc[0] += rho * rho * av; acc[1] += lc * lc * av; acc[2] += res * res * av;
-        } break;
-        case 7: {                                                          // objective :417-431
-            if (t == 0) acc[0] += c.phi[v] * (r * c.bnd0[v]);
-            if (t == nT - 1) acc[1] += c.phi[(size_t)nT * V + v] * (r * c.bnd1[v]);
-            const double lc = c.lam_c[i];
-            acc[2] += lc * lc * av;
-        } break;
-        default: break;
-        }
+        if (mask & 1u) kkt_vertex_terms<0>(c, i, t, v, av, r, s, d, cong, dt, acc[0]);
+        if (mask & 2u) kkt_vertex_terms<1>(c, i, t, v, av, r, s, d, cong, dt, acc[1]);
+        if (mask & 4u) kkt_vertex_terms<2>(c, i, t, v, av, r, s, d, cong, dt, acc[2]);
+        if (mask & 8u) kkt_vertex_terms<3>(c, i, t, v, av, r, s, d, cong, dt, acc[3]);
+        if (mask & 16u) kkt_vertex_terms<4>(c, i, t, v, av, r, s, d, cong, dt, acc[4]);
+        if (mask & 64u) kkt_vertex_terms<6>(c, i, t, v, av, r, s, d, cong, dt, acc[6]);
+        if (mask & 128u) kkt_vertex_terms<7>(c, i, t, v, av, r, s, d, cong, dt, acc[7]);
     }
-    block_reduce_store<4>(acc, c.red_part, 0);
+    kkt_block_store(acc, mask & 0xdfu, c.red_part, 0);
 }
 
-// ---- triangle-side sums: slots 4..7 ----------------------------------------------------------------
-__global__ void __launch_bounds__(KKT_THREADS) k_kkt_tri(dots_ctx_t c, int which)
+__global__ void __launch_bounds__(KKT_THREADS) k_kkt_tri(dots_ctx_t c, unsigned mask)
 {
-    const int V = c.n_vert, nT = c.n_time;
     const size_t T = (size_t)c.n_tri;
     const double *prm = c.params;
     const double r = prm[DOTS_P_R], s = prm[DOTS_P_S];
     const double cs = s / sqrt(3.0);
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double acc[KKT_CONDS][4];
+#pragma unroll
+    for (int w = 0; w < KKT_CONDS; ++w)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[w][k] = 0.0;
     const size_t i0 = (size_t)c.lvl_begin * T, n = (size_t)c.lvl_end * T;
     for (size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int tau = (int)(i / T);
         const size_t f = i - (size_t)tau * T;
         const double af = c.area_f[f];
-        const double *Bp = c.B + (size_t)tau * 3 * T + f;
-        switch (which) {
-        case 0: {                                                          // ||dx_phi - B||, ||dx_phi||, ||B||
-            const double *ph = c.phi + (size_t)tau * V;
-            const double p0 = ph[c.tri[f]], p1 = ph[c.tri[T + f]], p2 = ph[c.tri[2 * T + f]];
-#pragma unroll
-            for (int x = 0; x < 3; ++x) {
-                const double dx = c.hat_grad[(0 * 3 + x) * T + f] * p0 + c.hat_grad[(1 * 3 + x) * T + f] * p1 + c.hat_grad[(2 * 3 + x) * T + f] * p2;
-                const double B = Bp[x * T], res = dx - B;
-                acc[0] += res * res * af; acc[1] += dx * dx * af; acc[2] += B * B * af;
-            }
-        } break;
-        case 1: {                                                          // ||s (z_mid - Bd(B))||_dec  :599
-            const double *zm = c.z_mid + (size_t)tau * 18 * T + f;
-#pragma unroll
-            for (int sd = 0; sd < 2; ++sd) {
-                if (sd == 0 ? tau >= nT : tau <= 0) continue;
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-#pragma unroll
-                    for (int x = 0; x < 3; ++x) {
-                        const double res = s * (zm[((sd * 3 + k) * 3 + x) * T] - cs * Bp[x * T]);
-                        acc[0] += res * res * af;
-                    }
-            }
-        } break;
-        case 3: {                                                          // ||E||, ||adj(b_mid)||, ||E + adj(b_mid)||
-            const double *bm = c.b_mid + (size_t)tau * 18 * T + f;
-            const double *Ep = c.E + (size_t)tau * 3 * T + f;
-#pragma unroll
-            for (int x = 0; x < 3; ++x) {
-                double a2 = 0.0;
-                if (tau < nT) a2 = cs * ((bm[(0 * 3 + x) * T] + bm[(1 * 3 + x) * T]) + bm[(2 * 3 + x) * T]);
-                if (tau > 0) {
-                    const double s1 = cs * ((bm[(9 + 0 * 3 + x) * T] + bm[(9 + 1 * 3 + x) * T]) + bm[(9 + 2 * 3 + x) * T]);
-                    a2 = (tau < nT) ? a2 + s1 : s1;
-                }
-                const double E = Ep[x * T], sum = E + a2;
-                acc[0] += E * E * af; acc[1] += a2 * a2 * af; acc[2] += sum * sum * af;
-            }
-        } break;
-        case 5: {                                                          // Comp(m, rho o B) :528-547
-            double avg = 0.0;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int v = c.tri[k * T + f];
-                const double cur = (tau < nT) ? r * c.mu[(size_t)tau * V + v] : 0.0;
-                const double prv = (tau > 0) ? r * c.mu[(size_t)(tau - 1) * V + v] : 0.0;
-                avg += (1.0 / 3.0) * (0.5 * cur + 0.5 * prv);              // :961-974, :163-166
-            }
-            const double *Ep = c.E + (size_t)tau * 3 * T + f;
-#pragma unroll
-            for (int x = 0; x < 3; ++x) {
-                const double m = r * Ep[x * T], aux = avg * Bp[x * T], res = aux - m;
-                acc[0] += m * m * af; acc[1] += aux * aux * af; acc[2] += res * res * af;
-            }
-        } break;
-        default: break;
-        }
+        if (mask & 1u) kkt_tri_terms<0>(c, tau, f, af, r, s, cs, acc[0]);
+        if (mask & 2u) kkt_tri_terms<1>(c, tau, f, af, r, s, cs, acc[1]);
+        if (mask & 8u) kkt_tri_terms<3>(c, tau, f, af, r, s, cs, acc[3]);
+        if (mask & 32u) kkt_tri_terms<5>(c, tau, f, af, r, s, cs, acc[5]);
     }
-    block_reduce_store<4>(acc, c.red_part, 4);
+    kkt_block_store(acc, mask & 0x2bu, c.red_part, 4);
 }
 
-// one warp per slot; fixed order over blocks
+// one warp per (condition, slot) pair, 8 pairs per block; fixed order over blocks
 __global__ void k_reduce_final(const double *__restrict__ part, int nblocks, double *__restrict__ out)
 {
-    const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     double v = 0.0;
-    for (int b = lane; b < nblocks; b += 32) v += part[(size_t)b * 8 + slot];
+    for (int b = lane; b < nblocks; b += 32) v += part[(size_t)b * (KKT_CONDS * 8) + slot];
     v = warp_sum(v);
     if (lane == 0) out[slot] = v;
 }
 
-extern "C" int dots_kkt_sums(const dots_ctx_t *c, int which, double *host_out, void *stream)
+// Raw sums of every condition in `mask` (bit i = condition i, bit 7 = objective) in ONE pass per side: host_out[8 * i + k].
+extern "C" int dots_kkt_sums_multi(const dots_ctx_t *c, unsigned mask, double *host_out, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
-    if (which < 0 || which > 7) { dots_set_error("kkt condition %d out of range", which); return DOTS_ERR_BAD_ARG; }
+    if (!mask || mask > 0xffu) { dots_set_error("kkt mask %u out of range", mask); return DOTS_ERR_BAD_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = c->red_blocks;
-    DOTS_CUDA(cudaMemsetAsync(c->red_part, 0, sizeof(double) * 8 * nb, st));
-    const bool vert = (which != 5), tri = (which == 0 || which == 1 || which == 3 || which == 5);
-    if (vert) { k_kkt_vertex<<<nb, KKT_THREADS, 0, st>>>(*c, which); DOTS_LAUNCH_CHECK(); }
-    if (tri) { k_kkt_tri<<<nb, KKT_THREADS, 0, st>>>(*c, which); DOTS_LAUNCH_CHECK(); }
-    k_reduce_final<<<1, 256, 0, st>>>(c->red_part, nb, c->red_out);
+    DOTS_CUDA(cudaMemsetAsync(c->red_part, 0, sizeof(double) * KKT_CONDS * 8 * nb, st));
+    if (mask & 0xdfu) { k_kkt_vertex<<<nb, KKT_THREADS, 0, st>>>(*c, mask); DOTS_LAUNCH_CHECK(); }
+    if (mask & 0x2bu) { k_kkt_tri<<<nb, KKT_THREADS, 0, st>>>(*c, mask); DOTS_LAUNCH_CHECK(); }
+    k_reduce_final<<<KKT_CONDS, 256, 0, st>>>(c->red_part, nb, c->red_out);
     DOTS_LAUNCH_CHECK();
-    DOTS_CUDA(cudaMemcpyAsync(host_out, c->red_out, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
+    DOTS_CUDA(cudaMemcpyAsync(host_out, c->red_out, sizeof(double) * KKT_CONDS * 8, cudaMemcpyDeviceToHost, st));
     DOTS_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int dots_kkt_sums(const dots_ctx_t *c, int which, double *host_out, void *stream)
+{
+    if (which < 0 || which > 7) { dots_set_error("kkt condition %d out of range", which); return DOTS_ERR_BAD_ARG; }
+    double all[KKT_CONDS * 8];
+    if (int e = dots_kkt_sums_multi(c, 1u << which, all, stream)) return e;
+    for (int k = 0; k < 8; ++k) host_out[k] = all[which * 8 + k];
     return 0;
 }

@@ -12,7 +12,11 @@
 //    there is no block-wide barrier in the contiguous kernel (k_sweep_run at the headline size: 31-35 % warps active,
 //    60-80 % long_scoreboard, 0.61-0.67 of the HBM peak);
 //  * the vector operand (r_S forward, [y_S ; x_B] backward) of a stage is fetched into registers before the warp waits
-//    for the stage's mbarrier, so its (L1 / L2) latency overlaps the wait;
+//    for the stage's mbarrier, so its (L1 / L2) latency overlaps the wait; WHICH row of Z an entry multiplies, and where an
+//    output ends, comes from a per-entry code array built once on the host (dots_ring_entry_rows), so the kernels carry no
+//    row / column cursor arithmetic and no index indirection (ncu on the first version: 53 warp instructions per 512-byte
+//    entry, issue slots 50-57 % busy - the kernel was instruction bound, not memory bound); lanes hold 2 consecutive
+//    modes and move them with 16-byte accesses;
 //  * "pull" extend-add: a node stores only ITS OWN contribution  -(L21 inv(L11)) r_S  to its boundary rows (`upd`, producer
 //    order).  Before a level is swept, k_ring_gather adds to every vertex of that level the contributions of ALL its
 //    descendants (fixed order: gidx lists them in post-order), in place in `hat`.  The pass-through gather at the end of
@@ -41,46 +45,92 @@ __device__ __forceinline__ size_t sr_col_off(int col, int s, int b)      // colu
 template <int DIR> __device__ __forceinline__ int sr_lo(int o) { return DIR == 0 ? 0 : o; }
 template <int DIR> __device__ __forceinline__ int sr_hi(int o, int s, int b) { return DIR == 0 ? min(o + 1, s) : s + b; }
 
+// Lane layout of one panel entry (ML doubles): VW consecutive modes per lane and access, NA accesses per entry.
+//   ML = 64 : 1 x 16-byte access (lane l: modes 2l, 2l+1)          ML = 128: 2 x 16-byte accesses
+//   ML = 32 : 1 x  8-byte access                                    ML = 96 : 3 x  8-byte accesses
+template <int ML> struct sr_lane {
+    static constexpr int VW = (ML % 64 == 0) ? 2 : 1;
+    static constexpr int NA = ML / (32 * VW);
+};
+template <int VW> struct sr_vec;
+template <> struct sr_vec<1> {
+    double x;
+    __device__ __forceinline__ void zero() { x = 0.0; }
+    __device__ __forceinline__ void fma(const sr_vec<1> &p, const sr_vec<1> &r) { x += p.x * r.x; }
+    __device__ __forceinline__ void add(const sr_vec<1> &p) { x += p.x; }
+    __device__ __forceinline__ sr_vec<1> scaled(double f) const { sr_vec<1> o; o.x = f * x; return o; }
+};
+template <> struct __align__(16) sr_vec<2> {
+    double x, y;
+    __device__ __forceinline__ void zero() { x = y = 0.0; }
+    __device__ __forceinline__ void fma(const sr_vec<2> &p, const sr_vec<2> &r) { x += p.x * r.x; y += p.y * r.y; }
+    __device__ __forceinline__ void add(const sr_vec<2> &p) { x += p.x; y += p.y; }
+    __device__ __forceinline__ sr_vec<2> scaled(double f) const { sr_vec<2> o; o.x = f * x; o.y = f * y; return o; }
+};
+
 template <int ML, int DIR>
-__device__ __forceinline__ void sr_flush(const dots_ctx_t &c, const dots_ring_task_t &t, int o, const double (&acc)[ML / 32], int lane)
+__device__ __forceinline__ void sr_flush(const dots_ctx_t &c, const dots_ring_task_t &t, int o,
+                                         const sr_vec<sr_lane<ML>::VW> (&acc)[sr_lane<ML>::NA], int lane)
 {
-    constexpr int MP = ML / 32;
+    constexpr int VW = sr_lane<ML>::VW, NA = sr_lane<ML>::NA;
     double *dst;
     double sign;
     if (DIR == 1) { dst = c.hat + (size_t)(t.off + o) * ML; sign = -1.0; }                 // x_S = -P^T [y_S ; x_B]
     else if (o < t.s) { dst = c.ywork + (size_t)(t.off + o) * ML; sign = 1.0; }            // y_S = inv(L11) r_S
     else { dst = c.upd + (size_t)(t.ubase + o - t.s) * ML; sign = -1.0; }                  // own contribution to boundary row o - s
 #pragma unroll
-    for (int m = 0; m < MP; ++m) dst[lane + 32 * m] = sign * acc[m];
+    for (int a = 0; a < NA; ++a) *reinterpret_cast<sr_vec<VW> *>(dst + a * 32 * VW + lane * VW) = acc[a].scaled(sign);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Vector operand of up to EC consecutive entries of ONE output piece [x, x + ne): rows of Z.
-template <int ML, int DIR, int EC>
-__device__ __forceinline__ void sr_fetch_vec(double (&rv)[EC][ML / 32], const double *z, const int32_t *bi, int off, int x, int ne)
+// One ring stage: `ne` (<= EC) consecutive panel entries in shared memory, `code` = this lane's entry code (lane e holds
+// the operand row of entry e; bit 31: last entry of its output).  The operand rows are fetched BEFORE the stage's
+// mbarrier is waited for, so their L1 / L2 latency overlaps the wait.  FLUSH: outputs may end inside the stage.
+template <int ML, int DIR, int EC, bool FLUSH>
+__device__ __forceinline__ void sr_stage(const dots_ctx_t &c, const dots_ring_task_t &t, const double *z, const double *sp,
+                                         uint64_t *bar, uint32_t phase, int ne, int code, int lane, int &o,
+                                         sr_vec<sr_lane<ML>::VW> (&acc)[sr_lane<ML>::NA])
 {
-    constexpr int MP = ML / 32;
-    int row[EC];
+    constexpr int VW = sr_lane<ML>::VW, NA = sr_lane<ML>::NA;
+    typedef sr_vec<VW> vec_t;
+    vec_t rv[EC][NA];
+    int cd[EC];
 #pragma unroll
-    for (int e = 0; e < EC; ++e) row[e] = (e < ne) ? ((DIR == 0) ? off + x + e : bi[x + e]) : 0;
+    for (int e = 0; e < EC; ++e) {                           // lanes >= ne hold code 0: row 0 is fetched and never used (no predication)
+        cd[e] = __shfl_sync(0xffffffffu, code, e);
+        unsigned long long va;                               // z + row * ML doubles in ONE instruction (IMAD.WIDE.U32)
+#ifdef SR_DEBUG_VEC0
+        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(va) : "r"(0u), "r"((unsigned)(ML * 8)), "l"((unsigned long long)z));   // timing experiment: WRONG results
+#else
+        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(va) : "r"((unsigned)cd[e] & 0x7fffffffu), "r"((unsigned)(ML * 8)), "l"((unsigned long long)z));
+#endif
+        const double *vp = reinterpret_cast<const double *>(va);
+#pragma unroll
+        for (int a = 0; a < NA; ++a) rv[e][a] = *reinterpret_cast<const vec_t *>(vp + a * 32 * VW);
+    }
+    mbar_wait(bar, phase);
 #pragma unroll
     for (int e = 0; e < EC; ++e) {
+        if (e < ne) {
 #pragma unroll
-        for (int m = 0; m < MP; ++m) rv[e][m] = (e < ne) ? z[(size_t)row[e] * ML + 32 * m] : 0.0;
+            for (int a = 0; a < NA; ++a) acc[a].fma(*reinterpret_cast<const vec_t *>(sp + e * ML + a * 32 * VW), rv[e][a]);
+            if (FLUSH && cd[e] < 0) {
+                sr_flush<ML, DIR>(c, t, o, acc, lane);
+#pragma unroll
+                for (int a = 0; a < NA; ++a) acc[a].zero();
+                ++o;
+            }
+        }
     }
 }
 
 // Contiguous tasks: one warp streams the outputs [oa, oa + n_out) of a node, i.e. n_ent consecutive panel entries.
-// SB = bytes per ring stage.  The vector operand of stage k + 1 is requested before the math of stage k (SR_VEC_PIPE), so a
-// whole stage period hides its L1 / L2 latency.
-#ifndef SR_VEC_PIPE
-#define SR_VEC_PIPE 1
-#endif
+// SB = bytes per ring stage.  No cursor arithmetic: the per-entry codes (erow_fwd / erow_bwd, built once on the host) say
+// which row of Z an entry multiplies and where an output ends; the codes of stage k + 1 are requested during stage k.
 template <int ML, int DIR, int SB>
-__global__ void __launch_bounds__(SR_THREADS, 2) k_ring_run(dots_ctx_t c, int task0, int task_end)
+__global__ void __launch_bounds__(SR_THREADS, 3) k_ring_run(dots_ctx_t c, int task0, int task_end)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // no-ops unless launched as a programmatic dependent
-    constexpr int MP = ML / 32;
+    constexpr int VW = sr_lane<ML>::VW, NA = sr_lane<ML>::NA;
     constexpr int EC = SB / (8 * ML);                                    // panel entries per stage
     extern __shared__ __align__(128) unsigned char sr_smem[];
     const int nst = c.ring_stages;
@@ -96,8 +146,8 @@ __global__ void __launch_bounds__(SR_THREADS, 2) k_ring_run(dots_ctx_t c, int ta
     __syncwarp();
     const dots_ring_task_t t = (DIR == 0 ? c.rt_fwd : c.rt_bwd)[ti];
     const double *src = (DIR == 0 ? c.panels : c.panels_t) + (size_t)t.pbase * ML;
+    const int32_t *codes = (DIR == 0 ? c.erow_fwd : c.erow_bwd) + t.pbase;
     const int n_ent = t.n_ent, n_stage = (n_ent + EC - 1) / EC;
-    const int s = t.s, b = t.b;
 
     auto issue = [&](int k, int slot) {                                  // lane 0: stage k of the run -> ring slot
         const uint32_t bytes = (uint32_t)min(EC, n_ent - k * EC) * (uint32_t)(ML * 8);
@@ -105,69 +155,24 @@ __global__ void __launch_bounds__(SR_THREADS, 2) k_ring_run(dots_ctx_t c, int ta
         tma_load_1d(ring + (size_t)slot * EC * ML, src + (size_t)k * EC * ML, bytes, &bar[slot]);
     };
     if (lane == 0) {
-        for (int k = 0; k < nst && k < n_stage; ++k) issue(k, k);        // the panels are read-only: stream before the wait
+        for (int k = 0; k < nst && k < n_stage; ++k) issue(k, k);        // panels and codes are read-only: stream before the wait
     }
+    int code_next = (lane < EC && lane < n_ent) ? codes[lane] : 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");                   // below: data written by the previous launches
 
-    const double *z = c.hat + lane;                                      // Z = [hat | ywork]
-    const int32_t *bi = c.bidx + t.fbase;
-    // vector operand of a stage's entries: walks over the output boundaries exactly like the math below
-    int vo = t.oa, vx = sr_lo<DIR>(vo), vhi = sr_hi<DIR>(vo, s, b);
-    auto fetch = [&](double (&rv)[EC][MP], int k) {
-        const int ne = min(EC, n_ent - k * EC);
-        int row[EC];
+    const double *z = c.hat + lane * VW;                                 // Z = [hat | ywork]
+    int o = t.oa;
+    sr_vec<VW> acc[NA];
 #pragma unroll
-        for (int e = 0; e < EC; ++e) {
-            row[e] = 0;
-            if (e < ne) {
-                row[e] = (DIR == 0) ? t.off + vx : bi[vx];
-#ifdef SR_DEBUG_VEC0
-                row[e] = 0;                                              // timing experiment only: no vector traffic, wrong results
-#endif
-                if (++vx == vhi) { ++vo; vx = sr_lo<DIR>(vo); vhi = sr_hi<DIR>(vo, s, b); }
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < EC; ++e) {
-#pragma unroll
-            for (int m = 0; m < MP; ++m) rv[e][m] = (e < ne) ? z[(size_t)row[e] * ML + 32 * m] : 0.0;
-        }
-    };
-    int o = t.oa, x = sr_lo<DIR>(o), hi = sr_hi<DIR>(o, s, b);
-    double acc[MP];
-#pragma unroll
-    for (int m = 0; m < MP; ++m) acc[m] = 0.0;
+    for (int a = 0; a < NA; ++a) acc[a].zero();
     int slot = 0;
     uint32_t phase = 0;
-    double rvn[EC][MP];
-    if (SR_VEC_PIPE) fetch(rvn, 0);
     for (int k = 0; k < n_stage; ++k) {
         const int ne = min(EC, n_ent - k * EC);
-        double rv[EC][MP];
-        if (SR_VEC_PIPE) {
-#pragma unroll
-            for (int e = 0; e < EC; ++e)
-#pragma unroll
-                for (int m = 0; m < MP; ++m) rv[e][m] = rvn[e][m];
-            fetch(rvn, k + 1);                                           // requested now, used one stage later
-        } else {
-            fetch(rv, k);
-        }
-        mbar_wait(&bar[slot], phase);
-        const double *sp = ring + (size_t)slot * EC * ML + lane;
-#pragma unroll
-        for (int e = 0; e < EC; ++e) {
-            if (e < ne) {
-#pragma unroll
-                for (int m = 0; m < MP; ++m) acc[m] += sp[e * ML + 32 * m] * rv[e][m];
-                if (++x == hi) {
-                    sr_flush<ML, DIR>(c, t, o, acc, lane);
-#pragma unroll
-                    for (int m = 0; m < MP; ++m) acc[m] = 0.0;
-                    ++o; x = sr_lo<DIR>(o); hi = sr_hi<DIR>(o, s, b);
-                }
-            }
-        }
+        const int code = code_next;
+        const int nxt = (k + 1) * EC + lane;
+        code_next = (lane < EC && nxt < n_ent) ? codes[nxt] : 0;
+        sr_stage<ML, DIR, EC, true>(c, t, z, ring + (size_t)slot * EC * ML + lane * VW, &bar[slot], phase, ne, code, lane, o, acc);
         __syncwarp();                                                    // every lane is done reading the slot
         if (lane == 0 && k + nst < n_stage) issue(k + nst, slot);
         if (++slot == nst) { slot = 0; phase ^= 1u; }
@@ -177,13 +182,12 @@ __global__ void __launch_bounds__(SR_THREADS, 2) k_ring_run(dots_ctx_t c, int ta
 // ------------------------------------------------------------------------------------------------
 // Split items: block = (node, outputs [oa, oa + n_out)); ROWS = 8 / WPR outputs per pass, the run of an output is cut into
 // WPR contiguous pieces (one per warp), partial sums combined in warp order through shared memory.  A warp's chunk
-// sequence runs over all passes of the item; three cursors walk it: the bulk copies (ring_stages chunks ahead), the vector
-// operand (one chunk ahead) and the math.
+// sequence runs over all passes of the item; two cursors walk it: the bulk copies (ring_stages chunks ahead) and the math.
 template <int ML, int WPR, int DIR, int SB>
 __global__ void __launch_bounds__(SR_THREADS, 2) k_ring_split(dots_ctx_t c, int item0)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    constexpr int MP = ML / 32;
+    constexpr int VW = sr_lane<ML>::VW, NA = sr_lane<ML>::NA;
     constexpr int EC = SB / (8 * ML);
     constexpr int ROWS = SR_WARPS / WPR;
     extern __shared__ __align__(128) unsigned char sr_smem[];
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(SR_THREADS, 2) k_ring_split(dots_ctx_t c, int 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *ring = reinterpret_cast<double *>(sr_smem) + (size_t)warp * nst * EC * ML;
     uint64_t *bar = reinterpret_cast<uint64_t *>(sr_smem + (size_t)SR_WARPS * nst * EC * ML * 8) + warp * nst;
-    double *red = reinterpret_cast<double *>(sr_smem + (size_t)SR_WARPS * nst * (EC * ML * 8 + 8));     // [SR_WARPS][ML]
+    double *red = reinterpret_cast<double *>(sr_smem + (((size_t)SR_WARPS * nst * (EC * ML * 8 + 8) + 15) & ~(size_t)15));   // [SR_WARPS][ML]
     if (lane == 0) {
         for (int i = 0; i < nst; ++i) mbar_init(&bar[i], 1);
         mbar_fence_init();
@@ -199,23 +203,26 @@ __global__ void __launch_bounds__(SR_THREADS, 2) k_ring_split(dots_ctx_t c, int 
     __syncwarp();
     const dots_ring_task_t t = (DIR == 0 ? c.rt_fwd : c.rt_bwd)[item0 + blockIdx.x];
     const double *pan = (DIR == 0 ? c.panels : c.panels_t) + (size_t)t.pbase * ML;
+    const int32_t *codes = (DIR == 0 ? c.erow_fwd : c.erow_bwd) + t.pbase;
     const int s = t.s, b = t.b, last = t.oa + t.n_out - 1;
     const int npass = (t.n_out + ROWS - 1) / ROWS;
     const int rslot = warp / WPR, cslot = warp % WPR;
 
-    struct Cur { int pass, o, x, xb; };                                  // chunk [x, min(x + EC, xb)) of output o in pass `pass`
-    // this warp's piece [xa, xb) of the output it shares in pass `pass`
+    struct Cur { int pass, x, xb; size_t ent; };                         // chunk [x, min(x + EC, xb)) of the piece; ent: panel entry of x
+    // this warp's piece of the output it shares in pass `pass`
     auto piece = [&](Cur &q) -> bool {
-        q.o = t.oa + q.pass * ROWS + rslot;
-        if (q.o > last) return false;
-        const int lo = sr_lo<DIR>(q.o), hi = sr_hi<DIR>(q.o, s, b);
+        const int o = t.oa + q.pass * ROWS + rslot;
+        if (o > last) return false;
+        const int lo = sr_lo<DIR>(o), hi = sr_hi<DIR>(o, s, b);
         const int plen = ((hi - lo + WPR - 1) / WPR + EC - 1) / EC * EC;
         q.x = lo + cslot * plen;
         q.xb = min(hi, q.x + plen);
+        q.ent = (DIR == 0 ? sr_row_off(o, s) : sr_col_off(o, s, b)) + (size_t)(q.x - lo);
         return q.x < q.xb;
     };
     auto next = [&](Cur &q) -> bool {                                    // advance to the warp's next chunk; false: no more
         q.x += EC;
+        q.ent += EC;
         while (q.x >= q.xb) {
             if (++q.pass >= npass) return false;
             if (!piece(q)) q.x = q.xb = 0;
@@ -224,74 +231,53 @@ __global__ void __launch_bounds__(SR_THREADS, 2) k_ring_split(dots_ctx_t c, int 
     };
     auto issue = [&](const Cur &q, int slot) {                           // lane 0
         const uint32_t bytes = (uint32_t)min(EC, q.xb - q.x) * (uint32_t)(ML * 8);
-        const size_t ent = (DIR == 0 ? sr_row_off(q.o, s) : sr_col_off(q.o, s, b)) + (size_t)(q.x - sr_lo<DIR>(q.o));
         mbar_expect_tx(&bar[slot], bytes);
-        tma_load_1d(ring + (size_t)slot * EC * ML, pan + ent * ML, bytes, &bar[slot]);
+        tma_load_1d(ring + (size_t)slot * EC * ML, pan + q.ent * ML, bytes, &bar[slot]);
     };
-    Cur pc{-1, 0, 0, 0}, vc{-1, 0, 0, 0}, cc{-1, 0, 0, 0};
-    bool pvalid = next(pc), vvalid = next(vc), cvalid = next(cc);
+    Cur pc{-1, 0, 0, 0}, cc{-1, 0, 0, 0};
+    bool pvalid = next(pc), cvalid = next(cc);
     for (int i = 0; i < nst && pvalid; ++i) {
         if (lane == 0) issue(pc, i);
         pvalid = next(pc);
     }
+    int code_next = (cvalid && lane < min(EC, cc.xb - cc.x)) ? codes[cc.ent + lane] : 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    const double *z = c.hat + lane;
-    const int32_t *bi = c.bidx + t.fbase;
-    int slot = 0;
+    const double *z = c.hat + lane * VW;
+    int slot = 0, o_unused = 0;
     uint32_t phase = 0;
-    double rvn[EC][MP];
-    if (SR_VEC_PIPE && vvalid) {
-        sr_fetch_vec<ML, DIR, EC>(rvn, z, bi, t.off, vc.x, min(EC, vc.xb - vc.x));
-        vvalid = next(vc);
-    }
     for (int pass = 0; pass < npass; ++pass) {
-        double acc[MP];
+        sr_vec<VW> acc[NA];
 #pragma unroll
-        for (int m = 0; m < MP; ++m) acc[m] = 0.0;
+        for (int a = 0; a < NA; ++a) acc[a].zero();
         while (cvalid && cc.pass == pass) {
             const int ne = min(EC, cc.xb - cc.x);
-            double rv[EC][MP];
-            if (SR_VEC_PIPE) {
-#pragma unroll
-                for (int e = 0; e < EC; ++e)
-#pragma unroll
-                    for (int m = 0; m < MP; ++m) rv[e][m] = rvn[e][m];
-                if (vvalid) {
-                    sr_fetch_vec<ML, DIR, EC>(rvn, z, bi, t.off, vc.x, min(EC, vc.xb - vc.x));
-                    vvalid = next(vc);
-                }
-            } else {
-                sr_fetch_vec<ML, DIR, EC>(rv, z, bi, t.off, cc.x, ne);
-            }
-            mbar_wait(&bar[slot], phase);
-            const double *sp = ring + (size_t)slot * EC * ML + lane;
-#pragma unroll
-            for (int e = 0; e < EC; ++e) {
-                if (e < ne) {
-#pragma unroll
-                    for (int m = 0; m < MP; ++m) acc[m] += sp[e * ML + 32 * m] * rv[e][m];
-                }
-            }
+            const int code = code_next;
+            const double *sp = ring + (size_t)slot * EC * ML + lane * VW;
+            uint64_t *bp = &bar[slot];
+            const uint32_t ph = phase;
+            cvalid = next(cc);                                           // the codes of the next chunk are requested now
+            code_next = (cvalid && lane < min(EC, cc.xb - cc.x)) ? codes[cc.ent + lane] : 0;
+            sr_stage<ML, DIR, EC, false>(c, t, z, sp, bp, ph, ne, code, lane, o_unused, acc);
             __syncwarp();
             if (pvalid) {
                 if (lane == 0) issue(pc, slot);
                 pvalid = next(pc);
             }
             if (++slot == nst) { slot = 0; phase ^= 1u; }
-            cvalid = next(cc);
         }
 #pragma unroll
-        for (int m = 0; m < MP; ++m) red[warp * ML + lane + 32 * m] = acc[m];
+        for (int a = 0; a < NA; ++a) *reinterpret_cast<sr_vec<VW> *>(red + warp * ML + a * 32 * VW + lane * VW) = acc[a];
         __syncthreads();
         const int o = t.oa + pass * ROWS + rslot;
         if (cslot == 0 && o <= last) {
 #pragma unroll
-            for (int m = 0; m < MP; ++m) {
-                double v = 0.0;
+            for (int a = 0; a < NA; ++a) {
+                sr_vec<VW> v;
+                v.zero();
 #pragma unroll
-                for (int w = 0; w < WPR; ++w) v += red[(rslot * WPR + w) * ML + lane + 32 * m];
-                acc[m] = v;
+                for (int w = 0; w < WPR; ++w) v.add(*reinterpret_cast<const sr_vec<VW> *>(red + (rslot * WPR + w) * ML + a * 32 * VW + lane * VW));
+                acc[a] = v;
             }
             sr_flush<ML, DIR>(c, t, o, acc, lane);
         }
@@ -347,7 +333,7 @@ static int sr_launch(void (*kern)(Args...), int grid, int threads, size_t smem, 
 static size_t sr_smem_bytes(int ML, int SB, int nst, bool split)
 {
     const int EC = SB / (8 * ML);
-    return (size_t)SR_WARPS * nst * ((size_t)EC * ML * 8 + 8) + (split ? (size_t)SR_WARPS * ML * 8 : 0) + 16;
+    return (((size_t)SR_WARPS * nst * ((size_t)EC * ML * 8 + 8) + 15) & ~(size_t)15) + (split ? (size_t)SR_WARPS * ML * 8 : 0) + 16;
 }
 
 template <int ML, int SB>
@@ -439,7 +425,7 @@ static int sr_dispatch(const dots_ctx_t *c, void *stream, sr_marks *mk)
     if (c->m_pad % 32 || c->m_pad > 128) { dots_set_error("ring sweeps need m_pad in {32, 64, 96, 128} (got %d)", c->m_pad); return DOTS_ERR_BAD_ARG; }
     if (c->ywork != c->hat + (size_t)c->n_vert * c->m_pad) { dots_set_error("ring sweeps need ywork == hat + n_vert * m_pad"); return DOTS_ERR_BAD_ARG; }
     if (c->ring_stages < 2 || c->ring_stages > 6) { dots_set_error("ring_stages=%d outside 2..6", c->ring_stages); return DOTS_ERR_BAD_ARG; }
-    if (!c->rt_fwd || !c->rt_bwd || !c->bidx || !c->gptr || !c->gidx) { dots_set_error("ring sweep plan missing from the context"); return DOTS_ERR_BAD_ARG; }
+    if (!c->rt_fwd || !c->rt_bwd || !c->erow_fwd || !c->erow_bwd || !c->gptr || !c->gidx) { dots_set_error("ring sweep plan missing from the context"); return DOTS_ERR_BAD_ARG; }
     const bool small = c->ring_stage_bytes == 2048;
     if (!small && c->ring_stage_bytes != 4096) { dots_set_error("ring_stage_bytes=%d: 2048 or 4096", c->ring_stage_bytes); return DOTS_ERR_BAD_ARG; }
     switch (c->m_pad) {

@@ -229,6 +229,9 @@ class Engine:
                 setattr(ctx, name, ten.data_ptr())
             for name in ("bidx", "gptr", "gidx", "gverts"):
                 setattr(ctx, name, up("ring_" + name, rp[name], np.int32).data_ptr())
+            rp["erow_fwd"], rp["erow_bwd"] = ring_plan.entry_rows(self.lib, sym, rp["bidx"])
+            for name in ("erow_fwd", "erow_bwd"):
+                setattr(ctx, name, up("ring_" + name, rp[name], np.int32).data_ptr())
             ctx.h_rt_fwd_ptr, ctx.h_rt_bwd_ptr = rp["fwd_ptr"].ctypes.data, rp["bwd_ptr"].ctypes.data
             ctx.h_rt_fwd_wpr, ctx.h_rt_bwd_wpr = rp["fwd_wpr"].ctypes.data, rp["bwd_wpr"].ctypes.data
             ctx.h_gv_ptr = rp["gv_ptr"].ctypes.data
@@ -257,13 +260,14 @@ class Engine:
         self.t = dict(params=z(capi.P_COUNT), bnd0=z(V), bnd1=z(V), rhs=z(part.world * part.chunk, V),
                       hat=hat_local, hat_all=hat_local if part.world == 1 else z(part.world, V, self.m_pad),
                       ywork=z_all[V:], upd=z(max(1, int(sym.upd_off[-1])), self.m_pad),
-                      red_part=z(self.red_blocks, 8), red_out=z(8))
+                      red_part=z(self.red_blocks, 64), red_out=z(64))
         for k, ten in self.t.items():
             setattr(ctx, k, ten.data_ptr())
         ctx.red_blocks = self.red_blocks
         self.ctx = ctx
         self._ctxp = C.byref(ctx)
-        self._host_out = np.zeros(8)
+        self._host_out = np.zeros(64)
+        self._sum_cache = {}                             # condition -> raw sums of the CURRENT state (prefetch_sums)
         self._host_params = np.zeros(capi.P_COUNT)
         self._halo_v = z(4, V)
         self._halo_c = z(3, T)
@@ -464,6 +468,7 @@ class Engine:
                 capi.check(self.lib.dots_graph_launch(self._graphs[key], st), "dots_graph_launch")
         self.launches += n * self.launches_per_iteration()
         self.z_valid = write_z
+        self._state_changed()
 
     def _iterate_sharded(self, write_z):
         """One iteration across ranks: the same kernels on this rank's slab / modes + the exchanges of dist.py."""
@@ -541,6 +546,7 @@ class Engine:
         self.launches += 2
 
     def adjust_penalty(self, f):                                                         # :367-371
+        self._state_changed()
         self.r *= f
         self._push_params()
         capi.check(self.lib.dots_scale_dual(self._ctxp, float(f), self.stream), "dots_scale_dual")
@@ -548,6 +554,7 @@ class Engine:
         self.launches += 8
 
     def scale_z(self, f):                                                                # :373-395
+        self._state_changed()
         self.s *= f
         self.d *= f
         self.norm_d *= f
@@ -605,6 +612,7 @@ class Engine:
 
     def set_scalars(self, r=None, s=None, d=None, norm_d=None):
         """Overwrite the driver scalars (tests / warm starts) and push them to the device."""
+        self._state_changed()
         if r is not None: self.r = float(r)
         if s is not None: self.s = float(s)
         if d is not None: self.d = float(d)
@@ -623,15 +631,40 @@ class Engine:
         self.slab["E"].levels(part.lvl_begin, part.lvl_end).copy_(-(scale / math.sqrt(3.0)) * bm.sum(dim=2).sum(dim=1))
 
     def refresh(self):
+        self._state_changed()
         capi.check(self.lib.dots_refresh_corner_terms(self._ctxp, self.stream), "dots_refresh_corner_terms")
         self.exchange_corner_halo()
         self.launches += 1
 
     # ------------------------------------------------------------------ residuals
     def sums(self, which):
-        capi.check(self.lib.dots_kkt_sums(self._ctxp, int(which), self._host_out.ctypes.data, self.stream), "dots_kkt_sums")
+        which = int(which)
+        if which in self._sum_cache:
+            return self._sum_cache[which]
+        capi.check(self.lib.dots_kkt_sums(self._ctxp, which, self._host_out.ctypes.data, self.stream), "dots_kkt_sums")
         self.launches += 3
-        return self.comm.sum_in_rank_order(self._host_out.copy(), self.device)
+        return self.comm.sum_in_rank_order(self._host_out[:8].copy(), self.device)
+
+    def prefetch_sums(self, conditions):
+        """Raw sums of several conditions (0..6, 7 = objective) in ONE fused pass per side and ONE host synchronisation
+        (dots_kkt_sums_multi); ``kkt`` / ``objective`` then read them from the cache until the state changes.  Used where
+        the reference is known to evaluate a whole set: the forced conditions of a penalty-update iteration
+        (solver_socp.py:728-729) and the step-by-step mode (:769-787)."""
+        conds = sorted({int(i) for i in conditions})
+        if not conds:
+            return
+        if 1 in conds and not self.z_valid:
+            raise capi.DotsError("KKT #1 needs z_mid of the current iteration: call iterate(..., write_z=True)")
+        if 4 in conds:
+            self.exchange_B_halo()
+        mask = sum(1 << i for i in conds)
+        capi.check(self.lib.dots_kkt_sums_multi(self._ctxp, mask, self._host_out.ctypes.data, self.stream), "dots_kkt_sums_multi")
+        self.launches += 4
+        total = self.comm.sum_in_rank_order(self._host_out.copy(), self.device)
+        self._sum_cache = {i: total[8 * i:8 * i + 8].copy() for i in conds}
+
+    def _state_changed(self):
+        self._sum_cache = {}
 
     def kkt(self, i):
         """Relative KKT residual i as [value, value] (conditions 0-3) or [value, None] (4-6):
@@ -639,7 +672,7 @@ class Engine:
         nT, sq = self.nT, math.sqrt
         if i == 1 and not self.z_valid:
             raise capi.DotsError("KKT #1 needs z_mid of the current iteration: call iterate(..., write_z=True)")
-        if i == 4:
+        if i == 4 and i not in self._sum_cache:
             self.exchange_B_halo()
         o = self.sums(i)
         v, t = o[0:4], o[4:8]

@@ -146,6 +146,43 @@ def build(sym, n_sm: int, m_pad: int, split_bytes: int = 96 * 1024, tasks_per_sm
                 gidx=gidx if gidx.size else np.zeros(1, np.int32), gverts=cat(gverts), gv_ptr=i32(gv_ptr))
 
 
+def entry_rows(lib, sym, bidx):
+    """(erow_fwd, erow_bwd): for every panel entry in streaming order the row of Z it multiplies (bit 31: last entry of its
+    output), built by the C++ helper ``dots_ring_entry_rows`` (a Python loop over 10 M entries would dominate the setup)."""
+    from . import capi
+    i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+    s, b, off, fo, po = i64(sym.s), i64(sym.b), i64(sym.off), i64(sym.front_off), i64(sym.panel_off)
+    bi = np.ascontiguousarray(bidx, dtype=np.int32)
+    ef, eb = np.zeros(max(1, sym.panel_entries), dtype=np.int32), np.zeros(max(1, sym.panel_entries), dtype=np.int32)
+    capi.check(lib.dots_ring_entry_rows(sym.n_nodes, s.ctypes.data, b.ctypes.data, off.ctypes.data, fo.ctypes.data, po.ctypes.data,
+                                        bi.ctypes.data, ef.ctypes.data, eb.ctypes.data), "dots_ring_entry_rows")
+    return ef, eb
+
+
+def entry_rows_numpy(sym, bidx):
+    """Plain statement of ``entry_rows`` (tests)."""
+    last = np.int32(-2 ** 31)
+    ef, eb = np.zeros(max(1, sym.panel_entries), dtype=np.int32), np.zeros(max(1, sym.panel_entries), dtype=np.int32)
+    for nd in range(sym.n_nodes):
+        s, b, off, p = int(sym.s[nd]), int(sym.b[nd]), int(sym.off[nd]), int(sym.panel_off[nd])
+        if s == 0:
+            continue
+        bi = bidx[sym.front_off[nd]:sym.front_off[nd] + s + b]
+        k = p
+        for i in range(s + b):
+            n = min(i + 1, s)
+            ef[k:k + n] = off + np.arange(n)
+            ef[k + n - 1] |= last
+            k += n
+        k = p
+        for j in range(s):
+            n = s + b - j
+            eb[k:k + n] = bi[j:]
+            eb[k + n - 1] |= last
+            k += n
+    return ef, eb
+
+
 def launches(plan) -> int:
     """Kernel launches of one pair of sweeps with this plan."""
     return int(np.count_nonzero(np.diff(plan["fwd_ptr"])) + np.count_nonzero(np.diff(plan["bwd_ptr"]))

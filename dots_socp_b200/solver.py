@@ -159,8 +159,11 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
             ev_b.record()
         t_k = time.perf_counter()
         if not check_kkt_step_by_step:
+            if required:
+                eng.prefetch_sums(required)           # the forced conditions are all evaluated (no early exit): one fused pass
             passed, _ = lazy.evaluate(required)                                           # :738
         else:
+            eng.prefetch_sums(range(8))               # all 7 residuals + the objective: one fused multi-reduction pass
             passed, _ = lazy.evaluate(list(range(7)))                                     # :770
             cost, lagr = eng.objective()                                                  # :773-775
         errs = lazy.collect()                                                             # :739-740
@@ -201,6 +204,7 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
             gap = max_or_none([src[k] for k in PRIM_SET]) / max_or_none([src[k] for k in DUAL_SET])
             eng.adjust_penalty(sched.next_penalty(eng.r, gap) / eng.r)
 
+    eng.prefetch_sums(range(8))
     final = [eng.kkt(i)[0] for i in range(7)]                                             # :826-828
     cost, lagr = eng.objective()                                                          # :829-831
     hist.record(current_it=it, kkt_errors=final, history={"Transportation cost": cost, "Objective value": lagr})

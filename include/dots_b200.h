@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DOTS_ABI_VERSION 10
+#define DOTS_ABI_VERSION 11
 
 /* scalar block read by the kernels from device memory (so CUDA graphs stay valid across penalty updates) */
 enum {
@@ -145,8 +145,8 @@ typedef struct dots_ctx {
     double *hat_all;           /* [n_ranks][V][m_pad] all ranks' solutions (== hat on one GPU)        */
     double *ywork;             /* [V][m_pad]  forward-sweep result                                    */
     double *upd;               /* [sum b][m_pad] update vectors                                       */
-    double *red_part;          /* [red_blocks][8] block partial sums                                  */
-    double *red_out;           /* [8] reduced sums (device)                                           */
+    double *red_part;          /* [red_blocks][64] block partial sums (8 conditions x 8 slots)        */
+    double *red_out;           /* [64] reduced sums (device)                                          */
     int32_t red_blocks;
     int32_t sweep_mode;        /* 0: k_sweep_run, register-staged loads (any m_pad); 4: ring-streamed sweeps, every warp feeds its
                                   own shared-memory ring with bulk async copies (m_pad a multiple of 32)                        */
@@ -171,6 +171,8 @@ typedef struct dots_ctx {
                                                    warps share one output                                                  */
     const int32_t *bidx;       /* [front_total] row of Z read by the backward sweep for every front row: n_vert + vertex for
                                   the S rows (y in ywork), vertex for the B rows (x of the ancestors in hat)               */
+    const int32_t *erow_fwd;   /* [panel_entries] per panel entry (row-major order): row of Z it multiplies | last-of-output << 31 */
+    const int32_t *erow_bwd;   /* [panel_entries] the same for the column-major copy                                     */
     const int32_t *gptr;       /* [V+1] ranges into gidx: the contributions landing on vertex v                           */
     const int32_t *gidx;       /* [sum b] rows of `upd` (producer order: nd_upd[node] + boundary row), grouped by the vertex
                                   they land on, producers in post-order (fixed summation order)                           */
@@ -230,6 +232,11 @@ int dots_set_params(const dots_ctx_t *c, const double *host_params, void *stream
  * Synchronises the stream.  Slot meaning per condition: csrc/kkt_kernels.cu (k_kkt_vertex / k_kkt_tri) and
  * dots_socp_b200/engine.py (Engine.kkt, which forms the relative residuals of solver_socp.py:433-559 from them). */
 int dots_kkt_sums(const dots_ctx_t *c, int which, double *host_out, void *stream);
+/* All conditions of `mask` (bit i = condition i, bit 7 = objective) in ONE pass over the vertex arrays and ONE over the
+ * triangle arrays (the --detail_runhist mode of solver_socp.py:769-787 evaluates all 7 + the objective every iteration; the
+ * penalty-update iterations force conditions 0-3, :728-729): host_out[8 * i + k] = slot k of condition i as in
+ * dots_kkt_sums.  red_part must hold red_blocks x 64 doubles, red_out 64.  Synchronises the stream.                      */
+int dots_kkt_sums_multi(const dots_ctx_t *c, unsigned mask, double *host_out, void *stream);
 
 /* ---- setup (row f1): numeric factorisation of the small fronts (n <= dots_front_nmax()) of one tree level, one block
  * per (node, time mode); replaces the per-mode SuperLU factorisations of utils/laplacian_inverse_socp.py:34-41 for the
@@ -268,6 +275,13 @@ int dots_order_sizes(const dots_order_t *o, int64_t *n_nodes, int64_t *front_tot
 int dots_order_export(const dots_order_t *o, int64_t *perm, int64_t *s, int64_t *b, int64_t *level, int64_t *parent,
                       int64_t *child, int64_t *front_idx, int64_t *child_pos);
 int dots_order_destroy(dots_order_t *o);
+
+/* ---- setup, host side: per-entry operand rows of the ring-streamed sweeps (sweep_mode 4).  HOST pointers.  For every
+ * panel entry in streaming order (rows_fwd: row-major panels, rows_bwd: column-major copy) the row of Z = [hat | ywork]
+ * the entry is multiplied with; bit 31 = last entry of its output.  s, b, off, front_off [n_nodes(+1)], panel_off
+ * [n_nodes+1] as in dots_order_export / nested.Symbolic; bidx [front_total] as in dots_ctx_t.                            */
+int dots_ring_entry_rows(int64_t n_nodes, const int64_t *s, const int64_t *b, const int64_t *off, const int64_t *front_off,
+                         const int64_t *panel_off, const int32_t *bidx, int32_t *rows_fwd, int32_t *rows_bwd);
 
 /* ---- operator-level entry points on the internal layout (rows a5, a6, a7, a8) ---------------------- */
 int dots_phi_rhs(const dots_ctx_t *c, void *stream);                       /* -> c->rhs                */

@@ -22,7 +22,7 @@ def load_golden(name):
     kw = {str(k): float(v) for k, v in zip(z["kw_keys"], z["kw_vals"])}
     if "nit" in kw:
         kw["nit"] = int(kw["nit"])
-    for flag in ("check_kkt_step_by_step", "is_palm"):
+    for flag in ("check_kkt_step_by_step", "is_palm", "is_constant_scaling"):
         if flag in kw:
             kw[flag] = bool(kw[flag])
     return z, geo, int(z["n_time"]), kw

@@ -21,7 +21,7 @@ from dots_socp_b200 import synth  # noqa: E402
 import refshim  # noqa: E402
 
 STATE = ("phi", "A", "B", "lambda_c", "mu", "E", "z_fst", "z_mid", "z_end", "beta_fst", "beta_mid", "beta_end")
-SCALARS = ("r", "scale_factor_z", "constant_d")
+SCALARS = ("r", "scale_factor_z", "constant_d", "prim_scale", "dual_scale", "congestion", "norm_constant_d", "norm_boundary")
 
 
 def run_reference(geo, n_time, snap_its=(), **kw):
@@ -84,6 +84,10 @@ CASES = {
     "knots5class_nt127_c0": ("knot", {}, 127, dict(tol=1e-3, nit=2000), (), False),
     # >= 10k vertices: fronts beyond the small-front factorisation kernel and split sweep items (round 2; ~10 min of reference time)
     "ico5_nt31_c0": ("icosphere5", {}, 31, dict(tol=1e-3, nit=1000), (), False),
+    # is_constant_scaling=True (solver-only knob, solver_socp.py:324-365, 574-587, 657-659): initial primal / dual scaling
+    # and re-scaling at iterations 10, 50, 150, ...; snapshots around the scaling iterations
+    "ico2_nt7_cscale": ("icosphere2", {}, 7, dict(tol=1e-3, nit=1000, congestion=0.05, is_constant_scaling=1.0), (0, 9, 10, 49, 50, 51), True),
+    "ico3_nt15_cscale_c0": ("icosphere3", {}, 15, dict(tol=1e-3, nit=1000, is_constant_scaling=1.0), (0, 10), False),
 }
 
 

@@ -41,26 +41,22 @@ def emulate(sym, plan, panels, panels_t, rhs):
         else:
             upd[t["ubase"] + o - t["s"]] = -acc
 
-    def run(t, forward):                                                   # k_ring_run
+    def run(t, forward):                                                   # k_ring_run: the per-entry codes drive everything
         src = panels if forward else panels_t
-        s, b = int(t["s"]), int(t["b"])
-        o = int(t["oa"])
-        lo = (lambda o: 0) if forward else (lambda o: o)
-        hi = (lambda o: min(o + 1, s)) if forward else (lambda o: s + b)
-        x, acc = lo(o), np.zeros(M)
+        codes = plan["erow_fwd"] if forward else plan["erow_bwd"]
+        o, acc = int(t["oa"]), np.zeros(M)
         for e in range(int(t["n_ent"])):
-            row = t["off"] + x if forward else plan["bidx"][t["fbase"] + x]
-            acc = acc + src[t["pbase"] + e] * z[row]
-            x += 1
-            if x == hi(o):
+            code = int(codes[t["pbase"] + e])
+            acc = acc + src[t["pbase"] + e] * z[code & 0x7fffffff]
+            if code < 0:
                 flush(t, o, acc, forward)
                 acc = np.zeros(M)
                 o += 1
-                x = lo(o)
-        assert o == t["oa"] + t["n_out"] and x == lo(o), "task does not end on an output boundary"
+        assert o == t["oa"] + t["n_out"], "task does not end on an output boundary"
 
     def split(t, forward, wpr):                                            # k_ring_split
         src = panels if forward else panels_t
+        codes = plan["erow_fwd"] if forward else plan["erow_bwd"]
         s, b = int(t["s"]), int(t["b"])
         for o in range(int(t["oa"]), int(t["oa"] + t["n_out"])):
             lo, hi = (0, min(o + 1, s)) if forward else (o, s + b)
@@ -71,8 +67,8 @@ def emulate(sym, plan, panels, panels_t, rhs):
                 xa, xb = lo + w * plen, min(hi, lo + (w + 1) * plen)
                 part = np.zeros(M)
                 for x in range(xa, xb):
-                    row = t["off"] + x if forward else plan["bidx"][t["fbase"] + x]
-                    part = part + src[t["pbase"] + base + (x - lo)] * z[row]
+                    ent = t["pbase"] + base + (x - lo)
+                    part = part + src[ent] * z[int(codes[ent]) & 0x7fffffff]
                 total = total + part
             flush(t, o, total, forward)
 

@@ -57,6 +57,10 @@ class OracleEngine:
         self.z_valid = bool(write_z)
         self.calls.append(bool(write_z))
 
+    def prefetch_sums(self, conditions):                 # the CUDA engine batches these reductions; nothing to do here
+        if 1 in set(conditions):
+            assert self.z_valid, "KKT #1 prefetched on an iteration that did not store z_mid"
+
     def kkt(self, i):
         if i == 1:
             assert self.z_valid, "KKT #1 requested on an iteration that did not store z_mid"

@@ -162,6 +162,7 @@ def test_ring_plan_reproduces_the_sparse_solve(example, leaf, m_pad, n_sm, kw):
     shifts = np.array([0.7, 31.0, 900.0])
     panels = hm.factor_batched(sym, K, mass, shifts)
     plan = ring_plan.build(sym, n_sm, m_pad, **kw)
+    plan["erow_fwd"], plan["erow_bwd"] = ring_plan.entry_rows_numpy(sym, plan["bidx"])
     rng = np.random.default_rng(11)
     rhs = rng.standard_normal((sym.n, shifts.size))
     x = emulate(sym, plan, panels, transpose_panels(sym, panels), rhs)
@@ -169,3 +170,19 @@ def test_ring_plan_reproduces_the_sparse_solve(example, leaf, m_pad, n_sm, kw):
     for m, sh in enumerate(shifts):
         ref = -spla.spsolve(Kp + sh * sp.diags(mass[sym.perm]), rhs[:, m])
         assert np.abs(x[:, m] - ref).max() <= 1e-10 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("example,leaf", [("icosphere3", 8), ("knot", 16), ("plane8", 6)])
+def test_entry_rows_native_equals_numpy_statement(example, leaf):
+    """dots_ring_entry_rows (C++) == ring_plan.entry_rows_numpy: operand row of every panel entry in both streaming orders,
+    with the end-of-output flag on exactly one entry per output."""
+    from dots_socp_b200 import capi
+    sym = _sym(example, leaf)
+    plan = ring_plan.build(sym, 148, 64)
+    ef, eb = ring_plan.entry_rows(capi.load(), sym, plan["bidx"])
+    rf, rb = ring_plan.entry_rows_numpy(sym, plan["bidx"])
+    assert np.array_equal(ef, rf) and np.array_equal(eb, rb)
+    live = sym.s > 0
+    assert int((ef[:sym.panel_entries] < 0).sum()) == int((sym.s + sym.b)[live].sum())      # one flag per panel row
+    assert int((eb[:sym.panel_entries] < 0).sum()) == int(sym.s[live].sum())                # one flag per panel column
+    assert (ef & 0x7fffffff).max() < sym.n and (eb & 0x7fffffff).max() < 2 * sym.n
