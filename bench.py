@@ -239,9 +239,18 @@ def run_reference(args):
 
 
 PARITY_RECORD = os.path.join(ROOT, "profiles", "r2_parity_record.json")
-SECONDARY = {   # workload -> iterations to tol 1e-3 of the unmodified reference (tests/golden/knots5class_*.npz); None: no reference run
-    "knots5class_nt31": 741, "knots5class_nt31_c01": 208, "knots5class_nt63": 678, "knots5class_nt127": 614,
+SECONDARY = {   # workload -> fixture written by the unmodified reference (tests/golden/make_golden.py); None: no reference run
+    "knots5class_nt31": "knots5class_nt31_c0", "knots5class_nt31_c01": "knots5class_nt31_c01",
+    "knots5class_nt63": "knots5class_nt63_c0", "knots5class_nt127": "knots5class_nt127_c0",
     "icosphere6_nt63": None}     # the size the reference arm falls back to when the host cannot hold the level-7 factors
+
+
+def reference_iterations(fixture):
+    """Number of ALM iterations of the unmodified reference (its log prints the last 0-based index: +1)."""
+    if fixture is None:
+        return None
+    z = np.load(os.path.join(ROOT, "tests", "golden", fixture + ".npz"), allow_pickle=False)
+    return int(z["iterations"]) + 1
 
 
 def parity_block(eng, workload, world):
@@ -290,7 +299,8 @@ def secondary_block(args):
     from dots_socp_b200 import synth
     out = {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    for name, want in SECONDARY.items():
+    for name, fixture in SECONDARY.items():
+        want = reference_iterations(fixture)
         ex, n_time, cong, _ = WORKLOADS[name]
         geo, _ = synth.example(ex)
         sol, hist, eng = b200.solver(n_time, geo, congestion=cong, tol=1e-3, nit=3000, return_engine=True, leaf_size=args.leaf)

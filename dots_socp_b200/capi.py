@@ -10,7 +10,7 @@ import os
 from . import build as _build
 
 ABI_VERSION = 11
-P_R, P_S, P_D, P_CONG, P_TAU, P_EPS, P_COUNT = 0, 1, 2, 3, 4, 5, 8
+P_R, P_S, P_D, P_CONG, P_TAU, P_EPS, P_PS, P_DS, P_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 _i32p, _i64p, _f64p = C.c_void_p, C.c_void_p, C.c_void_p      # raw device/host addresses
 
@@ -80,9 +80,9 @@ def load(build_if_missing: bool = True):
         raise DotsError(f"dots_ctx_t size mismatch: library {lib.dots_ctx_sizeof()} binding {C.sizeof(DotsCtx)}")
     ctxp, vp, i, d = C.POINTER(DotsCtx), C.c_void_p, C.c_int, C.c_double
     protos = {
-        "dots_step_phi": (ctxp, vp), "dots_step_vertex": (ctxp, vp), "dots_step_tri": (ctxp, i, vp),
+        "dots_step_phi": (ctxp, vp), "dots_step_vertex": (ctxp, vp), "dots_step_q0": (ctxp, vp), "dots_step_tri": (ctxp, i, vp),
         "dots_iterate": (ctxp, i, i, vp), "dots_refresh_corner_terms": (ctxp, vp),
-        "dots_scale_dual": (ctxp, d, vp), "dots_scale_z": (ctxp, d, vp), "dots_set_params": (ctxp, vp, vp),
+        "dots_scale_dual": (ctxp, d, vp), "dots_scale_z": (ctxp, d, vp), "dots_scale_prim_dual": (ctxp, d, d, vp), "dots_set_params": (ctxp, vp, vp),
         "dots_kkt_sums": (ctxp, i, vp, vp), "dots_kkt_sums_multi": (ctxp, C.c_uint, vp, vp), "dots_phi_rhs": (ctxp, vp), "dots_time_transform": (ctxp, i, vp),
         "dots_mode_solves": (ctxp, vp), "dots_grad_space": (ctxp, vp, vp, vp), "dots_div_space": (ctxp, vp, vp, vp),
         "dots_graph_create": (ctxp, i, vp, C.POINTER(vp)), "dots_graph_launch": (vp, vp), "dots_graph_destroy": (vp,),
@@ -104,7 +104,7 @@ def load(build_if_missing: bool = True):
 
 
 EXPORTS = ("dots_abi_version", "dots_ctx_sizeof", "dots_last_error", "dots_step_phi", "dots_step_vertex",
-           "dots_step_tri", "dots_iterate", "dots_refresh_corner_terms", "dots_scale_dual", "dots_scale_z",
+           "dots_step_tri", "dots_step_q0", "dots_iterate", "dots_refresh_corner_terms", "dots_scale_dual", "dots_scale_z", "dots_scale_prim_dual",
            "dots_set_params", "dots_kkt_sums", "dots_kkt_sums_multi", "dots_phi_rhs", "dots_time_transform", "dots_mode_solves",
            "dots_grad_space", "dots_div_space", "dots_graph_create", "dots_graph_launch", "dots_graph_destroy",
            "dots_factor_small_fronts", "dots_front_nmax", "dots_enable_peer", "dots_ipc_export", "dots_ipc_import",

@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(256) k_vertex(dots_ctx_t c)
 
 // ------------------------------------------------------------------------------------------------
 // MODE 0: full step.  MODE 1: full step + store z_mid.  MODE 2: only recompute corner_nrm / corner_div.
+// MODE 3: the triangle half of the is_palm Step 0 (solver_socp.py:668-672 = vanilla_solve_q_lambda :1044-1065 with the
+//         STORED z_mid): B = (dx_phi + E + adj(z_mid + b_mid)) / diag_b, then the corner terms of the new B (E, b_mid unchanged).
 // One thread owns triangle f for TRI_TCH consecutive time levels, so the mesh constants (hat gradients, cone
 // diagonal, vertex ids) are loaded once per chunk and lam[tau] is reused as lam[tau-1] of the next level.
 // beta_mid is streamed twice per level from the same thread (second time out of L1) instead of being held in
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(128, 4) k_tri(dots_ctx_t c)
     double lam_prev[3] = {0.0, 0.0, 0.0};
     if (MODE != 2) {
         vk[0] = c.tri[f]; vk[1] = c.tri[T + f]; vk[2] = c.tri[2 * T + f];
-        if (tau_begin > 0) {
+        if (MODE != 3 && tau_begin > 0) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) lam_prev[k] = c.lam[(size_t)(tau_begin - 1) * V + vk[k]];
         }
@@ -155,6 +157,26 @@ __global__ void __launch_bounds__(128, 4) k_tri(dots_ctx_t c)
         if (MODE == 2) {
 #pragma unroll
             for (int x = 0; x < 3; ++x) { Bn[x] = Bp[x * T]; En[x] = Ep[x * T]; }
+        } else if (MODE == 3) {
+            const double *ph = c.phi + (size_t)tau * V;
+            const double p0 = ph[vk[0]], p1 = ph[vk[1]], p2 = ph[vk[2]];
+            const double *zq = c.z_mid + (size_t)tau * 18 * T + f;
+            const double db = (tau == 0 || tau == nT) ? (1.0 + s * s) : (1.0 + (2.0 * s * s));    // :195-197
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                const double dx = g[0][x] * p0 + g[1][x] * p1 + g[2][x] * p2;                 // :902-906
+                double adj = 0.0;
+                if (has0) adj = cs * (((zq[(0 * 3 + x) * T] + bm[(0 * 3 + x) * T]) + (zq[(1 * 3 + x) * T] + bm[(1 * 3 + x) * T]))
+                                      + (zq[(2 * 3 + x) * T] + bm[(2 * 3 + x) * T]));          // :1052, :953
+                if (has1) {
+                    const double s1 = cs * (((zq[(9 + 0 * 3 + x) * T] + bm[(9 + 0 * 3 + x) * T]) + (zq[(9 + 1 * 3 + x) * T] + bm[(9 + 1 * 3 + x) * T]))
+                                            + (zq[(9 + 2 * 3 + x) * T] + bm[(9 + 2 * 3 + x) * T]));
+                    adj = has0 ? adj + s1 : s1;                                               // :955-957
+                }
+                En[x] = Ep[x * T];
+                Bn[x] = (dx + En[x] + adj) / db;                                              // :1064
+                Bp[x * T] = Bn[x];
+            }
         } else {
             const double *ph = c.phi + (size_t)tau * V;
             const double p0 = ph[vk[0]], p1 = ph[vk[1]], p2 = ph[vk[2]];
@@ -214,7 +236,7 @@ __global__ void __launch_bounds__(128, 4) k_tri(dots_ctx_t c)
 #pragma unroll
                     for (int x = 0; x < 3; ++x) {
                         double b = bm[((sd * 3 + k) * 3 + x) * T];
-                        if (MODE != 2) {
+                        if (MODE == 0 || MODE == 1) {
                             const double zz = lt * (dg[k] * (bs[x] - b));                     // same arithmetic as pass one
                             b = b + step * (zz - cs * Bn[x]);                                 // :717, :721
                             bm[((sd * 3 + k) * 3 + x) * T] = b;
@@ -409,6 +431,28 @@ __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c)
 }
 
 // ------------------------------------------------------------------------------------------------
+// is_palm Step 0, vertex half (solver_socp.py:668-672): A, lam_c from the gradient of the CURRENT phi and the current
+// z, beta, mu (vanilla_solve_q_lambda :1049-1065).
+__global__ void __launch_bounds__(256) k_palm_vertex(dots_ctx_t c)
+{
+    const int V = c.n_vert, nT = c.n_time;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = c.lvl_begin + blockIdx.y;
+    if (v >= V) return;
+    const double *prm = c.params;
+    const double r = prm[DOTS_P_R], s = prm[DOTS_P_S], cong = prm[DOTS_P_CONG];
+    const double dt = 1.0 / nT;
+    const size_t i = (size_t)t * V + v;
+    const double dtphi = (c.phi[i + V] - c.phi[i]) / dt;                                      // :884
+    const double c1 = s * (1.0 + cong * r);                                                   // :1049
+    const double c2 = 1.0 + 2.0 * s * c1;                                                     // :1050
+    const double memo_a = dtphi + c.mu[i];                                                    // :1051
+    const double An = (1.0 / c2) * memo_a + (c1 / c2) * (c.z_end[i] + c.b_end[i] - c.z_fst[i] - c.b_fst[i]);   // :1062
+    c.A[i] = An;
+    c.lam_c[i] = (cong * r / (1. + cong * r)) * (memo_a - An);                                // :1065
+}
+
+// ------------------------------------------------------------------------------------------------
 // rescaling helpers (row a12)
 __global__ void k_div_scalar(double *__restrict__ a, size_t n, double f)
 {
@@ -519,6 +563,21 @@ extern "C" int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream)
     return 0;
 }
 
+extern "C" int dots_step_q0(const dots_ctx_t *c, void *stream)
+{
+    if (int e = dots_check_ctx(c)) return e;
+    if (c->n_ranks != 1) { dots_set_error("dots_step_q0 (is_palm) is single-GPU"); return DOTS_ERR_BAD_ARG; }
+    if (dots_t_end(c) > c->lvl_begin) {
+        dim3 gv(ceil_div(c->n_vert, 256), dots_t_end(c) - c->lvl_begin);
+        k_palm_vertex<<<gv, 256, 0, (cudaStream_t)stream>>>(*c);
+        DOTS_LAUNCH_CHECK();
+    }
+    dim3 grid(ceil_div(c->n_tri, 128), ceil_div(c->lvl_end - c->lvl_begin, TRI_TCH));
+    k_tri<3><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int dots_refresh_corner_terms(const dots_ctx_t *c, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
@@ -590,6 +649,33 @@ extern "C" int dots_scale_z(const dots_ctx_t *c, double s_cum, void *stream)
     k_E_from_beta<<<grid, 128, 0, st>>>(*c, s_cum);
     DOTS_LAUNCH_CHECK();
     return 0;   // caller sets params (s, d) and then calls dots_refresh_corner_terms
+}
+
+extern "C" int dots_scale_prim_dual(const dots_ctx_t *c, double prim_div, double dual_div, void *stream)
+{
+    if (int e = dots_check_ctx(c)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t V = c->n_vert, T = c->n_tri;
+    const long long l0 = c->lvl_begin;
+    const size_t nl = c->lvl_end - c->lvl_begin, nt = dots_t_end(c) - c->lvl_begin;
+    int e;
+    // primal variables (:347-349); A, lam_c, lam carry a halo step in front (t = lvl_begin-1), phi a halo level behind
+    if ((e = launch_div(c->phi + l0 * (long long)V, (nl + 1) * V, prim_div, c->n_sm, st))) return e;
+    if ((e = launch_div(c->A + (l0 - 1) * (long long)V, (nt + 1) * V, prim_div, c->n_sm, st))) return e;
+    if ((e = launch_div(c->lam_c + (l0 - 1) * (long long)V, (nt + 1) * V, prim_div, c->n_sm, st))) return e;
+    if ((e = launch_div(c->B + l0 * 3 * (long long)T, nl * 3 * T, prim_div, c->n_sm, st))) return e;
+    if ((e = launch_div(c->z_fst + l0 * (long long)V, nt * V, prim_div, c->n_sm, st))) return e;
+    if ((e = launch_div(c->z_mid + l0 * 18 * (long long)T, nl * 18 * T, prim_div, c->n_sm, st))) return e;
+    if ((e = launch_div(c->z_end + l0 * (long long)V, nt * V, prim_div, c->n_sm, st))) return e;
+    // dual variables (:352-354)
+    if ((e = launch_div(c->mu + (l0 - 1) * (long long)V, (nt + 1) * V, dual_div, c->n_sm, st))) return e;
+    if ((e = launch_div(c->E + l0 * 3 * (long long)T, nl * 3 * T, dual_div, c->n_sm, st))) return e;
+    if ((e = launch_div(c->bnd0, V, dual_div, c->n_sm, st))) return e;
+    if ((e = launch_div(c->bnd1, V, dual_div, c->n_sm, st))) return e;
+    if ((e = launch_div(c->b_fst + l0 * (long long)V, nt * V, dual_div, c->n_sm, st))) return e;
+    if ((e = launch_div(c->b_mid + l0 * 18 * (long long)T, nl * 18 * T, dual_div, c->n_sm, st))) return e;
+    if ((e = launch_div(c->b_end + l0 * (long long)V, nt * V, dual_div, c->n_sm, st))) return e;
+    return dots_refresh_corner_terms(c, stream);
 }
 
 extern "C" int dots_set_params(const dots_ctx_t *c, const double *host_params, void *stream)

@@ -71,12 +71,14 @@ extern "C" int dots_ipc_import(const void *handle_64, unsigned long long offset,
 }
 
 #define KKT_THREADS 256
-#define KKT_CONDS 8            // 7 KKT conditions + the objective (which = 7)
+#define KKT_CONDS 9            // 7 KKT conditions + the objective (7) + the variable norms of scale_prim_dual (8)
 
 // ---- vertex-side terms of condition W at (t, v): acc[0..3] += ...  (slots 0..3 of the condition's row) ---------------
+// ps / ds: prim_scale / dual_scale (1 unless is_constant_scaling): conditions 4-6 and the objective are formed from the
+// UN-scaled variables (dual_scale r) mu, prim_scale A, ... (solver_socp.py:617-637, :829-831)
 template <int W>
 __device__ __forceinline__ void kkt_vertex_terms(const dots_ctx_t &c, size_t i, int t, int v, double av, double r, double s, double d,
-                                                 double cong, double dt, double (&acc)[4])
+                                                 double cong, double dt, double ps, double ds, double (&acc)[4])
 {
     const int V = c.n_vert, nT = c.n_time;
     const size_t T = (size_t)c.n_tri;
@@ -121,33 +123,36 @@ __device__ __forceinline__ void kkt_vertex_terms(const dots_ctx_t &c, size_t i, 
             const size_t k = cid / T, f = cid - k * T;
             double sq = 0.0;
 #pragma unroll
-            for (int x = 0; x < 3; ++x) { const double a = c3 * B0[x * T + f]; sq += a * a; }
+            for (int x = 0; x < 3; ++x) { const double a = c3 * (ps * B0[x * T + f]); sq += a * a; }
 #pragma unroll
-            for (int x = 0; x < 3; ++x) { const double a = c3 * B1[x * T + f]; sq += a * a; }
+            for (int x = 0; x < 3; ++x) { const double a = c3 * (ps * B1[x * T + f]); sq += a * a; }
             q += c.area_f[f] * sq;
         }
-        const double rho = r * c.mu[i];
-        const double aux = c.A[i] + .25 * (q / av);
+        const double rho = (ds * r) * c.mu[i];
+        const double aux = ps * c.A[i] + .25 * (q / av);
         double pos = aux + rho;
         pos = (pos < 0.) ? 0. : pos;                                       // np.maximum(0., .) keeps NaN
         const double res = pos - rho;
         acc[0] += rho * rho * av; acc[1] += aux * aux * av; acc[2] += res * res * av;
     } else if (W == 6) {                                                   // Comp(rho, cong.) :549-559
-        const double rho = r * c.mu[i], lc = c.lam_c[i];
+        const double rho = (ds * r) * c.mu[i], lc = ps * c.lam_c[i];
         const double res = cong * rho - lc;
         acc[0] += rho * rho * av; acc[1] += lc * lc * av; acc[2] += res * res * av;
     } else if (W == 7) {                                                   // objective :417-431
-        if (t == 0) acc[0] += c.phi[v] * (r * c.bnd0[v]);
-        if (t == nT - 1) acc[1] += c.phi[(size_t)nT * V + v] * (r * c.bnd1[v]);
-        const double lc = c.lam_c[i];
+        if (t == 0) acc[0] += (ps * c.phi[v]) * ((ds * r) * c.bnd0[v]);
+        if (t == nT - 1) acc[1] += (ps * c.phi[(size_t)nT * V + v]) * ((ds * r) * c.bnd1[v]);
+        const double lc = ps * c.lam_c[i];
         acc[2] += lc * lc * av;
+    } else if (W == 8) {                                                   // variable norms of scale_prim_dual :331-340
+        const double zf = c.z_fst[i], ze = c.z_end[i], bf = c.b_fst[i], be = c.b_end[i];
+        acc[0] += zf * zf * av; acc[1] += ze * ze * av; acc[2] += bf * bf * av; acc[3] += be * be * av;
     }
 }
 
 // ---- triangle-side terms of condition W at (tau, f): slots 4..7 of the condition's row ------------------------------
 template <int W>
 __device__ __forceinline__ void kkt_tri_terms(const dots_ctx_t &c, int tau, size_t f, double af, double r, double s, double cs,
-                                              double (&acc)[4])
+                                              double ps, double ds, double (&acc)[4])
 {
     const int V = c.n_vert, nT = c.n_time;
     const size_t T = (size_t)c.n_tri;
@@ -193,15 +198,24 @@ __device__ __forceinline__ void kkt_tri_terms(const dots_ctx_t &c, int tau, size
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const int v = c.tri[k * T + f];
-            const double cur = (tau < nT) ? r * c.mu[(size_t)tau * V + v] : 0.0;
-            const double prv = (tau > 0) ? r * c.mu[(size_t)(tau - 1) * V + v] : 0.0;
+            const double cur = (tau < nT) ? (ds * r) * c.mu[(size_t)tau * V + v] : 0.0;
+            const double prv = (tau > 0) ? (ds * r) * c.mu[(size_t)(tau - 1) * V + v] : 0.0;
             avg += (1.0 / 3.0) * (0.5 * cur + 0.5 * prv);                  // :961-974, :163-166
         }
         const double *Ep = c.E + (size_t)tau * 3 * T + f;
 #pragma unroll
         for (int x = 0; x < 3; ++x) {
-            const double m = r * Ep[x * T], aux = avg * Bp[x * T], res = aux - m;
+            const double m = (ds * r) * Ep[x * T], aux = avg * (ps * Bp[x * T]), res = aux - m;
             acc[0] += m * m * af; acc[1] += aux * aux * af; acc[2] += res * res * af;
+        }
+    } else if (W == 8) {                                                   // ||z_mid||^2_dec, ||b_mid||^2_dec (absent side slots are zero)
+        const double *zm = c.z_mid + (size_t)tau * 18 * T + f;
+        const double *bm = c.b_mid + (size_t)tau * 18 * T + f;
+#pragma unroll
+        for (int p = 0; p < 18; ++p) {
+            if (p < 9 ? tau >= nT : tau <= 0) continue;
+            const double zz = zm[p * T], bb = bm[p * T];
+            acc[0] += zz * zz * af; acc[1] += bb * bb * af;
         }
     }
 }
@@ -234,6 +248,7 @@ __global__ void __launch_bounds__(KKT_THREADS) k_kkt_vertex(dots_ctx_t c, unsign
     const int V = c.n_vert, nT = c.n_time;
     const double *prm = c.params;
     const double r = prm[DOTS_P_R], s = prm[DOTS_P_S], d = prm[DOTS_P_D], cong = prm[DOTS_P_CONG];
+    const double ps = prm[DOTS_P_PS], ds = prm[DOTS_P_DS];
     const double dt = 1.0 / nT;
     double acc[KKT_CONDS][4];
 #pragma unroll
@@ -246,22 +261,23 @@ __global__ void __launch_bounds__(KKT_THREADS) k_kkt_vertex(dots_ctx_t c, unsign
     for (size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int t = (int)(i / V), v = (int)(i - (size_t)t * V);
         const double av = c.area_v[v];
-        if (mask & 1u) kkt_vertex_terms<0>(c, i, t, v, av, r, s, d, cong, dt, acc[0]);
-        if (mask & 2u) kkt_vertex_terms<1>(c, i, t, v, av, r, s, d, cong, dt, acc[1]);
-        if (mask & 4u) kkt_vertex_terms<2>(c, i, t, v, av, r, s, d, cong, dt, acc[2]);
-        if (mask & 8u) kkt_vertex_terms<3>(c, i, t, v, av, r, s, d, cong, dt, acc[3]);
-        if (mask & 16u) kkt_vertex_terms<4>(c, i, t, v, av, r, s, d, cong, dt, acc[4]);
-        if (mask & 64u) kkt_vertex_terms<6>(c, i, t, v, av, r, s, d, cong, dt, acc[6]);
-        if (mask & 128u) kkt_vertex_terms<7>(c, i, t, v, av, r, s, d, cong, dt, acc[7]);
+        if (mask & 1u) kkt_vertex_terms<0>(c, i, t, v, av, r, s, d, cong, dt, ps, ds, acc[0]);
+        if (mask & 2u) kkt_vertex_terms<1>(c, i, t, v, av, r, s, d, cong, dt, ps, ds, acc[1]);
+        if (mask & 4u) kkt_vertex_terms<2>(c, i, t, v, av, r, s, d, cong, dt, ps, ds, acc[2]);
+        if (mask & 8u) kkt_vertex_terms<3>(c, i, t, v, av, r, s, d, cong, dt, ps, ds, acc[3]);
+        if (mask & 16u) kkt_vertex_terms<4>(c, i, t, v, av, r, s, d, cong, dt, ps, ds, acc[4]);
+        if (mask & 64u) kkt_vertex_terms<6>(c, i, t, v, av, r, s, d, cong, dt, ps, ds, acc[6]);
+        if (mask & 128u) kkt_vertex_terms<7>(c, i, t, v, av, r, s, d, cong, dt, ps, ds, acc[7]);
+        if (mask & 256u) kkt_vertex_terms<8>(c, i, t, v, av, r, s, d, cong, dt, ps, ds, acc[8]);
     }
-    kkt_block_store(acc, mask & 0xdfu, c.red_part, 0);
+    kkt_block_store(acc, mask & 0x1dfu, c.red_part, 0);
 }
 
 __global__ void __launch_bounds__(KKT_THREADS) k_kkt_tri(dots_ctx_t c, unsigned mask)
 {
     const size_t T = (size_t)c.n_tri;
     const double *prm = c.params;
-    const double r = prm[DOTS_P_R], s = prm[DOTS_P_S];
+    const double r = prm[DOTS_P_R], s = prm[DOTS_P_S], ps = prm[DOTS_P_PS], ds = prm[DOTS_P_DS];
     const double cs = s / sqrt(3.0);
     double acc[KKT_CONDS][4];
 #pragma unroll
@@ -273,12 +289,13 @@ __global__ void __launch_bounds__(KKT_THREADS) k_kkt_tri(dots_ctx_t c, unsigned 
         const int tau = (int)(i / T);
         const size_t f = i - (size_t)tau * T;
         const double af = c.area_f[f];
-        if (mask & 1u) kkt_tri_terms<0>(c, tau, f, af, r, s, cs, acc[0]);
-        if (mask & 2u) kkt_tri_terms<1>(c, tau, f, af, r, s, cs, acc[1]);
-        if (mask & 8u) kkt_tri_terms<3>(c, tau, f, af, r, s, cs, acc[3]);
-        if (mask & 32u) kkt_tri_terms<5>(c, tau, f, af, r, s, cs, acc[5]);
+        if (mask & 1u) kkt_tri_terms<0>(c, tau, f, af, r, s, cs, ps, ds, acc[0]);
+        if (mask & 2u) kkt_tri_terms<1>(c, tau, f, af, r, s, cs, ps, ds, acc[1]);
+        if (mask & 8u) kkt_tri_terms<3>(c, tau, f, af, r, s, cs, ps, ds, acc[3]);
+        if (mask & 32u) kkt_tri_terms<5>(c, tau, f, af, r, s, cs, ps, ds, acc[5]);
+        if (mask & 256u) kkt_tri_terms<8>(c, tau, f, af, r, s, cs, ps, ds, acc[8]);
     }
-    kkt_block_store(acc, mask & 0x2bu, c.red_part, 4);
+    kkt_block_store(acc, mask & 0x12bu, c.red_part, 4);
 }
 
 // one warp per (condition, slot) pair, 8 pairs per block; fixed order over blocks
@@ -295,12 +312,12 @@ __global__ void k_reduce_final(const double *__restrict__ part, int nblocks, dou
 extern "C" int dots_kkt_sums_multi(const dots_ctx_t *c, unsigned mask, double *host_out, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
-    if (!mask || mask > 0xffu) { dots_set_error("kkt mask %u out of range", mask); return DOTS_ERR_BAD_ARG; }
+    if (!mask || mask > 0x1ffu) { dots_set_error("kkt mask %u out of range", mask); return DOTS_ERR_BAD_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = c->red_blocks;
     DOTS_CUDA(cudaMemsetAsync(c->red_part, 0, sizeof(double) * KKT_CONDS * 8 * nb, st));
-    if (mask & 0xdfu) { k_kkt_vertex<<<nb, KKT_THREADS, 0, st>>>(*c, mask); DOTS_LAUNCH_CHECK(); }
-    if (mask & 0x2bu) { k_kkt_tri<<<nb, KKT_THREADS, 0, st>>>(*c, mask); DOTS_LAUNCH_CHECK(); }
+    if (mask & 0x1dfu) { k_kkt_vertex<<<nb, KKT_THREADS, 0, st>>>(*c, mask); DOTS_LAUNCH_CHECK(); }
+    if (mask & 0x12bu) { k_kkt_tri<<<nb, KKT_THREADS, 0, st>>>(*c, mask); DOTS_LAUNCH_CHECK(); }
     k_reduce_final<<<KKT_CONDS, 256, 0, st>>>(c->red_part, nb, c->red_out);
     DOTS_LAUNCH_CHECK();
     DOTS_CUDA(cudaMemcpyAsync(host_out, c->red_out, sizeof(double) * KKT_CONDS * 8, cudaMemcpyDeviceToHost, st));

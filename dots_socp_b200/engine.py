@@ -175,6 +175,7 @@ class Engine:
         self.n_sm = props.multi_processor_count
         area_f_n, area_v_n = area_f[self.perm_f], area_v[self.perm_v]
         self.area_f_new, self.area_v_new = area_f_n, area_v_n
+        self._host_mesh = dict(tri=tri_new, hat=hat[self.perm_f])                        # internal numbering, (T,3) / (T,3,3)
         hat_n = hat[self.perm_f]                                                         # (T,3,3)
         diag = np.sqrt(area_f_n[None, :] / area_v_n[tri_new.T])                          # (3,T)  solver_socp.py:172-180
         vc_ptr, vc_tri, vc_corner = surface.corner_adjacency(V, tri_new)
@@ -260,13 +261,13 @@ class Engine:
         self.t = dict(params=z(capi.P_COUNT), bnd0=z(V), bnd1=z(V), rhs=z(part.world * part.chunk, V),
                       hat=hat_local, hat_all=hat_local if part.world == 1 else z(part.world, V, self.m_pad),
                       ywork=z_all[V:], upd=z(max(1, int(sym.upd_off[-1])), self.m_pad),
-                      red_part=z(self.red_blocks, 64), red_out=z(64))
+                      red_part=z(self.red_blocks, 72), red_out=z(72))
         for k, ten in self.t.items():
             setattr(ctx, k, ten.data_ptr())
         ctx.red_blocks = self.red_blocks
         self.ctx = ctx
         self._ctxp = C.byref(ctx)
-        self._host_out = np.zeros(64)
+        self._host_out = np.zeros(72)
         self._sum_cache = {}                             # condition -> raw sums of the CURRENT state (prefetch_sums)
         self._host_params = np.zeros(capi.P_COUNT)
         self._halo_v = z(4, V)
@@ -274,6 +275,8 @@ class Engine:
 
         # ---- scalars of the reference driver (:97, :267-270, :296-313, :318-321) ------------------
         self.r, self.s, self.d = 1.0, 1.0, 1.0
+        self.ps, self.ds = 1.0, 1.0                      # prim_scale, dual_scale (:318-319; change only under is_constant_scaling)
+        self.cong0 = self.cong                           # the caller's congestion (self.cong is rescaled with the variables)
         mu0 = np.asarray(geometry["mu0"], dtype=np.float64)[self.perm_v]
         mu1 = np.asarray(geometry["mu1"], dtype=np.float64)[self.perm_v]
         b0, b1 = -mu0 / (self.r * self.dt), mu1 / (self.r * self.dt)
@@ -282,6 +285,8 @@ class Engine:
         self._bnd_init = (self.t["bnd0"].clone(), self.t["bnd1"].clone())
         self.norm_bnd = self.r * self.dt * math.sqrt((np.sum((b0 / area_v_n) ** 2 * area_v_n)
                                                       + np.sum((b1 / area_v_n) ** 2 * area_v_n)) / (nT + 1))
+        self._norm_bnd_init = self.norm_bnd
+        self._bnd_host = (b0, b1)
         self.area_mesh = float(np.sum(area_f))
         self.norm_d = math.sqrt(2 * self.area_mesh)
         ma_v, ma_f = float(np.mean(area_v)), float(np.mean(area_f))
@@ -315,6 +320,7 @@ class Engine:
         p = self._host_params
         p[capi.P_R], p[capi.P_S], p[capi.P_D] = self.r, self.s, self.d
         p[capi.P_CONG], p[capi.P_TAU], p[capi.P_EPS] = self.cong, self.tau, self.eps
+        p[capi.P_PS], p[capi.P_DS] = self.ps, self.ds
         capi.check(self.lib.dots_set_params(self._ctxp, p.ctypes.data, self.stream), "dots_set_params")
 
     def launches_per_iteration(self):
@@ -525,24 +531,14 @@ class Engine:
 
     def step_q0(self):
         """``is_palm=True`` only (solver_socp.py:668-672): the q / lambda solve that opens an iteration, from the gradients
-        of the current phi and the current z, beta, mu, E (``palm.q_lambda_step``), followed by a refresh of the corner
-        terms the fused kernels derive from (B, E, beta_mid).  Needs z_mid of the previous iteration (write_z=True)."""
-        from . import palm
+        of the current phi and the current z, beta, mu, E: two fused kernels (``dots_step_q0``: vertex half -> A, lam_c;
+        triangle half -> B and the corner terms of the new B).  Needs z_mid of the previous iteration (write_z=True)."""
         if self.comm.enabled:
             raise NotImplementedError("is_palm is not available on the sharded (multi-GPU) path")
         if not self.z_valid:
             raise capi.DotsError("is_palm needs z_mid of the previous iteration: call iterate(..., write_z=True)")
-        nT, sl = self.nT, self.slab
-        dx_phi = torch.empty((nT + 1, 3, self.T), dtype=torch.float64, device=self.device)
-        capi.check(self.lib.dots_grad_space(self._ctxp, sl["phi"].base_ptr, dx_phi.data_ptr(), self.stream), "dots_grad_space")
-        A, lam_c, B = palm.q_lambda_step(
-            self.dt, self.s, self.cong, self.r, sl["phi"].levels(0, nT + 1), dx_phi, sl["mu"].levels(0, nT),
-            sl["E"].levels(0, nT + 1), sl["z_fst"].levels(0, nT), sl["z_end"].levels(0, nT), sl["z_mid"].levels(0, nT + 1),
-            sl["b_fst"].levels(0, nT), sl["b_end"].levels(0, nT), sl["b_mid"].levels(0, nT + 1))
-        sl["A"].levels(0, nT).copy_(A)
-        sl["lam_c"].levels(0, nT).copy_(lam_c)
-        sl["B"].levels(0, nT + 1).copy_(B)
-        self.refresh()
+        self._state_changed()
+        capi.check(self.lib.dots_step_q0(self._ctxp, self.stream), "dots_step_q0")
         self.launches += 2
 
     def adjust_penalty(self, f):                                                         # :367-371
@@ -564,12 +560,71 @@ class Engine:
         self.refresh()
         self.launches += 8
 
+    # ------------------------------------------------------------------ is_constant_scaling (solver_socp.py:324-365, :574-587)
+    def variable_norms(self):
+        """The five norms scale_prim_dual compares (:329-340): ([prim x3], [dual x2]) of the scaled variables, from ONE fused
+        reduction pass (conditions 0 and 3 carry dt_phi, dx_phi, A, B, mu, E; slot 8 the z / beta norms).  Needs z_mid of the
+        current iteration."""
+        if not self.z_valid:
+            raise capi.DotsError("scale_prim_dual needs z_mid of the current iteration: call iterate(..., write_z=True)")
+        self.prefetch_sums((0, 3, 8))
+        c0, c3, c8 = self._sum_cache[0], self._sum_cache[3], self._sum_cache[8]
+        tn, sn, sq = 1.0 / self.nT, 1.0 / (self.nT + 1), math.sqrt
+        prim = [sq(c0[1] * tn + c0[5] * sn), sq(c0[2] * tn + c0[6] * sn), sq(c8[0] * tn + c8[4] * tn + c8[1] * tn)]
+        dual = [self.r * sq(c3[0] * tn + c3[4] * sn), self.r * sq(c8[2] * tn + c8[5] * tn + c8[3] * tn)]
+        return prim, dual
+
+    def scale_prim_dual(self, factors=None):
+        """scale_prim_dual (:324-365): rescale primal variables by 1/p and dual ones by p/d^2 when the two factors differ by
+        more than 2x; ``factors`` None = from the current variable norms (admm_tools.compute_scale_factor)."""
+        if factors is None:
+            prim, dual = self.variable_norms()
+            p, d = max(prim) / 1.0, max(dual) / 1.0
+        else:
+            p, d = float(factors[0]), float(factors[1])
+        if not max(p, d) / min(p, d) > 2.0:                                              # :344
+            return False
+        self._state_changed()
+        self.ps *= p
+        self.ds *= d
+        capi.check(self.lib.dots_scale_prim_dual(self._ctxp, p, d ** 2 / p, self.stream), "dots_scale_prim_dual")
+        self.r *= d / p
+        self.cong *= d / p
+        self.d /= p
+        self.norm_d /= p
+        self.norm_bnd /= d
+        self._push_params()
+        self.exchange_corner_halo()
+        self.launches += 15
+        return True
+
+    def initial_constant_scaling(self):
+        """The initial scaling of :574-587 (after the initial z scaling): factors from the boundary data, then r -> 1."""
+        nT, dt, sq = self.nT, self.dt, math.sqrt
+        av, af = self.area_v_new, self.area_f_new
+        tri, hat = self._host_mesh["tri"], self._host_mesh["hat"]
+        b0, b1 = (self.r * self._bnd_host[0]) / av, (self.r * self._bnd_host[1]) / av     # _boundary_time rows 0 and nT
+        norm_c = sq((np.sum(b0 ** 2 * av) + np.sum(b1 ** 2 * av)) / (nT + 1))
+        if nT == 1:
+            gt = np.sum(((b1 - b0) / dt) ** 2 * av)
+        else:
+            gt = np.sum((b0 / dt) ** 2 * av) + np.sum((b1 / dt) ** 2 * av)                 # rows 0 and nT-1 of grad_time
+        gs = 0.0
+        for bt in (b0, b1):
+            g = np.einsum("fkx,fk->fx", hat, bt[tri])                                     # vanilla_grad_space (:898-907)
+            gs += np.sum(g ** 2 * af[:, None])
+        norm_ac = sq(gt / nT + gs / (nT + 1))
+        self.scale_prim_dual((self.norm_d, sq(nT) * norm_c ** 2 / norm_ac))
+        self.adjust_penalty(1.0 / self.r)
+
     def reset_state(self):
         """Back to the state solver_socp starts from (socp/solver_socp.py:239-270: all arrays zero, r = 1, unscaled z)."""
         for st_ in self.slab.values():
             st_.data.zero_()
         self.r, self.s, self.d = 1.0, 1.0, 1.0
+        self.ps, self.ds, self.cong = 1.0, 1.0, self.cong0
         self.norm_d = math.sqrt(2 * self.area_mesh)
+        self.norm_bnd = self._norm_bnd_init
         self.t["bnd0"].copy_(self._bnd_init[0])
         self.t["bnd1"].copy_(self._bnd_init[1])
         self.z_valid = True
@@ -679,18 +734,18 @@ class Engine:
         tn, sn = 1.0 / nT, 1.0 / (nT + 1)
         if i == 0:                                                                       # :433-450
             norm_sum = sq(v[1] * tn + t[1] * sn) + sq(v[2] * tn + t[2] * sn) + sq(v[3] * tn)
-            val = sq(v[0] * tn + t[0] * sn) / (self.k_prim_q / 1.0 + norm_sum)
-            return [val, val]
+            res = sq(v[0] * tn + t[0] * sn)
+            return [res / (self.k_prim_q / self.ps + norm_sum), res / (self.k_prim_q / 1.0 + norm_sum)]
         if i == 1:                                                                       # :452-464
-            val = sq(v[0] * tn + v[1] * tn + t[0] * tn) / (self.k_prim_z / 1.0 + self.norm_d)
-            return [val, val]
+            res = sq(v[0] * tn + v[1] * tn + t[0] * tn)
+            return [res / (self.k_prim_z / self.ps + self.norm_d), res / (self.k_prim_z / 1.0 + self.norm_d)]
         if i == 2:                                                                       # :466-482
-            val = sq(v[0] * sn) / (self.k_dual_a / 1.0 + self.norm_bnd)
-            return [val, val]
+            res = sq(v[0] * sn)
+            return [res / (self.k_dual_a / self.ds + self.norm_bnd), res / (self.k_dual_a / 1.0 + self.norm_bnd)]
         if i == 3:                                                                       # :484-503
             norm_sum = self.r * (sq(v[0] * tn + t[0] * sn) + sq(v[1] * tn + t[1] * sn))
-            val = self.r * sq(v[2] * tn + t[2] * sn) / (self.k_dual_b / 1.0 + norm_sum)
-            return [val, val]
+            res = self.r * sq(v[2] * tn + t[2] * sn)
+            return [res / (self.k_dual_b / self.ds + norm_sum), res / (self.k_dual_b / 1.0 + norm_sum)]
         if i == 4:                                                                       # :505-526
             return [sq(v[2] * tn) / (self.k_comp_rho + sq(v[0] * tn) + sq(v[1] * tn)), None]
         if i == 5:                                                                       # :528-547
@@ -702,8 +757,9 @@ class Engine:
     def objective(self):                                                                 # :417-431
         o = self.sums(7)
         cost = self.dt * (o[0] + o[1])
-        if self.cong > 10 ** (-10):
-            return cost, cost - 1. / (2. * self.cong) * (o[2] / self.nT)
+        cong = self.cong * self.ps / self.ds                                             # :830
+        if cong > 10 ** (-10):
+            return cost, cost - 1. / (2. * cong) * (o[2] / self.nT)
         return cost, cost
 
     # ------------------------------------------------------------------ layout conversion (host <-> device)
@@ -792,12 +848,12 @@ class Engine:
         dev = self.device
         av = torch.as_tensor(np.asarray(geometry["area_vertices"], dtype=np.float64), device=dev)[None, :] / 3.0
         af = torch.as_tensor(np.asarray(geometry["area_triangles"], dtype=np.float64), device=dev)[None, :, None]
-        mu = (self.from_internal("mu") * self.r) * av
+        mu = (self.from_internal("mu") * (self.r * self.ds)) * av
         if centred:
             mu0 = torch.as_tensor(np.asarray(geometry["mu0"], dtype=np.float64), device=dev)[None, :]
             mu1 = torch.as_tensor(np.asarray(geometry["mu1"], dtype=np.float64), device=dev)[None, :]
             mu = torch.cat([mu0, 0.5 * (mu[:-1] + mu[1:]), mu1], dim=0)
-        E = (self.from_internal("E") * self.r) * af
+        E = (self.from_internal("E") * (self.r * self.ds)) * af
         # utils/evaluate_solution.py:7-45 on the device: per-layer mass and per-layer negative mass of the returned mu
         layers = torch.stack([mu.sum(dim=1), torch.where(mu < 0, mu, torch.zeros_like(mu)).sum(dim=1)]).cpu().numpy()
         n = layers.shape[1]
@@ -809,7 +865,8 @@ class Engine:
     def congestion_norm(self):
         """``||lambda_c - congestion * mu||_2`` of the un-scaled solution (the solver's closing log line,
         socp/solver_socp.py:846-853), formed on the device; a norm does not care about the vertex ordering."""
-        diff = self.full("lam_c") - self.cong * self.r * self.full("mu")
+        # on the un-scaled solution, with the congestion as the reference holds it at that point (:846-853)
+        diff = self.ps * self.full("lam_c") - self.cong * (self.r * self.ds) * self.full("mu")
         return float(torch.linalg.vector_norm(diff))
 
     def solution(self, keys=None):
@@ -820,9 +877,9 @@ class Engine:
         keys = tuple(REF_KEYS) if keys is None else tuple(keys)
         if "z_mid" in keys and not self.z_valid:
             raise capi.DotsError("z_mid was not materialised on the last iteration")
-        r, s = self.r, self.s
-        scale = dict(phi=1.0, A=1.0, B=1.0, lam_c=1.0, z_fst=1.0 / s, z_mid=1.0 / s, z_end=1.0 / s,
-                     mu=r, E=r, b_fst=r * s, b_mid=r * s, b_end=r * s)
+        r, s, ps, ds = self.r, self.s, self.ps, self.ds                                 # :397-405
+        scale = dict(phi=ps, A=ps, B=ps, lam_c=ps, z_fst=ps / s, z_mid=ps / s, z_end=ps / s,
+                     mu=r * ds, E=r * ds, b_fst=r * s * ds, b_mid=r * s * ds, b_end=r * s * ds)
         out = {}
         for key in keys:
             name = REF_KEYS[key]

@@ -89,14 +89,8 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
     ("staggered" / "centred", set by ``solver_raw`` / ``solver``) returns the DOT-unit ``mu``, ``E`` formed on the device;
     ``is_multi_threads`` is accepted and ignored (the two reference threads become stream order).
     ``is_palm=True`` and ``is_constant_scaling=True`` are solver-only knobs that the reference's CLI / interface cannot
-    reach (interface.py:275-284).  ``is_palm`` is served outside the fused kernels (``Engine.step_q0``: whole-array
-    device operations before every fused iteration, single GPU only) and stays behind ``DOTS_EXPERIMENTAL=1`` until it
-    has been validated on hardware; ``is_constant_scaling`` is not built and raises."""
-    if is_constant_scaling:
-        raise NotImplementedError("is_constant_scaling is not part of the B200 hot path (see DESIGN.md)")
-    if is_palm and os.environ.get("DOTS_EXPERIMENTAL") != "1":
-        raise NotImplementedError("is_palm: the extra q/lambda step (Engine.step_q0) is written and checked on the CPU but has "
-                                  "not run on a GPU yet; set DOTS_EXPERIMENTAL=1 to use it (see DESIGN.md)")
+    reach (interface.py:275-284); both are built: ``is_palm`` as two fused kernels before every iteration (``Engine.step_q0``,
+    single GPU only), ``is_constant_scaling`` as the reference's primal / dual rescaling (``Engine.scale_prim_dual``)."""
     logging.basicConfig(level=LOG_INFO, format="%(message)s")
     tol_checkpoints = _validate_checkpoints(tol_checkpoints, tol)
     checkpoints = []
@@ -120,6 +114,9 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
     if is_z_scaling:
         logging.log(LOG_SCALING, "Initially scale z with z factor: 2.0")
         eng.scale_z(2.0)                                                                  # :571-572
+    if is_constant_scaling:
+        eng.initial_constant_scaling()                                                    # :574-587
+    to_scale = lambda k: is_constant_scaling and (k == 10 or k == 50 or k % 100 == 50)    # admm_tools.is_to_scale :98-104
     use_org = False
     it, passed = -1, False
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -129,6 +126,9 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
     kkt_seconds = 0.0
     start = time.perf_counter()                                                           # :655
     for it in range(nit):                                                                 # :656
+        if to_scale(it):                                                                  # :657-659
+            if eng.scale_prim_dual():
+                logging.log(LOG_SCALING, f"Var Norm at iteration {it}: rescaled, (prim, dual) scale = {eng.ps}, {eng.ds}")
         if is_z_scaling and sched.z_rescale_due(it, hist.get_current_kkt_errors()):       # :661-666
             row = hist.get_current_kkt_errors()
             with np.errstate(all="ignore"):
@@ -151,7 +151,7 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
         will_check = check_kkt_step_by_step or lazy.will_fire(required) or it == nit - 1
         if is_palm:
             eng.step_q0()                                                                 # Step 0, :668-672
-        eng.iterate(1, write_z=will_check or is_palm)                                     # Steps 1-3, :674-722
+        eng.iterate(1, write_z=will_check or is_palm or to_scale(it + 1))                 # Steps 1-3, :674-722
         pending = True
 
         cost = lagr = None
@@ -189,8 +189,8 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
             hist.show_tol_progress(it, error)                                             # :757-768
 
         if tol_checkpoints and error is not None and error <= tol_checkpoints[0]:         # :790-801
-            checkpoints.append(dict(mu=(eng.r * eng.from_internal("mu")).cpu().numpy(),
-                                    E=(eng.r * eng.from_internal("E")).cpu().numpy(),
+            checkpoints.append(dict(mu=((eng.r * eng.ds) * eng.from_internal("mu")).cpu().numpy(),
+                                    E=((eng.r * eng.ds) * eng.from_internal("E")).cpu().numpy(),
                                     iteration=it, time=hist.get_running_time(), kkt=np.array(org, dtype=object)))
             tol_checkpoints.pop(0)
 

@@ -47,6 +47,8 @@ enum {
     DOTS_P_CONG,         /* congestion                     (:28)                                      */
     DOTS_P_TAU,          /* multiplier step tau            (:32)                                      */
     DOTS_P_EPS,          /* Laplacian regularisation eps   (:30)                                      */
+    DOTS_P_PS,           /* prim_scale (1 unless is_constant_scaling; :318, :324-365): read by KKT #4-#6 / objective */
+    DOTS_P_DS,           /* dual_scale (:319)                                                         */
     DOTS_P_COUNT = 8
 };
 
@@ -145,8 +147,8 @@ typedef struct dots_ctx {
     double *hat_all;           /* [n_ranks][V][m_pad] all ranks' solutions (== hat on one GPU)        */
     double *ywork;             /* [V][m_pad]  forward-sweep result                                    */
     double *upd;               /* [sum b][m_pad] update vectors                                       */
-    double *red_part;          /* [red_blocks][64] block partial sums (8 conditions x 8 slots)        */
-    double *red_out;           /* [64] reduced sums (device)                                          */
+    double *red_part;          /* [red_blocks][72] block partial sums (9 conditions x 8 slots)        */
+    double *red_out;           /* [72] reduced sums (device)                                          */
     int32_t red_blocks;
     int32_t sweep_mode;        /* 0: k_sweep_run, register-staged loads (any m_pad); 4: ring-streamed sweeps, every warp feeds its
                                   own shared-memory ring with bulk async copies (m_pad a multiple of 32)                        */
@@ -206,6 +208,10 @@ int dots_step_phi(const dots_ctx_t *c, void *stream);
 int dots_step_vertex(const dots_ctx_t *c, void *stream);
 int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream);
 int dots_iterate(const dots_ctx_t *c, int n_iter, int write_z, void *stream);
+/* is_palm=True only (solver_socp.py:253-257, :668-672): the extra q / lambda solve that opens an iteration, from the gradients
+ * of the current phi and the STORED z (z_mid of the previous iteration must have been written): A, lam_c (vertex kernel), B and
+ * the corner terms of the new B (triangle kernel).  Single GPU.                                                           */
+int dots_step_q0(const dots_ctx_t *c, void *stream);
 
 /* One iteration captured as a CUDA graph (same work as dots_iterate(c, 1, write_z)); the context must outlive it and
  * must not be modified afterwards (scalars go through dots_set_params, which the graph picks up).  Call
@@ -225,6 +231,10 @@ int dots_refresh_corner_terms(const dots_ctx_t *c, void *stream);
  * The caller updates params[] itself (dots_set_params).                                              */
 int dots_scale_dual(const dots_ctx_t *c, double factor, void *stream);
 int dots_scale_z(const dots_ctx_t *c, double s_cum, void *stream);
+/* dots_scale_prim_dual: scale_prim_dual :324-365 (is_constant_scaling): phi, A, B, lam_c, z_* divided by prim_div and
+ *                  boundary, mu, E, b_* divided by dual_div (= dual_rescale^2 / prim_rescale), incl. the halo rows, + refresh.
+ *                  The caller updates r, congestion, constant_d, the two scales in params[] itself.                       */
+int dots_scale_prim_dual(const dots_ctx_t *c, double prim_div, double dual_div, void *stream);
 int dots_set_params(const dots_ctx_t *c, const double *host_params, void *stream);
 
 /* ---- residuals (rows a9-a11).  Writes the raw weighted sums (un-normalised, un-rooted) of KKT condition
@@ -235,7 +245,9 @@ int dots_kkt_sums(const dots_ctx_t *c, int which, double *host_out, void *stream
 /* All conditions of `mask` (bit i = condition i, bit 7 = objective) in ONE pass over the vertex arrays and ONE over the
  * triangle arrays (the --detail_runhist mode of solver_socp.py:769-787 evaluates all 7 + the objective every iteration; the
  * penalty-update iterations force conditions 0-3, :728-729): host_out[8 * i + k] = slot k of condition i as in
- * dots_kkt_sums.  red_part must hold red_blocks x 64 doubles, red_out 64.  Synchronises the stream.                      */
+ * dots_kkt_sums.  Bit 8: the variable norms of scale_prim_dual (:331-340): vertex slots z_fst^2, z_end^2, b_fst^2,
+ * b_end^2 (x area_v), triangle slots z_mid^2, b_mid^2 (x area_f).  red_part must hold red_blocks x 72 doubles, red_out and
+ * host_out 72.  Synchronises the stream.                                                                                  */
 int dots_kkt_sums_multi(const dots_ctx_t *c, unsigned mask, double *host_out, void *stream);
 
 /* ---- setup (row f1): numeric factorisation of the small fronts (n <= dots_front_nmax()) of one tree level, one block

@@ -366,6 +366,8 @@ class OracleALM:
         self.r = 1.0
         self.s = 1.0            # scale_factor_z
         self.d = 1.0            # constant_d
+        self.ps = 1.0           # prim_scale  (:318, is_constant_scaling only)
+        self.ds = 1.0           # dual_scale  (:319)
         self.norm_d = math.sqrt(2 * o.area_mesh)                                   # :297
         z = np.zeros
         self.phi = z((nT + 1, V))
@@ -406,6 +408,40 @@ class OracleALM:
         self.r *= f
         for a in (self.mu, self.E, self.bnd, self.b_fst, self.b_mid, self.b_end):
             a /= f
+
+    def scale_prim_dual(self, factors=None):                                       # :324-365
+        o, sq = self.ops, math.sqrt
+        if factors is None:                                                        # admm_tools.compute_scale_factor :171-174
+            prim = [sq(o.nsq_time(self.dt_phi) + o.nsq_space(self.dx_phi)), sq(o.nsq_time(self.A) + o.nsq_space(self.B)),
+                    sq(o.nsq_time(self.z_fst) + o.nsq_dec(self.z_mid) + o.nsq_time(self.z_end))]
+            dual = [self.r * sq(o.nsq_time(self.mu) + o.nsq_space(self.E)),
+                    self.r * sq(o.nsq_time(self.b_fst) + o.nsq_dec(self.b_mid) + o.nsq_time(self.b_end))]
+            p, d = max(prim) / 1.0, max(dual) / 1.0
+        else:
+            p, d = factors
+        if max(p, d) / min(p, d) > 2.0:                                            # :344
+            self.ps *= p
+            self.ds *= d
+            for name in ("phi", "A", "B", "lam_c", "dt_phi", "dx_phi", "z_fst", "z_mid", "z_end"):
+                setattr(self, name, getattr(self, name) / p)
+            f = d ** 2 / p
+            for name in ("bnd", "mu", "E", "b_fst", "b_mid", "b_end"):
+                setattr(self, name, getattr(self, name) / f)
+            self.r *= d / p
+            self.cong *= d / p
+            self.d /= p
+            self.norm_d /= p
+            self.norm_bnd /= d
+            return True
+        return False
+
+    def initial_constant_scaling(self):                                            # :574-587
+        o, sq = self.ops, math.sqrt
+        bt = self.r * np.divide(self.bnd, o.w_center)
+        norm_c = sq(o.nsq_center(bt))
+        norm_ac = sq(o.nsq_time(grad_time(o.dt, bt)) + o.nsq_space(grad_space(o.G, bt)))
+        self.scale_prim_dual((self.norm_d, sq(o.nT) * norm_c ** 2 / norm_ac))
+        self.adjust_penalty(1.0 / self.r)
 
     def scale_z(self, f):
         self.s *= f; self.d *= f; self.norm_d *= f
@@ -458,50 +494,49 @@ class OracleALM:
             norm_sum = (sq(o.nsq_time(self.dt_phi) + o.nsq_space(self.dx_phi))
                         + sq(o.nsq_time(self.A) + o.nsq_space(self.B)) + sq(o.nsq_time(self.lam_c)))
             res = sq(o.nsq_time(self.dt_phi - self.A - self.lam_c) + o.nsq_space(self.dx_phi - self.B))
-            v = res / (self.k_prim_q / 1.0 + norm_sum)
-            return [v, v]
+            return [res / (self.k_prim_q / self.ps + norm_sum), res / (self.k_prim_q / 1.0 + norm_sum)]
         if i == 1:                                                                         # :452-464, :597-603
             res = sq(o.nsq_time(self.z_fst + s * self.A - self.d) + o.nsq_time(self.z_end - s * self.A - self.d)
                      + o.nsq_dec(s * (self.z_mid - self.Bd_new)))
-            v = res / (self.k_prim_z / 1.0 + self.norm_d)
-            return [v, v]
+            return [res / (self.k_prim_z / self.ps + self.norm_d), res / (self.k_prim_z / 1.0 + self.norm_d)]
         if i == 2:                                                                         # :466-482
             aux = (r * o.dt) * np.divide(self.bnd + div_time(o.dt, self.mu * o.w_time)
                                          + div_space(o.D, self.E * o.w_space), o.w_center)
-            v = sq(o.nsq_center(aux)) / (self.k_dual_a / 1.0 + self.norm_bnd)
-            return [v, v]
+            res = sq(o.nsq_center(aux))
+            return [res / (self.k_dual_a / self.ds + self.norm_bnd), res / (self.k_dual_a / 1.0 + self.norm_bnd)]
         if i == 3:                                                                         # :484-503
             a1 = s * (self.b_end - self.b_fst)
             a2 = decouple_adjoint(self.b_mid, s)
             norm_sum = r * (sq(o.nsq_time(self.mu) + o.nsq_space(self.E)) + sq(o.nsq_time(a1) + o.nsq_space(a2)))
             res = r * sq(o.nsq_time(self.mu + a1) + o.nsq_space(self.E + a2))
-            v = res / (self.k_dual_b / 1.0 + norm_sum)
-            return [v, v]
-        rho = r * self.mu
+            return [res / (self.k_dual_b / self.ds + norm_sum), res / (self.k_dual_b / 1.0 + norm_sum)]
+        rho = (self.ds * r) * self.mu                                                      # :619-637: un-scaled arguments
+        qA, qB, lam_c = self.ps * self.A, self.ps * self.B, self.ps * self.lam_c
         if i == 4:                                                                         # :505-526
-            corner = np.sum(np.square(decouple(self.B)), axis=(1, 4)).reshape(o.nT, 3 * o.T)
-            aux = self.A + .25 * np.divide(o.M_area.dot(corner.T).T, o.w_time)
+            corner = np.sum(np.square(decouple(qB)), axis=(1, 4)).reshape(o.nT, 3 * o.T)
+            aux = qA + .25 * np.divide(o.M_area.dot(corner.T).T, o.w_time)
             norm_sum = sq(o.nsq_time(rho)) + sq(o.nsq_time(aux))
             res = sq(o.nsq_time(np.maximum(0., aux + rho) - rho))
             return [res / (self.k_comp_rho + norm_sum), None]
         if i == 5:                                                                         # :528-547
-            m = r * self.E
-            avg = o.V2T_third.dot(adjoint_time_average(rho).T).T[:, :, None] * self.B
+            m = (self.ds * r) * self.E
+            avg = o.V2T_third.dot(adjoint_time_average(rho).T).T[:, :, None] * qB
             norm_sum = sq(o.nsq_space(m)) + sq(o.nsq_space(avg))
             res = sq(o.nsq_space(avg - m))
             return [res / (self.k_comp_m + norm_sum), None]
         if i == 6:                                                                         # :549-559
-            norm_sum = sq(o.nsq_time(rho)) + sq(o.nsq_time(self.lam_c))
-            res = sq(o.nsq_time(self.cong * rho - self.lam_c))
+            norm_sum = sq(o.nsq_time(rho)) + sq(o.nsq_time(lam_c))
+            res = sq(o.nsq_time(self.cong * rho - lam_c))                                  # the (scaled) congestion, as the reference has it
             return [res / (self.k_comp_rho + norm_sum), None]
         raise IndexError(i)
 
     def objective(self):                                                                   # :417-431, :829-831
         o = self.ops
-        bnd = self.r * self.bnd
-        cost = o.dt * (np.dot(self.phi[0], bnd[0]) + np.dot(self.phi[-1], bnd[-1]))
-        if self.cong > 10 ** (-10):
-            return cost, cost - 1. / (2. * self.cong) * o.nsq_time(self.lam_c)
+        phi, lam_c, bnd = self.ps * self.phi, self.ps * self.lam_c, (self.ds * self.r) * self.bnd
+        cong = self.cong * self.ps / self.ds
+        cost = o.dt * (np.dot(phi[0], bnd[0]) + np.dot(phi[-1], bnd[-1]))
+        if cong > 10 ** (-10):
+            return cost, cost - 1. / (2. * cong) * o.nsq_time(lam_c)
         return cost, cost
 
     def state(self, copy=True):
@@ -510,20 +545,23 @@ class OracleALM:
 
     def solution(self):
         """Un-scaled output dict, keys of utils/type.py:22-38 (ref :397-405, :855-869)."""
-        r, s = self.r, self.s
-        return dict(phi=self.phi.copy(), A=self.A.copy(), B=self.B.copy(), lambda_c=self.lam_c.copy(),
-                    mu=r * self.mu, E=r * self.E,
-                    z_fst=self.z_fst / s, z_mid=self.z_mid / s, z_end=self.z_end / s,
-                    beta_fst=(r * s) * self.b_fst, beta_mid=(r * s) * self.b_mid, beta_end=(r * s) * self.b_end)
+        r, s, ps, ds = self.r, self.s, self.ps, self.ds
+        return dict(phi=ps * self.phi, A=ps * self.A, B=ps * self.B, lambda_c=ps * self.lam_c,
+                    mu=(r * ds) * self.mu, E=(r * ds) * self.E,
+                    z_fst=(ps / s) * self.z_fst, z_mid=(ps / s) * self.z_mid, z_end=(ps / s) * self.z_end,
+                    beta_fst=(r * s * ds) * self.b_fst, beta_mid=(r * s * ds) * self.b_mid, beta_end=(r * s * ds) * self.b_end)
 
 
 def solve(n_time, geometry, congestion=0.0, nit=1000, eps=0.0, tol=1e-4, tau=1.9, is_palm=False,
-          is_z_scaling=True, time_limit=1000, trace=None, ops=None, check_kkt_step_by_step=False, init_solution=None):
+          is_z_scaling=True, time_limit=1000, trace=None, ops=None, check_kkt_step_by_step=False, init_solution=None,
+          is_constant_scaling=False):
     """The reference's outer loop (:565-871) around OracleALM.  Returns (solution, info).
 
     ``info``: iterations (= last 0-based index, what the reference prints), kkt rows (nan = not
     evaluated), r per iteration, costs.  ``trace(it, alm)`` is called after every iteration."""
     alm = OracleALM(n_time, geometry, congestion, eps, tau, is_palm, is_z_scaling, ops=ops, init_solution=init_solution)
+    if is_constant_scaling:
+        alm.initial_constant_scaling()                                                     # :574-587
     t0 = time.perf_counter()
     prim_gap = 1.0 + 1.0 * np.exp(-100 * congestion)                                       # :568
     lazy = LazyKKT([(lambda i=i: alm.kkt(i)) for i in range(7)], tol)
@@ -532,6 +570,8 @@ def solve(n_time, geometry, congestion=0.0, nit=1000, eps=0.0, tol=1e-4, tau=1.9
     last_row = np.full(7, np.inf)
     it, passed = -1, False
     for it in range(nit):
+        if is_constant_scaling and (it == 10 or it == 50 or it % 100 == 50):              # :657-659, admm_tools :98-104
+            alm.scale_prim_dual()
         if is_z_scaling and it >= 100 and z_rescales < 1 and max(last_row) < 5e-3:        # :661-666, admm_tools :107-114
             z_rescales += 1
             f = prim_gap * math.sqrt(last_row[1] / last_row[0])

@@ -181,7 +181,8 @@ def test_kkt_and_objective_rows_a9_a11():
                                   "ico1_nt1_c005", "ico1_nt2_c0",                       # smallest time grids
                                   "ico2_nt7_eps1e-2",                                   # regularised Laplacian (eps > 0)
                                   "ico2_nt7_tl0",                                       # time limit hit on the first iteration
-                                  "ico5_nt31_c0"])                                      # 10 242 vertices: large fronts, split sweep items
+                                  "ico5_nt31_c0",                                       # 10 242 vertices: large fronts, split sweep items
+                                  "ico2_nt7_cscale", "ico3_nt15_cscale_c0"])            # is_constant_scaling=True (primal / dual rescaling)
 def test_solver_matches_reference_fixture(golden, name):
     """Through the public solver_socp: iteration count, KKT schedule (which residual on which iteration), penalty
     path, transport cost and the returned mu against the fixtures generated by the unmodified reference."""
@@ -456,11 +457,33 @@ def test_small_root_front_is_pinned_deterministically():
         assert torch.equal(p, first)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("DOTS_TEST_EXPERIMENTAL") != "1",
-                    reason="opt-in: Engine.step_q0 (is_palm) has not run on hardware yet; set DOTS_TEST_EXPERIMENTAL=1")
-def test_is_palm_matches_reference_fixture(golden, monkeypatch):
-    monkeypatch.setenv("DOTS_EXPERIMENTAL", "1")
+def test_is_palm_matches_reference_fixture(golden):
+    """is_palm=True (solver_socp.py:668-672): the fused Step-0 kernels (dots_step_q0) against the unmodified reference."""
     _check_against_fixture(golden, "ico2_nt7_palm")
+
+
+def test_is_palm_step_matches_oracle():
+    """One Step 0 from a random state: A, B, lam_c and the refreshed corner terms (through the next fused iteration)."""
+    n_time = 6
+    geo, alm, eng = make_pair("icosphere2", n_time, congestion=0.07)
+    o = alm.ops
+    rng = np.random.default_rng(8)
+    for name in ("A", "lam_c", "mu", "b_fst", "b_end", "z_fst", "z_end"):
+        setattr(alm, name, rng.standard_normal((n_time, o.V)))
+    for name in ("B", "E"):
+        setattr(alm, name, rng.standard_normal((n_time + 1, o.T, 3)))
+    alm.b_mid = rng.standard_normal((n_time, 2, 3, o.T, 3))
+    alm.z_mid = rng.standard_normal((n_time, 2, 3, o.T, 3))
+    alm.phi = rng.standard_normal((n_time + 1, o.V))
+    alm.r = 1.3
+    push_state(alm, eng)
+    alm.dt_phi, alm.dx_phi = orc.grad_time(o.dt, alm.phi), orc.grad_space(o.G, alm.phi)
+    alm.step_q()
+    eng.step_q0()
+    compare_states(alm, eng, 1e-12, "Step 0")
+    alm.iterate()                                   # the corner terms Step 0 refreshed feed the next projection / rhs
+    eng.iterate(1, write_z=True)
+    compare_states(alm, eng, 1e-8, "iteration after Step 0")
 
 
 def test_plugin_callables_match_the_reference_decorators_on_gpu():

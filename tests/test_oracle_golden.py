@@ -21,7 +21,8 @@ def phi_mod_const(phi):
 
 @pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005",
                                   "ico2_nt7_stepwise", "refplane20_nt15", "ico1_nt1_c005", "ico1_nt2_c0",
-                                  "ico2_nt7_eps1e-2", "ico2_nt7_tl0", "ico2_nt7_nit20", "ico2_nt7_palm"])
+                                  "ico2_nt7_eps1e-2", "ico2_nt7_tl0", "ico2_nt7_nit20", "ico2_nt7_palm",
+                                  "ico2_nt7_cscale", "ico3_nt15_cscale_c0"])        # is_constant_scaling=True
 def test_iterates_match_reference(golden, name):
     z, geo, n_time, kw = golden(name)
     snap_its = [int(i) for i in z["snap_its"]]
@@ -29,14 +30,18 @@ def test_iterates_match_reference(golden, name):
 
     def trace(it, alm):
         if it in snap_its:
-            got[it] = (alm.state(), alm.r, alm.s, alm.d)
+            got[it] = (alm.state(), alm.r, alm.s, alm.d, alm.ps, alm.ds, alm.cong)
 
     sol, info = orc.solve(n_time, geo, trace=trace, **kw)
     assert info["iterations"] == int(z["iterations"])
     for it in snap_its:
-        st, r, s, d = got[it]
+        st, r, s, d, ps, ds, cong = got[it]
         assert r == pytest.approx(float(z[f"it{it}_r"]), rel=1e-12)
-        assert s == float(z[f"it{it}_scale_factor_z"]) and d == float(z[f"it{it}_constant_d"])
+        assert s == float(z[f"it{it}_scale_factor_z"]) and d == pytest.approx(float(z[f"it{it}_constant_d"]), rel=1e-13)
+        if f"it{it}_prim_scale" in z:                      # fixtures written since the constant-scaling knob is covered
+            assert ps == pytest.approx(float(z[f"it{it}_prim_scale"]), rel=1e-12)
+            assert ds == pytest.approx(float(z[f"it{it}_dual_scale"]), rel=1e-12)
+            assert cong == pytest.approx(float(z[f"it{it}_congestion"]), rel=1e-12, abs=0.0)
         for ref_name, my_name in ORACLE_NAMES.items():
             a, b = st[my_name], z[f"it{it}_{ref_name}"]
             if ref_name == "phi":

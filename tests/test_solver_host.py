@@ -1,5 +1,5 @@
 """Host-side behaviour of the solver plug-in that can be checked without a GPU: argument validation in the order and
-wording of the reference (socp/solver_socp.py:85-94), the knobs that are deliberately not built, the loud failure
+wording of the reference (socp/solver_socp.py:85-94), the solver-only knobs, the loud failure
 when no CUDA device exists, and the numpy DOT-unit translation used for checkpoints (utils/type.py:48-65,
 socp/solver_decorator.py:32-34)."""
 import numpy as np
@@ -21,12 +21,13 @@ def geo():
     return synth.example("icosphere1")[0]
 
 
-def test_unbuilt_knobs_raise_before_any_work(geo, monkeypatch):
-    with pytest.raises(NotImplementedError):
-        b200.solver_socp(3, geo, is_constant_scaling=True)
-    monkeypatch.delenv("DOTS_EXPERIMENTAL", raising=False)
-    with pytest.raises(NotImplementedError, match="DOTS_EXPERIMENTAL=1"):        # written, not yet validated on a GPU
-        b200.solver_socp(3, geo, is_palm=True)
+@no_gpu
+def test_solver_only_knobs_reach_the_engine(geo):
+    """is_palm / is_constant_scaling are built (no NotImplementedError any more): without a GPU the call gets as far as the
+    engine, which refuses loudly (no CPU fallback)."""
+    for kw in (dict(is_constant_scaling=True), dict(is_palm=True)):
+        with pytest.raises(capi.DotsError, match="CUDA"):
+            b200.solver_socp(3, geo, **kw)
 
 
 @pytest.mark.parametrize("cps,msg", [([], "non-empty list"), ((1e-2,), "non-empty list"), ([1.5], "between 0 and 1"),

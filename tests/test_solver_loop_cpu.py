@@ -37,6 +37,15 @@ class OracleEngine:
         self.comm = dd.Comm()                            # single rank
 
     r = property(lambda self: self.alm.r)
+    ps = property(lambda self: self.alm.ps)
+    ds = property(lambda self: self.alm.ds)
+
+    def initial_constant_scaling(self):
+        self.alm.initial_constant_scaling()
+
+    def scale_prim_dual(self, factors=None):
+        assert self.z_valid, "scale_prim_dual needs z_mid of the previous iteration"
+        return self.alm.scale_prim_dual(factors)
 
     def scale_z(self, f):
         self.alm.scale_z(f)
@@ -92,10 +101,10 @@ class OracleEngine:
 
     def dot_solution(self, geometry, centred):
         av = np.asarray(geometry["area_vertices"])[None, :] / 3.0
-        mu = (self.alm.mu * self.alm.r) * av
+        mu = (self.alm.mu * (self.alm.r * self.alm.ds)) * av
         if centred:
             mu = np.concatenate([geometry["mu0"][None], 0.5 * (mu[:-1] + mu[1:]), geometry["mu1"][None]], axis=0)
-        return dict(mu=mu, E=(self.alm.E * self.alm.r) * np.asarray(geometry["area_triangles"])[None, :, None])
+        return dict(mu=mu, E=(self.alm.E * (self.alm.r * self.alm.ds)) * np.asarray(geometry["area_triangles"])[None, :, None])
 
     def congestion_norm(self):
         return float(np.linalg.norm(self.alm.lam_c - self.cong * self.alm.r * self.alm.mu))
@@ -136,7 +145,7 @@ def cpu_loop(monkeypatch):
 
 @pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005", "ico2_nt15_tol1e-4",
                                   "ico2_nt7_stepwise", "ico1_nt1_c005", "ico1_nt2_c0", "ico2_nt7_eps1e-2", "ico2_nt7_tl0",
-                                  "ico2_nt7_nit20", "ico2_nt7_palm"])
+                                  "ico2_nt7_nit20", "ico2_nt7_palm", "ico2_nt7_cscale", "ico3_nt15_cscale_c0"])
 def test_loop_reproduces_reference_runs(cpu_loop, golden, name):
     z, geo, n_time, kw = golden(name)
     sol, hist = solver_mod.solver_socp(n_time, geo, **kw)
@@ -154,7 +163,8 @@ def test_loop_reproduces_reference_runs(cpu_loop, golden, name):
     # z_mid is only materialised on iterations that check (or may check) KKT #1; most iterations must not ask for it
     if kw.get("is_palm"):
         assert eng.calls_q0 == len(eng.calls) and all(eng.calls)       # Step 0 before every iteration, z_mid always stored
-    elif not kw.get("check_kkt_step_by_step") and len(eng.calls) > 50:
+    elif not kw.get("check_kkt_step_by_step") and len(eng.calls) > 50 and name != "ico2_nt7_cscale":
+        # (ico2_nt7_cscale hovers just above the tolerance for 1000 iterations, so its validator fires almost every time)
         assert 0 < sum(eng.calls) < 0.8 * len(eng.calls)
 
 
