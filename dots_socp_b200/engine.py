@@ -186,11 +186,15 @@ class Engine:
         env_kb = lambda name, default: int(float(os.environ.get(name, default)) * 1024)
         self.ring = None
         if self.sweep_mode == 4:
+            self.ring_stages = int(os.environ.get("DOTS_RING_STAGES", 2))
+            self.ring_stage_bytes = int(os.environ.get("DOTS_RING_STAGE_BYTES", 4096))
+            blocks = C.c_int(0)
+            capi.check(self.lib.dots_ring_resident_blocks(self.m_pad, self.ring_stages, self.ring_stage_bytes, C.byref(blocks)),
+                       "dots_ring_resident_blocks")
             self.ring = ring_plan.build(
-                sym, self.n_sm, self.m_pad, split_bytes=env_kb("DOTS_RING_SPLIT_KB", 96),
-                tasks_per_sm=int(os.environ.get("DOTS_RING_TASKS_PER_SM", 64)),
-                task_bytes=(env_kb("DOTS_RING_TASK_MIN_KB", 16), env_kb("DOTS_RING_TASK_MAX_KB", 96)),
-                wpr_max=int(os.environ.get("DOTS_RING_WPR_MAX", 8)))
+                sym, self.n_sm, self.m_pad, split_bytes=env_kb("DOTS_RING_SPLIT_KB", 64),
+                resident_warps=8 * blocks.value * int(os.environ.get("DOTS_RING_OVERSUB", 1)),
+                min_share_bytes=env_kb("DOTS_RING_SHARE_MIN_KB", 32), wpr_max=int(os.environ.get("DOTS_RING_WPR_MAX", 8)))
         fwd_ptr, fwd_items, bwd_ptr, bwd_items = plan["fwd_ptr"], plan["fwd_items"], plan["bwd_ptr"], plan["bwd_items"]
         self._h_fwd_ptr, self._h_bwd_ptr = fwd_ptr, bwd_ptr
 
@@ -236,9 +240,12 @@ class Engine:
             ctx.h_rt_fwd_ptr, ctx.h_rt_bwd_ptr = rp["fwd_ptr"].ctypes.data, rp["bwd_ptr"].ctypes.data
             ctx.h_rt_fwd_wpr, ctx.h_rt_bwd_wpr = rp["fwd_wpr"].ctypes.data, rp["bwd_wpr"].ctypes.data
             ctx.h_gv_ptr = rp["gv_ptr"].ctypes.data
-            ctx.ring_stages = int(os.environ.get("DOTS_RING_STAGES", 3))
-            ctx.ring_pdl = int(os.environ.get("DOTS_RING_PDL", 0))
-            ctx.ring_stage_bytes = int(os.environ.get("DOTS_RING_STAGE_BYTES", 4096))
+            for name in ("fwd_wptr", "bwd_wptr"):
+                setattr(ctx, "rt_" + name, up("ring_" + name, rp[name], np.int32).data_ptr())
+            ctx.h_rt_fwd_wlv, ctx.h_rt_bwd_wlv = rp["fwd_wlv"].ctypes.data, rp["bwd_wlv"].ctypes.data
+            ctx.ring_stages = self.ring_stages
+            ctx.ring_pdl = int(os.environ.get("DOTS_RING_PDL", 1))
+            ctx.ring_stage_bytes = self.ring_stage_bytes
         self._keep["phase_clock"] = torch.zeros(2 * sym.n_levels + 1, dtype=torch.int64, device=dev)
         if os.environ.get("DOTS_PHASE_CLOCK"):
             ctx.phase_clock = self._keep["phase_clock"].data_ptr()

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DOTS_ABI_VERSION 11
+#define DOTS_ABI_VERSION 13
 
 /* scalar block read by the kernels from device memory (so CUDA graphs stay valid across penalty updates) */
 enum {
@@ -184,6 +184,9 @@ typedef struct dots_ctx {
     int32_t ring_pdl;          /* 1: chain the level launches with programmatic dependent launch                          */
     int32_t ring_stage_bytes;  /* bytes per ring stage: 2048 or 4096                                                      */
     int32_t reserved2;
+    const int32_t *rt_fwd_wptr, *rt_bwd_wptr;   /* device: per level a list of n_warps + 1 record offsets: warp w of the level's
+                                                   launch streams the records [wptr[w], wptr[w+1]) (byte-balanced shares)      */
+    const int32_t *h_rt_fwd_wlv, *h_rt_bwd_wlv; /* HOST [n_levels+1] start of every level's list inside rt_*_wptr             */
 } dots_ctx_t;
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -301,6 +304,8 @@ int dots_time_transform(const dots_ctx_t *c, int inverse, void *stream);   /* rh
 int dots_mode_solves(const dots_ctx_t *c, void *stream);                   /* hat <- (K+shift M)^-1 hat */
 /* profiling aid: one pair of ring sweeps (sweep_mode 4) with a CUDA event before every launch; ms_out[i] = start of launch i ->
  * start of launch i+1, tag_out[i] = tree level (+1000: gather, +2000: backward).  Synchronises the stream.              */
+/* resident blocks (blocks per SM x SMs) of the contiguous-task kernel for this configuration on the current device */
+int dots_ring_resident_blocks(int m_pad, int stages, int stage_bytes, int *blocks_out);
 int dots_ring_level_times(const dots_ctx_t *c, void *stream, float *ms_out, int32_t *tag_out, int cap, int *n_out);
 int dots_grad_space(const dots_ctx_t *c, const double *phi, double *out, void *stream);  /* [nT+1][3][T] */
 int dots_div_space(const dots_ctx_t *c, const double *x, double *out, void *stream);     /* [nT+1][V]    */
