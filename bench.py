@@ -358,7 +358,7 @@ def run_own(args):
     t0 = time.perf_counter()
     # the plug-in callable run_dot_surface(opts, solver=...) receives: DOT-unit mu (centred grid) and E come back
     sol, hist, eng = b200.solver(n_time, geo, congestion=cong, tol=1e-3, nit=args.e2e_nit, return_engine=True,
-                                 leaf_size=args.leaf)
+                                 leaf_size=args.leaf, solution_root=0)          # sharded: rank 0 assembles and downloads
     wall = time.perf_counter() - t0
     iters = int(hist.kkt_iteration[-1]) + 1
     setup_s = eng.timings["setup_total"]
@@ -366,7 +366,7 @@ def run_own(args):
     upload_s = float(eng.timings.get("upload", 0.0))      # host -> device copy of the mesh constants, masses and initial state
     timed_s = upload_s + loop_s                           # e2e timed region: H2D of the inputs + loop + D2H of the result
     h2d = sum(t.numel() * t.element_size() for k, t in eng._keep.items() if k not in ("panels", "panels_t", "phase_clock"))
-    d2h_solution = sum(v.nbytes for v in sol.values() if isinstance(v, np.ndarray))
+    d2h_solution = sum(v.nbytes for v in sol.values() if isinstance(v, np.ndarray))      # rank 0 (the only downloader)
     d2h = d2h_solution + 64 * (sum(hist.evaluations) + 8)
     e2e = {"value": iters / timed_s, "unit": UNIT, "h2d_bytes_per_step": h2d / iters, "d2h_bytes_per_step": d2h / iters,
            "iterations_to_tol": iters, "time_to_tol_s": hist.running_time, "timed_s": timed_s, "upload_s": upload_s,

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdots_b200.so")
-SOURCES = ["iter_kernels.cu", "lap_kernels.cu", "sweep_ring.cu", "kkt_kernels.cu", "factor_kernels.cu", "host_order.cpp"]
+SOURCES = ["iter_kernels.cu", "lap_kernels.cu", "sweep_ring.cu", "kkt_kernels.cu", "factor_kernels.cu", "front_large.cu", "host_order.cpp"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]
 

@@ -9,7 +9,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 P_R, P_S, P_D, P_CONG, P_TAU, P_EPS, P_PS, P_DS, P_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 _i32p, _i64p, _f64p = C.c_void_p, C.c_void_p, C.c_void_p      # raw device/host addresses
@@ -35,8 +35,7 @@ class DotsCtx(C.Structure):
            ("peer_rhs", C.c_void_p * 8), ("peer_hat", C.c_void_p * 8)]
         + [(n, C.c_void_p) for n in ("rt_fwd", "rt_bwd", "h_rt_fwd_ptr", "h_rt_bwd_ptr", "h_rt_fwd_wpr", "h_rt_bwd_wpr",
                                      "bidx", "erow_fwd", "erow_bwd", "gptr", "gidx", "gverts", "h_gv_ptr")]
-        + [("ring_stages", C.c_int32), ("ring_pdl", C.c_int32), ("ring_stage_bytes", C.c_int32), ("reserved2", C.c_int32),
-           ("rt_fwd_wptr", C.c_void_p), ("rt_bwd_wptr", C.c_void_p), ("h_rt_fwd_wlv", C.c_void_p), ("h_rt_bwd_wlv", C.c_void_p)]
+        + [("ring_stages", C.c_int32), ("ring_pdl", C.c_int32), ("ring_stage_bytes", C.c_int32), ("reserved2", C.c_int32)]
     )
 
 
@@ -87,10 +86,10 @@ def load(build_if_missing: bool = True):
         "dots_kkt_sums": (ctxp, i, vp, vp), "dots_kkt_sums_multi": (ctxp, C.c_uint, vp, vp), "dots_phi_rhs": (ctxp, vp), "dots_time_transform": (ctxp, i, vp),
         "dots_mode_solves": (ctxp, vp), "dots_grad_space": (ctxp, vp, vp, vp), "dots_div_space": (ctxp, vp, vp, vp),
         "dots_graph_create": (ctxp, i, vp, C.POINTER(vp)), "dots_graph_launch": (vp, vp), "dots_graph_destroy": (vp,),
-        "dots_factor_small_fronts": (C.POINTER(FrontArgs), i, i, vp), "dots_front_nmax": (), "dots_enable_peer": (i,),
+        "dots_factor_small_fronts": (C.POINTER(FrontArgs), i, i, vp), "dots_front_nmax": (),
+        "dots_factor_large_fronts": (C.POINTER(FrontArgs), i, i, i, i, vp, vp, vp, vp, vp), "dots_enable_peer": (i,),
         "dots_ipc_export": (vp, vp, C.POINTER(C.c_ulonglong)), "dots_ipc_import": (vp, C.c_ulonglong, C.POINTER(vp)),
         "dots_ring_level_times": (ctxp, vp, vp, vp, i, C.POINTER(C.c_int)),
-        "dots_ring_resident_blocks": (i, i, i, C.POINTER(C.c_int)),
     }
     i64 = C.c_int64
     protos.update({
@@ -109,8 +108,8 @@ EXPORTS = ("dots_abi_version", "dots_ctx_sizeof", "dots_last_error", "dots_step_
            "dots_step_tri", "dots_step_q0", "dots_iterate", "dots_refresh_corner_terms", "dots_scale_dual", "dots_scale_z", "dots_scale_prim_dual",
            "dots_set_params", "dots_kkt_sums", "dots_kkt_sums_multi", "dots_phi_rhs", "dots_time_transform", "dots_mode_solves",
            "dots_grad_space", "dots_div_space", "dots_graph_create", "dots_graph_launch", "dots_graph_destroy",
-           "dots_factor_small_fronts", "dots_front_nmax", "dots_enable_peer", "dots_ipc_export", "dots_ipc_import",
-           "dots_ring_level_times", "dots_ring_entry_rows", "dots_ring_resident_blocks",
+           "dots_factor_small_fronts", "dots_front_nmax", "dots_factor_large_fronts", "dots_enable_peer", "dots_ipc_export", "dots_ipc_import",
+           "dots_ring_level_times", "dots_ring_entry_rows",
            "dots_order_create", "dots_order_sizes", "dots_order_export", "dots_order_destroy")
 
 

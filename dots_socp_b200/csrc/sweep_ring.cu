@@ -18,8 +18,8 @@
 //    entry, issue slots 50-57 % busy - the kernel was instruction bound, not memory bound); lanes hold 2 consecutive
 //    modes and move them with 16-byte accesses;
 //  * "pull" extend-add: a node stores only ITS OWN contribution  -(L21 inv(L11)) r_S  to its boundary rows (`upd`, producer
-//    order).  Before a level is swept, every vertex of that level receives the contributions of ALL its descendants
-//    (fixed order: gidx lists them in post-order), in place in `hat` (k_ring_gather).  The pass-through gather at the end of
+//    order).  Before a level is swept, k_ring_gather adds to every vertex of that level the contributions of ALL its
+//    descendants (fixed order: gidx lists them in post-order), in place in `hat`.  The pass-through gather at the end of
 //    every boundary row of k_sweep_run (two dependent loads per 4-20 streamed entries on the lower levels) is gone;
 //  * outputs whose run is long (top of the tree) are shared by WPR warps as contiguous pieces and combined in a fixed
 //    order through shared memory (k_ring_split);
@@ -59,7 +59,6 @@ template <> struct sr_vec<1> {
     __device__ __forceinline__ void fma(const sr_vec<1> &p, const sr_vec<1> &r) { x += p.x * r.x; }
     __device__ __forceinline__ void add(const sr_vec<1> &p) { x += p.x; }
     __device__ __forceinline__ sr_vec<1> scaled(double f) const { sr_vec<1> o; o.x = f * x; return o; }
-    static __device__ __forceinline__ sr_vec<1> ldcg(const double *p) { sr_vec<1> o; o.x = __ldcg(p); return o; }
 };
 template <> struct __align__(16) sr_vec<2> {
     double x, y;
@@ -67,11 +66,6 @@ template <> struct __align__(16) sr_vec<2> {
     __device__ __forceinline__ void fma(const sr_vec<2> &p, const sr_vec<2> &r) { x += p.x * r.x; y += p.y * r.y; }
     __device__ __forceinline__ void add(const sr_vec<2> &p) { x += p.x; y += p.y; }
     __device__ __forceinline__ sr_vec<2> scaled(double f) const { sr_vec<2> o; o.x = f * x; o.y = f * y; return o; }
-    static __device__ __forceinline__ sr_vec<2> ldcg(const double *p)
-    {
-        const double2 d = __ldcg(reinterpret_cast<const double2 *>(p));
-        sr_vec<2> o; o.x = d.x; o.y = d.y; return o;
-    }
 };
 
 template <int ML, int DIR>
@@ -129,21 +123,11 @@ __device__ __forceinline__ void sr_stage(const dots_ctx_t &c, const dots_ring_ta
     }
 }
 
-// Contiguous tasks, one share per warp.  A task record = the outputs [oa, oa + n_out) of a node = n_ent consecutive panel
-// entries.  The plan (ring_plan.py) cuts every level into byte-balanced SHARES at output granularity, one per warp of the
-// launch: warp w streams the records [wptr[w], wptr[w+1]) back to back.  Its ring never drains between records (the
-// producer walks ahead through the record list, whose next entry is prefetched), so small nodes cost no start-up bubble,
-// every warp moves the same number of bytes (no wave quantisation, no block tails: the grid is at most the resident set)
-// and there is no queue to contend on.  No cursor arithmetic: the per-entry codes (erow_fwd / erow_bwd, built once on the
-// host) say which row of Z an entry multiplies and where an output ends.
-#define SR_FIFO 8                                                     // records a warp's producer may run ahead of its math
-struct sr_rec {                                                       // what the math needs of a record (shared-memory FIFO)
-    long long pbase;
-    int n_ent, oa, off, s, ubase, pad;
-};
-
+// Contiguous tasks: one warp streams the outputs [oa, oa + n_out) of a node, i.e. n_ent consecutive panel entries.
+// SB = bytes per ring stage.  No cursor arithmetic: the per-entry codes (erow_fwd / erow_bwd, built once on the host) say
+// which row of Z an entry multiplies and where an output ends; the codes of stage k + 1 are requested during stage k.
 template <int ML, int DIR, int SB>
-__global__ void __launch_bounds__(SR_THREADS, 3) k_ring_run(dots_ctx_t c, int w0, int n_warps)
+__global__ void __launch_bounds__(SR_THREADS, 3) k_ring_run(dots_ctx_t c, int task0, int task_end)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // no-ops unless launched as a programmatic dependent
     constexpr int VW = sr_lane<ML>::VW, NA = sr_lane<ML>::NA;
@@ -151,84 +135,47 @@ __global__ void __launch_bounds__(SR_THREADS, 3) k_ring_run(dots_ctx_t c, int w0
     extern __shared__ __align__(128) unsigned char sr_smem[];
     const int nst = c.ring_stages;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * SR_WARPS + warp;
-    if (gw >= n_warps) return;                                           // warps are independent: no block barrier below
     double *ring = reinterpret_cast<double *>(sr_smem) + (size_t)warp * nst * EC * ML;
     uint64_t *bar = reinterpret_cast<uint64_t *>(sr_smem + (size_t)SR_WARPS * nst * EC * ML * 8) + warp * nst;
-    sr_rec *fifo = reinterpret_cast<sr_rec *>(sr_smem + (((size_t)SR_WARPS * nst * (EC * ML * 8 + 8) + 15) & ~(size_t)15)) + warp * SR_FIFO;
-    const dots_ring_task_t *tasks = (DIR == 0 ? c.rt_fwd : c.rt_bwd);
-    const int32_t *wptr = (DIR == 0 ? c.rt_fwd_wptr : c.rt_bwd_wptr) + w0 + gw;
-    const double *panels = (DIR == 0 ? c.panels : c.panels_t);
-    const int32_t *codes_all = (DIR == 0 ? c.erow_fwd : c.erow_bwd);
+    const int ti = task0 + blockIdx.x * SR_WARPS + warp;
+    if (ti >= task_end) return;                                          // warps are independent: no block barrier below
     if (lane == 0) {
         for (int i = 0; i < nst; ++i) mbar_init(&bar[i], 1);
         mbar_fence_init();
     }
     __syncwarp();
-    int i_next = wptr[0];
-    const int i_end = wptr[1];
-    if (i_next >= i_end) return;
-    // ---- producer: walks the warp's records; the record after the current one is requested one record ahead
-    dots_ring_task_t r_next = tasks[i_next];
-    const double *p_src = nullptr;
-    int p_nent = 0, p_k = 0, p_nstage = 0;
-    int tail = 0, head = 0;                                              // FIFO of records between producer and math
-    auto produce = [&](int slot) -> bool {                               // issue the next stage of the warp's stream into `slot`
-        while (p_k >= p_nstage) {
-            if (i_next >= i_end) return false;
-            const dots_ring_task_t r = r_next;                           // requested one record ago
-            if (lane == 0) {
-                sr_rec q;
-                q.pbase = r.pbase; q.n_ent = r.n_ent; q.oa = r.oa; q.off = r.off; q.s = r.s; q.ubase = r.ubase; q.pad = 0;
-                fifo[tail & (SR_FIFO - 1)] = q;
-            }
-            ++tail;
-            p_src = panels + (size_t)r.pbase * ML;
-            p_nent = r.n_ent;
-            p_nstage = (r.n_ent + EC - 1) / EC;
-            p_k = 0;
-            if (++i_next < i_end) r_next = tasks[i_next];
-        }
-        if (lane == 0) {
-            const uint32_t bytes = (uint32_t)min(EC, p_nent - p_k * EC) * (uint32_t)(ML * 8);
-            mbar_expect_tx(&bar[slot], bytes);
-            tma_load_1d(ring + (size_t)slot * EC * ML, p_src + (size_t)p_k * EC * ML, bytes, &bar[slot]);
-        }
-        ++p_k;
-        return true;
+    const dots_ring_task_t t = (DIR == 0 ? c.rt_fwd : c.rt_bwd)[ti];
+    const double *src = (DIR == 0 ? c.panels : c.panels_t) + (size_t)t.pbase * ML;
+    const int32_t *codes = (DIR == 0 ? c.erow_fwd : c.erow_bwd) + t.pbase;
+    const int n_ent = t.n_ent, n_stage = (n_ent + EC - 1) / EC;
+
+    auto issue = [&](int k, int slot) {                                  // lane 0: stage k of the run -> ring slot
+        const uint32_t bytes = (uint32_t)min(EC, n_ent - k * EC) * (uint32_t)(ML * 8);
+        mbar_expect_tx(&bar[slot], bytes);
+        tma_load_1d(ring + (size_t)slot * EC * ML, src + (size_t)k * EC * ML, bytes, &bar[slot]);
     };
-    int in_flight = 0;
-    while (in_flight < nst && produce(in_flight)) ++in_flight;           // panels are read-only: stream before the wait
-    __syncwarp();                                                        // the FIFO records written by lane 0 are visible
+    if (lane == 0) {
+        for (int k = 0; k < nst && k < n_stage; ++k) issue(k, k);        // panels and codes are read-only: stream before the wait
+    }
+    int code_next = (lane < EC && lane < n_ent) ? codes[lane] : 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");                   // below: data written by the previous launches
 
     const double *z = c.hat + lane * VW;                                 // Z = [hat | ywork]
+    int o = t.oa;
+    sr_vec<VW> acc[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) acc[a].zero();
     int slot = 0;
     uint32_t phase = 0;
-    while (in_flight > 0) {                                              // one record per trip
-        const sr_rec q = fifo[head & (SR_FIFO - 1)];
-        ++head;
-        dots_ring_task_t t;                                              // the fields sr_flush reads
-        t.off = q.off; t.s = q.s; t.ubase = q.ubase;
-        const int32_t *codes = codes_all + q.pbase;
-        const int n_ent = q.n_ent, n_stage = (n_ent + EC - 1) / EC;
-        int o = q.oa;
-        sr_vec<VW> acc[NA];
-#pragma unroll
-        for (int a = 0; a < NA; ++a) acc[a].zero();
-        int code_next = (lane < EC && lane < n_ent) ? codes[lane] : 0;
-        for (int k = 0; k < n_stage; ++k) {
-            const int ne = min(EC, n_ent - k * EC);
-            const int code = code_next;
-            const int nxt = (k + 1) * EC + lane;
-            code_next = (lane < EC && nxt < n_ent) ? codes[nxt] : 0;
-            sr_stage<ML, DIR, EC, true>(c, t, z, ring + (size_t)slot * EC * ML + lane * VW, &bar[slot], phase, ne, code, lane, o, acc);
-            __syncwarp();                                                // every lane is done reading the slot
-            --in_flight;
-            if (tail - head < SR_FIFO - 1 && produce(slot)) ++in_flight;
-            if (++slot == nst) { slot = 0; phase ^= 1u; }
-        }
-        __syncwarp();                                                    // records pushed by lane 0 during this trip
+    for (int k = 0; k < n_stage; ++k) {
+        const int ne = min(EC, n_ent - k * EC);
+        const int code = code_next;
+        const int nxt = (k + 1) * EC + lane;
+        code_next = (lane < EC && nxt < n_ent) ? codes[nxt] : 0;
+        sr_stage<ML, DIR, EC, true>(c, t, z, ring + (size_t)slot * EC * ML + lane * VW, &bar[slot], phase, ne, code, lane, o, acc);
+        __syncwarp();                                                    // every lane is done reading the slot
+        if (lane == 0 && k + nst < n_stage) issue(k + nst, slot);
+        if (++slot == nst) { slot = 0; phase ^= 1u; }
     }
 }
 
@@ -386,43 +333,31 @@ static int sr_launch(void (*kern)(Args...), int grid, int threads, size_t smem, 
 static size_t sr_smem_bytes(int ML, int SB, int nst, bool split)
 {
     const int EC = SB / (8 * ML);
-    return (((size_t)SR_WARPS * nst * ((size_t)EC * ML * 8 + 8) + 15) & ~(size_t)15)
-           + (split ? (size_t)SR_WARPS * ML * 8 : (size_t)SR_WARPS * SR_FIFO * sizeof(sr_rec)) + 16;
+    return (((size_t)SR_WARPS * nst * ((size_t)EC * ML * 8 + 8) + 15) & ~(size_t)15) + (split ? (size_t)SR_WARPS * ML * 8 : 0) + 16;
 }
 
-// Per (device, instantiation): opt in to the dynamic shared memory and measure how many blocks of the persistent kernel are
-// resident (its grid).  Keyed by device so that a second engine on another GPU of the same process configures its own copy.
 template <int ML, int SB>
-static int sr_configure(int nst, int *resident_out)
+static int sr_configure(int nst)
 {
-    static int done[64] = {0}, resident[64] = {0};
+    // the opt-in is per device and per function: keyed by (device, stages) so that a second engine on another GPU of the
+    // same process configures its own copy
+    static int done[64] = {0};
     int dev = 0;
     DOTS_CUDA(cudaGetDevice(&dev));
-    dev = (dev >= 0 && dev < 64) ? dev : 0;
-    if (done[dev] != nst) {
-        const int run = (int)sr_smem_bytes(ML, SB, nst, false), split = (int)sr_smem_bytes(ML, SB, nst, true);
-        DOTS_CUDA(cudaFuncSetAttribute(k_ring_run<ML, 0, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, run));
-        DOTS_CUDA(cudaFuncSetAttribute(k_ring_run<ML, 1, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, run));
-        DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 2, 0, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
-        DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 4, 0, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
-        DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 8, 0, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
-        DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 2, 1, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
-        DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 4, 1, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
-        DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 8, 1, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
-        int occ0 = 0, occ1 = 0, n_sm = 0;
-        DOTS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, k_ring_run<ML, 0, SB>, SR_THREADS, (size_t)run));
-        DOTS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_ring_run<ML, 1, SB>, SR_THREADS, (size_t)run));
-        DOTS_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        const int occ = occ0 < occ1 ? occ0 : occ1;
-        if (occ < 1) { dots_set_error("ring sweep: the persistent kernel does not fit an SM (%d stages)", nst); return DOTS_ERR_BAD_ARG; }
-        resident[dev] = occ * n_sm;
-        done[dev] = nst;
-    }
-    *resident_out = resident[dev];
+    if (dev >= 0 && dev < 64 && done[dev] == nst) return 0;
+    const int run = (int)sr_smem_bytes(ML, SB, nst, false), split = (int)sr_smem_bytes(ML, SB, nst, true);
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_run<ML, 0, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, run));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_run<ML, 1, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, run));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 2, 0, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 4, 0, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 8, 0, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 2, 1, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 4, 1, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    DOTS_CUDA(cudaFuncSetAttribute(k_ring_split<ML, 8, 1, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, split));
+    if (dev >= 0 && dev < 64) done[dev] = nst;
     return 0;
 }
 
-// One level of one sweep.  Contiguous (wpr 1): one warp per share of the level (h_rt_*_wptr_lv ranges into rt_*_wptr).
 template <int ML, int DIR, int SB>
 static int sr_level(const dots_ctx_t *c, int lv, bool chain, cudaStream_t st)
 {
@@ -431,12 +366,7 @@ static int sr_level(const dots_ctx_t *c, int lv, bool chain, cudaStream_t st)
     const int i0 = ptr[lv], n = ptr[lv + 1] - i0;
     if (n <= 0) return 0;
     const int nst = c->ring_stages;
-    if (wpr == 1) {
-        const int32_t *wl = DIR == 0 ? c->h_rt_fwd_wlv : c->h_rt_bwd_wlv;       // [n_levels+1] offsets into rt_*_wptr
-        const int w0 = wl[lv], n_warps = wl[lv + 1] - w0 - 1;                    // a level's list has n_warps + 1 entries
-        if (n_warps <= 0) return 0;
-        return sr_launch(k_ring_run<ML, DIR, SB>, ceil_div(n_warps, SR_WARPS), SR_THREADS, sr_smem_bytes(ML, SB, nst, false), st, chain, *c, w0, n_warps);
-    }
+    if (wpr == 1) return sr_launch(k_ring_run<ML, DIR, SB>, ceil_div(n, SR_WARPS), SR_THREADS, sr_smem_bytes(ML, SB, nst, false), st, chain, *c, i0, i0 + n);
     const size_t smem = sr_smem_bytes(ML, SB, nst, true);
     switch (wpr) {
     case 2: return sr_launch(k_ring_split<ML, 2, DIR, SB>, n, SR_THREADS, smem, st, chain, *c, i0);
@@ -465,8 +395,7 @@ static int sr_mark(sr_marks *mk, int tag, cudaStream_t st)
 template <int ML, int SB>
 static int sr_sweeps(const dots_ctx_t *c, cudaStream_t st, sr_marks *mk)
 {
-    int resident = 0;
-    if (int e = sr_configure<ML, SB>(c->ring_stages, &resident)) return e;
+    if (int e = sr_configure<ML, SB>(c->ring_stages)) return e;
     const bool pdl = c->ring_pdl != 0;
     bool chain = false;                                                   // the first launch waits for the transform normally
     for (int lv = 0; lv < c->n_levels; ++lv) {
@@ -490,31 +419,13 @@ static int sr_sweeps(const dots_ctx_t *c, cudaStream_t st, sr_marks *mk)
     return sr_mark(mk, -1, st);
 }
 
-// Resident blocks of the contiguous-task kernel for this configuration (the plan sizes its shares with it).
-extern "C" int dots_ring_resident_blocks(int m_pad, int stages, int stage_bytes, int *blocks_out)
-{
-    if (!blocks_out || stages < 2 || stages > 6 || (stage_bytes != 2048 && stage_bytes != 4096)) { dots_set_error("dots_ring_resident_blocks: bad arguments"); return DOTS_ERR_BAD_ARG; }
-    switch (m_pad * 2 + (stage_bytes == 2048)) {
-    case 64: return sr_configure<32, 4096>(stages, blocks_out);
-    case 65: return sr_configure<32, 2048>(stages, blocks_out);
-    case 128: return sr_configure<64, 4096>(stages, blocks_out);
-    case 129: return sr_configure<64, 2048>(stages, blocks_out);
-    case 192: return sr_configure<96, 4096>(stages, blocks_out);
-    case 193: return sr_configure<96, 2048>(stages, blocks_out);
-    case 256: return sr_configure<128, 4096>(stages, blocks_out);
-    case 257: return sr_configure<128, 2048>(stages, blocks_out);
-    }
-    dots_set_error("dots_ring_resident_blocks: m_pad=%d unsupported", m_pad);
-    return DOTS_ERR_BAD_ARG;
-}
-
 static int sr_dispatch(const dots_ctx_t *c, void *stream, sr_marks *mk)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (c->m_pad % 32 || c->m_pad > 128) { dots_set_error("ring sweeps need m_pad in {32, 64, 96, 128} (got %d)", c->m_pad); return DOTS_ERR_BAD_ARG; }
     if (c->ywork != c->hat + (size_t)c->n_vert * c->m_pad) { dots_set_error("ring sweeps need ywork == hat + n_vert * m_pad"); return DOTS_ERR_BAD_ARG; }
     if (c->ring_stages < 2 || c->ring_stages > 6) { dots_set_error("ring_stages=%d outside 2..6", c->ring_stages); return DOTS_ERR_BAD_ARG; }
-    if (!c->rt_fwd || !c->rt_bwd || !c->erow_fwd || !c->erow_bwd || !c->gptr || !c->gidx || !c->rt_fwd_wptr || !c->rt_bwd_wptr) { dots_set_error("ring sweep plan missing from the context"); return DOTS_ERR_BAD_ARG; }
+    if (!c->rt_fwd || !c->rt_bwd || !c->erow_fwd || !c->erow_bwd || !c->gptr || !c->gidx) { dots_set_error("ring sweep plan missing from the context"); return DOTS_ERR_BAD_ARG; }
     const bool small = c->ring_stage_bytes == 2048;
     if (!small && c->ring_stage_bytes != 4096) { dots_set_error("ring_stage_bytes=%d: 2048 or 4096", c->ring_stage_bytes); return DOTS_ERR_BAD_ARG; }
     switch (c->m_pad) {

@@ -178,12 +178,22 @@ class SlabStore:
         return self.data[lo - self.lo:hi - self.lo]
 
 
-def gather_levels(comm: Comm, part: Partition, store: SlabStore, n_levels_total: int, owned_hi=None) -> torch.Tensor:
-    """Assemble the full (n_levels_total, ...) field from the owned slabs of all ranks (on every rank)."""
+def gather_levels(comm: Comm, part: Partition, store: SlabStore, n_levels_total: int, owned_hi=None, root=None):
+    """Assemble the full (n_levels_total, ...) field from the owned slabs of all ranks: on every rank (``root`` None,
+    all_gather) or on rank ``root`` only (gather; the other ranks get None)."""
     lo, hi = part.lvl_begin, part.lvl_end if owned_hi is None else owned_hi
     mine = torch.zeros((part.chunk,) + store.row_shape, dtype=store.data.dtype, device=store.data.device)
     if hi > lo:
         mine[:hi - lo] = store.levels(lo, hi)
-    full = torch.empty((part.world * part.chunk,) + store.row_shape, dtype=store.data.dtype, device=store.data.device)
-    comm.all_gather_into(full, mine)
-    return full[:n_levels_total]
+    shape = (part.world * part.chunk,) + store.row_shape
+    if root is None:
+        full = torch.empty(shape, dtype=store.data.dtype, device=store.data.device)
+        comm.all_gather_into(full, mine)
+        return full[:n_levels_total]
+    if comm.rank == root:
+        full = torch.empty(shape, dtype=store.data.dtype, device=store.data.device)
+        parts = list(full.view((part.world, part.chunk) + store.row_shape).unbind(0))
+        comm.dist.gather(mine, gather_list=parts, dst=comm._peer(root), group=comm.group)
+        return full[:n_levels_total]
+    comm.dist.gather(mine, gather_list=None, dst=comm._peer(root), group=comm.group)
+    return None

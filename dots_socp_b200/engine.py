@@ -157,7 +157,8 @@ class Engine:
         else:
             panels, panels_t = nested.factor_hybrid_device(sym, K, area_v, shifts, self.m_pad, self.device, self.lib,
                                                            lambda: torch.cuda.current_stream(self.device).cuda_stream,
-                                                           stats=self.factor_stats)
+                                                           stats=self.factor_stats,
+                                                           use_library=os.environ.get("DOTS_FACTOR") == "mixed")
         torch.cuda.synchronize(self.device)
         tm["factorization"] = time.perf_counter() - t0
 
@@ -186,15 +187,11 @@ class Engine:
         env_kb = lambda name, default: int(float(os.environ.get(name, default)) * 1024)
         self.ring = None
         if self.sweep_mode == 4:
-            self.ring_stages = int(os.environ.get("DOTS_RING_STAGES", 2))
-            self.ring_stage_bytes = int(os.environ.get("DOTS_RING_STAGE_BYTES", 4096))
-            blocks = C.c_int(0)
-            capi.check(self.lib.dots_ring_resident_blocks(self.m_pad, self.ring_stages, self.ring_stage_bytes, C.byref(blocks)),
-                       "dots_ring_resident_blocks")
             self.ring = ring_plan.build(
                 sym, self.n_sm, self.m_pad, split_bytes=env_kb("DOTS_RING_SPLIT_KB", 64),
-                resident_warps=8 * blocks.value * int(os.environ.get("DOTS_RING_OVERSUB", 1)),
-                min_share_bytes=env_kb("DOTS_RING_SHARE_MIN_KB", 32), wpr_max=int(os.environ.get("DOTS_RING_WPR_MAX", 8)))
+                tasks_per_sm=int(os.environ.get("DOTS_RING_TASKS_PER_SM", 64)),
+                task_bytes=(env_kb("DOTS_RING_TASK_MIN_KB", 16), env_kb("DOTS_RING_TASK_MAX_KB", 48)),
+                wpr_max=int(os.environ.get("DOTS_RING_WPR_MAX", 8)))
         fwd_ptr, fwd_items, bwd_ptr, bwd_items = plan["fwd_ptr"], plan["fwd_items"], plan["bwd_ptr"], plan["bwd_items"]
         self._h_fwd_ptr, self._h_bwd_ptr = fwd_ptr, bwd_ptr
 
@@ -240,12 +237,9 @@ class Engine:
             ctx.h_rt_fwd_ptr, ctx.h_rt_bwd_ptr = rp["fwd_ptr"].ctypes.data, rp["bwd_ptr"].ctypes.data
             ctx.h_rt_fwd_wpr, ctx.h_rt_bwd_wpr = rp["fwd_wpr"].ctypes.data, rp["bwd_wpr"].ctypes.data
             ctx.h_gv_ptr = rp["gv_ptr"].ctypes.data
-            for name in ("fwd_wptr", "bwd_wptr"):
-                setattr(ctx, "rt_" + name, up("ring_" + name, rp[name], np.int32).data_ptr())
-            ctx.h_rt_fwd_wlv, ctx.h_rt_bwd_wlv = rp["fwd_wlv"].ctypes.data, rp["bwd_wlv"].ctypes.data
-            ctx.ring_stages = self.ring_stages
+            ctx.ring_stages = int(os.environ.get("DOTS_RING_STAGES", 2))      # measured: 2 x 4 KB stages, 3 blocks / SM
             ctx.ring_pdl = int(os.environ.get("DOTS_RING_PDL", 1))
-            ctx.ring_stage_bytes = self.ring_stage_bytes
+            ctx.ring_stage_bytes = int(os.environ.get("DOTS_RING_STAGE_BYTES", 4096))
         self._keep["phase_clock"] = torch.zeros(2 * sym.n_levels + 1, dtype=torch.int64, device=dev)
         if os.environ.get("DOTS_PHASE_CLOCK"):
             ctx.phase_clock = self._keep["phase_clock"].data_ptr()
@@ -792,8 +786,9 @@ class Engine:
             return out
         raise KeyError(name)
 
-    def full(self, name):
-        """All time levels of a state field in the internal layout (gathered from the ranks when sharded)."""
+    def full(self, name, root=None):
+        """All time levels of a state field in the internal layout (gathered from the ranks when sharded: on every rank, or
+        on rank ``root`` only - the others get None)."""
         n_total = self.nT + 1 if name in ("phi", "rhs") + STATE_TRI + STATE_CORNER else self.nT
         if name == "rhs":
             return self.t["rhs"][:n_total]
@@ -801,12 +796,15 @@ class Engine:
         hi = self.part.lvl_end if n_total == self.nT + 1 else self.part.t_end
         if not self.comm.enabled:
             return st_.levels(0, n_total)
-        return dd.gather_levels(self.comm, self.part, st_, n_total, owned_hi=hi)
+        return dd.gather_levels(self.comm, self.part, st_, n_total, owned_hi=hi, root=root)
 
-    def from_internal(self, name, ten=None):
-        """Internal tensor with all time levels (default: the current state field) -> reference-layout device tensor."""
+    def from_internal(self, name, ten=None, root=None):
+        """Internal tensor with all time levels (default: the current state field) -> reference-layout device tensor
+        (None on the ranks other than ``root`` when a root is given)."""
         pv, pf = self._perm_v_t()
-        x = self.full(name) if ten is None else ten
+        x = self.full(name, root=root) if ten is None else ten
+        if x is None:
+            return None
         if name in STATE_VERTEX or name in ("lam", "rhs"):
             out = torch.empty_like(x)
             out[:, pv] = x
@@ -841,26 +839,55 @@ class Engine:
         names = names or (STATE_VERTEX + STATE_TRI + STATE_CORNER)
         return {n: self.from_internal(n).cpu().numpy() for n in names}
 
-    def _download(self, ten):
-        """Device tensor -> numpy through a pinned staging buffer (about 2x the pageable rate for the 0.5 GB fields)."""
-        host = torch.empty(ten.shape, dtype=ten.dtype, pin_memory=True)
-        host.copy_(ten, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return host.numpy()
+    _STAGE_BYTES = 64 << 20
+    _stage_cache = {}                                  # device index -> two pinned staging buffers, reused by every download
 
-    def dot_solution(self, geometry, centred):
+    def _download(self, ten):
+        """Device tensor -> fresh numpy array through two cached pinned staging buffers (64 MB each): the copy of chunk
+        i + 1 over PCIe overlaps the host memcpy of chunk i, and no 0.5 GB pinned allocation is made per call."""
+        ten = ten.contiguous()
+        out = np.empty(tuple(ten.shape), dtype=np.float64)
+        flat_d, flat_h = ten.view(-1), out.reshape(-1)
+        key = self.device.index
+        if key not in Engine._stage_cache:
+            Engine._stage_cache[key] = [torch.empty(Engine._STAGE_BYTES // 8, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        bufs = Engine._stage_cache[key]
+        step = bufs[0].numel()
+        stream = torch.cuda.current_stream(self.device)
+        evs = [torch.cuda.Event(), torch.cuda.Event()]
+        n = flat_d.numel()
+        chunks = [(o, min(step, n - o)) for o in range(0, n, step)]
+        for i, (o, m) in enumerate(chunks):
+            bufs[i & 1][:m].copy_(flat_d[o:o + m], non_blocking=True)
+            evs[i & 1].record(stream)
+            if i:
+                po, pm = chunks[i - 1]
+                evs[(i - 1) & 1].synchronize()
+                flat_h[po:po + pm] = bufs[(i - 1) & 1][:pm].numpy()
+        if chunks:
+            po, pm = chunks[-1]
+            evs[(len(chunks) - 1) & 1].synchronize()
+            flat_h[po:po + pm] = bufs[(len(chunks) - 1) & 1][:pm].numpy()
+        return out
+
+    def dot_solution(self, geometry, centred, root=None):
         """The DOT-unit solution of utils/type.py:48-65 (mu * area_v / 3, E * area_f) and, if ``centred``, the time-centred
         mu of socp/solver_decorator.py:32-34, formed on the device so that only the final mu and E cross PCIe.  The mass
-        diagnostics the caller prints (interface.py:313-314) come along as ``diagnostics`` (2 x (nT [+1]) doubles)."""
+        diagnostics the caller prints (interface.py:313-314) come along as ``diagnostics`` (2 x (nT [+1]) doubles).
+        Sharded runs: ``root`` = the rank that assembles and downloads the solution (the other ranks return mu = E = None);
+        None = every rank gets the full solution."""
         dev = self.device
+        mu_i, E_i = self.from_internal("mu", root=root), self.from_internal("E", root=root)
+        if mu_i is None:
+            return dict(mu=None, E=None, diagnostics=None, root=root)
         av = torch.as_tensor(np.asarray(geometry["area_vertices"], dtype=np.float64), device=dev)[None, :] / 3.0
         af = torch.as_tensor(np.asarray(geometry["area_triangles"], dtype=np.float64), device=dev)[None, :, None]
-        mu = (self.from_internal("mu") * (self.r * self.ds)) * av
+        mu = (mu_i * (self.r * self.ds)) * av
         if centred:
             mu0 = torch.as_tensor(np.asarray(geometry["mu0"], dtype=np.float64), device=dev)[None, :]
             mu1 = torch.as_tensor(np.asarray(geometry["mu1"], dtype=np.float64), device=dev)[None, :]
             mu = torch.cat([mu0, 0.5 * (mu[:-1] + mu[1:]), mu1], dim=0)
-        E = (self.from_internal("E") * (self.r * self.ds)) * af
+        E = (E_i * (self.r * self.ds)) * af
         # utils/evaluate_solution.py:7-45 on the device: per-layer mass and per-layer negative mass of the returned mu
         layers = torch.stack([mu.sum(dim=1), torch.where(mu < 0, mu, torch.zeros_like(mu)).sum(dim=1)]).cpu().numpy()
         n = layers.shape[1]
@@ -871,10 +898,15 @@ class Engine:
 
     def congestion_norm(self):
         """``||lambda_c - congestion * mu||_2`` of the un-scaled solution (the solver's closing log line,
-        socp/solver_socp.py:846-853), formed on the device; a norm does not care about the vertex ordering."""
+        socp/solver_socp.py:846-853), formed on the device from the owned steps (+ a rank-ordered sum of the partial squares);
+        a norm does not care about the vertex ordering."""
+        part = self.part
+        lc = self.slab["lam_c"].levels(part.lvl_begin, max(part.t_end, part.lvl_begin))
+        mu = self.slab["mu"].levels(part.lvl_begin, max(part.t_end, part.lvl_begin))
         # on the un-scaled solution, with the congestion as the reference holds it at that point (:846-853)
-        diff = self.ps * self.full("lam_c") - self.cong * (self.r * self.ds) * self.full("mu")
-        return float(torch.linalg.vector_norm(diff))
+        diff = self.ps * lc - self.cong * (self.r * self.ds) * mu
+        local = np.array([float((diff * diff).sum())])
+        return float(math.sqrt(self.comm.sum_in_rank_order(local, self.device)[0]))
 
     def solution(self, keys=None):
         """Un-scaled solution dict with the reference's keys and layouts (:397-405, :855-869).

@@ -360,10 +360,12 @@ def front_maps(sym: Symbolic, Kp: sp.csr_matrix):
 
 
 def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shifts: np.ndarray, m_pad: int, device, lib,
-                         stream_fn, stats: dict | None = None, front_nmax: int | None = None):
-    """Numeric factorisation on the GPU, level by level: small fronts by the hand-written ``k_front_small`` kernel (one
-    block per node and mode), the few large fronts near the root by batched dense torch.linalg calls.  Returns
-    (panels, panels_t), both (panel_entries, m_pad) on ``device``."""
+                         stream_fn, stats: dict | None = None, front_nmax: int | None = None, use_library: bool = False):
+    """Numeric factorisation on the GPU, level by level, with hand-written kernels only: small fronts by ``k_front_small``
+    (one block per node and mode, front in shared memory), the large fronts near the root by the blocked kernels of
+    csrc/front_large.cu (``dots_factor_large_fronts``, one call per level).  ``use_library=True`` (DOTS_FACTOR=mixed) routes
+    the large fronts through batched torch.linalg calls instead (the path the kernels replaced; kept as a cross-check).
+    Returns (panels, panels_t), both (panel_entries, m_pad) on ``device``."""
     import ctypes as C
     import torch
     from . import capi
@@ -419,25 +421,7 @@ def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shif
     args.u_ptr = u_ptr_dev.data_ptr()
     args.pin_node, args.pin_value = pin_node, pin_value
 
-    for lv, nodes in enumerate(levels):
-        b_l = sym.b[nodes].astype(np.int64)
-        offs = np.concatenate([[0], np.cumsum(b_l * b_l)])
-        buf = torch.zeros((max(1, int(offs[-1])), m_pad), dtype=torch.float64, device=device)
-        level_buf[lv] = buf
-        for nd, o0, bb in zip(nodes, offs[:-1], b_l):
-            if bb:
-                u_view[int(nd)] = buf[int(o0):int(o0 + bb * bb)].view(int(bb), int(bb), m_pad)
-                u_ptr_host[nd] = buf.data_ptr() + int(o0) * m_pad * 8
-        u_ptr_dev.copy_(torch.from_numpy(u_ptr_host))
-        nfront = sym.s[nodes] + sym.b[nodes]
-        small = nodes[nfront <= nmax]
-        large = nodes[nfront > nmax]
-        if small.size:
-            nodes_dev = dev(small, np.int32)
-            args.nodes = nodes_dev.data_ptr()
-            capi.check(lib.dots_factor_small_fronts(C.byref(args), int(small.size), int(nfront[nfront <= nmax].max()), stream_fn()),
-                       "dots_factor_small_fronts")
-            n_small += int(small.size)
+    def _library_large_fronts(large):
         for i in large:                                                    # batched dense algebra over the modes
             i = int(i)
             s, b = int(sym.s[i]), int(sym.b[i])
@@ -484,7 +468,46 @@ def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shif
                 jj = torch.arange(s, device=device)
                 panels[p0 + jj * (jj + 1) // 2 + jj, n_modes:] = 1.0
                 panels_t[p0 + jj * (s + b) - jj * (jj - 1) // 2, n_modes:] = 1.0
-            n_large += 1
+
+    for lv, nodes in enumerate(levels):
+        b_l = sym.b[nodes].astype(np.int64)
+        offs = np.concatenate([[0], np.cumsum(b_l * b_l)])
+        buf = torch.zeros((max(1, int(offs[-1])), m_pad), dtype=torch.float64, device=device)
+        level_buf[lv] = buf
+        for nd, o0, bb in zip(nodes, offs[:-1], b_l):
+            if bb:
+                u_view[int(nd)] = buf[int(o0):int(o0 + bb * bb)].view(int(bb), int(bb), m_pad)
+                u_ptr_host[nd] = buf.data_ptr() + int(o0) * m_pad * 8
+        u_ptr_dev.copy_(torch.from_numpy(u_ptr_host))
+        nfront = sym.s[nodes] + sym.b[nodes]
+        small = nodes[nfront <= nmax]
+        large = nodes[nfront > nmax]
+        if small.size:
+            nodes_dev = dev(small, np.int32)
+            args.nodes = nodes_dev.data_ptr()
+            capi.check(lib.dots_factor_small_fronts(C.byref(args), int(small.size), int(nfront[nfront <= nmax].max()), stream_fn()),
+                       "dots_factor_small_fronts")
+            n_small += int(small.size)
+        if large.size and use_library:
+            _library_large_fronts(large)
+            n_large += int(large.size)
+        elif large.size:                                                   # hand-written blocked factorisation (csrc/front_large.cu)
+            cap = max(1, 65535 // n_modes)
+            for c0 in range(0, large.size, cap):
+                part = large[c0:c0 + cap]
+                n_l = (sym.s[part] + sym.b[part]).astype(np.int64)
+                s_l = sym.s[part].astype(np.int64)
+                foff = np.concatenate([[0], np.cumsum(n_l * n_l * n_modes)])
+                goff = np.concatenate([[0], np.cumsum(n_l * s_l * n_modes)])
+                Fw = torch.empty(int(foff[-1]), dtype=torch.float64, device=device)
+                Gw = torch.empty(max(1, int(goff[-1])), dtype=torch.float64, device=device)
+                nodes_dev, foff_d, goff_d = dev(part, np.int32), dev_i64(foff[:-1]), dev_i64(goff[:-1])
+                args.nodes = nodes_dev.data_ptr()
+                capi.check(lib.dots_factor_large_fronts(C.byref(args), int(part.size), int(n_l.max()), int(s_l.max()),
+                                                        int(sym.b[part].max()), foff_d.data_ptr(), goff_d.data_ptr(),
+                                                        Fw.data_ptr(), Gw.data_ptr(), stream_fn()), "dots_factor_large_fronts")
+                n_large += int(part.size)
+                del Fw, Gw
         for old in [k for k, lu in last_use.items() if lu <= lv and k in level_buf and k < lv]:
             for nd in levels[old]:
                 u_view.pop(int(nd), None)

@@ -5,10 +5,9 @@ Vocabulary: an *output* is a panel row in the forward sweep (columns ``[0, min(o
 panel column in the backward sweep (rows ``[o, s+b)`` of the column-major copy).  The entries of consecutive outputs of one
 node are contiguous in memory in both directions.
 
-* contiguous records (``wpr`` 1): the outputs ``[oa, oa+n_out)`` of a node = ``n_ent`` consecutive panel entries starting
-  at ``pbase``.  A level is cut into byte-balanced SHARES at output granularity, one per warp of its launch (at most the
-  resident set of the device); a share is a run of consecutive records (it may span several small nodes), listed by
-  ``wptr``: warp w streams ``records[wptr[w]:wptr[w+1]]`` back to back;
+* contiguous tasks (``wpr`` 1): one warp streams the outputs ``[oa, oa+n_out)`` of a node = ``n_ent`` consecutive panel
+  entries starting at ``pbase``; tasks are cut so that a level has enough of them to fill the machine and none is much
+  longer than ``target`` entries;
 * split items (``wpr`` 2/4/8): near the root the runs of single outputs are hundreds of KB; there a block takes a group of
   outputs and ``wpr`` warps share each of them;
 * pull lists: every boundary row of every node contributes to exactly one vertex of an ancestor; ``gidx[gptr[v]:gptr[v+1]]``
@@ -37,38 +36,36 @@ def _out_lengths(s, b, forward):
     return lens.astype(np.int64), owner, o, first
 
 
-def _shares(sym, nodes, forward, n_warps):
-    """Contiguous records of one level and direction, cut into ``n_warps`` byte-balanced shares at output granularity.
-
-    Returns (records, wptr): ``records`` in node order = memory order (a record never crosses its node), ``wptr``
-    (n_warps + 1) with warp w streaming ``records[wptr[w]:wptr[w+1]]``."""
+def _tasks(sym, nodes, forward, target):
+    """Contiguous warp tasks of one level and direction (structured array, node order = memory order)."""
     nodes = nodes[sym.s[nodes] > 0]
     if nodes.size == 0:
-        return np.zeros(0, dtype=TASK_DTYPE), np.zeros(n_warps + 1, dtype=np.int64)
+        return np.zeros(0, dtype=TASK_DTYPE)
     s, b = sym.s[nodes].astype(np.int64), sym.b[nodes].astype(np.int64)
     lens, owner, o, first = _out_lengths(s, b, forward)
     cum = np.concatenate([[0], np.cumsum(lens)])                      # entries before every output (level-wide)
-    n_out = lens.size
-    want = (np.arange(n_warps + 1, dtype=np.int64) * int(cum[-1])) // n_warps
-    cut = np.searchsorted(cum, want, side="left")                     # share w = outputs [cut[w], cut[w+1])
-    cut[0], cut[-1] = 0, n_out
-    cut = np.minimum.accumulate(cut[::-1])[::-1]                      # keep it monotone
-    starts = np.unique(np.concatenate([cut[:-1], first[:-1]]))        # a record starts at every share and every node boundary
-    starts = starts[starts < n_out]
-    ends = np.concatenate([starts[1:], [n_out]])
-    t_owner = owner[starts]
     node_cum0 = cum[first[:-1]]
-    out = np.zeros(starts.size, dtype=TASK_DTYPE)
+    tot = cum[first[1:]] - node_cum0                                  # panel entries per node
+    n_t = np.clip(np.rint(tot / float(target)).astype(np.int64), 1, first[1:] - first[:-1])
+    t_owner = np.repeat(np.arange(nodes.size), n_t)
+    k = np.arange(t_owner.size) - np.repeat(np.cumsum(n_t) - n_t, n_t)
+    want = node_cum0[t_owner] + (k * tot[t_owner]) // n_t[t_owner]    # entry where task k should start
+    start = np.searchsorted(cum, want, side="right") - 1              # output containing that entry (level-wide index)
+    start = np.maximum(start, first[t_owner])
+    keep = np.ones(start.size, dtype=bool)
+    keep[1:] = start[1:] != start[:-1]                                # an output longer than a step: merge the duplicates
+    start, t_owner = start[keep], t_owner[keep]
+    end = np.concatenate([start[1:], [first[-1]]])
+    end = np.minimum(end, first[t_owner + 1])                         # a task never crosses its node
+    out = np.zeros(start.size, dtype=TASK_DTYPE)
     nd = nodes[t_owner]
-    out["pbase"] = sym.panel_off[nd] + (cum[starts] - node_cum0[t_owner])
-    out["n_ent"] = cum[ends] - cum[starts]
-    out["oa"] = o[starts]
-    out["n_out"] = ends - starts
+    out["pbase"] = sym.panel_off[nd] + (cum[start] - node_cum0[t_owner])
+    out["n_ent"] = cum[end] - cum[start]
+    out["oa"] = o[start]
+    out["n_out"] = end - start
     out["s"], out["b"], out["off"] = sym.s[nd], sym.b[nd], sym.off[nd]
     out["ubase"], out["fbase"] = sym.upd_off[nd], sym.front_off[nd]
-    wptr = np.searchsorted(starts, cut, side="left")
-    wptr[-1] = starts.size
-    return out, wptr
+    return out
 
 
 def _split_items(sym, nodes, forward, group):
@@ -103,18 +100,12 @@ def pull_lists(sym):
     return gptr, gidx
 
 
-def build(sym, n_sm: int, m_pad: int, split_bytes: int = 64 * 1024, resident_warps: int | None = None,
-          min_share_bytes: int = 32 * 1024, wpr_max: int = 8):
-    """Plan of both sweeps.  Returns a dict of contiguous numpy arrays (see the module docstring).
-
-    ``resident_warps``: warps of the contiguous-task kernel the device holds at once (dots_ring_resident_blocks x 8;
-    default 3 blocks per SM): a level is cut into at most that many shares, fewer when a share would fall below
-    ``min_share_bytes``."""
+def build(sym, n_sm: int, m_pad: int, split_bytes: int = 96 * 1024, tasks_per_sm: int = 64,
+          task_bytes=(16 * 1024, 96 * 1024), wpr_max: int = 8):
+    """Plan of both sweeps.  Returns a dict of contiguous numpy arrays (see the module docstring)."""
     ent_bytes = 8 * m_pad
-    W = int(resident_warps) if resident_warps else 24 * n_sm
+    lo_ent, hi_ent = max(1, task_bytes[0] // ent_bytes), max(1, task_bytes[1] // ent_bytes)
     fwd, bwd, fptr, bptr, fw, bw = [], [], [0], [0], [], []
-    wlist = {True: [], False: []}
-    wlv = {True: [0], False: [0]}
     gverts, gv_ptr = [], [0]
     gptr, gidx = pull_lists(sym)
     has = np.diff(gptr) > 0
@@ -124,7 +115,6 @@ def build(sym, n_sm: int, m_pad: int, split_bytes: int = 64 * 1024, resident_war
         for forward, acc, ptr, wl in ((True, fwd, fptr, fw), (False, bwd, bptr, bw)):
             if live.size == 0:
                 acc.append(np.zeros(0, dtype=TASK_DTYPE)); ptr.append(ptr[-1]); wl.append(1)
-                wlv[forward].append(wlv[forward][-1])
                 continue
             work = s_l * (s_l + 1) // 2 + s_l * b_l
             n_out = int((s_l + b_l).sum() if forward else s_l.sum())
@@ -136,16 +126,12 @@ def build(sym, n_sm: int, m_pad: int, split_bytes: int = 64 * 1024, resident_war
             while wpr < wpr_max and run_bytes / wpr > split_bytes:
                 wpr *= 2
             if wpr == 1:
-                n_w = int(np.clip(int(work.sum()) * ent_bytes // max(1, min_share_bytes), 1, W))
-                n_w = min(W, -(-n_w // 8) * 8)
-                items, wp = _shares(sym, live, forward, n_w)
-                wlist[forward].append(wp + ptr[-1])                     # absolute record indices
-                wlv[forward].append(wlv[forward][-1] + wp.size)
+                target = int(np.clip(work.sum() // (n_sm * tasks_per_sm), lo_ent, hi_ent))
+                items = _tasks(sym, live, forward, target)
             else:
                 rows = 8 // wpr
                 passes = int(min(8, max(1, n_out // (rows * 4 * n_sm))))
                 items = _split_items(sym, live, forward, rows * passes)
-                wlv[forward].append(wlv[forward][-1])
             acc.append(items); ptr.append(ptr[-1] + items.size); wl.append(wpr)
         mine = np.repeat(sym.off[live], s_l) + (np.arange(int(s_l.sum())) - np.repeat(np.cumsum(s_l) - s_l, s_l))
         mine = mine[has[mine]] if mine.size else mine.astype(np.int64)
@@ -155,9 +141,7 @@ def build(sym, n_sm: int, m_pad: int, split_bytes: int = 64 * 1024, resident_war
     bidx = (sym.front_idx + sym.n * (pos < np.repeat(sym.s, nfront))).astype(np.int32)
     cat = lambda parts: np.ascontiguousarray(np.concatenate(parts)) if sum(p.size for p in parts) else np.zeros(1, dtype=parts[0].dtype if parts else np.int32)
     i32 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.int32))
-    catw = lambda parts: i32(np.concatenate(parts)) if parts else np.zeros(1, np.int32)
     return dict(rt_fwd=cat(fwd), rt_bwd=cat(bwd), fwd_ptr=i32(fptr), bwd_ptr=i32(bptr), fwd_wpr=i32(fw), bwd_wpr=i32(bw),
-                fwd_wptr=catw(wlist[True]), bwd_wptr=catw(wlist[False]), fwd_wlv=i32(wlv[True]), bwd_wlv=i32(wlv[False]),
                 bidx=np.ascontiguousarray(bidx), gptr=np.ascontiguousarray(gptr),
                 gidx=gidx if gidx.size else np.zeros(1, np.int32), gverts=cat(gverts), gv_ptr=i32(gv_ptr))
 

@@ -79,7 +79,7 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
                 is_palm=False, is_multi_threads=True, is_z_scaling=True, is_constant_scaling=False,
                 check_kkt_step_by_step=False, init_solution=None, tol_checkpoints=None, time_limit=1000,
                 device=None, leaf_size=16, show_progress=False, return_engine=False, comm=None, solution_keys=None,
-                dot_units=None):
+                dot_units=None, solution_root=None):
     """B200 implementation of ``dot_surface_socp.socp.solver_socp.solver_socp``.
 
     Extra keyword arguments (``device``, ``leaf_size``, ``show_progress``, ``return_engine``, ``comm``) are additions;
@@ -87,6 +87,8 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
     (default: the world group) and every rank returns the full solution; ``solution_keys`` limits which of the twelve
     solution arrays are converted and copied to the host (default: all, as the reference returns them); ``dot_units``
     ("staggered" / "centred", set by ``solver_raw`` / ``solver``) returns the DOT-unit ``mu``, ``E`` formed on the device;
+    ``solution_root`` (sharded ``solver`` / ``solver_raw`` runs only): the rank that assembles and downloads the DOT-unit solution,
+    the other ranks return ``mu = E = None`` (default None: every rank returns it, as a single process would);
     ``is_multi_threads`` is accepted and ignored (the two reference threads become stream order).
     ``is_palm=True`` and ``is_constant_scaling=True`` are solver-only knobs that the reference's CLI / interface cannot
     reach (interface.py:275-284); both are built: ``is_palm`` as two fused kernels before every iteration (``Engine.step_q0``,
@@ -215,7 +217,8 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
     if dot_units is None:
         solution = eng.solution(solution_keys)                                            # :845, :855-869
     else:                                                  # decorators' translate / centring done on the device
-        solution = eng.dot_solution(geometry, centred=(dot_units == "centred"))
+        solution = eng.dot_solution(geometry, centred=(dot_units == "centred"),
+                                    root=solution_root if eng.comm.enabled else None)
     solution["checkpoints"] = checkpoints if checkpoints else None
     logging.log(LOG_INFO, "---- Overview of solution ".ljust(42, "-") + "\n"
                 f"Congestion norm: {eng.congestion_norm():.2f}\n"

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DOTS_ABI_VERSION 13
+#define DOTS_ABI_VERSION 14
 
 /* scalar block read by the kernels from device memory (so CUDA graphs stay valid across penalty updates) */
 enum {
@@ -184,9 +184,6 @@ typedef struct dots_ctx {
     int32_t ring_pdl;          /* 1: chain the level launches with programmatic dependent launch                          */
     int32_t ring_stage_bytes;  /* bytes per ring stage: 2048 or 4096                                                      */
     int32_t reserved2;
-    const int32_t *rt_fwd_wptr, *rt_bwd_wptr;   /* device: per level a list of n_warps + 1 record offsets: warp w of the level's
-                                                   launch streams the records [wptr[w], wptr[w+1]) (byte-balanced shares)      */
-    const int32_t *h_rt_fwd_wlv, *h_rt_bwd_wlv; /* HOST [n_levels+1] start of every level's list inside rt_*_wptr             */
 } dots_ctx_t;
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -274,6 +271,14 @@ typedef struct dots_front_args {
 } dots_front_args_t;
 int dots_factor_small_fronts(const dots_front_args_t *a, int n_launch, int max_front, void *stream);
 int dots_front_nmax(void);
+/* The fronts with more rows than dots_front_nmax() (near the root: up to 1 277 rows at V = 164k), batched over the `n_launch`
+ * nodes a->nodes of one tree level and all modes: blocked right-looking partial Cholesky, triangular inverse,
+ * L21 inv(L11), panels in both layouts and the update matrices for the parents (csrc/front_large.cu).  foff / goff
+ * (device, [n_launch]): offsets, in doubles, of every node's block of n_modes fronts (n x n each) / panel buffers (n x s each)
+ * inside the work arrays Fwork / Gwork; n_max, s_max, b_max: largest sizes in the launch.  At most 65535 / n_modes nodes
+ * per call.                                                                                                             */
+int dots_factor_large_fronts(const dots_front_args_t *a, int n_launch, int n_max, int s_max, int b_max,
+                             const int64_t *foff, const int64_t *goff, double *Fwork, double *Gwork, void *stream);
 
 /* ---- setup (row f1), host side: ONE nested-dissection ordering + symbolic multifrontal analysis shared by all time
  * modes (the reference lets SuperLU order and analyse each of its nT+1 matrices, utils/laplacian_inverse_socp.py:34-41).
@@ -304,8 +309,6 @@ int dots_time_transform(const dots_ctx_t *c, int inverse, void *stream);   /* rh
 int dots_mode_solves(const dots_ctx_t *c, void *stream);                   /* hat <- (K+shift M)^-1 hat */
 /* profiling aid: one pair of ring sweeps (sweep_mode 4) with a CUDA event before every launch; ms_out[i] = start of launch i ->
  * start of launch i+1, tag_out[i] = tree level (+1000: gather, +2000: backward).  Synchronises the stream.              */
-/* resident blocks (blocks per SM x SMs) of the contiguous-task kernel for this configuration on the current device */
-int dots_ring_resident_blocks(int m_pad, int stages, int stage_bytes, int *blocks_out);
 int dots_ring_level_times(const dots_ctx_t *c, void *stream, float *ms_out, int32_t *tag_out, int cap, int *n_out);
 int dots_grad_space(const dots_ctx_t *c, const double *phi, double *out, void *stream);  /* [nT+1][3][T] */
 int dots_div_space(const dots_ctx_t *c, const double *x, double *out, void *stream);     /* [nT+1][V]    */

@@ -50,7 +50,8 @@ def _worker(rank, world, port, name, out_dir):
         # (2) full solve through the public API
         sol, hist = b200.solver_socp(n_time, geo, leaf_size=8, **kw)
         # (3) the DOT-unit plug-in (device-side translation, centring and mass diagnostics) on the sharded state
-        dot, _ = b200.solver(n_time, _with_areas(geo), leaf_size=8, **kw)
+        dot, _ = b200.solver(n_time, _with_areas(geo), leaf_size=8, solution_root=0, **kw)
+        assert (dot["mu"] is not None) == (rank == 0)          # only the root assembles and downloads the DOT-unit solution
         if rank == 0:
             np.savez(os.path.join(out_dir, "multi.npz"), kkt=np.array(kk), cost=np.array(cost), iters=int(hist.kkt_iteration[-1]),
                      rows=hist.kkt_errors, sol_mu=sol["mu"], sol_z_mid=sol["z_mid"], dot_mu=dot["mu"], dot_E=dot["E"],
@@ -59,7 +60,7 @@ def _worker(rank, world, port, name, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("name", ["ico2_nt7_c01", "ico3_nt31_c0"])
 def test_sharded_solver_matches_single_gpu_and_reference(tmp_path, golden, name, world):
     if torch.cuda.device_count() < world:

@@ -191,7 +191,7 @@ def test_native_ordering_rejects_bad_arguments():
 
 @pytest.mark.parametrize("example,leaf,n_time", [("icosphere3", 8, 7), ("plane8", 6, 6), ("knot_small", 12, 15)])
 def test_hybrid_driver_library_branch_matches_the_library_factorisation(example, leaf, n_time):
-    """The large-front branch of ``factor_hybrid_device`` (the one that stays on library dense algebra, here forced for
+    """The library cross-check branch of ``factor_hybrid_device`` (``use_library=True``, DOTS_FACTOR=mixed; here forced for
     every front with front_nmax=0 so that no CUDA kernel is needed) against ``factor_batched_device``: same panels, both
     layouts.  Its index data is uploaded once and sliced per front; this pins that bookkeeping on the CPU."""
     from dots_socp_b200.engine import time_basis
@@ -207,8 +207,9 @@ def test_hybrid_driver_library_branch_matches_the_library_factorisation(example,
     m_pad = 8 if n_time + 1 <= 8 else 16
     ref, ref_t = nested.factor_batched_device(sym, K, mass, -lam, m_pad, "cpu", transposed=True)
     stats = {}
-    got, got_t = nested.factor_hybrid_device(sym, K, mass, -lam, m_pad, "cpu", None, lambda: 0, stats=stats, front_nmax=0)
-    assert stats["small_fronts"] == 0 and stats["large_fronts"] == int((sym.s > 0).sum())
+    got, got_t = nested.factor_hybrid_device(sym, K, mass, -lam, m_pad, "cpu", None, lambda: 0, stats=stats, front_nmax=0,
+                                             use_library=True)
+    assert stats["small_fronts"] == 0 and stats["large_fronts"] == sym.n_nodes
     scale = np.abs(ref.numpy()).max()
     assert np.abs(got.numpy() - ref.numpy()).max() <= 1e-12 * scale
     assert np.abs(got_t.numpy() - ref_t.numpy()).max() <= 1e-12 * scale

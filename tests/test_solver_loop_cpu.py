@@ -99,7 +99,7 @@ class OracleEngine:
         sol = self.alm.solution()
         return sol if keys is None else {k: sol[k] for k in keys}
 
-    def dot_solution(self, geometry, centred):
+    def dot_solution(self, geometry, centred, root=None):
         av = np.asarray(geometry["area_vertices"])[None, :] / 3.0
         mu = (self.alm.mu * (self.alm.r * self.alm.ds)) * av
         if centred:

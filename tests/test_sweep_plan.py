@@ -78,9 +78,8 @@ def test_children_sit_on_strictly_lower_levels():
 RING_CASES = [("icosphere3", 16, 32, 148, {}), ("icosphere4", 16, 64, 148, {}), ("knot", 16, 128, 148, {}),
               ("plane8", 6, 96, 4, {}),
               # tiny thresholds: every kind of item (many short tasks, split outputs with 2 / 4 / 8 warps) on a small mesh
-              ("icosphere3", 8, 64, 2, dict(split_bytes=2048, min_share_bytes=1024, resident_warps=48)),
-              ("icosphere2", 8, 32, 2, dict(split_bytes=1024, min_share_bytes=256, resident_warps=16, wpr_max=4)),
-              ("icosphere4", 16, 64, 148, dict(split_bytes=1 << 30, min_share_bytes=4096, resident_warps=3552))]   # no split level at all
+              ("icosphere3", 8, 64, 2, dict(split_bytes=2048, task_bytes=(512, 2048))),
+              ("icosphere2", 8, 32, 2, dict(split_bytes=1024, task_bytes=(256, 1024), wpr_max=4))]
 
 
 @pytest.mark.parametrize("example,leaf,m_pad,n_sm,kw", RING_CASES)
@@ -187,30 +186,3 @@ def test_entry_rows_native_equals_numpy_statement(example, leaf):
     assert int((ef[:sym.panel_entries] < 0).sum()) == int((sym.s + sym.b)[live].sum())      # one flag per panel row
     assert int((eb[:sym.panel_entries] < 0).sum()) == int(sym.s[live].sum())                # one flag per panel column
     assert (ef & 0x7fffffff).max() < sym.n and (eb & 0x7fffffff).max() < 2 * sym.n
-
-
-@pytest.mark.parametrize("example,leaf,m_pad,n_sm,kw", RING_CASES)
-def test_ring_shares_are_balanced_and_cover_the_level(example, leaf, m_pad, n_sm, kw):
-    """Contiguous levels: the warps' record ranges are consecutive, cover the level's records exactly once, and every share
-    carries the level's mean number of entries up to the longest output it could not cut."""
-    sym = _sym(example, leaf)
-    plan = ring_plan.build(sym, n_sm, m_pad, **kw)
-    n_contig = 0
-    for d in ("fwd", "bwd"):
-        for lv in range(sym.n_levels):
-            r0, r1 = int(plan[d + "_ptr"][lv]), int(plan[d + "_ptr"][lv + 1])
-            w0, w1 = int(plan[d + "_wlv"][lv]), int(plan[d + "_wlv"][lv + 1])
-            if plan[d + "_wpr"][lv] != 1 or r1 == r0:
-                assert w1 == w0
-                continue
-            n_contig += 1
-            wp = plan[d + "_wptr"][w0:w1]
-            assert wp[0] == r0 and wp[-1] == r1 and (np.diff(wp) >= 0).all()
-            recs = plan["rt_" + d][r0:r1]
-            ent = np.concatenate([[0], np.cumsum(recs["n_ent"])])
-            share = ent[wp[1:] - r0] - ent[wp[:-1] - r0]
-            n_w = wp.size - 1
-            assert n_w % 8 == 0 or n_w == 1
-            longest = int(max(recs["s"].max() if d == "fwd" else (recs["s"] + recs["b"]).max(), 1))
-            assert share.max() <= ent[-1] / n_w + longest + 1, (d, lv, share.max(), ent[-1] / n_w, longest)
-    assert n_contig > 0

@@ -7,8 +7,9 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-ENV = dict(stages="DOTS_RING_STAGES", pdl="DOTS_RING_PDL", split="DOTS_RING_SPLIT_KB", over="DOTS_RING_OVERSUB",
-           share="DOTS_RING_SHARE_MIN_KB", wpr="DOTS_RING_WPR_MAX", sb="DOTS_RING_STAGE_BYTES")
+ENV = dict(stages="DOTS_RING_STAGES", pdl="DOTS_RING_PDL", split="DOTS_RING_SPLIT_KB", tasks="DOTS_RING_TASKS_PER_SM",
+           tmin="DOTS_RING_TASK_MIN_KB", tmax="DOTS_RING_TASK_MAX_KB", wpr="DOTS_RING_WPR_MAX",
+           sb="DOTS_RING_STAGE_BYTES")
 args = [a for a in sys.argv[1:] if "=" not in a]
 for kv in (a for a in sys.argv[1:] if "=" in a):
     k, v = kv.split("=")

@@ -18,8 +18,9 @@ from bench import WORKLOADS                      # noqa: E402
 from dots_socp_b200 import capi, synth           # noqa: E402
 from dots_socp_b200.engine import Engine         # noqa: E402
 
-ENV = dict(stages="DOTS_RING_STAGES", pdl="DOTS_RING_PDL", split="DOTS_RING_SPLIT_KB", over="DOTS_RING_OVERSUB",
-           share="DOTS_RING_SHARE_MIN_KB", wpr="DOTS_RING_WPR_MAX", sb="DOTS_RING_STAGE_BYTES")
+ENV = dict(stages="DOTS_RING_STAGES", pdl="DOTS_RING_PDL", split="DOTS_RING_SPLIT_KB", tasks="DOTS_RING_TASKS_PER_SM",
+           tmin="DOTS_RING_TASK_MIN_KB", tmax="DOTS_RING_TASK_MAX_KB", wpr="DOTS_RING_WPR_MAX",
+           sb="DOTS_RING_STAGE_BYTES")
 
 workload = sys.argv[1] if len(sys.argv) > 1 else "icosphere7_nt63"
 variants = sys.argv[2:] or ["0", "4"]
