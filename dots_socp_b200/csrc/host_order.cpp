@@ -9,6 +9,7 @@
 //
 // Plain C++, no CUDA: geometric recursive bisection with vertex separators, then boundary sets by a post-order sweep.
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <new>
@@ -272,5 +273,138 @@ extern "C" int dots_ring_entry_rows(int64_t n_nodes, const int64_t *s, const int
             for (int64_t i = j; i < sn + bn; ++i) *t++ = bi[i] | (i == sn + bn - 1 ? LAST : 0);
         if (f - rows_fwd != panel_off[nd + 1] || t - rows_bwd != panel_off[nd + 1]) { dots_set_error("dots_ring_entry_rows: panel size mismatch at node %lld", (long long)nd); return -1; }
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mesh operators of the hot path (row f1; reference utils/surface_pre_computations_socp.py:11-132, Python loops over the
+// triangles): per triangle the area, the P1 hat-function gradients g[f][k][:] (altitude vector of corner k over its squared
+// length, :30-37) and the corner cotangents; per vertex the incident area sum (:121-124); the cotan stiffness matrix
+// K = -L (:68-84) in CSR with sorted columns; and the CSR vertex -> incident corner lists (:112-127).
+//   mesh_create: computes everything, returns a handle;  mesh_sizes: nnz(K);  mesh_export: copies into caller arrays.
+struct dots_mesh {
+    int64_t V = 0, T = 0;
+    std::vector<double> area_f, hat, area_sum, kval;
+    std::vector<int64_t> kptr, kidx, cptr, ctri, ccorner;
+};
+
+namespace {
+inline void sub3(const double *a, const double *b, double *o) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
+inline double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+inline void cross3(const double *a, const double *b, double *o)
+{
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline double norm3(const double *a) { return std::sqrt(dot3(a, a)); }
+}  // namespace
+
+extern "C" int dots_mesh_create(int64_t V, int64_t T, const double *vertices, const int64_t *triangles, dots_mesh_t **out)
+{
+    if (!vertices || !triangles || !out || V <= 0 || T <= 0) { dots_set_error("dots_mesh_create: bad arguments"); return -1; }
+    dots_mesh *m = new (std::nothrow) dots_mesh;
+    if (!m) { dots_set_error("dots_mesh_create: out of memory"); return -1; }
+    m->V = V; m->T = T;
+    m->area_f.assign(T, 0.0); m->hat.assign(9 * T, 0.0); m->area_sum.assign(V, 0.0);
+    std::vector<double> w(3 * T);                                          // half cotangent of the angle at corner k
+    for (int64_t f = 0; f < T; ++f) {
+        const int64_t *t = triangles + 3 * f;
+        for (int k = 0; k < 3; ++k)
+            if (t[k] < 0 || t[k] >= V) { dots_set_error("dots_mesh_create: triangle %lld has vertex %lld", (long long)f, (long long)t[k]); delete m; return -1; }
+        const double *p0 = vertices + 3 * t[0], *p1 = vertices + 3 * t[1], *p2 = vertices + 3 * t[2];
+        double e[3][3], n[3];                                              // e01, e12, e20
+        sub3(p1, p0, e[0]); sub3(p2, p1, e[1]); sub3(p0, p2, e[2]);
+        cross3(e[0], e[1], n);
+        m->area_f[f] = 0.5 * norm3(n);
+        for (int k = 0; k < 3; ++k) {                                      // altitude(into = e[k], along = e[(k+1)%3])
+            const double *into = e[k], *along = e[(k + 1) % 3];
+            const double coef = dot3(into, along) / dot3(along, along);
+            double h[3] = {-into[0] + along[0] * coef, -into[1] + along[1] * coef, -into[2] + along[2] * coef};
+            const double hh = dot3(h, h);
+            for (int x = 0; x < 3; ++x) m->hat[(size_t)f * 9 + k * 3 + x] = h[x] / hh;
+            const double *a = e[k], *bb = e[(k + 2) % 3];                  // cot(e[k], -e[(k+2)%3]) = angle at corner k
+            double nb[3] = {-bb[0], -bb[1], -bb[2]}, c[3];
+            cross3(a, nb, c);
+            w[3 * f + k] = 0.5 * (dot3(a, nb) / norm3(c));
+        }
+        for (int k = 0; k < 3; ++k) m->area_sum[t[k]] += m->area_f[f];
+    }
+    // ---- K: every corner k weights its opposite edge (a, b): K[a][b] -= w, K[b][a] -= w, K[a][a] += w, K[b][b] += w
+    std::vector<int64_t> cnt(V + 1, 0);
+    for (int64_t f = 0; f < T; ++f)
+        for (int k = 0; k < 3; ++k) { cnt[triangles[3 * f + (k + 1) % 3] + 1] += 2; cnt[triangles[3 * f + (k + 2) % 3] + 1] += 2; }
+    for (int64_t v = 0; v < V; ++v) cnt[v + 1] += cnt[v];
+    std::vector<int64_t> col(cnt[V]), fill(cnt.begin(), cnt.end() - 1);
+    std::vector<double> val(cnt[V]);
+    for (int64_t f = 0; f < T; ++f)
+        for (int k = 0; k < 3; ++k) {
+            const int64_t a = triangles[3 * f + (k + 1) % 3], b = triangles[3 * f + (k + 2) % 3];
+            const double wk = w[3 * f + k];
+            col[fill[a]] = b; val[fill[a]++] = -wk; col[fill[a]] = a; val[fill[a]++] = wk;
+            col[fill[b]] = a; val[fill[b]++] = -wk; col[fill[b]] = b; val[fill[b]++] = wk;
+        }
+    m->kptr.assign(V + 1, 0);
+    m->kidx.reserve(8 * V); m->kval.reserve(8 * V);
+    std::vector<std::pair<int64_t, double>> row;
+    for (int64_t v = 0; v < V; ++v) {
+        row.clear();
+        for (int64_t q = cnt[v]; q < cnt[v + 1]; ++q) row.emplace_back(col[q], val[q]);
+        std::stable_sort(row.begin(), row.end(), [](const std::pair<int64_t, double> &x, const std::pair<int64_t, double> &y) { return x.first < y.first; });
+        for (size_t q = 0; q < row.size();) {
+            size_t e2 = q;
+            double sum = 0.0;
+            while (e2 < row.size() && row[e2].first == row[q].first) sum += row[e2++].second;
+            m->kidx.push_back(row[q].first); m->kval.push_back(sum);
+            q = e2;
+        }
+        m->kptr[v + 1] = (int64_t)m->kidx.size();
+    }
+    // ---- corners around every vertex, ordered by (corner, triangle): column k*T + f of the reference's incidence map
+    m->cptr.assign(V + 1, 0);
+    for (int64_t i = 0; i < 3 * T; ++i) ++m->cptr[triangles[i] + 1];
+    for (int64_t v = 0; v < V; ++v) m->cptr[v + 1] += m->cptr[v];
+    m->ctri.assign(3 * T, 0); m->ccorner.assign(3 * T, 0);
+    std::vector<int64_t> pos(m->cptr.begin(), m->cptr.end() - 1);
+    for (int k = 0; k < 3; ++k)
+        for (int64_t f = 0; f < T; ++f) {
+            const int64_t v = triangles[3 * f + k];
+            m->ctri[pos[v]] = f; m->ccorner[pos[v]++] = k;
+        }
+    *out = m;
+    return 0;
+}
+
+extern "C" int dots_mesh_sizes(const dots_mesh_t *m, int64_t *nnz)
+{
+    if (!m || !nnz) { dots_set_error("dots_mesh_sizes: null argument"); return -1; }
+    *nnz = (int64_t)m->kidx.size();
+    return 0;
+}
+
+extern "C" int dots_mesh_export(const dots_mesh_t *m, double *area_f, double *hat, double *area_sum, int64_t *k_ptr, int64_t *k_idx,
+                                double *k_val, int64_t *c_ptr, int64_t *c_tri, int64_t *c_corner)
+{
+    if (!m) { dots_set_error("dots_mesh_export: null handle"); return -1; }
+    auto cp = [](auto *dst, const auto &src) { if (dst) std::copy(src.begin(), src.end(), dst); };
+    cp(area_f, m->area_f); cp(hat, m->hat); cp(area_sum, m->area_sum); cp(k_ptr, m->kptr); cp(k_idx, m->kidx); cp(k_val, m->kval);
+    cp(c_ptr, m->cptr); cp(c_tri, m->ctri); cp(c_corner, m->ccorner);
+    return 0;
+}
+
+extern "C" int dots_mesh_destroy(dots_mesh_t *m) { delete m; return 0; }
+
+// CSR vertex -> incident corner ids (k * T + f), ordered by (corner, triangle), for any triangle numbering (the engine calls it
+// on the renumbered mesh).  c_ptr [V+1] int32, c_idx [3T] int32.
+extern "C" int dots_corner_lists(int64_t V, int64_t T, const int64_t *triangles, int32_t *c_ptr, int32_t *c_idx)
+{
+    if (!triangles || !c_ptr || !c_idx || V <= 0 || T <= 0 || 3 * T > 0x7fffffffLL) { dots_set_error("dots_corner_lists: bad arguments"); return -1; }
+    std::fill(c_ptr, c_ptr + V + 1, 0);
+    for (int64_t i = 0; i < 3 * T; ++i) {
+        if (triangles[i] < 0 || triangles[i] >= V) { dots_set_error("dots_corner_lists: vertex id out of range"); return -1; }
+        ++c_ptr[triangles[i] + 1];
+    }
+    for (int64_t v = 0; v < V; ++v) c_ptr[v + 1] += c_ptr[v];
+    std::vector<int32_t> pos(c_ptr, c_ptr + V);
+    for (int k = 0; k < 3; ++k)
+        for (int64_t f = 0; f < T; ++f) c_idx[pos[triangles[3 * f + k]]++] = (int32_t)(k * T + f);
     return 0;
 }

@@ -130,10 +130,9 @@ class Engine:
         self.m_pad = part.m_pad
 
         # ---- mesh operators (host, vectorised) --------------------------------------------------
-        area_f = surface.triangle_areas(v, tri_old)
-        area_v = surface.incident_area_sum(V, tri_old, area_f) / 3.0                    # solver_socp.py:112
-        hat = surface.hat_gradients(v, tri_old)                                         # (T,3,3) [f,k,xyz]
-        K = surface.stiffness_matrix(v, tri_old)
+        mesh = surface.mesh_operators_native(self.lib, v, tri_old)                      # C++ (csrc/host_order.cpp, dots_mesh_*)
+        area_f, hat, K = mesh["area_f"], mesh["hat"], mesh["K"]                         # hat: (T,3,3) [f,k,xyz]
+        area_v = mesh["area_sum"] / 3.0                                                 # solver_socp.py:112
         tm["mesh_operators"] = time.perf_counter() - t_start
 
         # ---- ordering + batched factorisation (this rank's time modes only) -------------------------
@@ -179,7 +178,9 @@ class Engine:
         self._host_mesh = dict(tri=tri_new, hat=hat[self.perm_f])                        # internal numbering, (T,3) / (T,3,3)
         hat_n = hat[self.perm_f]                                                         # (T,3,3)
         diag = np.sqrt(area_f_n[None, :] / area_v_n[tri_new.T])                          # (3,T)  solver_socp.py:172-180
-        vc_ptr, vc_tri, vc_corner = surface.corner_adjacency(V, tri_new)
+        vc_ptr, vc_idx = np.empty(V + 1, dtype=np.int32), np.empty(3 * T, dtype=np.int32)
+        tri_c = np.ascontiguousarray(tri_new, dtype=np.int64)
+        capi.check(self.lib.dots_corner_lists(V, T, tri_c.ctypes.data, vc_ptr.ctypes.data, vc_idx.ctypes.data), "dots_corner_lists")
         qf, qb, n_phi_out = dd.transform_matrices(Q, part)
         self.sweep_grid = 0
         plan = _sweep_items(sym, self.n_sm, self.m_pad)
@@ -204,7 +205,7 @@ class Engine:
             tri=up("tri", tri_new.T, np.int32), hat_grad=up("hat_grad", hat_n.transpose(1, 2, 0), np.float64),
             area_f=up("area_f", area_f_n, np.float64), area_v=up("area_v", area_v_n, np.float64),
             diag_soc=up("diag_soc", diag, np.float64), vc_ptr=up("vc_ptr", vc_ptr, np.int32),
-            vc_idx=up("vc_idx", vc_corner * T + vc_tri, np.int32), qf=up("qf", qf, np.float64), qb=up("qb", qb, np.float64),
+            vc_idx=up("vc_idx", vc_idx, np.int32), qf=up("qf", qf, np.float64), qb=up("qb", qb, np.float64),
             panels=panels, panels_t=panels_t,
             nd_off=up("nd_off", sym.off, np.int32), nd_s=up("nd_s", sym.s, np.int32), nd_b=up("nd_b", sym.b, np.int32),
             nd_child=up("nd_child", sym.child, np.int32), nd_panel=up("nd_panel", sym.panel_off[:-1], np.int64),

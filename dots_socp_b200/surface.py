@@ -87,3 +87,30 @@ def corner_adjacency(n_vertices, triangles):
     np.cumsum(counts, out=ptr[1:])
     sorted_cols = col[order]
     return ptr, (sorted_cols % n_t).astype(np.int64), (sorted_cols // n_t).astype(np.int64)
+
+
+def mesh_operators_native(lib, vertices, triangles):
+    """All of the above in one pass of the C++ helper ``dots_mesh_*`` (csrc/host_order.cpp): returns a dict with
+    ``area_f`` (T,), ``hat`` (T,3,3), ``area_sum`` (V,), ``K`` (CSR, sorted columns) and the corner lists
+    ``(c_ptr, c_tri, c_corner)`` of the GIVEN triangle numbering.  The numpy functions of this module are the readable
+    statement and the checker (tests/test_nested_host.py)."""
+    import ctypes as C
+    from . import capi
+    v = np.ascontiguousarray(vertices, dtype=np.float64)
+    t = np.ascontiguousarray(triangles, dtype=np.int64)
+    n_v, n_t = v.shape[0], t.shape[0]
+    handle = C.c_void_p()
+    capi.check(lib.dots_mesh_create(n_v, n_t, v.ctypes.data, t.ctypes.data, C.byref(handle)), "dots_mesh_create")
+    try:
+        nnz = C.c_int64()
+        capi.check(lib.dots_mesh_sizes(handle, C.byref(nnz)), "dots_mesh_sizes")
+        area_f, hat, area_sum = np.empty(n_t), np.empty((n_t, 3, 3)), np.empty(n_v)
+        k_ptr, k_idx, k_val = np.empty(n_v + 1, np.int64), np.empty(nnz.value, np.int64), np.empty(nnz.value)
+        c_ptr, c_tri, c_corner = np.empty(n_v + 1, np.int64), np.empty(3 * n_t, np.int64), np.empty(3 * n_t, np.int64)
+        capi.check(lib.dots_mesh_export(handle, *(a.ctypes.data for a in (area_f, hat, area_sum, k_ptr, k_idx, k_val, c_ptr, c_tri, c_corner))),
+                   "dots_mesh_export")
+    finally:
+        lib.dots_mesh_destroy(handle)
+    K = sp.csr_matrix((k_val, k_idx, k_ptr), shape=(n_v, n_v))
+    K.has_sorted_indices = True
+    return dict(area_f=area_f, hat=hat, area_sum=area_sum, K=K, corners=(c_ptr, c_tri, c_corner))

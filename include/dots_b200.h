@@ -296,6 +296,22 @@ int dots_order_export(const dots_order_t *o, int64_t *perm, int64_t *s, int64_t 
                       int64_t *child, int64_t *front_idx, int64_t *child_pos);
 int dots_order_destroy(dots_order_t *o);
 
+/* ---- setup (row f1), host side: the mesh operators of the hot path (reference utils/surface_pre_computations_socp.py:11-132,
+ * Python loops over the triangles, ~25 s each at T = 328k).  HOST pointers.  vertices [V][3] f64, triangles [T][3] int64.
+ * dots_mesh_export fills caller arrays (NULL = skip): area_f [T]; hat [T][3][3] P1 hat-function gradients g[f][k][xyz] (:30-37);
+ * area_sum [V] UN-divided sum of incident |f| (:121-124); the cotan stiffness matrix K = -L (:68-84) as CSR with ascending
+ * columns (k_ptr [V+1], k_idx / k_val [nnz], nnz from dots_mesh_sizes); c_ptr [V+1], c_tri / c_corner [3T]: corners around every
+ * vertex ordered by (corner, triangle), the rows of the reference's vertex <- corner incidence map (:112-127).            */
+typedef struct dots_mesh dots_mesh_t;
+int dots_mesh_create(int64_t n_vert, int64_t n_tri, const double *vertices, const int64_t *triangles, dots_mesh_t **out);
+int dots_mesh_sizes(const dots_mesh_t *m, int64_t *nnz);
+int dots_mesh_export(const dots_mesh_t *m, double *area_f, double *hat, double *area_sum, int64_t *k_ptr, int64_t *k_idx,
+                     double *k_val, int64_t *c_ptr, int64_t *c_tri, int64_t *c_corner);
+int dots_mesh_destroy(dots_mesh_t *m);
+/* CSR vertex -> incident corner ids k * T + f, ordered by (corner, triangle), for any triangle numbering: c_ptr [V+1], c_idx [3T]
+ * (int32; dots_ctx_t.vc_ptr / vc_idx).                                                                                  */
+int dots_corner_lists(int64_t n_vert, int64_t n_tri, const int64_t *triangles, int32_t *c_ptr, int32_t *c_idx);
+
 /* ---- setup, host side: per-entry operand rows of the ring-streamed sweeps (sweep_mode 4).  HOST pointers.  For every
  * panel entry in streaming order (rows_fwd: row-major panels, rows_bwd: column-major copy) the row of Z = [hat | ywork]
  * the entry is multiplied with; bit 31 = last entry of its output.  s, b, off, front_off [n_nodes(+1)], panel_off

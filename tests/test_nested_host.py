@@ -213,3 +213,27 @@ def test_hybrid_driver_library_branch_matches_the_library_factorisation(example,
     scale = np.abs(ref.numpy()).max()
     assert np.abs(got.numpy() - ref.numpy()).max() <= 1e-12 * scale
     assert np.abs(got_t.numpy() - ref_t.numpy()).max() <= 1e-12 * scale
+
+
+@pytest.mark.parametrize("example", ["icosphere3", "plane8", "knot"])
+def test_native_mesh_operators_equal_the_numpy_statement(example):
+    """dots_mesh_* / dots_corner_lists (C++) against dots_socp_b200/surface.py (numpy): areas, hat gradients and incident
+    area sums bit for bit, the cotan stiffness matrix with the same pattern and values to rounding (different summation
+    order of the duplicates), the corner lists identical."""
+    from dots_socp_b200 import capi
+    lib = capi.load()
+    geo, _ = synth.example(example)
+    v, t = np.ascontiguousarray(geo["vertices"], dtype=np.float64), np.ascontiguousarray(geo["triangles"], dtype=np.int64)
+    m = surface.mesh_operators_native(lib, v, t)
+    af = surface.triangle_areas(v, t)
+    assert np.array_equal(m["area_f"], af)
+    assert np.array_equal(m["hat"], surface.hat_gradients(v, t))
+    assert np.array_equal(m["area_sum"], surface.incident_area_sum(v.shape[0], t, af))
+    K = surface.stiffness_matrix(v, t)
+    assert np.array_equal(m["K"].indptr, K.indptr) and np.array_equal(m["K"].indices, K.indices)
+    assert np.abs(m["K"].data - K.data).max() <= 1e-14 * np.abs(K.data).max()
+    ptr, tri_of, corner_of = surface.corner_adjacency(v.shape[0], t)
+    assert all(np.array_equal(a, b) for a, b in zip(m["corners"], (ptr, tri_of, corner_of)))
+    cp, ci = np.empty(v.shape[0] + 1, np.int32), np.empty(3 * t.shape[0], np.int32)
+    assert lib.dots_corner_lists(v.shape[0], t.shape[0], t.ctypes.data, cp.ctypes.data, ci.ctypes.data) == 0
+    assert np.array_equal(cp, ptr) and np.array_equal(ci, corner_of * t.shape[0] + tri_of)
