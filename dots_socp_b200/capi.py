@@ -9,7 +9,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 14
+ABI_VERSION = 17
 P_R, P_S, P_D, P_CONG, P_TAU, P_EPS, P_PS, P_DS, P_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 _i32p, _i64p, _f64p = C.c_void_p, C.c_void_p, C.c_void_p      # raw device/host addresses
@@ -25,7 +25,7 @@ class DotsCtx(C.Structure):
             "front_idx", "child_pos", "lvl_ptr", "lvl_items", "lvb_ptr", "lvb_items", "lvn_nodes", "h_lvl_ptr", "h_lvb_ptr",
             "h_lvn_ptr", "h_lvl_wpr", "h_lvb_cw")]
         + [("front_total", C.c_int64)]
-        + [(n, C.c_int32) for n in ("lvl_begin", "lvl_end", "n_ranks", "tt_kf", "tt_kb", "tt_nb", "tt_nout", "reserved1")]
+        + [(n, C.c_int32) for n in ("lvl_begin", "lvl_end", "n_ranks", "tt_kf", "tt_kb", "tt_nb", "tt_nout", "tt_sym")]
         + [(n, C.c_void_p) for n in (
             "params", "phi", "A", "lam_c", "mu", "z_fst", "z_end", "b_fst", "b_end", "lam",
             "bnd0", "bnd1", "B", "E", "b_mid", "z_mid", "corner_nrm", "corner_div",

@@ -116,6 +116,116 @@ __global__ void __launch_bounds__(256) k_time_mma(dots_ctx_t c, int n_tiles)
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same transforms with HALF the tensor work, for an even number of time levels n on one GPU.  The time eigenbasis is the
+// DCT-II basis, Q[t][k] = c_k cos(pi k (t + 1/2) / n), so Q[n-1-t][k] = (-1)^k Q[t][k].  With the modes stored even-first
+// (the engine permutes them: [k = 0, 2, 4, ... | 1, 3, 5, ...], tt_sym = 1) both GEMMs split into two of half the depth:
+//   DIR 0:  hat[v][even] = sum_{t < n/2} (rhs[t] + rhs[n-1-t]) Q[t][even],   hat[v][odd] = sum_{t < n/2} (rhs[t] - rhs[n-1-t]) Q[t][odd]
+//   DIR 1:  E[t] = sum_even hat Q[t][even], O[t] = sum_odd hat Q[t][odd]  (t < n/2);   phi[t] = E + O,  phi[n-1-t] = E - O
+// (ncu on k_time_mma: tensor pipe 71 % / 36 % busy at 0.14 ms each: the transforms were DMMA bound, not HBM bound).
+template <int DIR>
+__global__ void __launch_bounds__(256) k_time_sym(dots_ctx_t c, int n_tiles)
+{
+    extern __shared__ double sm[];
+    const int n = c.n_time + 1, h = n / 2, M = c.m_pad, V = c.n_vert;      // M == n (checked by the host)
+    const int NT = n / 8, HT = NT / 2;                                     // 8-column tiles: HT per half
+    const double *Bg = (DIR == 0) ? c.qf : c.qb;                           // qf [tt_kf][M]: rows t;  qb [tt_kb][tt_nb]: rows = modes, columns t
+    const int ldg = (DIR == 0) ? M : c.tt_nb;
+    const int lda = n + 4, ldb = n + 8;
+    double *Bs = sm;                                                       // DIR 0: [h][ldb] rows t < h; DIR 1: [n][ldb] rows = modes, columns t < h used
+    const int b_rows = (DIR == 0) ? h : n;
+    double *As = sm + (size_t)b_rows * ldb;                                // [TT_VT][lda]: DIR 0: [sum | difference] halves; DIR 1: hat row
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < b_rows * n; i += 256) {
+        const int p = i / n, j = i - p * n;
+        Bs[p * ldb + j] = (DIR == 0 || j < c.tt_nb) ? Bg[(size_t)p * ldg + j] : 0.0;
+    }
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int v0 = tile * TT_VT;
+        __syncthreads();
+        if (DIR == 0) {                                                    // pairs (t, n-1-t): 8 pairs per thread in flight
+            for (int i0 = tid; i0 < h * TT_VT; i0 += 256 * 8) {
+                double lo[8], hi[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * 256;
+                    lo[u] = hi[u] = 0.0;
+                    if (i < h * TT_VT) {
+                        const int p = i / TT_VT, vv = i - p * TT_VT;
+                        if (v0 + vv < V) { lo[u] = c.rhs[(size_t)p * V + v0 + vv]; hi[u] = c.rhs[(size_t)(n - 1 - p) * V + v0 + vv]; }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * 256;
+                    if (i < h * TT_VT) {
+                        const int p = i / TT_VT, vv = i - p * TT_VT;
+                        As[vv * lda + p] = lo[u] + hi[u];
+                        As[vv * lda + h + p] = lo[u] - hi[u];
+                    }
+                }
+            }
+        } else {
+            for (int i0 = tid; i0 < n * TT_VT; i0 += 256 * 8) {
+                double val[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * 256;
+                    val[u] = 0.0;
+                    if (i < n * TT_VT) {
+                        const int vv = i / n, p = i - vv * n;
+                        if (v0 + vv < V) val[u] = c.hat[(size_t)(v0 + vv) * M + p];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * 256;
+                    if (i < n * TT_VT) { const int vv = i / n, p = i - vv * n; As[vv * lda + p] = val[u]; }
+                }
+            }
+        }
+        __syncthreads();
+        double acc[16][2];
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+        const double *ap = As + (8 * warp + (lane >> 2)) * lda + (lane & 3);
+        const double *bp = Bs + (lane & 3) * ldb + (lane >> 2);
+        for (int p0 = 0; p0 < h; p0 += 4) {
+            const double a0 = ap[p0], a1 = ap[h + p0];                     // DIR 0: sum / difference;  DIR 1: even / odd modes
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                if (nt < HT) {
+                    if (DIR == 0) {
+                        dmma_m8n8k4(acc[nt][0], acc[nt][1], a0, bp[(size_t)p0 * ldb + nt * 8]);                    // even modes
+                        dmma_m8n8k4(acc[8 + nt][0], acc[8 + nt][1], a1, bp[(size_t)p0 * ldb + (HT + nt) * 8]);     // odd modes
+                    } else {
+                        dmma_m8n8k4(acc[nt][0], acc[nt][1], a0, bp[(size_t)p0 * ldb + nt * 8]);                    // E[t]
+                        dmma_m8n8k4(acc[8 + nt][0], acc[8 + nt][1], a1, bp[(size_t)(h + p0) * ldb + nt * 8]);      // O[t]
+                    }
+                }
+            }
+        }
+        const int vrow = v0 + 8 * warp + (lane >> 2);
+        if (vrow < V) {
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                if (nt < HT) {
+                    const int j = nt * 8 + 2 * (lane & 3);
+                    if (DIR == 0) {
+                        *reinterpret_cast<double2 *>(c.hat + (size_t)vrow * M + j) = make_double2(acc[nt][0], acc[nt][1]);
+                        *reinterpret_cast<double2 *>(c.hat + (size_t)vrow * M + h + j) = make_double2(acc[8 + nt][0], acc[8 + nt][1]);
+                    } else {
+                        c.phi[(size_t)j * V + vrow] = acc[nt][0] + acc[8 + nt][0];
+                        c.phi[(size_t)(j + 1) * V + vrow] = acc[nt][1] + acc[8 + nt][1];
+                        c.phi[(size_t)(n - 1 - j) * V + vrow] = acc[nt][0] - acc[8 + nt][0];
+                        c.phi[(size_t)(n - 2 - j) * V + vrow] = acc[nt][1] - acc[8 + nt][1];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ size_t panel_row_off(int row, int s)
 {
     return (row < s) ? (size_t)row * (row + 1) / 2 : (size_t)s * (s + 1) / 2 + (size_t)(row - s) * s;
@@ -408,6 +518,27 @@ extern "C" int dots_time_transform(const dots_ctx_t *c, int inverse, void *strea
 {
     if (int e = dots_check_ctx(c)) return e;
     cudaStream_t st = (cudaStream_t)stream;
+    if (c->tt_sym) {                                                       // even level count on one GPU, modes stored even-first
+        const int n = c->n_time + 1;
+        if (c->n_ranks != 1 || n % 16 || n != c->m_pad || n > 128 || c->tt_nout != n || c->lvl_begin != 0) { dots_set_error("tt_sym needs one rank and n_time + 1 = m_pad in {16, 32, ..., 128}"); return DOTS_ERR_BAD_ARG; }
+        const size_t smem_s = ((size_t)(inverse ? n : n / 2) * (n + 8) + (size_t)TT_VT * (n + 4)) * sizeof(double);
+        const int tiles = ceil_div(c->n_vert, TT_VT);
+        const int per = (smem_s <= 72 * 1024) ? 3 : (smem_s <= 110 * 1024 ? 2 : 1);
+        const int grid_s = tiles < c->n_sm * per ? tiles : c->n_sm * per;
+        static size_t conf[64][2] = {{0, 0}};
+        int dv = 0;
+        DOTS_CUDA(cudaGetDevice(&dv));
+        dv = (dv >= 0 && dv < 64) ? dv : 0;
+        if (smem_s > 48 * 1024 && smem_s > conf[dv][inverse ? 1 : 0]) {
+            if (inverse) DOTS_CUDA(cudaFuncSetAttribute(k_time_sym<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+            else DOTS_CUDA(cudaFuncSetAttribute(k_time_sym<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+            conf[dv][inverse ? 1 : 0] = smem_s;
+        }
+        if (inverse) k_time_sym<1><<<grid_s, 256, smem_s, st>>>(*c, tiles);
+        else k_time_sym<0><<<grid_s, 256, smem_s, st>>>(*c, tiles);
+        DOTS_LAUNCH_CHECK();
+        return 0;
+    }
     const int K = inverse ? c->tt_kb : c->tt_kf, N = inverse ? c->tt_nb : c->m_pad;
     if (K % 4 || N % 8 || N > 128 || K <= 0) { dots_set_error("time transform shape K=%d N=%d unsupported", K, N); return DOTS_ERR_BAD_ARG; }
     const size_t smem = ((size_t)K * (N + 8) + (size_t)TT_VT * (K + 4)) * sizeof(double);

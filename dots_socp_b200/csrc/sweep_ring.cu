@@ -59,6 +59,7 @@ template <> struct sr_vec<1> {
     __device__ __forceinline__ void fma(const sr_vec<1> &p, const sr_vec<1> &r) { x += p.x * r.x; }
     __device__ __forceinline__ void add(const sr_vec<1> &p) { x += p.x; }
     __device__ __forceinline__ sr_vec<1> scaled(double f) const { sr_vec<1> o; o.x = f * x; return o; }
+    static __device__ __forceinline__ sr_vec<1> ldcg(const double *p) { sr_vec<1> o; o.x = __ldcg(p); return o; }
 };
 template <> struct __align__(16) sr_vec<2> {
     double x, y;
@@ -66,6 +67,11 @@ template <> struct __align__(16) sr_vec<2> {
     __device__ __forceinline__ void fma(const sr_vec<2> &p, const sr_vec<2> &r) { x += p.x * r.x; y += p.y * r.y; }
     __device__ __forceinline__ void add(const sr_vec<2> &p) { x += p.x; y += p.y; }
     __device__ __forceinline__ sr_vec<2> scaled(double f) const { sr_vec<2> o; o.x = f * x; o.y = f * y; return o; }
+    static __device__ __forceinline__ sr_vec<2> ldcg(const double *p)                     // L2 only: data written by other SMs in this launch
+    {
+        const double2 d = __ldcg(reinterpret_cast<const double2 *>(p));
+        sr_vec<2> o; o.x = d.x; o.y = d.y; return o;
+    }
 };
 
 template <int ML, int DIR>

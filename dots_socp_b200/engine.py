@@ -112,22 +112,8 @@ class Engine:
         tri_old = np.ascontiguousarray(geometry["triangles"]).astype(np.int64)
         self.nT, self.V, self.T = int(n_time), v.shape[0], tri_old.shape[0]
         nT, V, T = self.nT, self.V, self.T
-        if sweep_mode is None:
-            sweep_mode = int(os.environ.get("DOTS_SWEEP_MODE", "-1"))
-        # ring-streamed sweeps (mode 4) need whole warps of modes: a single rank pads small time grids up to 32 modes
-        # (identity padding, a few KB); mode-sharded ranks with fewer than 32 modes keep the register-staged kernel (mode 0)
-        min_pad = 32 if (self.comm.world == 1 and sweep_mode in (-1, 4)) else 0
-        self.part = dd.partition(nT, self.comm.rank, self.comm.world, min_pad=min_pad)
-        part = self.part
-        if sweep_mode == -1:
-            sweep_mode = 4 if part.m_pad % 32 == 0 else 0
-        if sweep_mode not in (0, 4):
-            raise capi.DotsError(f"sweep_mode={sweep_mode} unsupported (0: k_sweep_run, 4: ring-streamed)")
-        if sweep_mode == 4 and part.m_pad % 32:
-            raise capi.DotsError(f"sweep_mode=4 needs a multiple of 32 time modes per rank, got {part.m_pad}")
         self.dt = 1.0 / nT
         self.cong, self.tau, self.eps = float(congestion), float(tau), float(eps)
-        self.m_pad = part.m_pad
 
         # ---- mesh operators (host, vectorised) --------------------------------------------------
         mesh = surface.mesh_operators_native(self.lib, v, tri_old)                      # C++ (csrc/host_order.cpp, dots_mesh_*)
@@ -144,10 +130,34 @@ class Engine:
         self.perm_f = np.argsort(tri_new.min(axis=1), kind="stable")                    # new -> old triangle
         tri_new = tri_new[self.perm_f]
         tm["ordering"] = time.perf_counter() - t0
+        # ---- which sweep kernels, how many padded modes ---------------------------------------------------
+        # 4: ring-streamed sweeps (csrc/sweep_ring.cu): whole warps of modes, so a single rank pads small time grids up to 32
+        #    modes (identity padding).  0: register-staged k_sweep_run: any mode count; kept for mode-sharded ranks with fewer than
+        #    32 modes and for factors of a few hundred MB, where every level launch is latency bound and its shorter
+        #    dependent chain wins (knots_5-class, nT = 31: 0.25 ms / iteration against 0.34; profiles/README.md).
+        if sweep_mode is None:
+            sweep_mode = int(os.environ.get("DOTS_SWEEP_MODE", "-1"))
+        if sweep_mode == -1:
+            n_pad32 = max(32, dd.pad_modes(-(-(nT + 1) // self.comm.world)))
+            small = 2 * 8 * n_pad32 * sym.panel_entries / 2 ** 20 < float(os.environ.get("DOTS_RING_MIN_MB", 300))
+            sweep_mode = 0 if (small or (self.comm.world > 1 and dd.pad_modes(-(-(nT + 1) // self.comm.world)) % 32)) else 4
+        if sweep_mode not in (0, 4):
+            raise capi.DotsError(f"sweep_mode={sweep_mode} unsupported (0: k_sweep_run, 4: ring-streamed)")
+        self.part = dd.partition(nT, self.comm.rank, self.comm.world, min_pad=32 if sweep_mode == 4 else 0)
+        part = self.part
+        if sweep_mode == 4 and part.m_pad % 32:
+            raise capi.DotsError(f"sweep_mode=4 needs a multiple of 32 time modes per rank, got {part.m_pad}")
+        self.m_pad = part.m_pad
         t0 = time.perf_counter()
         Q, lam_t = time_basis(nT)
         self.Q, self.lam_t = Q, lam_t
-        shifts = (-lam_t + self.eps)[part.lvl_begin:part.lvl_end]   # (L + (lam - eps) M) = -(K + (|lam| + eps) M)   (laplacian_inverse_socp.py:37-38)
+        # Mode storage order.  One rank with an even, warp-aligned level count: even modes first, so that the transforms can
+        # use the symmetry Q[n-1-t][k] = (-1)^k Q[t][k] of the DCT-II basis (k_time_sym: half the tensor work).
+        n_lv = nT + 1
+        self.tt_sym = bool(part.world == 1 and n_lv % 16 == 0 and part.m_pad == n_lv and os.environ.get("DOTS_TT_SYM", "1") == "1")
+        self.mode_order = (np.concatenate([np.arange(0, n_lv, 2), np.arange(1, n_lv, 2)]) if self.tt_sym else np.arange(n_lv))
+        Q_st, lam_st = Q[:, self.mode_order], lam_t[self.mode_order]            # column j of `hat` holds mode mode_order[j]
+        shifts = (-lam_st + self.eps)[part.lvl_begin:part.lvl_end]   # (L + (lam - eps) M) = -(K + (|lam| + eps) M)   (laplacian_inverse_socp.py:37-38)
         self.sweep_mode = int(sweep_mode)
         self.factor_stats = {}
         if os.environ.get("DOTS_FACTOR", "hybrid") == "library":
@@ -181,7 +191,7 @@ class Engine:
         vc_ptr, vc_idx = np.empty(V + 1, dtype=np.int32), np.empty(3 * T, dtype=np.int32)
         tri_c = np.ascontiguousarray(tri_new, dtype=np.int64)
         capi.check(self.lib.dots_corner_lists(V, T, tri_c.ctypes.data, vc_ptr.ctypes.data, vc_idx.ctypes.data), "dots_corner_lists")
-        qf, qb, n_phi_out = dd.transform_matrices(Q, part)
+        qf, qb, n_phi_out = dd.transform_matrices(Q_st, part)
         self.sweep_grid = 0
         plan = _sweep_items(sym, self.n_sm, self.m_pad)
         self.plan = plan                                                                 # host arrays stay alive
@@ -189,7 +199,7 @@ class Engine:
         self.ring = None
         if self.sweep_mode == 4:
             self.ring = ring_plan.build(
-                sym, self.n_sm, self.m_pad, split_bytes=env_kb("DOTS_RING_SPLIT_KB", 64),
+                sym=sym, n_sm=self.n_sm, m_pad=self.m_pad, split_bytes=env_kb("DOTS_RING_SPLIT_KB", 64),
                 tasks_per_sm=int(os.environ.get("DOTS_RING_TASKS_PER_SM", 64)),
                 task_bytes=(env_kb("DOTS_RING_TASK_MIN_KB", 16), env_kb("DOTS_RING_TASK_MAX_KB", 48)),
                 wpr_max=int(os.environ.get("DOTS_RING_WPR_MAX", 8)))
@@ -201,6 +211,7 @@ class Engine:
         ctx.m_pad, ctx.n_nodes, ctx.n_levels, ctx.n_sm = self.m_pad, sym.n_nodes, sym.n_levels, self.n_sm
         ctx.lvl_begin, ctx.lvl_end, ctx.n_ranks = part.lvl_begin, part.lvl_end, part.world
         ctx.tt_kf, ctx.tt_kb, ctx.tt_nb, ctx.tt_nout = qf.shape[0], qb.shape[0], qb.shape[1], n_phi_out
+        ctx.tt_sym = int(self.tt_sym)
         const = dict(
             tri=up("tri", tri_new.T, np.int32), hat_grad=up("hat_grad", hat_n.transpose(1, 2, 0), np.float64),
             area_f=up("area_f", area_f_n, np.float64), area_v=up("area_v", area_v_n, np.float64),
@@ -470,8 +481,14 @@ class Engine:
                     if self._cap_stream is None:
                         self._cap_stream = torch.cuda.Stream(self.device)
                     h = C.c_void_p()
-                    capi.check(self.lib.dots_graph_create(self._ctxp, int(wz), self._cap_stream.cuda_stream, C.byref(h)),
-                               "dots_graph_create")
+                    rc = self.lib.dots_graph_create(self._ctxp, int(wz), self._cap_stream.cuda_stream, C.byref(h))
+                    if rc != 0:                      # capture refused (e.g. a launch kind the driver cannot capture): stay eager
+                        msg = self.lib.dots_last_error()
+                        self.graph_error = msg.decode() if msg else f"dots_graph_create -> {rc}"
+                        self.use_graphs = False
+                        torch.cuda.synchronize(self.device)
+                        capi.check(self.lib.dots_iterate(self._ctxp, n - i, int(write_z), st), "dots_iterate")
+                        break
                     self._graphs[key] = h
                 capi.check(self.lib.dots_graph_launch(self._graphs[key], st), "dots_graph_launch")
         self.launches += n * self.launches_per_iteration()

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DOTS_ABI_VERSION 14
+#define DOTS_ABI_VERSION 17
 
 /* scalar block read by the kernels from device memory (so CUDA graphs stay valid across penalty updates) */
 enum {
@@ -130,7 +130,8 @@ typedef struct dots_ctx {
     int32_t tt_kb;             /* rows of qb (n_ranks * m_pad)                                        */
     int32_t tt_nb;             /* columns of qb (tt_nout rounded up to 8)                             */
     int32_t tt_nout;           /* phi levels written by the inverse transform                         */
-    int32_t reserved1;
+    int32_t tt_sym;            /* 1: one rank, n_time + 1 = m_pad a multiple of 16, modes stored even-first (k = 0, 2, ... | 1, 3, ...):
+                                  the transforms use the even / odd symmetry of the DCT-II basis (half the tensor work)      */
 
     /* ---- ALM state (read-write) ---- */
     double *params;            /* [DOTS_P_COUNT]                                                      */
@@ -151,7 +152,7 @@ typedef struct dots_ctx {
     double *red_out;           /* [72] reduced sums (device)                                          */
     int32_t red_blocks;
     int32_t sweep_mode;        /* 0: k_sweep_run, register-staged loads (any m_pad); 4: ring-streamed sweeps, every warp feeds its
-                                  own shared-memory ring with bulk async copies (m_pad a multiple of 32)                        */
+                                  own shared-memory ring with bulk async copies (m_pad a multiple of 32), one launch per level   */
     int32_t sweep_grid;        /* unused (kept for layout stability)                                   */
     int32_t reserved0;
     uint64_t *phase_clock;     /* optional [2*n_levels+1]: %globaltimer (ns) at the start and after each sweep phase */
@@ -184,6 +185,7 @@ typedef struct dots_ctx {
     int32_t ring_pdl;          /* 1: chain the level launches with programmatic dependent launch                          */
     int32_t ring_stage_bytes;  /* bytes per ring stage: 2048 or 4096                                                      */
     int32_t reserved2;
+
 } dots_ctx_t;
 
 /* ------------------------------------------------------------------------------------------------ */

@@ -30,10 +30,10 @@ def centred(phi, w):
     return phi - (phi * w[None, :]).sum() / (w.sum() * phi.shape[0])
 
 
-def make_pair(example, n_time, congestion=0.0, leaf=8, **exkw):
+def make_pair(example, n_time, congestion=0.0, leaf=8, sweep_mode=None, **exkw):
     geo, _ = synth.example(example, **exkw)
     alm = orc.OracleALM(n_time, geo, congestion=congestion)
-    eng = Engine(n_time, geo, congestion=congestion, leaf_size=leaf)
+    eng = Engine(n_time, geo, congestion=congestion, leaf_size=leaf, sweep_mode=sweep_mode)
     eng.scale_z(2.0)
     return geo, alm, eng
 
@@ -142,8 +142,9 @@ def test_fused_step_rows_a1_a4(congestion):
 @pytest.mark.parametrize("example,n_time,congestion,exkw", [
     ("icosphere2", 7, 0.0, {}), ("icosphere2", 7, 0.1, {}), ("plane8", 6, 0.0, {}),
     ("knot", 8, 0.05, dict(n_u=40, n_v=6)), ("icosphere3", 31, 0.0, {}), ("icosphere2", 127, 0.0, {})])
-def test_iterates_match_oracle(example, n_time, congestion, exkw):
-    geo, alm, eng = make_pair(example, n_time, congestion=congestion, **exkw)
+@pytest.mark.parametrize("sweep_mode", [None, 4])          # None: the engine's choice (small factors: k_sweep_run); 4: ring-streamed
+def test_iterates_match_oracle(example, n_time, congestion, exkw, sweep_mode):
+    geo, alm, eng = make_pair(example, n_time, congestion=congestion, sweep_mode=sweep_mode, **exkw)
     done = 0
     for k in (1, 2, 5, 50):
         for _ in range(k - done):
@@ -377,9 +378,38 @@ def test_both_sweep_kernels_match_the_sparse_solve(mode, example, n_time, leaf):
     K = surface.stiffness_matrix(geo["vertices"], geo["triangles"])
     Kp = K[eng.perm_v][:, eng.perm_v].tocsc()
     M = sp.diags(eng.area_v_new)
-    for m in range(1, n_time + 1, max(1, n_time // 6)):            # mode 0 is singular (pinned): covered through phi elsewhere
-        ref = -spla.spsolve(Kp + (-eng.lam_t[m] + eng.eps) * M, rhs[:, m])
+    for m in range(1, n_time + 1, max(1, n_time // 6)):            # column 0 = mode 0 is singular (pinned): covered through phi elsewhere
+        ref = -spla.spsolve(Kp + (-eng.lam_t[eng.mode_order[m]] + eng.eps) * M, rhs[:, m])        # column m holds mode mode_order[m]
         assert rel(x[:, m], ref) < 1e-10, (m, rel(x[:, m], ref))
+
+
+@pytest.mark.parametrize("n_time", [15, 31, 63, 95, 127])
+def test_symmetric_time_transforms_match_the_full_ones(monkeypatch, n_time):
+    """k_time_sym (even / odd split of the DCT-II basis, modes stored even-first) against k_time_mma on the same data:
+    forward transform of a random rhs (columns compared through the mode order) and inverse transform back; and against
+    numpy's Q^T rhs (laplacian_inverse_socp.py:54,61)."""
+    from dots_socp_b200 import capi
+    geo, _ = synth.example("icosphere2")
+    rng = np.random.default_rng(21)
+    out = {}
+    for sym in ("1", "0"):
+        monkeypatch.setenv("DOTS_TT_SYM", sym)
+        eng = Engine(n_time, geo, leaf_size=8)
+        assert eng.tt_sym == (sym == "1" and (n_time + 1) % 16 == 0 and eng.m_pad == n_time + 1)
+        rhs = rng.standard_normal((n_time + 1, eng.V)) if "rhs" not in out else out["rhs"]
+        out["rhs"] = rhs
+        eng.t["rhs"][:n_time + 1].copy_(torch.from_numpy(rhs))
+        capi.check(eng.lib.dots_time_transform(eng._ctxp, 0, eng.stream))
+        hat = eng.t["hat"].cpu().numpy()[:, :n_time + 1]
+        nat = np.empty_like(hat)
+        nat[:, eng.mode_order] = hat                                   # natural mode order
+        capi.check(eng.lib.dots_time_transform(eng._ctxp, 1, eng.stream))
+        out[sym] = (nat, eng.slab["phi"].levels(0, n_time + 1).cpu().numpy(), eng.Q)
+    ref_hat = (out["0"][2].T @ out["rhs"]).T
+    for sym in ("1", "0"):
+        assert rel(out[sym][0], ref_hat) < 1e-13
+        assert rel(out[sym][1], out["rhs"]) < 1e-12                    # Q Q^T = I
+    assert rel(out["1"][0], out["0"][0]) < 1e-13
 
 
 @pytest.mark.parametrize("stages,pdl", [(2, 0), (4, 1), (3, 1)])
@@ -397,7 +427,6 @@ def test_ring_sweep_variants_match(monkeypatch, stages, pdl):
         outs.append(eng.get_state(("phi", "mu", "B")))
     for k in outs[0]:
         assert np.array_equal(outs[0][k], outs[1][k]), k
-
 
 @pytest.mark.parametrize("example,leaf,n_time", [("icosphere3", 8, 7), ("icosphere5", 24, 31), ("plane8", 6, 6), ("icosphere5", 16, 63)])
 def test_setup_factorisation_matches_numpy_multifrontal_row_f1(example, leaf, n_time):
