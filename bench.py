@@ -261,14 +261,14 @@ def parity_block(eng, workload, world):
     eng.scale_z(2.0)
     eng.iterate(3)
     out = {"iterations": 3}
+    sums = eng.state_checksums()                      # the iterate after exactly 3 iterations, at every rank count
+    out["state_checksums"] = sums
     if world == 1:
         from dots_socp_b200 import capi
-        capi.check(eng.lib.dots_step_phi(eng._ctxp, eng.stream), "dots_step_phi")
+        capi.check(eng.lib.dots_step_phi(eng._ctxp, eng.stream), "dots_step_phi")       # the phi-step of iteration 4
         res = eng.phi_residual()
         out["phi_solve_residual_max_over_modes"] = float(res.max())
         out["phi_solve_residual_ok"] = bool(np.isfinite(res).all() and res.max() < 1e-9)
-    sums = eng.state_checksums()
-    out["state_checksums"] = sums
     key = workload
     rec = {}
     if os.path.exists(PARITY_RECORD):
@@ -363,7 +363,7 @@ def run_own(args):
     iters = int(hist.kkt_iteration[-1]) + 1
     setup_s = eng.timings["setup_total"]
     loop_s = wall - setup_s                               # loop + KKT syncs + solution download to host numpy
-    upload_s = float(eng.timings.get("upload", 0.0))      # host -> device copy of the mesh constants, masses and initial state
+    upload_s = float(eng.timings.get("upload", 0.0))      # host -> device copy of the mesh constants, index maps, masses + state allocation
     timed_s = upload_s + loop_s                           # e2e timed region: H2D of the inputs + loop + D2H of the result
     h2d = sum(t.numel() * t.element_size() for k, t in eng._keep.items() if k not in ("panels", "panels_t", "phase_clock"))
     d2h_solution = sum(v.nbytes for v in sol.values() if isinstance(v, np.ndarray))      # rank 0 (the only downloader)

@@ -31,14 +31,28 @@ def needs_build():
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
+    import fcntl
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("DOTS_NVCC_EXTRA", "").split()
-    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-o", LIB]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libdots_b200.so")
-    if verbose:
-        print(res.stderr)
+    # several ranks of one torchrun may arrive here together: one builds, the others wait on the lock and find the
+    # library fresh; the output appears under its final name only when complete (rename is atomic)
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB
+            tmp = f"{LIB}.{os.getpid()}.tmp"
+            cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-o", tmp]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building libdots_b200.so")
+            os.replace(tmp, LIB)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

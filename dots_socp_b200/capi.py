@@ -9,7 +9,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 17
+ABI_VERSION = 18
 P_R, P_S, P_D, P_CONG, P_TAU, P_EPS, P_PS, P_DS, P_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 _i32p, _i64p, _f64p = C.c_void_p, C.c_void_p, C.c_void_p      # raw device/host addresses
@@ -20,7 +20,7 @@ class DotsCtx(C.Structure):
     _fields_ = (
         [(n, C.c_int32) for n in ("abi_version", "n_time", "n_vert", "n_tri", "m_pad", "n_nodes", "n_levels", "n_sm")]
         + [(n, C.c_void_p) for n in (
-            "tri", "hat_grad", "area_f", "area_v", "diag_soc", "vc_ptr", "vc_idx", "qf", "qb",
+            "tri", "hat_grad", "area_f", "area_v", "diag_soc", "vc_ptr", "vc_idx", "vc_ell", "qf", "qb",
             "panels", "panels_t", "nd_off", "nd_s", "nd_b", "nd_child", "nd_panel", "nd_front", "nd_upd",
             "front_idx", "child_pos", "lvl_ptr", "lvl_items", "lvb_ptr", "lvb_items", "lvn_nodes", "h_lvl_ptr", "h_lvb_ptr",
             "h_lvn_ptr", "h_lvl_wpr", "h_lvb_cw")]

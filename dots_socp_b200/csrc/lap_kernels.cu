@@ -241,10 +241,35 @@ __device__ __forceinline__ void sweep_stamp(const dots_ctx_t &c, int idx)
     }
 }
 
+// Programmatic dependent launch: the sweep launches of one solve are chained (launch_level / launch_sweeps pass the
+// attribute when ctx.ring_pdl is set).  A block announces itself at once, reads only constant data (index lists, panels)
+// and then waits for the previous launch to finish and flush; every block executes the wait, so "this grid has completed"
+// still implies "all earlier grids have completed" for whatever follows.  No-ops when launched normally.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... Args>
+static int pdl_launch(void (*kern)(Args...), int grid, int threads, size_t smem, cudaStream_t st, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    DOTS_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+    return 0;
+}
+
 // Gather step of the forward sweep, one tree level: r_S = hat_S + (children's updates landing on S), in place.
 // Block = one item (node, first S row, n rows) of the level's gather list (leaves have no children: no items).
 __global__ void __launch_bounds__(256) k_sweep_gather(dots_ctx_t c, int item0, int stamp)
 {
+    pdl_launch_dependents();
     sweep_stamp(c, stamp);
     const int M = c.m_pad;
     const int *it = c.lvn_nodes + 3 * (size_t)(item0 + blockIdx.x);
@@ -255,6 +280,7 @@ __global__ void __launch_bounds__(256) k_sweep_gather(dots_ctx_t c, int item0, i
     const double *u1 = (ch1 >= 0) ? c.upd + (size_t)c.nd_upd[ch1] * M : nullptr;
     const int32_t *cp0 = c.child_pos + c.nd_front[node];
     const int32_t *cp1 = cp0 + c.front_total;
+    pdl_wait();
     for (int i = threadIdx.x; i < nj * M; i += blockDim.x) {
         const int j = j0 + i / M, m = i % M;
         const int a = cp0[j], b = cp1[j];
@@ -296,6 +322,7 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) 
 template <int ML, int WPR, int DIR, bool FG>
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS) k_sweep_run(dots_ctx_t c, int item0, int stamp)
 {
+    pdl_launch_dependents();
     sweep_stamp(c, stamp);
     extern __shared__ double rsm[];                    // [s][M] staged r_S (FG only)
     constexpr int M = ML;
@@ -336,6 +363,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS) k_sweep_run(d
     };
 #pragma unroll
     for (int k = 0; k < 2 * NR; ++k) prefetch(o0 + k * ROWS + rslot);
+    pdl_wait();                                        // below: vectors written by the previous launches
 
     if (FG) {                                          // r_S = hat_S + children's updates landing on S
         const int ncol = min(s, last + 1);
@@ -442,7 +470,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS) k_sweep_run(d
 
 // ------------------------------------------------------------------------------------------------
 template <int ML, int DIR>
-static int launch_level(const dots_ctx_t *c, int wpr_code, int i0, int n, int stamp, cudaStream_t st)
+static int launch_level(const dots_ctx_t *c, int wpr_code, int i0, int n, int stamp, bool pdl, cudaStream_t st)
 {
     const bool fuse = (DIR == 0) && (wpr_code & 16);
     const size_t smem = fuse ? (size_t)SWEEP_FG_SMAX * ML * sizeof(double) : 0;
@@ -458,38 +486,43 @@ static int launch_level(const dots_ctx_t *c, int wpr_code, int i0, int n, int st
             configured[dev] = true;
         }
         switch (wpr_code & 15) {
-        case 1: k_sweep_run<ML, 1, 0, true><<<n, SWEEP_THREADS, smem, st>>>(*c, i0, stamp); break;
-        default: k_sweep_run<ML, 2, 0, true><<<n, SWEEP_THREADS, smem, st>>>(*c, i0, stamp); break;
+        case 1: return pdl_launch(k_sweep_run<ML, 1, 0, true>, n, SWEEP_THREADS, smem, st, pdl, *c, i0, stamp);
+        default: return pdl_launch(k_sweep_run<ML, 2, 0, true>, n, SWEEP_THREADS, smem, st, pdl, *c, i0, stamp);
         }
     } else {
         switch (wpr_code & 15) {
-        case 1: k_sweep_run<ML, 1, DIR, false><<<n, SWEEP_THREADS, 0, st>>>(*c, i0, stamp); break;
-        case 2: k_sweep_run<ML, 2, DIR, false><<<n, SWEEP_THREADS, 0, st>>>(*c, i0, stamp); break;
-        case 4: k_sweep_run<ML, 4, DIR, false><<<n, SWEEP_THREADS, 0, st>>>(*c, i0, stamp); break;
-        default: k_sweep_run<ML, 8, DIR, false><<<n, SWEEP_THREADS, 0, st>>>(*c, i0, stamp); break;
+        case 1: return pdl_launch(k_sweep_run<ML, 1, DIR, false>, n, SWEEP_THREADS, (size_t)0, st, pdl, *c, i0, stamp);
+        case 2: return pdl_launch(k_sweep_run<ML, 2, DIR, false>, n, SWEEP_THREADS, (size_t)0, st, pdl, *c, i0, stamp);
+        case 4: return pdl_launch(k_sweep_run<ML, 4, DIR, false>, n, SWEEP_THREADS, (size_t)0, st, pdl, *c, i0, stamp);
+        default: return pdl_launch(k_sweep_run<ML, 8, DIR, false>, n, SWEEP_THREADS, (size_t)0, st, pdl, *c, i0, stamp);
         }
     }
-    DOTS_LAUNCH_CHECK();
-    return 0;
 }
 
 template <int ML>
 static int launch_sweeps(const dots_ctx_t *c, cudaStream_t st)
 {
+    const bool pdl = c->ring_pdl != 0;
+    bool chain = false;                                // the first launch waits for the time transform normally
     for (int lv = 0; lv < c->n_levels; ++lv) {
         const int g0 = c->h_lvn_ptr[lv], gn = c->h_lvn_ptr[lv + 1] - g0;
         // stamps: slot lv = start of forward level lv (its gather when there is one), slot L + k = start of the k-th backward level
         const bool fused = (c->h_lvl_wpr[lv] & 16) != 0;      // the level's blocks fold the children's updates themselves
         const bool gather = lv > 0 && gn > 0 && !fused;
-        if (gather) { k_sweep_gather<<<gn, 256, 0, st>>>(*c, g0, lv); DOTS_LAUNCH_CHECK(); }
+        if (gather) {
+            if (int e = pdl_launch(k_sweep_gather, gn, 256, (size_t)0, st, pdl && chain, *c, g0, lv)) return e;
+            chain = true;
+        }
         const int i0 = c->h_lvl_ptr[lv], n = c->h_lvl_ptr[lv + 1] - i0;
         if (n <= 0) continue;
-        if (int e = launch_level<ML, 0>(c, c->h_lvl_wpr[lv], i0, n, gather ? -1 : lv, st)) return e;
+        if (int e = launch_level<ML, 0>(c, c->h_lvl_wpr[lv], i0, n, gather ? -1 : lv, pdl && chain, st)) return e;
+        chain = true;
     }
     for (int lv = c->n_levels - 1; lv >= 0; --lv) {
         const int i0 = c->h_lvb_ptr[lv], n = c->h_lvb_ptr[lv + 1] - i0;
         if (n <= 0) continue;
-        if (int e = launch_level<ML, 1>(c, c->h_lvb_cw[lv], i0, n, 2 * c->n_levels - 1 - lv, st)) return e;
+        if (int e = launch_level<ML, 1>(c, c->h_lvb_cw[lv], i0, n, 2 * c->n_levels - 1 - lv, pdl && chain, st)) return e;
+        chain = true;
     }
     return 0;
 }

@@ -191,6 +191,12 @@ class Engine:
         vc_ptr, vc_idx = np.empty(V + 1, dtype=np.int32), np.empty(3 * T, dtype=np.int32)
         tri_c = np.ascontiguousarray(tri_new, dtype=np.int64)
         capi.check(self.lib.dots_corner_lists(V, T, tri_c.ctypes.data, vc_ptr.ctypes.data, vc_idx.ctypes.data), "dots_corner_lists")
+        deg = np.diff(vc_ptr)
+        vc_ell = np.full((V, 8), -1, dtype=np.int32)                                      # ELL form of the same lists (iter_kernels.cu: vc_load)
+        slot = np.arange(3 * T) - np.repeat(vc_ptr[:-1], deg)
+        keep = slot < 8
+        vc_ell[np.repeat(np.arange(V), deg)[keep], slot[keep]] = vc_idx[keep]
+        vc_ell[deg > 8, 7] = -2                                                          # long lists: the kernels walk the CSR form
         qf, qb, n_phi_out = dd.transform_matrices(Q_st, part)
         self.sweep_grid = 0
         plan = _sweep_items(sym, self.n_sm, self.m_pad)
@@ -203,8 +209,11 @@ class Engine:
                 tasks_per_sm=int(os.environ.get("DOTS_RING_TASKS_PER_SM", 64)),
                 task_bytes=(env_kb("DOTS_RING_TASK_MIN_KB", 16), env_kb("DOTS_RING_TASK_MAX_KB", 48)),
                 wpr_max=int(os.environ.get("DOTS_RING_WPR_MAX", 8)))
+            self.ring["erow_fwd"], self.ring["erow_bwd"] = ring_plan.entry_rows(self.lib, sym, self.ring["bidx"])
         fwd_ptr, fwd_items, bwd_ptr, bwd_items = plan["fwd_ptr"], plan["fwd_items"], plan["bwd_ptr"], plan["bwd_items"]
         self._h_fwd_ptr, self._h_bwd_ptr = fwd_ptr, bwd_ptr
+        tm["plan"] = time.perf_counter() - t0            # host-side launch plans and index maps (analysis, like the ordering)
+        t0 = time.perf_counter()
 
         ctx = capi.DotsCtx()
         ctx.abi_version, ctx.n_time, ctx.n_vert, ctx.n_tri = capi.ABI_VERSION, nT, V, T
@@ -216,7 +225,7 @@ class Engine:
             tri=up("tri", tri_new.T, np.int32), hat_grad=up("hat_grad", hat_n.transpose(1, 2, 0), np.float64),
             area_f=up("area_f", area_f_n, np.float64), area_v=up("area_v", area_v_n, np.float64),
             diag_soc=up("diag_soc", diag, np.float64), vc_ptr=up("vc_ptr", vc_ptr, np.int32),
-            vc_idx=up("vc_idx", vc_idx, np.int32), qf=up("qf", qf, np.float64), qb=up("qb", qb, np.float64),
+            vc_idx=up("vc_idx", vc_idx, np.int32), vc_ell=up("vc_ell", vc_ell, np.int32), qf=up("qf", qf, np.float64), qb=up("qb", qb, np.float64),
             panels=panels, panels_t=panels_t,
             nd_off=up("nd_off", sym.off, np.int32), nd_s=up("nd_s", sym.s, np.int32), nd_b=up("nd_b", sym.b, np.int32),
             nd_child=up("nd_child", sym.child, np.int32), nd_panel=up("nd_panel", sym.panel_off[:-1], np.int64),
@@ -243,19 +252,20 @@ class Engine:
                 setattr(ctx, name, ten.data_ptr())
             for name in ("bidx", "gptr", "gidx", "gverts"):
                 setattr(ctx, name, up("ring_" + name, rp[name], np.int32).data_ptr())
-            rp["erow_fwd"], rp["erow_bwd"] = ring_plan.entry_rows(self.lib, sym, rp["bidx"])
             for name in ("erow_fwd", "erow_bwd"):
                 setattr(ctx, name, up("ring_" + name, rp[name], np.int32).data_ptr())
             ctx.h_rt_fwd_ptr, ctx.h_rt_bwd_ptr = rp["fwd_ptr"].ctypes.data, rp["bwd_ptr"].ctypes.data
             ctx.h_rt_fwd_wpr, ctx.h_rt_bwd_wpr = rp["fwd_wpr"].ctypes.data, rp["bwd_wpr"].ctypes.data
             ctx.h_gv_ptr = rp["gv_ptr"].ctypes.data
             ctx.ring_stages = int(os.environ.get("DOTS_RING_STAGES", 2))      # measured: 2 x 4 KB stages, 3 blocks / SM
-            ctx.ring_pdl = int(os.environ.get("DOTS_RING_PDL", 1))
             ctx.ring_stage_bytes = int(os.environ.get("DOTS_RING_STAGE_BYTES", 4096))
+        ctx.ring_pdl = int(os.environ.get("DOTS_RING_PDL", 1))                # both sweep kernels chain their level launches
         self._keep["phase_clock"] = torch.zeros(2 * sym.n_levels + 1, dtype=torch.int64, device=dev)
         if os.environ.get("DOTS_PHASE_CLOCK"):
             ctx.phase_clock = self._keep["phase_clock"].data_ptr()
 
+        torch.cuda.synchronize(dev)
+        tm["upload_constants"] = time.perf_counter() - t0
         # ---- state: level-indexed slabs (+ halo levels), addressed through virtual bases -------------------
         l0, l1, te = part.lvl_begin, part.lvl_end, part.t_end
         S = lambda lo, hi, *row: dd.SlabStore(lo, hi, row, dev)
@@ -858,34 +868,58 @@ class Engine:
         return {n: self.from_internal(n).cpu().numpy() for n in names}
 
     _STAGE_BYTES = 64 << 20
-    _stage_cache = {}                                  # device index -> two pinned staging buffers, reused by every download
+    _STAGE_BUFS = 3
+    _COPY_THREADS = 4
+    _stage_cache = {}                                  # device index -> pinned staging buffers, reused by every download
+    _copy_pool = None
 
     def _download(self, ten):
-        """Device tensor -> fresh numpy array through two cached pinned staging buffers (64 MB each): the copy of chunk
-        i + 1 over PCIe overlaps the host memcpy of chunk i, and no 0.5 GB pinned allocation is made per call."""
+        """Device tensor -> fresh numpy array through cached pinned staging buffers (3 x 64 MB): the copy of chunk i + 1
+        over PCIe overlaps the host memcpy of chunk i, which a few threads share (numpy releases the GIL while copying;
+        first-touch page faults of the fresh array dominate a single-threaded copy), and no 0.5 GB pinned allocation is
+        made per call."""
+        from concurrent.futures import ThreadPoolExecutor
         ten = ten.contiguous()
         out = np.empty(tuple(ten.shape), dtype=np.float64)
         flat_d, flat_h = ten.view(-1), out.reshape(-1)
         key = self.device.index
+        nb = Engine._STAGE_BUFS
         if key not in Engine._stage_cache:
-            Engine._stage_cache[key] = [torch.empty(Engine._STAGE_BYTES // 8, dtype=torch.float64, pin_memory=True) for _ in range(2)]
-        bufs = Engine._stage_cache[key]
+            Engine._stage_cache[key] = [torch.empty(Engine._STAGE_BYTES // 8, dtype=torch.float64, pin_memory=True) for _ in range(nb)]
+        if Engine._copy_pool is None:
+            Engine._copy_pool = ThreadPoolExecutor(Engine._COPY_THREADS, thread_name_prefix="dots-d2h")
+        bufs, pool = Engine._stage_cache[key], Engine._copy_pool
+        host = [b.numpy() for b in bufs]
         step = bufs[0].numel()
         stream = torch.cuda.current_stream(self.device)
-        evs = [torch.cuda.Event(), torch.cuda.Event()]
+        evs = [torch.cuda.Event() for _ in range(nb)]
+        pending = [[] for _ in range(nb)]                # host copies still reading staging buffer j
         n = flat_d.numel()
         chunks = [(o, min(step, n - o)) for o in range(0, n, step)]
+
+        def drain(i):                                    # chunk i has arrived: hand its slices to the copy threads
+            o, m = chunks[i]
+            j = i % nb
+            evs[j].synchronize()
+            piece = -(-m // Engine._COPY_THREADS)
+            for q in range(0, m, piece):
+                e = min(m, q + piece)
+                pending[j].append(pool.submit(np.copyto, flat_h[o + q:o + e], host[j][q:e]))
+
         for i, (o, m) in enumerate(chunks):
-            bufs[i & 1][:m].copy_(flat_d[o:o + m], non_blocking=True)
-            evs[i & 1].record(stream)
+            j = i % nb
+            for f in pending[j]:
+                f.result()
+            pending[j] = []
+            bufs[j][:m].copy_(flat_d[o:o + m], non_blocking=True)
+            evs[j].record(stream)
             if i:
-                po, pm = chunks[i - 1]
-                evs[(i - 1) & 1].synchronize()
-                flat_h[po:po + pm] = bufs[(i - 1) & 1][:pm].numpy()
+                drain(i - 1)
         if chunks:
-            po, pm = chunks[-1]
-            evs[(len(chunks) - 1) & 1].synchronize()
-            flat_h[po:po + pm] = bufs[(len(chunks) - 1) & 1][:pm].numpy()
+            drain(len(chunks) - 1)
+        for lst in pending:
+            for f in lst:
+                f.result()
         return out
 
     def dot_solution(self, geometry, centred, root=None):

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DOTS_ABI_VERSION 17
+#define DOTS_ABI_VERSION 18
 
 /* scalar block read by the kernels from device memory (so CUDA graphs stay valid across penalty updates) */
 enum {
@@ -89,6 +89,8 @@ typedef struct dots_ctx {
     const double  *diag_soc;   /* [3][T]    sqrt(|f| / area_v[tri[k][f]])         (:172-192)           */
     const int32_t *vc_ptr;     /* [V+1]     CSR vertex -> incident corners                            */
     const int32_t *vc_idx;     /* [3T]      corner ids k*T+f, ascending per vertex                    */
+    const int32_t *vc_ell;     /* [V][8]    the same lists in ELL form: first 8 corner ids, -1 padded; [v][7] == -2: more than 8
+                                  corners, walk the CSR list (32-byte rows, 16-byte aligned)                                */
     const double  *qf;         /* [tt_kf][m_pad]   forward transform matrix: rows = time levels (all), columns = this rank's modes
                                   (Q[t][mode] of laplacian_inverse_socp.py:31, zero padded)             */
     const double  *qb;         /* [tt_kb][tt_nb]   inverse transform matrix: rows = gathered modes (rank-major, padded),

@@ -428,6 +428,26 @@ def test_ring_sweep_variants_match(monkeypatch, stages, pdl):
     for k in outs[0]:
         assert np.array_equal(outs[0][k], outs[1][k]), k
 
+@pytest.mark.parametrize("example,n_time", [("icosphere4", 31), ("knots_5", 15), ("icosphere3", 7)])
+def test_chained_level_launches_of_the_small_sweep_kernel_match(monkeypatch, example, n_time):
+    """k_sweep_run with its level launches chained by programmatic dependent launch (the default) against plain
+    stream-ordered launches: scheduling only, bit-identical iterates (graph replay and eager launches)."""
+    from dots_socp_b200 import capi
+    geo, _ = synth.example(example)
+    outs = []
+    for pd in (0, 1):
+        monkeypatch.setenv("DOTS_RING_PDL", str(pd))
+        eng = Engine(n_time, geo, leaf_size=16, sweep_mode=0)
+        assert eng.ctx.ring_pdl == pd
+        eng.scale_z(2.0)
+        eng.iterate(6, write_z=True)                      # graph replays after the warm-up launches
+        capi.check(eng.lib.dots_iterate(eng._ctxp, 3, 1, eng.stream))     # eager, several iterations in one chain
+        outs.append(eng.get_state(("phi", "mu", "B")))
+        eng.close()
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
 @pytest.mark.parametrize("example,leaf,n_time", [("icosphere3", 8, 7), ("icosphere5", 24, 31), ("plane8", 6, 6), ("icosphere5", 16, 63)])
 def test_setup_factorisation_matches_numpy_multifrontal_row_f1(example, leaf, n_time):
     """GPU setup factorisation (hand-written front kernels) against the independent numpy multifrontal checker
