@@ -33,6 +33,47 @@ static inline int dots_check_ctx(const dots_ctx_t *c)
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline int dots_t_end(const dots_ctx_t *c) { return c->lvl_end < c->n_time ? c->lvl_end : c->n_time; }   // staggered steps owned: [lvl_begin, t_end)
 
+// Programmatic dependent launch: the launches of one iteration are chained (the attribute is passed when ctx.ring_pdl is
+// set).  A block announces itself at once, reads only constant data (index lists, mesh constants, Q, factor panels) and then
+// waits for the previous launch to finish and flush; every block executes the wait, so "this grid has completed" still
+// implies "all earlier grids have completed" for whatever follows (normal launches, NCCL kernels, graph ends).  Nothing is
+// written before the wait.  The two instructions are no-ops in a kernel that was launched normally.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... Args>
+static inline int pdl_launch2(void (*kern)(Args...), dim3 grid, int threads, cudaStream_t st, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    DOTS_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+    return 0;
+}
+
+template <typename... Args>
+static inline int pdl_launch(void (*kern)(Args...), int grid, int threads, size_t smem, cudaStream_t st, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    DOTS_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+    return 0;
+}
+
 // np.clip semantics: NaN passes through (fmin/fmax would drop it)
 __device__ __forceinline__ double clip01(double x) { return x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x); }
 

@@ -39,6 +39,8 @@ __device__ __forceinline__ vc_row vc_load(const dots_ctx_t &c, int v)
 // rhs[t][v] = div_t((A + lam_c - mu) area_v) + D((B - E) area_f) - boundary - eps area_v phi      (:979-986)
 __global__ void __launch_bounds__(256) k_phi_rhs(dots_ctx_t c)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const int V = c.n_vert, nT = c.n_time, T = c.n_tri;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     const int t = c.lvl_begin + blockIdx.y;
@@ -82,6 +84,8 @@ __global__ void __launch_bounds__(256) k_phi_rhs(dots_ctx_t c)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_vertex(dots_ctx_t c)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const int V = c.n_vert, nT = c.n_time, T = c.n_tri;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     const int t = c.lvl_begin + blockIdx.y;         // owned staggered steps
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(128, 4) k_tri(dots_ctx_t c)
 #define TRI_TMA_TCH 16
 #define TRI_TMA_SMEM (TRI_STAGES * TRI_PLANES * TRI_TILE * 8 + 64)
 template <int MODE>
-__global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c)
+__global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c, int tch)
 {
     extern __shared__ __align__(128) unsigned char smraw[];
     double *tile = reinterpret_cast<double *>(smraw);                       // [stage][plane][TRI_TILE]
@@ -322,17 +326,32 @@ __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c)
     const int nf = min(TRI_TILE, c.n_tri - f0);
     const int f = f0 + tid;
     const bool active = tid < nf;
-    const int tau_begin = c.lvl_begin + blockIdx.y * TRI_TMA_TCH;
-    const int tau_end = min(tau_begin + TRI_TMA_TCH, c.lvl_end);
-    const double *prm = c.params;
-    const double s = prm[DOTS_P_S], step = prm[DOTS_P_TAU];
-    const double cs = s / sqrt(3.0);
+    const int tau_begin = c.lvl_begin + blockIdx.y * tch;
+    const int tau_end = min(tau_begin + tch, c.lvl_end);
+    pdl_launch_dependents();
 
     if (tid == 0) {
         for (int i = 0; i < TRI_STAGES; ++i) mbar_init(&bar[i], 1);
         mbar_fence_init();
     }
     __syncthreads();
+
+    double g[3][3], dg[3], af = 0.0;                                        // mesh constants: before the wait
+    int vk[3] = {0, 0, 0};
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            dg[k] = c.diag_soc[k * T + f];
+            vk[k] = c.tri[k * T + f];
+#pragma unroll
+            for (int x = 0; x < 3; ++x) g[k][x] = c.hat_grad[(k * 3 + x) * T + f];
+        }
+        af = c.area_f[f];
+    }
+    pdl_wait();                                                             // below: state written by the previous launches
+    const double *prm = c.params;
+    const double s = prm[DOTS_P_S], step = prm[DOTS_P_TAU];
+    const double cs = s / sqrt(3.0);
 
     auto issue = [&](int tau, int stage) {                                  // thread 0 only
         const uint32_t bytes = (uint32_t)nf * 8u;
@@ -354,22 +373,10 @@ __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c)
         for (int i = 0; i < TRI_STAGES && tau_begin + i < tau_end; ++i) issue(tau_begin + i, i);
     }
 
-    double g[3][3], dg[3], af = 0.0;
-    int vk[3] = {0, 0, 0};
     double lam_prev[3] = {0.0, 0.0, 0.0};
-    if (active) {
+    if (active && tau_begin > 0) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            dg[k] = c.diag_soc[k * T + f];
-            vk[k] = c.tri[k * T + f];
-#pragma unroll
-            for (int x = 0; x < 3; ++x) g[k][x] = c.hat_grad[(k * 3 + x) * T + f];
-        }
-        af = c.area_f[f];
-        if (tau_begin > 0) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) lam_prev[k] = c.lam[(size_t)(tau_begin - 1) * V + vk[k]];
-        }
+        for (int k = 0; k < 3; ++k) lam_prev[k] = c.lam[(size_t)(tau_begin - 1) * V + vk[k]];
     }
 
     for (int tau = tau_begin, it = 0; tau < tau_end; ++tau, ++it) {
@@ -558,20 +565,14 @@ __global__ void k_div_space(dots_ctx_t c, const double *__restrict__ x, double *
 extern "C" int dots_phi_rhs(const dots_ctx_t *c, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
-    dim3 grid(ceil_div(c->n_vert, 256), c->lvl_end - c->lvl_begin);
-    k_phi_rhs<<<grid, 256, 0, (cudaStream_t)stream>>>(*c);
-    DOTS_LAUNCH_CHECK();
-    return 0;
+    return pdl_launch2(k_phi_rhs, dim3(ceil_div(c->n_vert, 256), c->lvl_end - c->lvl_begin), 256, (cudaStream_t)stream, c->ring_pdl != 0, *c);
 }
 
 extern "C" int dots_step_vertex(const dots_ctx_t *c, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
     if (dots_t_end(c) <= c->lvl_begin) return 0;
-    dim3 grid(ceil_div(c->n_vert, 256), dots_t_end(c) - c->lvl_begin);
-    k_vertex<<<grid, 256, 0, (cudaStream_t)stream>>>(*c);
-    DOTS_LAUNCH_CHECK();
-    return 0;
+    return pdl_launch2(k_vertex, dim3(ceil_div(c->n_vert, 256), dots_t_end(c) - c->lvl_begin), 256, (cudaStream_t)stream, c->ring_pdl != 0, *c);
 }
 
 extern "C" int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream)
@@ -587,9 +588,30 @@ extern "C" int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream)
             DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM));
             configured[dev] = true;
         }
-        dim3 grid(ceil_div(c->n_tri, TRI_TILE), ceil_div(c->lvl_end - c->lvl_begin, TRI_TMA_TCH));
-        if (write_z) k_tri_tma<1><<<grid, TRI_TILE, TRI_TMA_SMEM, (cudaStream_t)stream>>>(*c);
-        else k_tri_tma<0><<<grid, TRI_TILE, TRI_TMA_SMEM, (cudaStream_t)stream>>>(*c);
+        // Time levels per block: TRI_TMA_TCH amortises the per-triangle constants over 16 levels.  Small meshes (fewer blocks
+        // than two waves of 3 blocks / SM) take shorter chunks instead, the shortest that still fits ONE wave: a
+        // knots_5-class mesh (68 triangle tiles, 32 levels) runs 6 levels per block on 408 blocks instead of 16 on 136.
+        const int tiles = ceil_div(c->n_tri, TRI_TILE), levels = c->lvl_end - c->lvl_begin;
+        const int wave = 3 * (c->n_sm > 0 ? c->n_sm : 148);
+        int tch = TRI_TMA_TCH;
+        if ((long long)tiles * ceil_div(levels, TRI_TMA_TCH) < 2LL * wave) {
+            tch = 2;
+            while (tch < TRI_TMA_TCH && (long long)tiles * ceil_div(levels, tch) > wave) ++tch;
+        }
+        const unsigned gx = (unsigned)tiles, gy = (unsigned)ceil_div(levels, tch);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(gx, gy);
+        cfg.blockDim = dim3(TRI_TILE);
+        cfg.dynamicSmemBytes = TRI_TMA_SMEM;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = c->ring_pdl ? 1 : 0;
+        if (write_z) DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<1>, *c, tch));
+        else DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<0>, *c, tch));
+        return 0;
     } else {
         dim3 grid(ceil_div(c->n_tri, 128), ceil_div(c->lvl_end - c->lvl_begin, TRI_TCH));
         if (write_z) k_tri<1><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);

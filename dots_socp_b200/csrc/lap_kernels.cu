@@ -43,10 +43,12 @@ __global__ void __launch_bounds__(256) k_time_mma(dots_ctx_t c, int n_tiles)
     double *Bs = sm;                       // [K][ldb]
     double *As = sm + (size_t)K * ldb;     // [TT_VT][lda]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();
     for (int i = tid; i < K * N; i += 256) {
         const int p = i / N, j = i - p * N;
         Bs[p * ldb + j] = Bg[i];
     }
+    pdl_wait();                                            // Q is constant; the tiles are the previous launch's output
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int v0 = tile * TT_VT;
         __syncthreads();
@@ -135,10 +137,12 @@ __global__ void __launch_bounds__(256) k_time_sym(dots_ctx_t c, int n_tiles)
     const int b_rows = (DIR == 0) ? h : n;
     double *As = sm + (size_t)b_rows * ldb;                                // [TT_VT][lda]: DIR 0: [sum | difference] halves; DIR 1: hat row
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();
     for (int i = tid; i < b_rows * n; i += 256) {
         const int p = i / n, j = i - p * n;
         Bs[p * ldb + j] = (DIR == 0 || j < c.tt_nb) ? Bg[(size_t)p * ldg + j] : 0.0;
     }
+    pdl_wait();                                                            // Q is constant; the tiles are the previous launch's output
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int v0 = tile * TT_VT;
         __syncthreads();
@@ -239,30 +243,6 @@ __device__ __forceinline__ void sweep_stamp(const dots_ctx_t &c, int idx)
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         c.phase_clock[idx] = t;
     }
-}
-
-// Programmatic dependent launch: the sweep launches of one solve are chained (launch_level / launch_sweeps pass the
-// attribute when ctx.ring_pdl is set).  A block announces itself at once, reads only constant data (index lists, panels)
-// and then waits for the previous launch to finish and flush; every block executes the wait, so "this grid has completed"
-// still implies "all earlier grids have completed" for whatever follows.  No-ops when launched normally.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
-template <typename... Args>
-static int pdl_launch(void (*kern)(Args...), int grid, int threads, size_t smem, cudaStream_t st, bool pdl, Args... args)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3((unsigned)threads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    DOTS_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
-    return 0;
 }
 
 // Gather step of the forward sweep, one tree level: r_S = hat_S + (children's updates landing on S), in place.
@@ -503,7 +483,7 @@ template <int ML>
 static int launch_sweeps(const dots_ctx_t *c, cudaStream_t st)
 {
     const bool pdl = c->ring_pdl != 0;
-    bool chain = false;                                // the first launch waits for the time transform normally
+    bool chain = true;                                 // the first launch chains to the time transform
     for (int lv = 0; lv < c->n_levels; ++lv) {
         const int g0 = c->h_lvn_ptr[lv], gn = c->h_lvn_ptr[lv + 1] - g0;
         // stamps: slot lv = start of forward level lv (its gather when there is one), slot L + k = start of the k-th backward level
@@ -567,10 +547,9 @@ extern "C" int dots_time_transform(const dots_ctx_t *c, int inverse, void *strea
             else DOTS_CUDA(cudaFuncSetAttribute(k_time_sym<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
             conf[dv][inverse ? 1 : 0] = smem_s;
         }
-        if (inverse) k_time_sym<1><<<grid_s, 256, smem_s, st>>>(*c, tiles);
-        else k_time_sym<0><<<grid_s, 256, smem_s, st>>>(*c, tiles);
-        DOTS_LAUNCH_CHECK();
-        return 0;
+        const bool pdl_s = c->ring_pdl != 0;
+        if (inverse) return pdl_launch(k_time_sym<1>, grid_s, 256, smem_s, st, pdl_s, *c, tiles);
+        return pdl_launch(k_time_sym<0>, grid_s, 256, smem_s, st, pdl_s, *c, tiles);
     }
     const int K = inverse ? c->tt_kb : c->tt_kf, N = inverse ? c->tt_nb : c->m_pad;
     if (K % 4 || N % 8 || N > 128 || K <= 0) { dots_set_error("time transform shape K=%d N=%d unsupported", K, N); return DOTS_ERR_BAD_ARG; }
@@ -590,10 +569,9 @@ extern "C" int dots_time_transform(const dots_ctx_t *c, int inverse, void *strea
         else DOTS_CUDA(cudaFuncSetAttribute(k_time_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev][inverse ? 1 : 0] = smem;
     }
-    if (inverse) k_time_mma<1><<<grid, 256, smem, st>>>(*c, n_tiles);
-    else k_time_mma<0><<<grid, 256, smem, st>>>(*c, n_tiles);
-    DOTS_LAUNCH_CHECK();
-    return 0;
+    const bool pdl = c->ring_pdl != 0;
+    if (inverse) return pdl_launch(k_time_mma<1>, grid, 256, smem, st, pdl, *c, n_tiles);
+    return pdl_launch(k_time_mma<0>, grid, 256, smem, st, pdl, *c, n_tiles);
 }
 
 extern "C" int dots_step_phi(const dots_ctx_t *c, void *stream)

@@ -403,7 +403,7 @@ static int sr_sweeps(const dots_ctx_t *c, cudaStream_t st, sr_marks *mk)
 {
     if (int e = sr_configure<ML, SB>(c->ring_stages)) return e;
     const bool pdl = c->ring_pdl != 0;
-    bool chain = false;                                                   // the first launch waits for the transform normally
+    bool chain = true;                                                    // the first launch chains to the time transform
     for (int lv = 0; lv < c->n_levels; ++lv) {
         const int g0 = c->h_gv_ptr[lv], gn = c->h_gv_ptr[lv + 1] - g0;
         if (gn > 0) {
