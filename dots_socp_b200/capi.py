@@ -35,7 +35,7 @@ class DotsCtx(C.Structure):
            ("peer_rhs", C.c_void_p * 8), ("peer_hat", C.c_void_p * 8)]
         + [(n, C.c_void_p) for n in ("rt_fwd", "rt_bwd", "h_rt_fwd_ptr", "h_rt_bwd_ptr", "h_rt_fwd_wpr", "h_rt_bwd_wpr",
                                      "bidx", "erow_fwd", "erow_bwd", "gptr", "gidx", "gverts", "h_gv_ptr")]
-        + [("ring_stages", C.c_int32), ("ring_pdl", C.c_int32), ("ring_stage_bytes", C.c_int32), ("reserved2", C.c_int32)]
+        + [("ring_stages", C.c_int32), ("ring_pdl", C.c_int32), ("ring_stage_bytes", C.c_int32), ("ring_flags", C.c_int32)]
     )
 
 

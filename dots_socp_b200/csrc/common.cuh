@@ -131,6 +131,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     }
 }
+// L2 eviction policy for data that is streamed once (factor panels): keeps the vectors the sweeps re-read resident
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
 // global -> shared bulk copy; bytes and both addresses must be multiples of 16
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
 {

@@ -154,11 +154,14 @@ __global__ void __launch_bounds__(SR_THREADS, 3) k_ring_run(dots_ctx_t c, int ta
     const double *src = (DIR == 0 ? c.panels : c.panels_t) + (size_t)t.pbase * ML;
     const int32_t *codes = (DIR == 0 ? c.erow_fwd : c.erow_bwd) + t.pbase;
     const int n_ent = t.n_ent, n_stage = (n_ent + EC - 1) / EC;
+    const bool evict_first = (c.ring_flags & 1) != 0;
+    const uint64_t policy = l2_policy_evict_first();
 
     auto issue = [&](int k, int slot) {                                  // lane 0: stage k of the run -> ring slot
         const uint32_t bytes = (uint32_t)min(EC, n_ent - k * EC) * (uint32_t)(ML * 8);
         mbar_expect_tx(&bar[slot], bytes);
-        tma_load_1d(ring + (size_t)slot * EC * ML, src + (size_t)k * EC * ML, bytes, &bar[slot]);
+        if (evict_first) tma_load_1d_hint(ring + (size_t)slot * EC * ML, src + (size_t)k * EC * ML, bytes, &bar[slot], policy);
+        else tma_load_1d(ring + (size_t)slot * EC * ML, src + (size_t)k * EC * ML, bytes, &bar[slot]);
     };
     if (lane == 0) {
         for (int k = 0; k < nst && k < n_stage; ++k) issue(k, k);        // panels and codes are read-only: stream before the wait
@@ -235,10 +238,13 @@ __global__ void __launch_bounds__(SR_THREADS, 2) k_ring_split(dots_ctx_t c, int 
         }
         return true;
     };
+    const bool evict_first = (c.ring_flags & 1) != 0;
+    const uint64_t policy = l2_policy_evict_first();
     auto issue = [&](const Cur &q, int slot) {                           // lane 0
         const uint32_t bytes = (uint32_t)min(EC, q.xb - q.x) * (uint32_t)(ML * 8);
         mbar_expect_tx(&bar[slot], bytes);
-        tma_load_1d(ring + (size_t)slot * EC * ML, pan + q.ent * ML, bytes, &bar[slot]);
+        if (evict_first) tma_load_1d_hint(ring + (size_t)slot * EC * ML, pan + q.ent * ML, bytes, &bar[slot], policy);
+        else tma_load_1d(ring + (size_t)slot * EC * ML, pan + q.ent * ML, bytes, &bar[slot]);
     };
     Cur pc{-1, 0, 0, 0}, cc{-1, 0, 0, 0};
     bool pvalid = next(pc), cvalid = next(cc);
@@ -292,30 +298,56 @@ __global__ void __launch_bounds__(SR_THREADS, 2) k_ring_split(dots_ctx_t c, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// r_S of one tree level, in place in `hat`:  hat[v] += sum of the descendants' contributions landing on v.
+// r_S of one tree level, in place in `hat`:  hat[v] += sum of the descendants' contributions landing on v (fixed order).
+// One warp per vertex: the warp reads up to 32 list entries with ONE coalesced load and hands them round with shuffles, so
+// the dependent chain is (list -> rows) once per 32 contributions instead of once per 4, and the rows of a batch of 8 are in
+// flight together; lanes hold VW consecutive modes (16-byte accesses where ML allows).
 template <int ML>
 __global__ void __launch_bounds__(256) k_ring_gather(dots_ctx_t c, int v0, int v_end)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    constexpr int VPB = 256 / ML;                                        // vertices per block: 8, 4, 2, 2
-    const int vs = threadIdx.x / ML, m = threadIdx.x - vs * ML;
-    const int i = v0 + blockIdx.x * VPB + vs;
-    const bool on = vs < VPB && i < v_end;
-    int v = 0, g0 = 0, g1 = 0;
-    if (on) { v = c.gverts[i]; g0 = c.gptr[v]; g1 = c.gptr[v + 1]; }     // structure: constant, safe before the wait
+    constexpr int VW = sr_lane<ML>::VW, NA = sr_lane<ML>::NA;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = v0 + blockIdx.x * SR_WARPS + warp;
+    const bool on = i < v_end;
+    int v = 0, g0 = 0, g1 = 0, idx = 0;
+    if (on) {                                                            // structure: constant, safe before the wait
+        v = c.gverts[i];
+        g0 = c.gptr[v];
+        g1 = c.gptr[v + 1];
+        if (g0 + lane < g1) idx = c.gidx[g0 + lane];
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (!on) return;
-    double *h = c.hat + (size_t)v * ML + m;
-    double r = *h;
-    int g = g0;
-    for (; g + 4 <= g1; g += 4) {
-        const int i0 = c.gidx[g], i1 = c.gidx[g + 1], i2 = c.gidx[g + 2], i3 = c.gidx[g + 3];
-        const double a0 = c.upd[(size_t)i0 * ML + m], a1 = c.upd[(size_t)i1 * ML + m];
-        const double a2 = c.upd[(size_t)i2 * ML + m], a3 = c.upd[(size_t)i3 * ML + m];
-        r += a0; r += a1; r += a2; r += a3;
+    double *h = c.hat + (size_t)v * ML + lane * VW;
+    sr_vec<VW> r[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) r[a] = *reinterpret_cast<const sr_vec<VW> *>(h + a * 32 * VW);
+    for (int g = g0; g < g1; g += 32) {
+        if (g > g0) idx = (g + lane < g1) ? c.gidx[g + lane] : 0;
+        const int n = min(32, g1 - g);
+        for (int j = 0; j < n; j += 8) {
+            sr_vec<VW> t[8][NA];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int row = __shfl_sync(0xffffffffu, idx, (j + u) & 31);
+                if (j + u < n) {
+                    const double *p = c.upd + (size_t)row * ML + lane * VW;
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) t[u][a] = *reinterpret_cast<const sr_vec<VW> *>(p + a * 32 * VW);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (j + u < n) {
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) r[a].add(t[u][a]);
+                }
+            }
+        }
     }
-    for (; g < g1; ++g) r += c.upd[(size_t)c.gidx[g] * ML + m];
-    *h = r;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) *reinterpret_cast<sr_vec<VW> *>(h + a * 32 * VW) = r[a];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -408,7 +440,7 @@ static int sr_sweeps(const dots_ctx_t *c, cudaStream_t st, sr_marks *mk)
         const int g0 = c->h_gv_ptr[lv], gn = c->h_gv_ptr[lv + 1] - g0;
         if (gn > 0) {
             if (int e = sr_mark(mk, 1000 + lv, st)) return e;
-            if (int e = sr_launch(k_ring_gather<ML>, ceil_div(gn, 256 / ML), 256, 0, st, pdl && chain, *c, g0, g0 + gn)) return e;
+            if (int e = sr_launch(k_ring_gather<ML>, ceil_div(gn, SR_WARPS), 256, 0, st, pdl && chain, *c, g0, g0 + gn)) return e;
             chain = true;
         }
         const int n = c->h_rt_fwd_ptr[lv + 1] - c->h_rt_fwd_ptr[lv];

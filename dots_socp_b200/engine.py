@@ -260,6 +260,7 @@ class Engine:
             ctx.ring_stages = int(os.environ.get("DOTS_RING_STAGES", 2))      # measured: 2 x 4 KB stages, 3 blocks / SM
             ctx.ring_stage_bytes = int(os.environ.get("DOTS_RING_STAGE_BYTES", 4096))
         ctx.ring_pdl = int(os.environ.get("DOTS_RING_PDL", 1))                # both sweep kernels chain their level launches
+        ctx.ring_flags = int(os.environ.get("DOTS_RING_L2HINT", 1))           # bit 0: the panel stream is marked evict_first in L2 (-2..4 % sweep time)
         self._keep["phase_clock"] = torch.zeros(2 * sym.n_levels + 1, dtype=torch.int64, device=dev)
         if os.environ.get("DOTS_PHASE_CLOCK"):
             ctx.phase_clock = self._keep["phase_clock"].data_ptr()

@@ -184,9 +184,10 @@ typedef struct dots_ctx {
     const int32_t *gverts;     /* vertices that receive contributions, grouped by the tree level of their owner node      */
     const int32_t *h_gv_ptr;   /* HOST [n_levels+1] ranges into gverts                                                    */
     int32_t ring_stages;       /* shared-memory stages per warp (2..6)                                                    */
-    int32_t ring_pdl;          /* 1: chain the level launches with programmatic dependent launch                          */
+    int32_t ring_pdl;          /* 1: chain the launches of an iteration with programmatic dependent launch                */
     int32_t ring_stage_bytes;  /* bytes per ring stage: 2048 or 4096                                                      */
-    int32_t reserved2;
+    int32_t ring_flags;        /* bit 0: the panel copies of the ring-streamed sweeps carry an L2 evict_first hint;
+                                  bit 1: so do the b_mid copies of k_tri_tma                                               */
 
 } dots_ctx_t;
 

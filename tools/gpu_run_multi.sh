@@ -1,18 +1,18 @@
-# usage: bash tools/gpu_run_multi.sh N      (inside gpurun --gpus N)
+# usage: bash tools/gpu_run_multi.sh N [tag]      (inside gpurun --gpus N): world-size tests up to N, then benches at 2..N
 set -x
 cd $GRAFT_REPO_ROOT
 N=$1
-nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/r2m_smi_n$N.log 2>&1
+TAG=${2:-r2m}
+nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/${TAG}_smi_n$N.log 2>&1
 if [ "$N" = "2" ]; then
-  timeout 900 python -m pytest tests/test_gpu_multi.py -q -m gpu > gpurun_out/r2m_tests_n$N.log 2>&1
-  echo "rc=$?" >> gpurun_out/r2m_tests_n$N.log
+  timeout 900 python -m pytest tests/test_gpu_multi.py -q -m gpu > gpurun_out/${TAG}_tests_n$N.log 2>&1
+else
+  timeout 900 python -m pytest tests/test_gpu_multi.py -q -m gpu -k "ico3_nt31" > gpurun_out/${TAG}_tests_n$N.log 2>&1
 fi
-if [ "$N" = "8" ]; then
-  timeout 900 python -m pytest tests/test_gpu_multi.py -q -m gpu -k "ico3_nt31" > gpurun_out/r2m_tests_n$N.log 2>&1
-  echo "rc=$?" >> gpurun_out/r2m_tests_n$N.log
-  for k in 2 4; do
-    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $k --master-addr 127.0.0.1 --master-port 2950$k bench.py --gpus $k --steps 50 --warmup 5 > gpurun_out/r2m_bench_n$k.json 2> gpurun_out/r2m_bench_n$k.err
-  done
-fi
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 50 --warmup 5 > gpurun_out/r2m_bench_n$N.json 2> gpurun_out/r2m_bench_n$N.err
-tail -3 gpurun_out/r2m_tests_n$N.log; tail -c 600 gpurun_out/r2m_bench_n$N.json
+echo "rc=$?" >> gpurun_out/${TAG}_tests_n$N.log
+for k in 2 4 8; do
+  if [ $k -le $N ]; then
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $k --master-addr 127.0.0.1 --master-port 2950$k bench.py --gpus $k --steps 50 --warmup 5 > gpurun_out/${TAG}_bench_n$k.json 2> gpurun_out/${TAG}_bench_n$k.err
+  fi
+done
+tail -3 gpurun_out/${TAG}_tests_n$N.log; tail -c 600 gpurun_out/${TAG}_bench_n$N.json

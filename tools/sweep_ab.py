@@ -3,7 +3,7 @@
     python tools/sweep_ab.py [workload] [variant ...]        (default: icosphere7_nt63, variants 0 4)
 
 A variant is ``mode[:key=value,...]`` with mode 0 (k_sweep_run) or 4 (ring-streamed, csrc/sweep_ring.cu) and the keys
-stages, pdl, split (KB), tasks (per SM), tmin / tmax (KB per contiguous task), wpr (max warps per output), e.g.
+stages, pdl, split (KB), tasks (per SM), tmin / tmax (KB per contiguous task), wpr (max warps per output), l2hint, e.g.
 ``4:stages=4,pdl=1,split=64``.  The factorisation is done once per variant (the plan is built in the Engine constructor).
 Wrap in `timeout`."""
 import json
@@ -20,7 +20,7 @@ from dots_socp_b200.engine import Engine         # noqa: E402
 
 ENV = dict(stages="DOTS_RING_STAGES", pdl="DOTS_RING_PDL", split="DOTS_RING_SPLIT_KB", tasks="DOTS_RING_TASKS_PER_SM",
            tmin="DOTS_RING_TASK_MIN_KB", tmax="DOTS_RING_TASK_MAX_KB", wpr="DOTS_RING_WPR_MAX",
-           sb="DOTS_RING_STAGE_BYTES")
+           sb="DOTS_RING_STAGE_BYTES", l2hint="DOTS_RING_L2HINT")
 
 workload = sys.argv[1] if len(sys.argv) > 1 else "icosphere7_nt63"
 variants = sys.argv[2:] or ["0", "4"]
