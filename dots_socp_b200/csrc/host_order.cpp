@@ -408,3 +408,51 @@ extern "C" int dots_corner_lists(int64_t V, int64_t T, const int64_t *triangles,
         for (int64_t f = 0; f < T; ++f) c_idx[pos[triangles[3 * f + k]]++] = (int32_t)(k * T + f);
     return 0;
 }
+
+// Index maps of the numeric assembly (nested.front_maps is the numpy statement and the checker).  All index lists are
+// ascending (front_idx inside a node, CSR columns inside a row), so every map is a two-pointer merge:
+//   a_pos[q]      position, in the front of the node that owns row(q), of CSR entry q of the permuted matrix; -1 when the
+//                 column lies before the owner's first vertex (already eliminated) or outside its front;
+//   parent_pos[p] row, in the PARENT's front, of boundary row p of every node (concatenated like upd_off); -1 at the root.
+extern "C" int dots_front_maps(int64_t n_vert, int64_t n_nodes, const int64_t *s, const int64_t *b, const int64_t *off,
+                               const int64_t *front_off, const int64_t *front_idx, const int64_t *upd_off, const int64_t *parent,
+                               const int64_t *a_ptr, const int64_t *a_idx, int32_t *a_pos, int32_t *parent_pos)
+{
+    if (!s || !b || !off || !front_off || !front_idx || !upd_off || !parent || !a_ptr || !a_idx || !a_pos || !parent_pos || n_vert <= 0 ||
+        n_nodes <= 0) {
+        dots_set_error("dots_front_maps: bad arguments");
+        return -1;
+    }
+    for (int64_t k = 0; k < n_nodes; ++k) {
+        const int64_t *fi = front_idx + front_off[k];
+        const int64_t nf = s[k] + b[k];
+        for (int64_t r = off[k]; r < off[k] + s[k]; ++r) {
+            int64_t j = 0;
+            for (int64_t q = a_ptr[r]; q < a_ptr[r + 1]; ++q) {
+                const int64_t col = a_idx[q];
+                int32_t pos = -1;
+                if (col >= off[k]) {
+                    while (j < nf && fi[j] < col) ++j;
+                    if (j < nf && fi[j] == col) pos = (int32_t)j;
+                }
+                a_pos[q] = pos;
+            }
+        }
+        const int64_t par = parent[k];
+        int32_t *pp = parent_pos + upd_off[k];
+        if (par < 0) {
+            for (int64_t p = 0; p < b[k]; ++p) pp[p] = -1;
+            continue;
+        }
+        const int64_t *pf = front_idx + front_off[par];
+        const int64_t npf = s[par] + b[par];
+        int64_t j = 0;
+        for (int64_t p = 0; p < b[k]; ++p) {
+            const int64_t vtx = fi[s[k] + p];
+            while (j < npf && pf[j] < vtx) ++j;
+            if (j >= npf || pf[j] != vtx) { dots_set_error("dots_front_maps: boundary of node %lld does not embed in its parent's front", (long long)k); return -1; }
+            pp[p] = (int32_t)j;
+        }
+    }
+    return 0;
+}

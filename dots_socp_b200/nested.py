@@ -359,6 +359,20 @@ def front_maps(sym: Symbolic, Kp: sp.csr_matrix):
     return a_pos, parent_pos
 
 
+def front_maps_native(lib, sym: Symbolic, Kp: sp.csr_matrix):
+    """``front_maps`` by the C++ helper ``dots_front_maps`` (csrc/host_order.cpp; linear-time merges instead of two global
+    binary searches).  ``Kp`` must have sorted column indices."""
+    from . import capi
+    i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+    s_, b_, off, f_off, f_idx, u_off, par = (i64(a) for a in (sym.s, sym.b, sym.off, sym.front_off, sym.front_idx, sym.upd_off, sym.parent))
+    a_ptr, a_idx = i64(Kp.indptr), i64(Kp.indices)
+    a_pos = np.empty(a_idx.size, dtype=np.int32)
+    parent_pos = np.empty(int(u_off[-1]), dtype=np.int32)
+    capi.check(lib.dots_front_maps(sym.n, sym.n_nodes, *(a.ctypes.data for a in (s_, b_, off, f_off, f_idx, u_off, par, a_ptr, a_idx,
+                                                                                   a_pos, parent_pos))), "dots_front_maps")
+    return a_pos, parent_pos
+
+
 def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shifts: np.ndarray, m_pad: int, device, lib,
                          stream_fn, stats: dict | None = None, front_nmax: int | None = None, use_library: bool = False):
     """Numeric factorisation on the GPU, level by level, with hand-written kernels only: small fronts by ``k_front_small``
@@ -374,7 +388,7 @@ def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shif
     nmax = int(lib.dots_front_nmax()) if front_nmax is None else int(front_nmax)   # 0: every front through the library path
     Kp = K[sym.perm][:, sym.perm].tocsr()
     Kp.sort_indices()
-    a_pos, parent_pos = front_maps(sym, Kp)
+    a_pos, parent_pos = front_maps_native(lib, sym, Kp) if lib is not None else front_maps(sym, Kp)
     dev = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device=device)
     shifts_t = dev(shifts, np.float64)
     massp = dev(np.asarray(mass, dtype=np.float64)[sym.perm], np.float64)
@@ -392,8 +406,8 @@ def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shif
     levels = level_schedule(sym)
     last_use = {}
     for lv, nodes in enumerate(levels):
-        par_lv = [int(sym.level[sym.parent[nd]]) for nd in nodes if sym.parent[nd] >= 0]
-        last_use[lv] = max(par_lv) if par_lv else lv
+        par = sym.parent[nodes]
+        last_use[lv] = int(sym.level[par[par >= 0]].max()) if (par >= 0).any() else lv
     pin_node = sym.n_nodes - 1
     pin_value = float(Kp.diagonal().mean())
     singular = [m for m in range(n_modes) if float(shifts[m]) == 0.0]
@@ -403,14 +417,15 @@ def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shif
     # Index data of the library path, uploaded ONCE (a host->device copy per large front used to cost more than its algebra):
     # the CSR entries whose column lies inside their owner's front ("kept"), as (row inside the owner's S block, front
     # position, value), in CSR order; kept_ptr[v] = number of kept entries in the rows before vertex v.
-    row_of = np.repeat(np.arange(sym.n), np.diff(Kp.indptr))
-    kept = a_pos >= 0
-    kept_ptr = np.concatenate([[0], np.cumsum(np.bincount(row_of[kept], minlength=sym.n))]).astype(np.int64)
-    node_of = np.repeat(np.arange(sym.n_nodes), sym.s)
-    kept_r = dev_i64((row_of - sym.off[node_of[row_of]])[kept])
-    kept_c = dev_i64(a_pos[kept])
-    kept_v = torch.as_tensor(np.ascontiguousarray(Kp.data[kept], dtype=np.float64), device=device)
-    parent_pos64 = dev_i64(parent_pos)
+    if use_library:
+        row_of = np.repeat(np.arange(sym.n), np.diff(Kp.indptr))
+        kept = a_pos >= 0
+        kept_ptr = np.concatenate([[0], np.cumsum(np.bincount(row_of[kept], minlength=sym.n))]).astype(np.int64)
+        node_of = np.repeat(np.arange(sym.n_nodes), sym.s)
+        kept_r = dev_i64((row_of - sym.off[node_of[row_of]])[kept])
+        kept_c = dev_i64(a_pos[kept])
+        kept_v = torch.as_tensor(np.ascontiguousarray(Kp.data[kept], dtype=np.float64), device=device)
+        parent_pos64 = dev_i64(parent_pos)
 
     args = capi.FrontArgs()
     args.n_modes, args.m_pad = n_modes, m_pad
@@ -474,10 +489,12 @@ def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shif
         offs = np.concatenate([[0], np.cumsum(b_l * b_l)])
         buf = torch.zeros((max(1, int(offs[-1])), m_pad), dtype=torch.float64, device=device)
         level_buf[lv] = buf
-        for nd, o0, bb in zip(nodes, offs[:-1], b_l):
-            if bb:
-                u_view[int(nd)] = buf[int(o0):int(o0 + bb * bb)].view(int(bb), int(bb), m_pad)
-                u_ptr_host[nd] = buf.data_ptr() + int(o0) * m_pad * 8
+        has_b = b_l > 0
+        u_ptr_host[nodes[has_b]] = buf.data_ptr() + offs[:-1][has_b] * (m_pad * 8)
+        if use_library:                                                    # per-node tensor views: only the cross-check path reads them
+            for nd, o0, bb in zip(nodes, offs[:-1], b_l):
+                if bb:
+                    u_view[int(nd)] = buf[int(o0):int(o0 + bb * bb)].view(int(bb), int(bb), m_pad)
         u_ptr_dev.copy_(torch.from_numpy(u_ptr_host))
         nfront = sym.s[nodes] + sym.b[nodes]
         small = nodes[nfront <= nmax]
@@ -509,8 +526,9 @@ def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shif
                 n_large += int(part.size)
                 del Fw, Gw
         for old in [k for k, lu in last_use.items() if lu <= lv and k in level_buf and k < lv]:
-            for nd in levels[old]:
-                u_view.pop(int(nd), None)
+            if use_library:
+                for nd in levels[old]:
+                    u_view.pop(int(nd), None)
             del level_buf[old]
     if stats is not None:
         stats.update(small_fronts=n_small, large_fronts=n_large, front_nmax=nmax)

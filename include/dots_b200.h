@@ -186,8 +186,7 @@ typedef struct dots_ctx {
     int32_t ring_stages;       /* shared-memory stages per warp (2..6)                                                    */
     int32_t ring_pdl;          /* 1: chain the launches of an iteration with programmatic dependent launch                */
     int32_t ring_stage_bytes;  /* bytes per ring stage: 2048 or 4096                                                      */
-    int32_t ring_flags;        /* bit 0: the panel copies of the ring-streamed sweeps carry an L2 evict_first hint;
-                                  bit 1: so do the b_mid copies of k_tri_tma                                               */
+    int32_t ring_flags;        /* bit 0: the panel copies of the ring-streamed sweeps carry an L2 evict_first hint        */
 
 } dots_ctx_t;
 
@@ -316,6 +315,13 @@ int dots_mesh_destroy(dots_mesh_t *m);
 /* CSR vertex -> incident corner ids k * T + f, ordered by (corner, triangle), for any triangle numbering: c_ptr [V+1], c_idx [3T]
  * (int32; dots_ctx_t.vc_ptr / vc_idx).                                                                                  */
 int dots_corner_lists(int64_t n_vert, int64_t n_tri, const int64_t *triangles, int32_t *c_ptr, int32_t *c_idx);
+/* Index maps of the numeric assembly: a_pos [nnz] = front position of every CSR entry of the PERMUTED matrix (a_ptr / a_idx, sorted
+ * columns) inside the front of the node that owns its row (-1: already eliminated), parent_pos [upd_off[n_nodes]] = row of every
+ * boundary row inside the parent's front (-1 at the root).  Arrays as in dots_order_export.  Replaces the symbolic part of
+ * pre_factorize_* (utils/laplacian_inverse_socp.py:11-49).                                                                */
+int dots_front_maps(int64_t n_vert, int64_t n_nodes, const int64_t *s, const int64_t *b, const int64_t *off, const int64_t *front_off,
+                    const int64_t *front_idx, const int64_t *upd_off, const int64_t *parent, const int64_t *a_ptr,
+                    const int64_t *a_idx, int32_t *a_pos, int32_t *parent_pos);
 
 /* ---- setup, host side: per-entry operand rows of the ring-streamed sweeps (sweep_mode 4).  HOST pointers.  For every
  * panel entry in streaming order (rows_fwd: row-major panels, rows_bwd: column-major copy) the row of Z = [hat | ywork]

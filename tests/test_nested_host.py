@@ -150,6 +150,22 @@ def test_front_maps_agree_with_the_per_node_search():
                 assert np.array_equal(cp[pp], np.arange(sym.b[k]))
 
 
+@pytest.mark.parametrize("example,leaf", [("icosphere2", 8), ("icosphere4", 16), ("plane20", 8), ("knot", 16), ("icosphere3", 1)])
+def test_native_front_maps_equal_the_numpy_statement(example, leaf):
+    """dots_front_maps (C++ merges) against nested.front_maps (global binary searches): identical index maps."""
+    geo, _ = synth.example(example)
+    v, t = geo["vertices"], geo["triangles"]
+    K = surface.stiffness_matrix(v, t)
+    sym = nested.analyse(v, K, leaf_size=leaf)
+    Kp = K[sym.perm][:, sym.perm].tocsr()
+    Kp.sort_indices()
+    a_pos, parent_pos = nested.front_maps(sym, Kp)
+    from dots_socp_b200 import capi
+    a_nat, p_nat = nested.front_maps_native(capi.load(), sym, Kp)
+    assert a_nat.dtype == a_pos.dtype and np.array_equal(a_nat, a_pos)
+    assert p_nat.dtype == parent_pos.dtype and np.array_equal(p_nat, parent_pos)
+
+
 def _same_symbolic(a, b):
     import dataclasses
     for f in dataclasses.fields(a):
