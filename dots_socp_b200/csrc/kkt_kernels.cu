@@ -99,12 +99,21 @@ __device__ __forceinline__ void kkt_vertex_terms(const dots_ctx_t &c, size_t i, 
         else divt = (c.mu[(size_t)t * V + v] * av - c.mu[(size_t)(t - 1) * V + v] * av) / dt;
         const double *Et = c.E + (size_t)t * 3 * T;
         double divx = 0.0;
-        for (int q = c.vc_ptr[v], qe = c.vc_ptr[v + 1]; q < qe; ++q) {
-            const int cid = c.vc_idx[q];
-            const size_t k = cid / T, f = cid - k * T;
+        auto corner = [&](int cid) -> double {                             // -(g_k . (E af)) of corner id = k T + f
+            const size_t k = (size_t)(cid >= (int)T) + (size_t)(cid >= 2 * (int)T), f = cid - k * T;
             const double af = c.area_f[f];
-            divx += -(c.hat_grad[(k * 3 + 0) * T + f] * (Et[f] * af) + c.hat_grad[(k * 3 + 1) * T + f] * (Et[T + f] * af)
-                      + c.hat_grad[(k * 3 + 2) * T + f] * (Et[2 * T + f] * af));
+            return -(c.hat_grad[(k * 3 + 0) * T + f] * (Et[f] * af) + c.hat_grad[(k * 3 + 1) * T + f] * (Et[T + f] * af)
+                     + c.hat_grad[(k * 3 + 2) * T + f] * (Et[2 * T + f] * af));
+        };
+        const vc_row vr = vc_load(c, v);                                   // all corner ids at once: independent gathers
+        if (vr.id[7] != -2) {
+            double val[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) val[q] = vr.id[q] >= 0 ? corner(vr.id[q]) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (vr.id[q] >= 0) divx += val[q];
+        } else {
+            for (int q = c.vc_ptr[v], qe = c.vc_ptr[v + 1]; q < qe; ++q) divx += corner(c.vc_idx[q]);
         }
         const double bnd = (t == 0) ? c.bnd0[v] : ((t == nT) ? c.bnd1[v] : 0.0);
         const double aux = (r * dt) * ((bnd + divt + divx) / av);
@@ -120,7 +129,7 @@ __device__ __forceinline__ void kkt_vertex_terms(const dots_ctx_t &c, size_t i, 
         double q = 0.0;
         for (int p = c.vc_ptr[v], pe = c.vc_ptr[v + 1]; p < pe; ++p) {
             const int cid = c.vc_idx[p];
-            const size_t k = cid / T, f = cid - k * T;
+            const size_t k = (size_t)(cid >= (int)T) + (size_t)(cid >= 2 * (int)T), f = cid - k * T;
             double sq = 0.0;
 #pragma unroll
             for (int x = 0; x < 3; ++x) { const double a = c3 * (ps * B0[x * T + f]); sq += a * a; }
@@ -243,8 +252,13 @@ __device__ __forceinline__ void kkt_block_store(double (&acc)[KKT_CONDS][4], uns
 }
 
 // One pass over the (time, vertex) pairs for ALL conditions in `mask`: shared operands (A, mu, lam_c, phi, ...) are loaded once.
-__global__ void __launch_bounds__(KKT_THREADS) k_kkt_vertex(dots_ctx_t c, unsigned mask)
+// CMASK != 0: the mask is a compile-time constant (the sets the solver asks for most: #2 alone on the lazy checks, #0-#3 on
+// the forced ones), so the untaken conditions cost neither registers nor branches; the mapping of items to threads and
+// blocks, hence the summation order and the sums, are the same in every instantiation.
+template <unsigned CMASK>
+__global__ void __launch_bounds__(KKT_THREADS) k_kkt_vertex(dots_ctx_t c, unsigned mask_rt)
 {
+    const unsigned mask = CMASK ? CMASK : mask_rt;
     const int V = c.n_vert, nT = c.n_time;
     const double *prm = c.params;
     const double r = prm[DOTS_P_R], s = prm[DOTS_P_S], d = prm[DOTS_P_D], cong = prm[DOTS_P_CONG];
@@ -273,8 +287,10 @@ __global__ void __launch_bounds__(KKT_THREADS) k_kkt_vertex(dots_ctx_t c, unsign
     kkt_block_store(acc, mask & 0x1dfu, c.red_part, 0);
 }
 
-__global__ void __launch_bounds__(KKT_THREADS) k_kkt_tri(dots_ctx_t c, unsigned mask)
+template <unsigned CMASK>
+__global__ void __launch_bounds__(KKT_THREADS) k_kkt_tri(dots_ctx_t c, unsigned mask_rt)
 {
+    const unsigned mask = CMASK ? CMASK : mask_rt;
     const size_t T = (size_t)c.n_tri;
     const double *prm = c.params;
     const double r = prm[DOTS_P_R], s = prm[DOTS_P_S], ps = prm[DOTS_P_PS], ds = prm[DOTS_P_DS];
@@ -316,8 +332,13 @@ extern "C" int dots_kkt_sums_multi(const dots_ctx_t *c, unsigned mask, double *h
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = c->red_blocks;
     DOTS_CUDA(cudaMemsetAsync(c->red_part, 0, sizeof(double) * KKT_CONDS * 8 * nb, st));
-    if (mask & 0x1dfu) { k_kkt_vertex<<<nb, KKT_THREADS, 0, st>>>(*c, mask); DOTS_LAUNCH_CHECK(); }
-    if (mask & 0x12bu) { k_kkt_tri<<<nb, KKT_THREADS, 0, st>>>(*c, mask); DOTS_LAUNCH_CHECK(); }
+    if (mask == 4u) k_kkt_vertex<4u><<<nb, KKT_THREADS, 0, st>>>(*c, mask);                     // lazy check of Dual(alpha) alone
+    else if (mask == 15u) k_kkt_vertex<15u><<<nb, KKT_THREADS, 0, st>>>(*c, mask);              // forced primal + dual set
+    else if (mask & 0x1dfu) k_kkt_vertex<0u><<<nb, KKT_THREADS, 0, st>>>(*c, mask);
+    DOTS_LAUNCH_CHECK();
+    if (mask == 15u) k_kkt_tri<11u><<<nb, KKT_THREADS, 0, st>>>(*c, mask);                       // #0, #1, #3 have triangle terms
+    else if (mask & 0x12bu) k_kkt_tri<0u><<<nb, KKT_THREADS, 0, st>>>(*c, mask);
+    DOTS_LAUNCH_CHECK();
     k_reduce_final<<<KKT_CONDS, 256, 0, st>>>(c->red_part, nb, c->red_out);
     DOTS_LAUNCH_CHECK();
     DOTS_CUDA(cudaMemcpyAsync(host_out, c->red_out, sizeof(double) * KKT_CONDS * 8, cudaMemcpyDeviceToHost, st));

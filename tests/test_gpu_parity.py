@@ -173,6 +173,29 @@ def test_kkt_and_objective_rows_a9_a11():
     assert c_got[0] == pytest.approx(c_ref[0], rel=1e-8) and c_got[1] == pytest.approx(c_ref[1], rel=1e-8)
 
 
+@pytest.mark.parametrize("example,n_time", [("icosphere3", 15), ("knots_5", 31)])
+def test_specialised_kkt_passes_equal_the_generic_one(example, n_time):
+    """The compile-time-mask instantiations of the KKT kernels (#2 alone, #0-#3) against the generic kernel (same sets plus the
+    objective): same mapping of items to threads, so the raw sums agree bit for bit."""
+    import ctypes as C
+    from dots_socp_b200 import capi
+    geo, _ = synth.example(example)
+    eng = Engine(n_time, geo, congestion=0.05)
+    eng.scale_z(2.0)
+    eng.iterate(9, write_z=True)
+
+    def multi(mask):
+        out = np.zeros(72)
+        capi.check(eng.lib.dots_kkt_sums_multi(eng._ctxp, C.c_uint(mask), out.ctypes.data, eng.stream))
+        return out.reshape(9, 8)
+
+    for mask, conds in ((4, [2]), (15, [0, 1, 2, 3])):
+        special, generic = multi(mask), multi(mask | 128)
+        for w in conds:
+            assert np.array_equal(special[w], generic[w]), (mask, w)
+            assert np.abs(special[w]).max() > 0.0
+
+
 # ---------------------------------------------------------------------------------------------- end to end
 @pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005",
                                   "ico2_nt15_tol1e-4", "ico3_nt31_c0", "ico3_nt31_c01",
