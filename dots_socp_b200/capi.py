@@ -84,6 +84,7 @@ def load(build_if_missing: bool = True):
         "dots_iterate": (ctxp, i, i, vp), "dots_refresh_corner_terms": (ctxp, vp),
         "dots_scale_dual": (ctxp, d, vp), "dots_scale_z": (ctxp, d, vp), "dots_scale_prim_dual": (ctxp, d, d, vp), "dots_set_params": (ctxp, vp, vp),
         "dots_kkt_sums": (ctxp, i, vp, vp), "dots_kkt_sums_multi": (ctxp, C.c_uint, vp, vp), "dots_phi_rhs": (ctxp, vp), "dots_time_transform": (ctxp, i, vp),
+        "dots_time_transform_plain": (ctxp, i, vp, i, vp),
         "dots_mode_solves": (ctxp, vp), "dots_grad_space": (ctxp, vp, vp, vp), "dots_div_space": (ctxp, vp, vp, vp),
         "dots_graph_create": (ctxp, i, vp, C.POINTER(vp)), "dots_graph_launch": (vp, vp), "dots_graph_destroy": (vp,),
         "dots_factor_small_fronts": (C.POINTER(FrontArgs), i, i, vp), "dots_front_nmax": (),
@@ -109,7 +110,7 @@ def load(build_if_missing: bool = True):
 
 EXPORTS = ("dots_abi_version", "dots_ctx_sizeof", "dots_last_error", "dots_step_phi", "dots_step_vertex",
            "dots_step_tri", "dots_step_q0", "dots_iterate", "dots_refresh_corner_terms", "dots_scale_dual", "dots_scale_z", "dots_scale_prim_dual",
-           "dots_set_params", "dots_kkt_sums", "dots_kkt_sums_multi", "dots_phi_rhs", "dots_time_transform", "dots_mode_solves",
+           "dots_set_params", "dots_kkt_sums", "dots_kkt_sums_multi", "dots_phi_rhs", "dots_time_transform", "dots_time_transform_plain", "dots_mode_solves",
            "dots_grad_space", "dots_div_space", "dots_graph_create", "dots_graph_launch", "dots_graph_destroy",
            "dots_factor_small_fronts", "dots_front_nmax", "dots_factor_large_fronts", "dots_enable_peer", "dots_ipc_export", "dots_ipc_import",
            "dots_ring_level_times", "dots_ring_entry_rows",

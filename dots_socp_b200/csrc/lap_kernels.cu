@@ -574,6 +574,112 @@ extern "C" int dots_time_transform(const dots_ctx_t *c, int inverse, void *strea
     return pdl_launch(k_time_mma<0>, grid, 256, smem, st, pdl, *c, n_tiles);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Plain (CUDA-core) time transforms for time grids beyond the tensor-core kernels' shared-memory budget (n_time + 1 > 128).
+// The modes are then solved in groups of m_pad <= 128 (the engine loops: transform -> sweeps -> inverse transform per
+// group), so one call handles ONE group:
+//   forward  hat[v][j]     = sum_t q[t][j] rhs[t][v]          q: [n_time + 1][m_pad], this group's columns of the DCT basis
+//   inverse  phi[t][v] (+)= sum_j q[j][t] hat[v][j]           q: [m_pad][n_time + 1]; accumulate: add to phi (groups after the first)
+// Block = 32 vertices; q is staged through shared memory in chunks of 32 rows / columns; sums run in index order.
+#define TP_VT 32
+#define TP_KC 32
+template <int DIR>
+__global__ void __launch_bounds__(256) k_time_plain(dots_ctx_t c, const double *__restrict__ q, int accumulate)
+{
+    extern __shared__ double tp_sm[];
+    const int n = c.n_time + 1, M = c.m_pad, V = c.n_vert;
+    const int v0 = blockIdx.x * TP_VT;
+    const int tid = threadIdx.x, vv = tid & 31, grp = tid >> 5;          // 8 groups of 32 lanes
+    if (DIR == 0) {
+        double *As = tp_sm;                                              // [TP_KC][TP_VT]   rhs chunk
+        double *Qs = tp_sm + TP_KC * TP_VT;                              // [TP_KC][M]       q chunk; reused as the output tile [TP_VT][M]
+        double acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+        for (int t0 = 0; t0 < n; t0 += TP_KC) {
+            const int kc = min(TP_KC, n - t0);
+            __syncthreads();
+            for (int i = tid; i < kc * TP_VT; i += 256) {
+                const int p = i >> 5, w = i & 31;
+                As[i] = (v0 + w < V) ? c.rhs[(size_t)(t0 + p) * V + v0 + w] : 0.0;
+            }
+            for (int i = tid; i < kc * M; i += 256) Qs[i] = q[(size_t)t0 * M + i];
+            __syncthreads();
+            for (int p = 0; p < kc; ++p) {
+                const double a = As[p * TP_VT + vv];
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (grp + 8 * i < M) acc[i] += a * Qs[p * M + grp + 8 * i];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (grp + 8 * i < M) Qs[vv * M + grp + 8 * i] = acc[i];
+        __syncthreads();
+        for (int i = tid; i < TP_VT * M; i += 256) {
+            const int w = i / M;
+            if (v0 + w < V) c.hat[(size_t)v0 * M + i] = Qs[i];
+        }
+    } else {
+        double *Hs = tp_sm;                                              // [TP_VT][M + 1]   hat rows of the block's vertices
+        double *Qs = tp_sm + TP_VT * (M + 1);                            // [M][TP_KC]       q chunk (columns t0 .. t0 + 31)
+        for (int i = tid; i < TP_VT * M; i += 256) {
+            const int w = i / M, j = i - w * M;
+            Hs[w * (M + 1) + j] = (v0 + w < V) ? c.hat[(size_t)v0 * M + i] : 0.0;
+        }
+        for (int t0 = 0; t0 < n; t0 += TP_KC) {
+            const int kc = min(TP_KC, n - t0);
+            __syncthreads();
+            for (int i = tid; i < M * TP_KC; i += 256) {
+                const int j = i >> 5, p = i & 31;
+                Qs[i] = (p < kc) ? q[(size_t)j * n + t0 + p] : 0.0;
+            }
+            __syncthreads();
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int j = 0; j < M; ++j) {
+                const double h = Hs[vv * (M + 1) + j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] += h * Qs[j * TP_KC + grp + 8 * i];
+            }
+            if (v0 + vv < V) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int t = t0 + grp + 8 * i;
+                    if (t < n) {
+                        double *dst = c.phi + (size_t)t * V + v0 + vv;
+                        *dst = accumulate ? *dst + acc[i] : acc[i];
+                    }
+                }
+            }
+        }
+    }
+}
+
+extern "C" int dots_time_transform_plain(const dots_ctx_t *c, int inverse, const double *q, int accumulate, void *stream)
+{
+    if (int e = dots_check_ctx(c)) return e;
+    if (!q) { dots_set_error("dots_time_transform_plain: null basis"); return DOTS_ERR_BAD_ARG; }
+    if (c->n_ranks != 1 || c->lvl_begin != 0 || c->lvl_end != c->n_time + 1) { dots_set_error("dots_time_transform_plain is single-GPU (whole time grid)"); return DOTS_ERR_BAD_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int M = c->m_pad, grid = ceil_div(c->n_vert, TP_VT);
+    const size_t smem = inverse ? ((size_t)TP_VT * (M + 1) + (size_t)M * TP_KC) * sizeof(double)
+                                : ((size_t)TP_KC * TP_VT + (size_t)(TP_KC > TP_VT ? TP_KC : TP_VT) * M) * sizeof(double);
+    static size_t configured[64][2] = {{0, 0}};
+    int dev = 0;
+    DOTS_CUDA(cudaGetDevice(&dev));
+    dev = (dev >= 0 && dev < 64) ? dev : 0;
+    if (smem > 48 * 1024 && smem > configured[dev][inverse ? 1 : 0]) {
+        if (inverse) DOTS_CUDA(cudaFuncSetAttribute(k_time_plain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else DOTS_CUDA(cudaFuncSetAttribute(k_time_plain<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev][inverse ? 1 : 0] = smem;
+    }
+    if (inverse) k_time_plain<1><<<grid, 256, smem, st>>>(*c, q, accumulate);
+    else k_time_plain<0><<<grid, 256, smem, st>>>(*c, q, accumulate);
+    DOTS_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int dots_step_phi(const dots_ctx_t *c, void *stream)
 {
     int e;

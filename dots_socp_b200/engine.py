@@ -135,15 +135,22 @@ class Engine:
         #    modes (identity padding).  0: register-staged k_sweep_run: any mode count; kept for mode-sharded ranks with fewer than
         #    32 modes and for factors of a few hundred MB, where every level launch is latency bound and its shorter
         #    dependent chain wins (knots_5-class, nT = 31: 0.25 ms / iteration against 0.34; profiles/README.md).
+        # More than 128 time levels on one GPU: the modes are solved in n_groups groups of at most 128 (own factor panels per
+        # group, shared work vectors), with the plain time transforms (dots_time_transform_plain) around each group's sweeps.
+        self.n_groups = -(-(nT + 1) // 128) if self.comm.world == 1 else 1
+        per_rank = -(-(nT + 1) // (self.comm.world * self.n_groups))          # modes per rank (per group)
         if sweep_mode is None:
             sweep_mode = int(os.environ.get("DOTS_SWEEP_MODE", "-1"))
         if sweep_mode == -1:
-            n_pad32 = max(32, dd.pad_modes(-(-(nT + 1) // self.comm.world)))
+            n_pad32 = max(32, dd.pad_modes(per_rank))
             small = 2 * 8 * n_pad32 * sym.panel_entries / 2 ** 20 < float(os.environ.get("DOTS_RING_MIN_MB", 300))
-            sweep_mode = 0 if (small or (self.comm.world > 1 and dd.pad_modes(-(-(nT + 1) // self.comm.world)) % 32)) else 4
+            sweep_mode = 0 if (small or (self.comm.world > 1 and dd.pad_modes(per_rank) % 32)) else 4
         if sweep_mode not in (0, 4):
             raise capi.DotsError(f"sweep_mode={sweep_mode} unsupported (0: k_sweep_run, 4: ring-streamed)")
-        self.part = dd.partition(nT, self.comm.rank, self.comm.world, min_pad=32 if sweep_mode == 4 else 0)
+        if self.n_groups > 1:
+            self.part = dd.Partition(nT, 0, 1, nT + 1, 0, nT + 1, max(dd.pad_modes(per_rank), 32 if sweep_mode == 4 else 0))
+        else:
+            self.part = dd.partition(nT, self.comm.rank, self.comm.world, min_pad=32 if sweep_mode == 4 else 0)
         part = self.part
         if sweep_mode == 4 and part.m_pad % 32:
             raise capi.DotsError(f"sweep_mode=4 needs a multiple of 32 time modes per rank, got {part.m_pad}")
@@ -160,14 +167,20 @@ class Engine:
         shifts = (-lam_st + self.eps)[part.lvl_begin:part.lvl_end]   # (L + (lam - eps) M) = -(K + (|lam| + eps) M)   (laplacian_inverse_socp.py:37-38)
         self.sweep_mode = int(sweep_mode)
         self.factor_stats = {}
-        if os.environ.get("DOTS_FACTOR", "hybrid") == "library":
-            panels, panels_t = nested.factor_batched_device(sym, K, area_v, shifts, m_pad=self.m_pad, device=self.device,
-                                                            transposed=True)
+
+        def factorise(shifts_g):
+            if os.environ.get("DOTS_FACTOR", "hybrid") == "library":
+                return nested.factor_batched_device(sym, K, area_v, shifts_g, m_pad=self.m_pad, device=self.device, transposed=True)
+            return nested.factor_hybrid_device(sym, K, area_v, shifts_g, self.m_pad, self.device, self.lib,
+                                               lambda: torch.cuda.current_stream(self.device).cuda_stream,
+                                               stats=self.factor_stats, use_library=os.environ.get("DOTS_FACTOR") == "mixed")
+
+        self.group_modes = [(g * per_rank, min(nT + 1, (g + 1) * per_rank)) for g in range(self.n_groups)] if self.n_groups > 1 else []
+        if self.n_groups > 1:
+            group_panels = [factorise(shifts[k0:k1]) for k0, k1 in self.group_modes]
+            panels, panels_t = group_panels[0]
         else:
-            panels, panels_t = nested.factor_hybrid_device(sym, K, area_v, shifts, self.m_pad, self.device, self.lib,
-                                                           lambda: torch.cuda.current_stream(self.device).cuda_stream,
-                                                           stats=self.factor_stats,
-                                                           use_library=os.environ.get("DOTS_FACTOR") == "mixed")
+            panels, panels_t = factorise(shifts)
         t_fact0, t_fact_enqueued = t0, time.perf_counter()    # the last (largest) fronts are still being factorised on the GPU
 
         # ---- launch plans and index maps (host; overlaps the tail of the factorisation), then upload ---------
@@ -196,7 +209,10 @@ class Engine:
         keep = slot < 8
         vc_ell[np.repeat(np.arange(V), deg)[keep], slot[keep]] = vc_idx[keep]
         vc_ell[deg > 8, 7] = -2                                                          # long lists: the kernels walk the CSR form
-        qf, qb, n_phi_out = dd.transform_matrices(Q_st, part)
+        if self.n_groups > 1:                                                            # the grouped path passes its bases per call
+            qf, qb, n_phi_out = np.zeros((4, 8)), np.zeros((8, 8)), nT + 1
+        else:
+            qf, qb, n_phi_out = dd.transform_matrices(Q_st, part)
         self.sweep_grid = 0
         plan = _sweep_items(sym, self.n_sm, self.m_pad)
         self.plan = plan                                                                 # host arrays stay alive
@@ -330,6 +346,18 @@ class Engine:
         self.peer_error = None
         if self.comm.enabled and os.environ.get("DOTS_PEER", "1") == "1" and part.world <= 8:
             self._setup_peers()
+        self.groups = []                                 # (context with the group's panels, qf [levels][m_pad], qb [m_pad][levels])
+        for g, (k0, k1) in enumerate(self.group_modes):
+            cg = capi.DotsCtx()
+            C.memmove(C.byref(cg), C.byref(ctx), C.sizeof(ctx))
+            pg, pgt = group_panels[g]
+            self._keep[f"panels_g{g}"], self._keep[f"panels_t_g{g}"] = pg, pgt
+            cg.panels, cg.panels_t = pg.data_ptr(), pgt.data_ptr()
+            qf_g = np.zeros((nT + 1, self.m_pad))
+            qf_g[:, :k1 - k0] = Q[:, k0:k1]
+            self.groups.append((cg, up(f"qf_g{g}", qf_g, np.float64), up(f"qb_g{g}", qf_g.T, np.float64)))
+        if self.groups:
+            self.use_graphs = False                      # eager launches: the group loop lives on the host
         self._push_params()
         torch.cuda.synchronize(dev)
         tm["upload"] = time.perf_counter() - t0
@@ -351,11 +379,12 @@ class Engine:
     def launches_per_iteration(self):
         """Kernel launches of one iteration: rhs, 2 transforms, the sweep launches, vertex, triangle."""
         if self.sweep_mode == 4:
-            return 5 + ring_plan.launches(self.ring)
+            sweeps = ring_plan.launches(self.ring)
+            return 3 + max(1, self.n_groups) * (2 + sweeps)
         n_f = int(np.count_nonzero(np.diff(self._h_fwd_ptr)))
         n_b = int(np.count_nonzero(np.diff(self._h_bwd_ptr)))
         n_g = int(np.count_nonzero(np.diff(self.plan["node_ptr"])[1:]))
-        return 5 + n_f + n_b + n_g
+        return 3 + max(1, self.n_groups) * (2 + n_f + n_b + n_g)
 
     def _call(self, fn, *args):
         capi.check(getattr(self.lib, fn)(self._ctxp, *args, self.stream), fn)
@@ -480,6 +509,11 @@ class Engine:
         if self.comm.enabled:
             for i in range(n):
                 self._iterate_sharded_graphed(write_z and i == n - 1)
+        elif self.groups:
+            for i in range(n):
+                self.step_phi()
+                self._call("dots_step_vertex")
+                self._call("dots_step_tri", int(write_z and i == n - 1))
         elif not self.use_graphs or not self._warm:
             capi.check(self.lib.dots_iterate(self._ctxp, n, int(write_z), st), "dots_iterate")
             self._warm = True
@@ -506,6 +540,18 @@ class Engine:
         self.launches += n * self.launches_per_iteration()
         self.z_valid = write_z
         self._state_changed()
+
+    def step_phi(self):
+        """Step 1 alone (single GPU): rhs, time transform, mode solves, inverse transform; with more than 128 time levels the
+        modes go through in groups (own panels, shared work vectors, phi accumulated group by group in a fixed order)."""
+        if not self.groups:
+            return self._call("dots_step_phi")
+        st = self.stream
+        self._call("dots_phi_rhs")
+        for g, (cg, qf_g, qb_g) in enumerate(self.groups):
+            capi.check(self.lib.dots_time_transform_plain(C.byref(cg), 0, qf_g.data_ptr(), 0, st), "dots_time_transform_plain")
+            capi.check(self.lib.dots_mode_solves(C.byref(cg), st), "dots_mode_solves")
+            capi.check(self.lib.dots_time_transform_plain(C.byref(cg), 1, qb_g.data_ptr(), int(g > 0), st), "dots_time_transform_plain")
 
     def _iterate_sharded(self, write_z):
         """One iteration across ranks: the same kernels on this rank's slab / modes + the exchanges of dist.py."""

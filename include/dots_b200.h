@@ -332,7 +332,12 @@ int dots_ring_entry_rows(int64_t n_nodes, const int64_t *s, const int64_t *b, co
 
 /* ---- operator-level entry points on the internal layout (rows a5, a6, a7, a8) ---------------------- */
 int dots_phi_rhs(const dots_ctx_t *c, void *stream);                       /* -> c->rhs                */
-int dots_time_transform(const dots_ctx_t *c, int inverse, void *stream);   /* rhs -> hat / hat -> phi   */
+int dots_time_transform(const dots_ctx_t *c, int inverse, void *stream);
+/* One mode group of a time grid with n_time + 1 > 128 levels (single GPU; the engine loops transform -> dots_mode_solves ->
+ * inverse transform over groups of ctx->m_pad modes, each with its own factor panels).  inverse = 0: ctx->hat[v][j] =
+ * sum_t q[t][j] rhs[t][v], q [n_time+1][m_pad]; inverse = 1: phi[t][v] (+)= sum_j q[j][t] hat[v][j], q [m_pad][n_time+1],
+ * accumulate != 0 adds to phi.  Same role as dots_time_transform (utils/laplacian_inverse_socp.py:52-61).               */
+int dots_time_transform_plain(const dots_ctx_t *ctx, int inverse, const double *q, int accumulate, void *stream);   /* rhs -> hat / hat -> phi   */
 int dots_mode_solves(const dots_ctx_t *c, void *stream);                   /* hat <- (K+shift M)^-1 hat */
 /* profiling aid: one pair of ring sweeps (sweep_mode 4) with a CUDA event before every launch; ms_out[i] = start of launch i ->
  * start of launch i+1, tag_out[i] = tree level (+1000: gather, +2000: backward).  Synchronises the stream.              */

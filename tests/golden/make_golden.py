@@ -88,6 +88,9 @@ CASES = {
     # and re-scaling at iterations 10, 50, 150, ...; snapshots around the scaling iterations
     "ico2_nt7_cscale": ("icosphere2", {}, 7, dict(tol=1e-3, nit=1000, congestion=0.05, is_constant_scaling=1.0), (0, 9, 10, 49, 50, 51), True),
     "ico3_nt15_cscale_c0": ("icosphere3", {}, 15, dict(tol=1e-3, nit=1000, is_constant_scaling=1.0), (0, 10), False),
+    # more than 128 time levels: the GPU path solves the modes in groups (160 levels -> 2 groups of 80; 300 -> 3 of 100)
+    "ico2_nt159_c0": ("icosphere2", {}, 159, dict(tol=1e-3, nit=1500), (), False),
+    "ico2_nt299_c005": ("icosphere2", {}, 299, dict(tol=1e-3, nit=1500, congestion=0.05), (), False),
 }
 
 

@@ -141,7 +141,8 @@ def test_fused_step_rows_a1_a4(congestion):
 # ---------------------------------------------------------------------------------------------- iterates
 @pytest.mark.parametrize("example,n_time,congestion,exkw", [
     ("icosphere2", 7, 0.0, {}), ("icosphere2", 7, 0.1, {}), ("plane8", 6, 0.0, {}),
-    ("knot", 8, 0.05, dict(n_u=40, n_v=6)), ("icosphere3", 31, 0.0, {}), ("icosphere2", 127, 0.0, {})])
+    ("knot", 8, 0.05, dict(n_u=40, n_v=6)), ("icosphere3", 31, 0.0, {}), ("icosphere2", 127, 0.0, {}),
+    ("icosphere2", 159, 0.0, {}), ("icosphere3", 299, 0.05, {})])      # > 128 time levels: 2 / 3 mode groups, plain time transforms
 @pytest.mark.parametrize("sweep_mode", [None, 4])          # None: the engine's choice (small factors: k_sweep_run); 4: ring-streamed
 def test_iterates_match_oracle(example, n_time, congestion, exkw, sweep_mode):
     geo, alm, eng = make_pair(example, n_time, congestion=congestion, sweep_mode=sweep_mode, **exkw)
@@ -158,6 +159,20 @@ def test_iterates_match_oracle(example, n_time, congestion, exkw, sweep_mode):
             alm.scale_z(1.3)
             eng.scale_z(1.3)
             compare_states(alm, eng, 1e-8, "after rescale")
+
+
+@pytest.mark.parametrize("n_time,groups,m_pad", [(128, 2, 96), (159, 2, 96), (255, 2, 128), (256, 3, 96)])
+def test_mode_groups_beyond_128_time_levels_solve_the_space_time_operator(n_time, groups, m_pad):
+    """More than 128 time levels on one GPU: the phi-step (rhs, plain forward transform, sweeps per mode group, accumulated
+    inverse transform) against the space-time operator formed from the stand-alone gradient / divergence kernels, per mode."""
+    geo, _ = synth.example("icosphere3")
+    eng = Engine(n_time, geo, congestion=0.05, leaf_size=12)
+    assert eng.n_groups == groups and eng.m_pad == m_pad and len(eng.groups) == groups
+    eng.scale_z(2.0)
+    eng.iterate(3, write_z=True)
+    eng.step_phi()
+    res = eng.phi_residual()
+    assert np.isfinite(res).all() and res.max() < 1e-9, res.max()
 
 
 def test_kkt_and_objective_rows_a9_a11():
@@ -206,7 +221,8 @@ def test_specialised_kkt_passes_equal_the_generic_one(example, n_time):
                                   "ico2_nt7_eps1e-2",                                   # regularised Laplacian (eps > 0)
                                   "ico2_nt7_tl0",                                       # time limit hit on the first iteration
                                   "ico5_nt31_c0",                                       # 10 242 vertices: large fronts, split sweep items
-                                  "ico2_nt7_cscale", "ico3_nt15_cscale_c0"])            # is_constant_scaling=True (primal / dual rescaling)
+                                  "ico2_nt7_cscale", "ico3_nt15_cscale_c0",            # is_constant_scaling=True (primal / dual rescaling)
+                                  "ico2_nt159_c0", "ico2_nt299_c005"])                  # > 128 time levels (mode groups)
 def test_solver_matches_reference_fixture(golden, name):
     """Through the public solver_socp: iteration count, KKT schedule (which residual on which iteration), penalty
     path, transport cost and the returned mu against the fixtures generated by the unmodified reference."""

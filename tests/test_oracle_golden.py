@@ -58,7 +58,8 @@ def test_iterates_match_reference(golden, name):
             assert rel_err(a, b) < 1e-8, ref_name
 
 
-@pytest.mark.parametrize("name", ["ico2_nt15_tol1e-4", "ico3_nt31_c0", "ico3_nt31_c01"])
+@pytest.mark.parametrize("name", ["ico2_nt15_tol1e-4", "ico3_nt31_c0", "ico3_nt31_c01",
+                                  "ico2_nt159_c0", "ico2_nt299_c005"])                   # more than 128 time levels
 def test_schedule_and_history_match_reference(golden, name):
     """Iteration count, which KKT conditions were evaluated when (nan pattern), their values, penalty path, cost."""
     z, geo, n_time, kw = golden(name)
