@@ -9,7 +9,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 18
+ABI_VERSION = 19
 P_R, P_S, P_D, P_CONG, P_TAU, P_EPS, P_PS, P_DS, P_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 _i32p, _i64p, _f64p = C.c_void_p, C.c_void_p, C.c_void_p      # raw device/host addresses
@@ -35,7 +35,8 @@ class DotsCtx(C.Structure):
            ("peer_rhs", C.c_void_p * 8), ("peer_hat", C.c_void_p * 8)]
         + [(n, C.c_void_p) for n in ("rt_fwd", "rt_bwd", "h_rt_fwd_ptr", "h_rt_bwd_ptr", "h_rt_fwd_wpr", "h_rt_bwd_wpr",
                                      "bidx", "erow_fwd", "erow_bwd", "gptr", "gidx", "gverts", "h_gv_ptr")]
-        + [("ring_stages", C.c_int32), ("ring_pdl", C.c_int32), ("ring_stage_bytes", C.c_int32), ("ring_flags", C.c_int32)]
+        + [("ring_stages", C.c_int32), ("ring_pdl", C.c_int32), ("ring_stage_bytes", C.c_int32), ("ring_flags", C.c_int32),
+           ("kkt1_part", C.c_void_p), ("kkt1_blocks", C.c_int32), ("reserved3", C.c_int32)]
     )
 
 

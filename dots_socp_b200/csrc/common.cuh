@@ -31,6 +31,23 @@ static inline int dots_check_ctx(const dots_ctx_t *c)
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Grid of the TMA-staged triangle kernel (iter_kernels.cu: k_tri_tma, 128 triangles per block): time levels per block and
+// the number of blocks.  16 levels amortise the per-triangle constants; small meshes (fewer blocks than two waves of
+// 3 blocks / SM) take the shortest chunk that still fits ONE wave: a knots_5-class mesh (68 triangle tiles, 32 levels) runs
+// 6 levels per block on 408 blocks instead of 16 on 136.  Shared with the reduction of the per-block KKT #1 partials.
+static inline int dots_tri_tma_blocks(const dots_ctx_t *c, int *tch_out)
+{
+    const int tiles = ceil_div(c->n_tri, 128), levels = c->lvl_end - c->lvl_begin;
+    const int wave = 3 * (c->n_sm > 0 ? c->n_sm : 148);
+    int tch = 16;
+    if ((long long)tiles * ceil_div(levels, 16) < 2LL * wave) {
+        tch = 2;
+        while (tch < 16 && (long long)tiles * ceil_div(levels, tch) > wave) ++tch;
+    }
+    if (tch_out) *tch_out = tch;
+    return tiles * ceil_div(levels, tch);
+}
 static inline int dots_t_end(const dots_ctx_t *c) { return c->lvl_end < c->n_time ? c->lvl_end : c->n_time; }   // staggered steps owned: [lvl_begin, t_end)
 
 // Programmatic dependent launch: the launches of one iteration are chained (the attribute is passed when ctx.ring_pdl is

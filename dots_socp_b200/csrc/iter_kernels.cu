@@ -260,11 +260,13 @@ __global__ void __launch_bounds__(128, 4) k_tri(dots_ctx_t c)
                         double b = bm[((sd * 3 + k) * 3 + x) * T];
                         if (MODE == 0 || MODE == 1) {
                             const double zz = lt * (dg[k] * (bs[x] - b));                     // same arithmetic as pass one
-                            b = b + step * (zz - cs * Bn[x]);                                 // :717, :721
+                            // explicit fused operations: the rounding of the update must not depend on what else a MODE does with
+                            // zz (the compiler contracted this line differently with and without the z_mid store: 1 ulp in b_mid)
+                            b = __fma_rn(step, __fma_rn(-cs, Bn[x], zz), b);                  // b + step (z - cs B)   :717, :721
                             bm[((sd * 3 + k) * 3 + x) * T] = b;
                             if (MODE == 1) zm[((sd * 3 + k) * 3 + x) * T] = zz;
                         }
-                        const double w = dg[k] * (cs * Bn[x] - b);                            // :995-998
+                        const double w = __dmul_rn(dg[k], __fma_rn(cs, Bn[x], -b));           // dg (cs B - b)   :995-998
                         acc += w * w;                                                         // :1003-1014
                     }
                 }
@@ -360,6 +362,7 @@ __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c, int tch)
 #pragma unroll
         for (int k = 0; k < 3; ++k) lam_prev[k] = c.lam[(size_t)(tau_begin - 1) * V + vk[k]];
     }
+    double kkt1 = 0.0;                                                      // MODE 2: this thread's share of KKT #1 (inactive threads: 0)
 
     for (int tau = tau_begin, it = 0; tau < tau_end; ++tau, ++it) {
         const int stage = it % TRI_STAGES;
@@ -430,10 +433,17 @@ __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c, int tch)
                         for (int x = 0; x < 3; ++x) {
                             double b = sm[((sd * 3 + k) * 3 + x) * TRI_TILE];
                             const double zz = lt * (dg[k] * (bs[x] - b));                     // same arithmetic as pass one
-                            b = b + step * (zz - cs * Bn[x]);                                 // :717, :721
+                            // explicit fused operations: the rounding of the update must not depend on what else a MODE does with
+                            // zz (the compiler contracted this line differently with and without the z_mid store: 1 ulp in b_mid)
+                            const double dz = __fma_rn(-cs, Bn[x], zz);                       // z - cs B: the residual of KKT #1 (:599)
+                            b = __fma_rn(step, dz, b);                                        // :717, :721
                             bm[((sd * 3 + k) * 3 + x) * T] = b;
                             if (MODE == 1) zm[((sd * 3 + k) * 3 + x) * T] = zz;
-                            const double w = dg[k] * (cs * Bn[x] - b);                        // :995-998
+                            if (MODE == 2) {                                                  // KKT #1, triangle term, as k_kkt_tri forms it
+                                const double res = __dmul_rn(s, dz);                          // from the stored z_mid and B
+                                kkt1 = __fma_rn(__dmul_rn(res, res), af, kkt1);
+                            }
+                            const double w = __dmul_rn(dg[k], __fma_rn(cs, Bn[x], -b));       // dg (cs B - b)   :995-998
                             acc += w * w;                                                     // :1003-1014
                         }
                     }
@@ -452,6 +462,18 @@ __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c, int tch)
         }
         __syncthreads();                                                    // everyone is done reading this stage
         if (tid == 0 && tau + TRI_STAGES < tau_end) issue(tau + TRI_STAGES, stage);
+    }
+    if (MODE == 2) {                                                        // fixed-order block sum -> one partial per block
+        __shared__ double kk[TRI_TILE / 32];
+        const double w = warp_sum(kkt1);
+        if ((tid & 31) == 0) kk[tid >> 5] = w;
+        __syncthreads();
+        if (tid == 0) {
+            double v = 0.0;
+#pragma unroll
+            for (int i = 0; i < TRI_TILE / 32; ++i) v += kk[i];
+            c.kkt1_part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = v;
+        }
     }
 }
 
@@ -568,19 +590,16 @@ extern "C" int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream)
         if (!configured[dev]) {
             DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM));
             DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM));
+            DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM));
             configured[dev] = true;
         }
-        // Time levels per block: TRI_TMA_TCH amortises the per-triangle constants over 16 levels.  Small meshes (fewer blocks
-        // than two waves of 3 blocks / SM) take shorter chunks instead, the shortest that still fits ONE wave: a
-        // knots_5-class mesh (68 triangle tiles, 32 levels) runs 6 levels per block on 408 blocks instead of 16 on 136.
-        const int tiles = ceil_div(c->n_tri, TRI_TILE), levels = c->lvl_end - c->lvl_begin;
-        const int wave = 3 * (c->n_sm > 0 ? c->n_sm : 148);
-        int tch = TRI_TMA_TCH;
-        if ((long long)tiles * ceil_div(levels, TRI_TMA_TCH) < 2LL * wave) {
-            tch = 2;
-            while (tch < TRI_TMA_TCH && (long long)tiles * ceil_div(levels, tch) > wave) ++tch;
+        int tch = 0;
+        const int n_blocks = dots_tri_tma_blocks(c, &tch);
+        const unsigned gx = (unsigned)ceil_div(c->n_tri, TRI_TILE), gy = (unsigned)(n_blocks / (int)gx);
+        if (write_z == 2 && (!c->kkt1_part || c->kkt1_blocks < n_blocks)) {
+            dots_set_error("dots_step_tri(write_z = 2): kkt1_part holds %d partials, the grid has %d blocks", c->kkt1_part ? c->kkt1_blocks : 0, n_blocks);
+            return DOTS_ERR_BAD_ARG;
         }
-        const unsigned gx = (unsigned)tiles, gy = (unsigned)ceil_div(levels, tch);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(gx, gy);
         cfg.blockDim = dim3(TRI_TILE);
@@ -591,10 +610,12 @@ extern "C" int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream)
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = c->ring_pdl ? 1 : 0;
-        if (write_z) DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<1>, *c, tch));
+        if (write_z == 2) DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<2>, *c, tch));
+        else if (write_z) DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<1>, *c, tch));
         else DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<0>, *c, tch));
         return 0;
     } else {
+        if (write_z == 2) { dots_set_error("dots_step_tri(write_z = 2) needs the TMA triangle kernel (even n_tri)"); return DOTS_ERR_BAD_ARG; }
         dim3 grid(ceil_div(c->n_tri, 128), ceil_div(c->lvl_end - c->lvl_begin, TRI_TCH));
         if (write_z) k_tri<1><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);
         else k_tri<0><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);

@@ -324,11 +324,36 @@ __global__ void k_reduce_final(const double *__restrict__ part, int nblocks, dou
     if (lane == 0) out[slot] = v;
 }
 
+// Triangle term of KKT #1 from the per-block partials an iteration with write_z = 2 left in kkt1_part: one block, fixed order.
+__global__ void __launch_bounds__(256) k_reduce_kkt1(const double *__restrict__ part, int n, double *__restrict__ out)
+{
+    __shared__ double sm[8];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) v += part[i];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sm[w];
+        out[1 * 8 + 4] = t;                                               // condition 1, first triangle slot
+    }
+}
+
 // Raw sums of every condition in `mask` (bit i = condition i, bit 7 = objective) in ONE pass per side: host_out[8 * i + k].
 extern "C" int dots_kkt_sums_multi(const dots_ctx_t *c, unsigned mask, double *host_out, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
-    if (!mask || mask > 0x1ffu) { dots_set_error("kkt mask %u out of range", mask); return DOTS_ERR_BAD_ARG; }
+    if (!mask || mask > 0x3ffu) { dots_set_error("kkt mask %u out of range", mask); return DOTS_ERR_BAD_ARG; }
+    const bool fused1 = (mask & 0x200u) != 0;                              // triangle term of #1 from kkt1_part
+    mask &= 0x1ffu;
+    int n_part = 0;
+    if (fused1) {
+        if (!(mask & 2u)) { dots_set_error("kkt mask: bit 9 without condition 1"); return DOTS_ERR_BAD_ARG; }
+        n_part = dots_tri_tma_blocks(c, nullptr);
+        if (!c->kkt1_part || c->kkt1_blocks < n_part || c->n_tri % 2) { dots_set_error("kkt mask: bit 9 needs kkt1_part from dots_step_tri(write_z = 2)"); return DOTS_ERR_BAD_ARG; }
+    }
+    const unsigned tmask = (mask & 0x12bu) & ~(fused1 ? 2u : 0u);
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = c->red_blocks;
     DOTS_CUDA(cudaMemsetAsync(c->red_part, 0, sizeof(double) * KKT_CONDS * 8 * nb, st));
@@ -336,11 +361,13 @@ extern "C" int dots_kkt_sums_multi(const dots_ctx_t *c, unsigned mask, double *h
     else if (mask == 15u) k_kkt_vertex<15u><<<nb, KKT_THREADS, 0, st>>>(*c, mask);              // forced primal + dual set
     else if (mask & 0x1dfu) k_kkt_vertex<0u><<<nb, KKT_THREADS, 0, st>>>(*c, mask);
     DOTS_LAUNCH_CHECK();
-    if (mask == 15u) k_kkt_tri<11u><<<nb, KKT_THREADS, 0, st>>>(*c, mask);                       // #0, #1, #3 have triangle terms
-    else if (mask & 0x12bu) k_kkt_tri<0u><<<nb, KKT_THREADS, 0, st>>>(*c, mask);
+    if (tmask == 11u) k_kkt_tri<11u><<<nb, KKT_THREADS, 0, st>>>(*c, tmask);                     // #0, #1, #3 have triangle terms
+    else if (tmask == 9u) k_kkt_tri<9u><<<nb, KKT_THREADS, 0, st>>>(*c, tmask);                  // the same set with #1 taken from kkt1_part
+    else if (tmask) k_kkt_tri<0u><<<nb, KKT_THREADS, 0, st>>>(*c, tmask);
     DOTS_LAUNCH_CHECK();
     k_reduce_final<<<KKT_CONDS, 256, 0, st>>>(c->red_part, nb, c->red_out);
     DOTS_LAUNCH_CHECK();
+    if (fused1) { k_reduce_kkt1<<<1, 256, 0, st>>>(c->kkt1_part, n_part, c->red_out); DOTS_LAUNCH_CHECK(); }
     DOTS_CUDA(cudaMemcpyAsync(host_out, c->red_out, sizeof(double) * KKT_CONDS * 8, cudaMemcpyDeviceToHost, st));
     DOTS_CUDA(cudaStreamSynchronize(st));
     return 0;

@@ -695,7 +695,7 @@ extern "C" int dots_iterate(const dots_ctx_t *c, int n_iter, int write_z, void *
         int e;
         if ((e = dots_step_phi(c, stream))) return e;
         if ((e = dots_step_vertex(c, stream))) return e;
-        if ((e = dots_step_tri(c, write_z && i == n_iter - 1, stream))) return e;
+        if ((e = dots_step_tri(c, (i == n_iter - 1) ? write_z : 0, stream))) return e;
     }
     return 0;
 }

@@ -306,6 +306,13 @@ class Engine:
         for k, ten in self.t.items():
             setattr(ctx, k, ten.data_ptr())
         ctx.red_blocks = self.red_blocks
+        # per-block partials of the triangle term of KKT #1 (iterate(kkt1=True)): one per block of k_tri_tma's grid, whose
+        # time chunks hold at least 2 levels; the plain-load triangle kernel (odd triangle counts) has no such mode
+        self.can_fuse_kkt1 = T % 2 == 0
+        n_k1 = -(-T // 128) * -(-(l1 - l0) // 2)
+        self.t["kkt1_part"] = z(max(1, n_k1))
+        ctx.kkt1_part, ctx.kkt1_blocks = self.t["kkt1_part"].data_ptr(), n_k1
+        self.kkt1_valid = False
         self.ctx = ctx
         self._ctxp = C.byref(ctx)
         self._host_out = np.zeros(72)
@@ -501,25 +508,30 @@ class Engine:
             sl["B"].level(part.lvl_end).copy_(recv)
 
     # ------------------------------------------------------------------ the iteration
-    def iterate(self, n=1, write_z=False):
-        """n ALM iterations (Steps 1-3); ``write_z`` stores z_mid on the last one.  On one GPU the iteration is
-        replayed from a captured CUDA graph after the first call (one per write_z flavour)."""
+    def iterate(self, n=1, write_z=False, kkt1=False):
+        """n ALM iterations (Steps 1-3); ``write_z`` stores z_mid on the last one; ``kkt1`` (without ``write_z``) makes the last
+        one accumulate the triangle term of KKT #1 instead (dots_step_tri mode 2): what a check iteration needs when z_mid
+        itself will not be returned (3 GB less to write, 3 GB less to read back at the headline size).  On one GPU the
+        iteration is replayed from a captured CUDA graph after the first call (one per flavour)."""
         n, write_z = int(n), bool(write_z)
+        if kkt1 and not write_z and not self.can_fuse_kkt1:
+            write_z = True                               # no accumulating mode in the plain-load kernel: store z_mid instead
+        mode = 1 if write_z else (2 if kkt1 else 0)
         st = self.stream
         if self.comm.enabled:
             for i in range(n):
-                self._iterate_sharded_graphed(write_z and i == n - 1)
+                self._iterate_sharded_graphed(mode if i == n - 1 else 0)
         elif self.groups:
             for i in range(n):
                 self.step_phi()
                 self._call("dots_step_vertex")
-                self._call("dots_step_tri", int(write_z and i == n - 1))
+                self._call("dots_step_tri", mode if i == n - 1 else 0)
         elif not self.use_graphs or not self._warm:
-            capi.check(self.lib.dots_iterate(self._ctxp, n, int(write_z), st), "dots_iterate")
+            capi.check(self.lib.dots_iterate(self._ctxp, n, mode, st), "dots_iterate")
             self._warm = True
         else:
             for i in range(n):
-                wz = write_z and i == n - 1
+                wz = mode if i == n - 1 else 0
                 key = (int(wz), st)
                 if key not in self._graphs:
                     # capture on a private stream (the legacy default stream cannot be captured); capturing does
@@ -533,13 +545,14 @@ class Engine:
                         self.graph_error = msg.decode() if msg else f"dots_graph_create -> {rc}"
                         self.use_graphs = False
                         torch.cuda.synchronize(self.device)
-                        capi.check(self.lib.dots_iterate(self._ctxp, n - i, int(write_z), st), "dots_iterate")
+                        capi.check(self.lib.dots_iterate(self._ctxp, n - i, mode, st), "dots_iterate")
                         break
                     self._graphs[key] = h
                 capi.check(self.lib.dots_graph_launch(self._graphs[key], st), "dots_graph_launch")
         self.launches += n * self.launches_per_iteration()
         self.z_valid = write_z
         self._state_changed()
+        self.kkt1_valid = mode == 2
 
     def step_phi(self):
         """Step 1 alone (single GPU): rhs, time transform, mode solves, inverse transform; with more than 128 time levels the
@@ -576,7 +589,7 @@ class Engine:
     def _iterate_sharded_graphed(self, write_z):
         """Replay the sharded iteration (kernels + NCCL collectives) from a torch CUDA graph; the first two calls of each
         flavour run eagerly (NCCL connection set-up, first-use kernel attributes), a failed capture falls back to eager."""
-        key = int(bool(write_z))
+        key = int(write_z)
         if not self.use_sharded_graphs or self._tgraph_warm.get(key, 0) < 2:
             self._tgraph_warm[key] = self._tgraph_warm.get(key, 0) + 1
             return self._iterate_sharded(write_z)
@@ -619,7 +632,7 @@ class Engine:
         self.launches += 2
 
     def adjust_penalty(self, f):                                                         # :367-371
-        self._state_changed()
+        self._state_changed(keep_kkt1=True)              # KKT #1 involves z, B, A and s only: untouched by the dual rescaling
         self.r *= f
         self._push_params()
         capi.check(self.lib.dots_scale_dual(self._ctxp, float(f), self.stream), "dots_scale_dual")
@@ -773,6 +786,9 @@ class Engine:
         which = int(which)
         if which in self._sum_cache:
             return self._sum_cache[which]
+        if which == 1 and not self.z_valid and self.kkt1_valid:
+            self.prefetch_sums([1])
+            return self._sum_cache[1]
         capi.check(self.lib.dots_kkt_sums(self._ctxp, which, self._host_out.ctypes.data, self.stream), "dots_kkt_sums")
         self.launches += 3
         return self.comm.sum_in_rank_order(self._host_out[:8].copy(), self.device)
@@ -785,25 +801,29 @@ class Engine:
         conds = sorted({int(i) for i in conditions})
         if not conds:
             return
-        if 1 in conds and not self.z_valid:
-            raise capi.DotsError("KKT #1 needs z_mid of the current iteration: call iterate(..., write_z=True)")
+        if 1 in conds and not (self.z_valid or self.kkt1_valid):
+            raise capi.DotsError("KKT #1 needs z_mid of the current iteration: call iterate(..., write_z=True) or iterate(..., kkt1=True)")
         if 4 in conds:
             self.exchange_B_halo()
         mask = sum(1 << i for i in conds)
+        if 1 in conds and not self.z_valid:
+            mask |= 0x200                                # triangle term of #1 from the partials the iteration accumulated
         capi.check(self.lib.dots_kkt_sums_multi(self._ctxp, mask, self._host_out.ctypes.data, self.stream), "dots_kkt_sums_multi")
         self.launches += 4
         total = self.comm.sum_in_rank_order(self._host_out.copy(), self.device)
-        self._sum_cache = {i: total[8 * i:8 * i + 8].copy() for i in conds}
+        self._sum_cache.update({i: total[8 * i:8 * i + 8].copy() for i in conds})
 
-    def _state_changed(self):
+    def _state_changed(self, keep_kkt1=False):
         self._sum_cache = {}
+        if not keep_kkt1:
+            self.kkt1_valid = False                      # the accumulated triangle term of KKT #1 belongs to the state it was formed from
 
     def kkt(self, i):
         """Relative KKT residual i as [value, value] (conditions 0-3) or [value, None] (4-6):
         the two-valued convention of solver_socp.py:589-643 with prim_scale = dual_scale = 1."""
         nT, sq = self.nT, math.sqrt
-        if i == 1 and not self.z_valid:
-            raise capi.DotsError("KKT #1 needs z_mid of the current iteration: call iterate(..., write_z=True)")
+        if i == 1 and not (self.z_valid or self.kkt1_valid):
+            raise capi.DotsError("KKT #1 needs z_mid of the current iteration: call iterate(..., write_z=True) or iterate(..., kkt1=True)")
         if i == 4 and i not in self._sum_cache:
             self.exchange_B_halo()
         o = self.sums(i)

@@ -120,6 +120,7 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
         eng.initial_constant_scaling()                                                    # :574-587
     to_scale = lambda k: is_constant_scaling and (k == 10 or k == 50 or k % 100 == 50)    # admm_tools.is_to_scale :98-104
     use_org = False
+    z_free_checks = dot_units is not None or (solution_keys is not None and "z_mid" not in solution_keys)
     it, passed = -1, False
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev_a.record()
@@ -153,7 +154,11 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
         will_check = check_kkt_step_by_step or lazy.will_fire(required) or it == nit - 1
         if is_palm:
             eng.step_q0()                                                                 # Step 0, :668-672
-        eng.iterate(1, write_z=will_check or is_palm or to_scale(it + 1))                 # Steps 1-3, :674-722
+        # z_mid itself is stored when something reads it back: Step 0 of is_palm, the variable norms of the re-scaling, the
+        # returned SOCP-unit solution.  A check iteration of a DOT-unit run (solver / solver_raw return mu and E only) needs just
+        # the triangle term of KKT #1, which the triangle kernel then accumulates on the fly (dots_step_tri mode 2).
+        store_z = is_palm or to_scale(it + 1) or (will_check and not z_free_checks)
+        eng.iterate(1, write_z=store_z, kkt1=will_check and not store_z)                  # Steps 1-3, :674-722
         pending = True
 
         cost = lagr = None

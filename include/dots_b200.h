@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DOTS_ABI_VERSION 18
+#define DOTS_ABI_VERSION 19
 
 /* scalar block read by the kernels from device memory (so CUDA graphs stay valid across penalty updates) */
 enum {
@@ -187,6 +187,10 @@ typedef struct dots_ctx {
     int32_t ring_pdl;          /* 1: chain the launches of an iteration with programmatic dependent launch                */
     int32_t ring_stage_bytes;  /* bytes per ring stage: 2048 or 4096                                                      */
     int32_t ring_flags;        /* bit 0: the panel copies of the ring-streamed sweeps carry an L2 evict_first hint        */
+    double *kkt1_part;         /* [kkt1_blocks] per-block partial sums of the triangle term of KKT #1, written by
+                                  dots_step_tri(write_z = 2) (one per block of its grid, fixed order)                     */
+    int32_t kkt1_blocks;       /* capacity of kkt1_part: >= ceil(n_tri / 128) * ceil(owned levels / 2)                     */
+    int32_t reserved3;
 
 } dots_ctx_t;
 
@@ -206,7 +210,10 @@ const char *dots_last_error(void);
  *                   (vertex halves of vanilla_solve_proj_soc :988-1042, vanilla_solve_q_lambda :1044-1065, Step 3 :716-722)
  * dots_step_tri   : per (tau,f): dx_phi, z_mid, B, E, b_mid and the corner terms of the next iteration
  *                   (triangle halves of the same three steps + decouple_spacial :923-942 / adjoint :944-959)
- *                   write_z != 0 also stores z_mid (needed by KKT #1 and by the returned solution).
+ *                   write_z = 1 also stores z_mid (needed by KKT #1, is_palm, the variable norms and the returned solution);
+ *                   write_z = 2 stores no z_mid but accumulates the triangle term of KKT #1, sum of area_f (s (z_mid -
+ *                   s/sqrt3 B))^2, per block into kkt1_part (TMA kernel only, i.e. even n_tri): what a check iteration
+ *                   needs when z_mid itself is not going to be returned.
  * dots_iterate    : n_iter x (phi, vertex, tri); write_z applies to the last one.                    */
 int dots_step_phi(const dots_ctx_t *c, void *stream);
 int dots_step_vertex(const dots_ctx_t *c, void *stream);
@@ -250,8 +257,9 @@ int dots_kkt_sums(const dots_ctx_t *c, int which, double *host_out, void *stream
  * triangle arrays (the --detail_runhist mode of solver_socp.py:769-787 evaluates all 7 + the objective every iteration; the
  * penalty-update iterations force conditions 0-3, :728-729): host_out[8 * i + k] = slot k of condition i as in
  * dots_kkt_sums.  Bit 8: the variable norms of scale_prim_dual (:331-340): vertex slots z_fst^2, z_end^2, b_fst^2,
- * b_end^2 (x area_v), triangle slots z_mid^2, b_mid^2 (x area_f).  red_part must hold red_blocks x 72 doubles, red_out and
- * host_out 72.  Synchronises the stream.                                                                                  */
+ * b_end^2 (x area_v), triangle slots z_mid^2, b_mid^2 (x area_f).  Bit 9: the triangle term of condition 1 is taken from
+ * kkt1_part (valid after dots_step_tri / dots_iterate with write_z = 2) instead of from z_mid.  red_part must hold
+ * red_blocks x 72 doubles, red_out and host_out 72.  Synchronises the stream.                                             */
 int dots_kkt_sums_multi(const dots_ctx_t *c, unsigned mask, double *host_out, void *stream);
 
 /* ---- setup (row f1): numeric factorisation of the small fronts (n <= dots_front_nmax()) of one tree level, one block

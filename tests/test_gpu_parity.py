@@ -211,6 +211,40 @@ def test_specialised_kkt_passes_equal_the_generic_one(example, n_time):
             assert np.abs(special[w]).max() > 0.0
 
 
+@pytest.mark.parametrize("example,n_time", [("icosphere4", 31), ("knots_5", 15), ("icosphere2", 7), ("icosphere3", 159)])
+def test_kkt1_accumulated_in_the_triangle_kernel_equals_the_stored_z_path(example, n_time):
+    """iterate(kkt1=True) (dots_step_tri mode 2: no z_mid store, the triangle term of KKT #1 accumulated per block) against
+    iterate(write_z=True) + the KKT pass over the stored z_mid: same iterates bit for bit, same per-element terms, only the
+    summation order of the one sum differs."""
+    geo, _ = synth.example(example)
+    out = {}
+    for tag in ("stored", "fused"):
+        eng = Engine(n_time, geo, congestion=0.05)
+        assert eng.can_fuse_kkt1
+        eng.scale_z(2.0)
+        eng.iterate(4)                                                   # eager first call, then graph replays
+        if tag == "stored":
+            eng.iterate(3, write_z=True)
+        else:
+            eng.iterate(3, kkt1=True)
+            assert eng.kkt1_valid and not eng.z_valid
+        eng.prefetch_sums([0, 1, 2, 3])                                  # the forced set of a penalty-update iteration
+        sums = {i: eng.sums(i).copy() for i in range(4)}
+        eng.adjust_penalty(1.3)                                          # keeps the accumulated term valid (z, B, s untouched)
+        single = eng.sums(1).copy()
+        out[tag] = (sums, single, eng.kkt(1), eng.get_state(("phi", "mu", "B", "b_mid")))
+        eng.close()
+    for k, v in out["stored"][3].items():
+        assert np.array_equal(v, out["fused"][3][k]), k
+    for i in (0, 2, 3):
+        assert np.array_equal(out["stored"][0][i], out["fused"][0][i]), i
+    a, b = out["stored"][0][1], out["fused"][0][1]
+    assert np.array_equal(a[:4], b[:4]) and np.array_equal(a[5:], b[5:])  # vertex slots and unused slots: identical
+    assert a[4] > 0.0 and abs(a[4] - b[4]) <= 1e-13 * a[4]
+    assert np.allclose(out["stored"][1], out["fused"][1], rtol=1e-13, atol=0.0)
+    assert out["stored"][2][0] == pytest.approx(out["fused"][2][0], rel=1e-13)
+
+
 # ---------------------------------------------------------------------------------------------- end to end
 @pytest.mark.parametrize("name", ["ico2_nt7_c0", "ico2_nt7_c01", "plane8_nt6_c0", "knot_small_nt8_c005",
                                   "ico2_nt15_tol1e-4", "ico3_nt31_c0", "ico3_nt31_c01",

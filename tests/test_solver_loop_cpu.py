@@ -60,19 +60,21 @@ class OracleEngine:
         self.alm.step_q()
         self.calls_q0 = getattr(self, "calls_q0", 0) + 1
 
-    def iterate(self, n=1, write_z=False):
+    def iterate(self, n=1, write_z=False, kkt1=False):
         for _ in range(n):
             self.alm.iterate()
         self.z_valid = bool(write_z)
+        self.kkt1_valid = bool(kkt1) and not write_z      # the triangle kernel accumulated the triangle term of KKT #1 instead
         self.calls.append(bool(write_z))
+        self.calls_kkt1 = getattr(self, "calls_kkt1", []) + [self.kkt1_valid]
 
     def prefetch_sums(self, conditions):                 # the CUDA engine batches these reductions; nothing to do here
         if 1 in set(conditions):
-            assert self.z_valid, "KKT #1 prefetched on an iteration that did not store z_mid"
+            assert self.z_valid or getattr(self, "kkt1_valid", False), "KKT #1 prefetched on an iteration that neither stored z_mid nor accumulated its sums"
 
     def kkt(self, i):
         if i == 1:
-            assert self.z_valid, "KKT #1 requested on an iteration that did not store z_mid"
+            assert self.z_valid or getattr(self, "kkt1_valid", False), "KKT #1 requested on an iteration that neither stored z_mid nor accumulated its sums"
         return self.alm.kkt(i)
 
     def objective(self):
@@ -194,6 +196,9 @@ def test_loop_checkpoints_and_dot_units(cpu_loop, golden):
     for cp, level in zip(cps, (1e-1, 1e-2)):
         assert cp["mu"].shape == sol["mu"].shape and cp["E"].shape == sol["E"].shape
         assert max(k for k in cp["kkt"] if k is not None) <= level
+    eng = cpu_loop[-1]
+    # a DOT-unit run returns mu and E only: its check iterations accumulate KKT #1 on the fly and never store z_mid
+    assert not any(eng.calls) and 0 < sum(eng.calls_kkt1) < len(eng.calls)
     raw, _ = solver_mod.solver_raw(n_time, geo, **kw)
     assert np.allclose(raw["mu"], mid, rtol=1e-7, atol=1e-14)
 
