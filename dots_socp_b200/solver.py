@@ -110,6 +110,9 @@ def solver_socp(n_time, geometry, congestion=0.0, nit=1000, eps=0.0 * 10 ** (-8)
     lazy = LazyResidualCheck([(lambda i=i: eng.kkt(i)) for i in range(7)], tol)
     hist.setup_time = dict(eng.timings)
 
+    if dot_units is not None and (not eng.comm.enabled or solution_root is None or eng.comm.rank == solution_root):
+        # the host side of the hand-off is made ready while the GPU iterates: pinned staging, copy threads, the result arrays
+        eng.prepare_download({"mu": (n_time + 1 if dot_units == "centred" else n_time, eng.V), "E": (n_time + 1, eng.T, 3)})
     hist.start()                                                                          # :565
     hist.create_tol_progress(target_tol=tol)
     prim_gap = 1.0 + 1.0 * np.exp(-100 * congestion)                                      # :568

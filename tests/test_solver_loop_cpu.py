@@ -68,6 +68,9 @@ class OracleEngine:
         self.calls.append(bool(write_z))
         self.calls_kkt1 = getattr(self, "calls_kkt1", []) + [self.kkt1_valid]
 
+    def prepare_download(self, shapes=None):             # host-side staging of the CUDA engine's hand-off: nothing to do here
+        self.prepared = dict(shapes or {})
+
     def prefetch_sums(self, conditions):                 # the CUDA engine batches these reductions; nothing to do here
         if 1 in set(conditions):
             assert self.z_valid or getattr(self, "kkt1_valid", False), "KKT #1 prefetched on an iteration that neither stored z_mid nor accumulated its sums"
