@@ -287,6 +287,76 @@ __global__ void __launch_bounds__(KKT_THREADS) k_kkt_vertex(dots_ctx_t c, unsign
     kkt_block_store(acc, mask & 0x1dfu, c.red_part, 0);
 }
 
+// Dual(alpha) (#2, :466-482) alone, the residual the lazy checks ask for most.  Thread = (vertex, KKT_TC consecutive time
+// levels): the corner ids, the hat gradients and the areas of a vertex are gathered once and serve all levels of the chunk,
+// so only E is gathered per level (the per-(t, v) kernel re-gathers 4 of 7 values per corner on every level and is bound by the
+// L2 sector traffic of those gathers).  Per (t, v) the arithmetic and the corner order are those of kkt_vertex_terms<2>.
+#define KKT_TC 8
+__global__ void __launch_bounds__(KKT_THREADS) k_kkt_dual_alpha(dots_ctx_t c)
+{
+    const int V = c.n_vert, nT = c.n_time;
+    const size_t T = (size_t)c.n_tri;
+    const double r = c.params[DOTS_P_R];
+    const double dt = 1.0 / nT;
+    const int l0 = c.lvl_begin, levels = c.lvl_end - c.lvl_begin;
+    const int n_chunks = (levels + KKT_TC - 1) / KKT_TC;
+    const size_t n_items = (size_t)n_chunks * V;
+    double total = 0.0;
+    for (size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(item / V), v = (int)(item - (size_t)ch * V);
+        const int t0 = l0 + ch * KKT_TC, nt = min(KKT_TC, c.lvl_end - t0);
+        const double av = c.area_v[v];
+        double divx[KKT_TC];
+#pragma unroll
+        for (int j = 0; j < KKT_TC; ++j) divx[j] = 0.0;
+        auto corner = [&](int cid) {                                       // adds -(g_k . (E af)) of corner id = k T + f to every level
+            const size_t k = (size_t)(cid >= (int)T) + (size_t)(cid >= 2 * (int)T), f = cid - k * T;
+            const double af = c.area_f[f];
+            const double g0 = c.hat_grad[(k * 3 + 0) * T + f], g1 = c.hat_grad[(k * 3 + 1) * T + f], g2 = c.hat_grad[(k * 3 + 2) * T + f];
+#pragma unroll
+            for (int j = 0; j < KKT_TC; ++j) {
+                if (j < nt) {
+                    const double *Et = c.E + (size_t)(t0 + j) * 3 * T;
+                    divx[j] += -(g0 * (Et[f] * af) + g1 * (Et[T + f] * af) + g2 * (Et[2 * T + f] * af));
+                }
+            }
+        };
+        const vc_row vr = vc_load(c, v);
+        if (vr.id[7] != -2) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (vr.id[q] >= 0) corner(vr.id[q]);
+        } else {
+            for (int q = c.vc_ptr[v], qe = c.vc_ptr[v + 1]; q < qe; ++q) corner(c.vc_idx[q]);
+        }
+        double mu_prev = (t0 > 0) ? c.mu[(size_t)(t0 - 1) * V + v] : 0.0;
+#pragma unroll
+        for (int j = 0; j < KKT_TC; ++j) {
+            if (j < nt) {
+                const int t = t0 + j;
+                const double mu_cur = (t < nT) ? c.mu[(size_t)t * V + v] : 0.0;
+                double divt;
+                if (t == 0) divt = (mu_cur * av) / dt;
+                else if (t == nT) divt = -(mu_prev * av) / dt;
+                else divt = (mu_cur * av - mu_prev * av) / dt;
+                const double bnd = (t == 0) ? c.bnd0[v] : ((t == nT) ? c.bnd1[v] : 0.0);
+                const double aux = (r * dt) * ((bnd + divt + divx[j]) / av);
+                total += aux * aux * av;
+                mu_prev = mu_cur;
+            }
+        }
+    }
+    __shared__ double sm[KKT_THREADS / 32];
+    const double w = warp_sum(total);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double vsum = 0.0;
+        for (int i = 0; i < KKT_THREADS / 32; ++i) vsum += sm[i];
+        c.red_part[(size_t)blockIdx.x * (KKT_CONDS * 8) + 2 * 8 + 0] = vsum;
+    }
+}
+
 template <unsigned CMASK>
 __global__ void __launch_bounds__(KKT_THREADS) k_kkt_tri(dots_ctx_t c, unsigned mask_rt)
 {
@@ -357,9 +427,11 @@ extern "C" int dots_kkt_sums_multi(const dots_ctx_t *c, unsigned mask, double *h
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = c->red_blocks;
     DOTS_CUDA(cudaMemsetAsync(c->red_part, 0, sizeof(double) * KKT_CONDS * 8 * nb, st));
-    if (mask == 4u) k_kkt_vertex<4u><<<nb, KKT_THREADS, 0, st>>>(*c, mask);                     // lazy check of Dual(alpha) alone
-    else if (mask == 15u) k_kkt_vertex<15u><<<nb, KKT_THREADS, 0, st>>>(*c, mask);              // forced primal + dual set
-    else if (mask & 0x1dfu) k_kkt_vertex<0u><<<nb, KKT_THREADS, 0, st>>>(*c, mask);
+    if (mask == 4u) k_kkt_dual_alpha<<<nb, KKT_THREADS, 0, st>>>(*c);                           // lazy check of Dual(alpha) alone
+    else if (mask == 15u) {                                                                     // forced primal + dual set
+        k_kkt_vertex<11u><<<nb, KKT_THREADS, 0, st>>>(*c, 11u);
+        k_kkt_dual_alpha<<<nb, KKT_THREADS, 0, st>>>(*c);
+    } else if (mask & 0x1dfu) k_kkt_vertex<0u><<<nb, KKT_THREADS, 0, st>>>(*c, mask);
     DOTS_LAUNCH_CHECK();
     if (tmask == 11u) k_kkt_tri<11u><<<nb, KKT_THREADS, 0, st>>>(*c, tmask);                     // #0, #1, #3 have triangle terms
     else if (tmask == 9u) k_kkt_tri<9u><<<nb, KKT_THREADS, 0, st>>>(*c, tmask);                  // the same set with #1 taken from kkt1_part

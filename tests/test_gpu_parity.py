@@ -190,8 +190,9 @@ def test_kkt_and_objective_rows_a9_a11():
 
 @pytest.mark.parametrize("example,n_time", [("icosphere3", 15), ("knots_5", 31)])
 def test_specialised_kkt_passes_equal_the_generic_one(example, n_time):
-    """The compile-time-mask instantiations of the KKT kernels (#2 alone, #0-#3) against the generic kernel (same sets plus the
-    objective): same mapping of items to threads, so the raw sums agree bit for bit."""
+    """The instantiations of the KKT kernels for the sets the solver asks for (#2 alone, #0-#3) against the generic kernel (same
+    sets plus the objective).  Compile-time masks keep the mapping of items to threads: those sums agree bit for bit; Dual(alpha)
+    has its own kernel (thread = vertex x 8 time levels): same per-(t, v) terms, another summation order."""
     import ctypes as C
     from dots_socp_b200 import capi
     geo, _ = synth.example(example)
@@ -207,7 +208,10 @@ def test_specialised_kkt_passes_equal_the_generic_one(example, n_time):
     for mask, conds in ((4, [2]), (15, [0, 1, 2, 3])):
         special, generic = multi(mask), multi(mask | 128)
         for w in conds:
-            assert np.array_equal(special[w], generic[w]), (mask, w)
+            if w == 2:
+                assert np.array_equal(special[w][1:], generic[w][1:]) and abs(special[w][0] - generic[w][0]) <= 1e-13 * generic[w][0]
+            else:
+                assert np.array_equal(special[w], generic[w]), (mask, w)
             assert np.abs(special[w]).max() > 0.0
 
 
