@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(KKT_THREADS) k_kkt_vertex(dots_ctx_t c, unsign
 // so only E is gathered per level (the per-(t, v) kernel re-gathers 4 of 7 values per corner on every level and is bound by the
 // L2 sector traffic of those gathers).  Per (t, v) the arithmetic and the corner order are those of kkt_vertex_terms<2>.
 #define KKT_TC 8
-__global__ void __launch_bounds__(KKT_THREADS) k_kkt_dual_alpha(dots_ctx_t c)
+__global__ void __launch_bounds__(KKT_THREADS, 4) k_kkt_dual_alpha(dots_ctx_t c)      // 4 blocks per SM = the persistent grid in one wave
 {
     const int V = c.n_vert, nT = c.n_time;
     const size_t T = (size_t)c.n_tri;
