@@ -16,7 +16,6 @@ in between are enqueued back to back.
 from __future__ import annotations
 
 import logging
-import os
 import time
 
 import numpy as np

@@ -144,7 +144,6 @@ def cpu_loop(monkeypatch):
 
     monkeypatch.setattr(solver_mod, "Engine", factory)
     monkeypatch.setattr(solver_mod, "torch", _TorchShim())
-    monkeypatch.setenv("DOTS_EXPERIMENTAL", "1")          # is_palm is gated until its engine step has run on hardware
     return made
 
 
