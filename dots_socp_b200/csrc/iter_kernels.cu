@@ -296,13 +296,17 @@ __global__ void __launch_bounds__(128, 4) k_tri(dots_ctx_t c)
 #define TRI_STAGES 3
 #define TRI_PLANES 24
 #define TRI_TMA_TCH 16
-#define TRI_TMA_SMEM (TRI_STAGES * TRI_PLANES * TRI_TILE * 8 + 64)
-template <int MODE>
+// ODD: the triangle count is odd (planes may start 8 bytes off a 16-byte boundary): shared-memory rows get room for the
+// leading element of a misaligned run and every read adds the plane's shift; with an even count both compile away.
+#define TRI_ROW_OF(ODD) (TRI_TILE + ((ODD) ? 2 : 0))
+#define TRI_TMA_SMEM_OF(ODD) (TRI_STAGES * TRI_PLANES * TRI_ROW_OF(ODD) * 8 + 64)
+template <int MODE, bool ODD>
 __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c, int tch)
 {
+    constexpr int TRI_ROW = TRI_ROW_OF(ODD);
     extern __shared__ __align__(128) unsigned char smraw[];
-    double *tile = reinterpret_cast<double *>(smraw);                       // [stage][plane][TRI_TILE]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + TRI_STAGES * TRI_PLANES * TRI_TILE * 8);
+    double *tile = reinterpret_cast<double *>(smraw);                       // [stage][plane][TRI_ROW]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smraw + TRI_STAGES * TRI_PLANES * TRI_ROW * 8);
     const int V = c.n_vert, nT = c.n_time;
     const size_t T = (size_t)c.n_tri;
     const int tid = threadIdx.x;
@@ -337,20 +341,32 @@ __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c, int tch)
     const double s = prm[DOTS_P_S], step = prm[DOTS_P_TAU];
     const double cs = s / sqrt(3.0);
 
+    // A bulk copy needs 16-byte aligned addresses and sizes.  With an odd triangle count every other plane starts 8 bytes off:
+    // such a run is fetched from one element earlier (`mis` = 1) and its data sits one slot later in the shared-memory row;
+    // sizes are rounded up to an even element count (the element after a plane is the next plane's first, or the padding
+    // the engine allocates behind the arrays).  Even counts: mis = 0 everywhere, the copies are exactly the planes.
+    auto misaligned = [](const double *p) -> unsigned { return ODD ? ((unsigned)(reinterpret_cast<uintptr_t>(p) >> 3) & 1u) : 0u; };
+    const unsigned todd = ODD ? 1u : 0u;
     auto issue = [&](int tau, int stage) {                                  // thread 0 only
-        const uint32_t bytes = (uint32_t)nf * 8u;
         const bool h0 = tau < nT, h1 = tau > 0;
-        const int n_planes = 6 + (h0 ? 9 : 0) + (h1 ? 9 : 0);
-        mbar_expect_tx(&bar[stage], bytes * n_planes);
-        double *dst = tile + (size_t)stage * TRI_PLANES * TRI_TILE;
+        double *dst = tile + (size_t)stage * TRI_PLANES * TRI_ROW;
         const double *bm = c.b_mid + (size_t)tau * 18 * T + f0;
-        for (int p = 0; p < 18; ++p) {                                      // (an L2 evict_first hint on these copies measured 0.8 % slower)
-            if ((p < 9) ? h0 : h1) tma_load_1d(dst + p * TRI_TILE, bm + (size_t)p * T, bytes, &bar[stage]);
-        }
         const double *Bp = c.B + (size_t)tau * 3 * T + f0, *Ep = c.E + (size_t)tau * 3 * T + f0;
+        auto count = [&](const double *src) -> uint32_t { return ((uint32_t)nf + misaligned(src) + 1u) & ~1u; };
+        uint32_t total = 0;
+        for (int p = 0; p < 18; ++p)
+            if ((p < 9) ? h0 : h1) total += count(bm + (size_t)p * T);
+        for (int x = 0; x < 3; ++x) total += count(Bp + (size_t)x * T) + count(Ep + (size_t)x * T);
+        mbar_expect_tx(&bar[stage], total * 8u);
+        auto fetch = [&](int row, const double *src) {
+            tma_load_1d(dst + row * TRI_ROW, src - misaligned(src), count(src) * 8u, &bar[stage]);
+        };
+        for (int p = 0; p < 18; ++p) {                                      // (an L2 evict_first hint on these copies measured 0.8 % slower)
+            if ((p < 9) ? h0 : h1) fetch(p, bm + (size_t)p * T);
+        }
         for (int x = 0; x < 3; ++x) {
-            tma_load_1d(dst + (18 + x) * TRI_TILE, Bp + (size_t)x * T, bytes, &bar[stage]);
-            tma_load_1d(dst + (21 + x) * TRI_TILE, Ep + (size_t)x * T, bytes, &bar[stage]);
+            fetch(18 + x, Bp + (size_t)x * T);
+            fetch(21 + x, Ep + (size_t)x * T);
         }
     };
     if (tid == 0) {
@@ -380,15 +396,20 @@ __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c, int tch)
         }
         mbar_wait(&bar[stage], parity);
         if (active) {
-            const double *sm = tile + (size_t)stage * TRI_PLANES * TRI_TILE + tid;
+            const double *srow = tile + (size_t)stage * TRI_PLANES * TRI_ROW + tid;
             double *Bp = c.B + (size_t)tau * 3 * T + f;
             double *Ep = c.E + (size_t)tau * 3 * T + f;
             double *bm = c.b_mid + (size_t)tau * 18 * T + f;
+            // slot of this triangle in the row of plane p: + 1 where the plane's run starts 8 bytes off (f - tid = f0 is even)
+            const unsigned mb = misaligned(bm - tid), mB = misaligned(Bp - tid), mE = misaligned(Ep - tid);
+            auto sm_b = [&](int p) -> double { return srow[p * TRI_ROW + ((mb + (unsigned)p * todd) & 1u)]; };
+            auto sm_B = [&](int x) -> double { return srow[(18 + x) * TRI_ROW + ((mB + (unsigned)x * todd) & 1u)]; };
+            auto sm_E = [&](int x) -> double { return srow[(21 + x) * TRI_ROW + ((mE + (unsigned)x * todd) & 1u)]; };
             double Bn[3], En[3], Eo[3], dx[3], bs[3];
 #pragma unroll
             for (int x = 0; x < 3; ++x) {
-                const double Bo = sm[(18 + x) * TRI_TILE];
-                Eo[x] = sm[(21 + x) * TRI_TILE];
+                const double Bo = sm_B(x);
+                Eo[x] = sm_E(x);
                 dx[x] = g[0][x] * ph[0] + g[1][x] * ph[1] + g[2][x] * ph[2];                  // :902-906
                 bs[x] = cs * Bo;                                                              // :932
             }
@@ -402,7 +423,7 @@ __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c, int tch)
                     const double lt = lamk[sd][k] / dg[k];                                    // :1023
 #pragma unroll
                     for (int x = 0; x < 3; ++x) {
-                        const double b = sm[((sd * 3 + k) * 3 + x) * TRI_TILE];
+                        const double b = sm_b((sd * 3 + k) * 3 + x);
                         const double w = dg[k] * (bs[x] - b);                                 // :998
                         const double zb = lt * w + b;                                         // :1041, :1052
                         sum[x] = (k == 0) ? zb : sum[x] + zb;                                 // np.sum(axis=2) :953
@@ -431,7 +452,7 @@ __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c, int tch)
                         const double lt = lamk[sd][k] / dg[k];
 #pragma unroll
                         for (int x = 0; x < 3; ++x) {
-                            double b = sm[((sd * 3 + k) * 3 + x) * TRI_TILE];
+                            double b = sm_b((sd * 3 + k) * 3 + x);
                             const double zz = lt * (dg[k] * (bs[x] - b));                     // same arithmetic as pass one
                             // explicit fused operations: the rounding of the update must not depend on what else a MODE does with
                             // zz (the compiler contracted this line differently with and without the z_mid store: 1 ulp in b_mid)
@@ -582,15 +603,18 @@ extern "C" int dots_step_vertex(const dots_ctx_t *c, void *stream)
 extern "C" int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
-    if (c->n_tri % 2 == 0) {                               // 16-byte aligned planes: TMA-staged kernel
+    if (!(c->ring_flags & 4)) {                            // TMA-staged kernel (ring_flags bit 2 selects the plain-load one: diagnostics)
         static bool configured[64] = {false};                  // per device (a second engine on another GPU of the process)
         int dev = 0;
         DOTS_CUDA(cudaGetDevice(&dev));
         dev = (dev >= 0 && dev < 64) ? dev : 0;
         if (!configured[dev]) {
-            DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM));
-            DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM));
-            DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM));
+            DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(false)));
+            DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(false)));
+            DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(false)));
+            DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(true)));
+            DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(true)));
+            DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(true)));
             configured[dev] = true;
         }
         int tch = 0;
@@ -603,19 +627,26 @@ extern "C" int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream)
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(gx, gy);
         cfg.blockDim = dim3(TRI_TILE);
-        cfg.dynamicSmemBytes = TRI_TMA_SMEM;
+        const bool odd = (c->n_tri & 1) != 0;
+        cfg.dynamicSmemBytes = odd ? TRI_TMA_SMEM_OF(true) : TRI_TMA_SMEM_OF(false);
         cfg.stream = (cudaStream_t)stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = c->ring_pdl ? 1 : 0;
-        if (write_z == 2) DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<2>, *c, tch));
-        else if (write_z) DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<1>, *c, tch));
-        else DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<0>, *c, tch));
+        if (odd) {
+            if (write_z == 2) DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<2, true>, *c, tch));
+            else if (write_z) DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<1, true>, *c, tch));
+            else DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<0, true>, *c, tch));
+        } else {
+            if (write_z == 2) DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<2, false>, *c, tch));
+            else if (write_z) DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<1, false>, *c, tch));
+            else DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<0, false>, *c, tch));
+        }
         return 0;
     } else {
-        if (write_z == 2) { dots_set_error("dots_step_tri(write_z = 2) needs the TMA triangle kernel (even n_tri)"); return DOTS_ERR_BAD_ARG; }
+        if (write_z == 2) { dots_set_error("dots_step_tri(write_z = 2) needs the TMA triangle kernel (ring_flags bit 2 is set)"); return DOTS_ERR_BAD_ARG; }
         dim3 grid(ceil_div(c->n_tri, 128), ceil_div(c->lvl_end - c->lvl_begin, TRI_TCH));
         if (write_z) k_tri<1><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);
         else k_tri<0><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);

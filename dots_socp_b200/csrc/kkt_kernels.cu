@@ -421,7 +421,7 @@ extern "C" int dots_kkt_sums_multi(const dots_ctx_t *c, unsigned mask, double *h
     if (fused1) {
         if (!(mask & 2u)) { dots_set_error("kkt mask: bit 9 without condition 1"); return DOTS_ERR_BAD_ARG; }
         n_part = dots_tri_tma_blocks(c, nullptr);
-        if (!c->kkt1_part || c->kkt1_blocks < n_part || c->n_tri % 2) { dots_set_error("kkt mask: bit 9 needs kkt1_part from dots_step_tri(write_z = 2)"); return DOTS_ERR_BAD_ARG; }
+        if (!c->kkt1_part || c->kkt1_blocks < n_part || (c->ring_flags & 4)) { dots_set_error("kkt mask: bit 9 needs kkt1_part from dots_step_tri(write_z = 2)"); return DOTS_ERR_BAD_ARG; }
     }
     const unsigned tmask = (mask & 0x12bu) & ~(fused1 ? 2u : 0u);
     cudaStream_t st = (cudaStream_t)stream;

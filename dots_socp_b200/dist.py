@@ -164,8 +164,12 @@ class SlabStore:
     def __init__(self, lo: int, hi: int, row_shape, device, dtype=torch.float64):
         self.lo, self.hi = lo, max(hi, lo + 1)
         self.row_shape = tuple(row_shape)
-        self.data = torch.zeros((self.hi - self.lo,) + self.row_shape, dtype=dtype, device=device)
         self.row_elems = int(np.prod(self.row_shape))
+        # two elements of padding behind the data: the bulk copies of the triangle kernel round their size up to 16 bytes and
+        # may read one element past the last plane when the triangle count is odd
+        n = (self.hi - self.lo) * self.row_elems
+        self._flat = torch.zeros(n + 2, dtype=dtype, device=device)
+        self.data = self._flat[:n].view((self.hi - self.lo,) + self.row_shape)
 
     @property
     def base_ptr(self):

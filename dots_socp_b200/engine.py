@@ -307,8 +307,10 @@ class Engine:
             setattr(ctx, k, ten.data_ptr())
         ctx.red_blocks = self.red_blocks
         # per-block partials of the triangle term of KKT #1 (iterate(kkt1=True)): one per block of k_tri_tma's grid, whose
-        # time chunks hold at least 2 levels; the plain-load triangle kernel (odd triangle counts) has no such mode
-        self.can_fuse_kkt1 = T % 2 == 0
+        # time chunks hold at least 2 levels; the plain-load triangle kernel (DOTS_TRI_PLAIN=1, diagnostics) has no such mode
+        if os.environ.get("DOTS_TRI_PLAIN", "0") == "1":
+            ctx.ring_flags |= 4                          # diagnostics: plain-load triangle kernel instead of the TMA-staged one
+        self.can_fuse_kkt1 = not (ctx.ring_flags & 4)
         n_k1 = -(-T // 128) * -(-(l1 - l0) // 2)
         self.t["kkt1_part"] = z(max(1, n_k1))
         ctx.kkt1_part, ctx.kkt1_blocks = self.t["kkt1_part"].data_ptr(), n_k1

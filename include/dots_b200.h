@@ -186,7 +186,9 @@ typedef struct dots_ctx {
     int32_t ring_stages;       /* shared-memory stages per warp (2..6)                                                    */
     int32_t ring_pdl;          /* 1: chain the launches of an iteration with programmatic dependent launch                */
     int32_t ring_stage_bytes;  /* bytes per ring stage: 2048 or 4096                                                      */
-    int32_t ring_flags;        /* bit 0: the panel copies of the ring-streamed sweeps carry an L2 evict_first hint        */
+    int32_t ring_flags;        /* bit 0: the panel copies of the ring-streamed sweeps carry an L2 evict_first hint;
+                                  bit 2: dots_step_tri uses the plain-load kernel instead of the TMA-staged one (diagnostics).
+                                  The TMA kernel may read up to 8 bytes past the end of B, E and b_mid: pad them by 16.     */
     double *kkt1_part;         /* [kkt1_blocks] per-block partial sums of the triangle term of KKT #1, written by
                                   dots_step_tri(write_z = 2) (one per block of its grid, fixed order)                     */
     int32_t kkt1_blocks;       /* capacity of kkt1_part: >= ceil(n_tri / 128) * ceil(owned levels / 2)                     */
@@ -212,8 +214,8 @@ const char *dots_last_error(void);
  *                   (triangle halves of the same three steps + decouple_spacial :923-942 / adjoint :944-959)
  *                   write_z = 1 also stores z_mid (needed by KKT #1, is_palm, the variable norms and the returned solution);
  *                   write_z = 2 stores no z_mid but accumulates the triangle term of KKT #1, sum of area_f (s (z_mid -
- *                   s/sqrt3 B))^2, per block into kkt1_part (TMA kernel only, i.e. even n_tri): what a check iteration
- *                   needs when z_mid itself is not going to be returned.
+ *                   s/sqrt3 B))^2, per block into kkt1_part (TMA kernel only): what a check iteration needs when z_mid
+ *                   itself is not going to be returned.
  * dots_iterate    : n_iter x (phi, vertex, tri); write_z applies to the last one.                    */
 int dots_step_phi(const dots_ctx_t *c, void *stream);
 int dots_step_vertex(const dots_ctx_t *c, void *stream);

@@ -142,7 +142,8 @@ def test_fused_step_rows_a1_a4(congestion):
 @pytest.mark.parametrize("example,n_time,congestion,exkw", [
     ("icosphere2", 7, 0.0, {}), ("icosphere2", 7, 0.1, {}), ("plane8", 6, 0.0, {}),
     ("knot", 8, 0.05, dict(n_u=40, n_v=6)), ("icosphere3", 31, 0.0, {}), ("icosphere2", 127, 0.0, {}),
-    ("icosphere2", 159, 0.0, {}), ("icosphere3", 299, 0.05, {})])      # > 128 time levels: 2 / 3 mode groups, plain time transforms
+    ("icosphere2", 159, 0.0, {}), ("icosphere3", 299, 0.05, {}),       # > 128 time levels: 2 / 3 mode groups, plain time transforms
+    ("plane20", 15, 0.05, {})])                                        # odd triangle count (909): 8-byte-misaligned planes in the TMA kernel
 @pytest.mark.parametrize("sweep_mode", [None, 4])          # None: the engine's choice (small factors: k_sweep_run); 4: ring-streamed
 def test_iterates_match_oracle(example, n_time, congestion, exkw, sweep_mode):
     geo, alm, eng = make_pair(example, n_time, congestion=congestion, sweep_mode=sweep_mode, **exkw)
@@ -215,7 +216,28 @@ def test_specialised_kkt_passes_equal_the_generic_one(example, n_time):
             assert np.abs(special[w]).max() > 0.0
 
 
-@pytest.mark.parametrize("example,n_time", [("icosphere4", 31), ("knots_5", 15), ("icosphere2", 7), ("icosphere3", 159)])
+@pytest.mark.parametrize("example,n_time", [("plane20", 15), ("plane100", 7), ("plane8", 6)])
+def test_tma_triangle_kernel_equals_the_plain_one_for_odd_and_even_triangle_counts(monkeypatch, example, n_time):
+    """k_tri_tma (bulk copies; with an odd triangle count every other plane starts 8 bytes off a 16-byte boundary and is fetched
+    from one element earlier) against the plain-load k_tri (DOTS_TRI_PLAIN=1): same arithmetic, bit-identical state, with and
+    without the z_mid store."""
+    geo, _ = synth.example(example)
+    out = {}
+    for plain in ("1", "0"):
+        monkeypatch.setenv("DOTS_TRI_PLAIN", plain)
+        eng = Engine(n_time, geo, congestion=0.05)
+        assert bool(eng.ctx.ring_flags & 4) == (plain == "1")
+        eng.scale_z(2.0)
+        eng.iterate(4)
+        eng.iterate(3, write_z=True)
+        out[plain] = eng.get_state()
+        eng.close()
+    for k, v in out["1"].items():
+        assert np.isfinite(v).all(), k
+        assert np.array_equal(v, out["0"][k]), k
+
+
+@pytest.mark.parametrize("example,n_time", [("icosphere4", 31), ("knots_5", 15), ("icosphere2", 7), ("icosphere3", 159), ("plane20", 15)])
 def test_kkt1_accumulated_in_the_triangle_kernel_equals_the_stored_z_path(example, n_time):
     """iterate(kkt1=True) (dots_step_tri mode 2: no z_mid store, the triangle term of KKT #1 accumulated per block) against
     iterate(write_z=True) + the KKT pass over the stored z_mid: same iterates bit for bit, same per-element terms, only the
