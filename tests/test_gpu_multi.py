@@ -61,10 +61,12 @@ def _worker(rank, world, port, name, out_dir):
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("name", ["ico2_nt7_c01", "ico3_nt31_c0"])
+@pytest.mark.parametrize("name", ["ico2_nt7_c01", "ico3_nt31_c0", "refplane20_nt15"])    # the last: 909 triangles (odd), open surface
 def test_sharded_solver_matches_single_gpu_and_reference(tmp_path, golden, name, world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
+    if name == "refplane20_nt15" and world > 2:
+        pytest.skip("the odd-triangle-count case runs at world 2 only")
     z, geo, n_time, kw = golden(name)
     if (world - 1) * -(-(n_time + 1) // world) >= n_time + 1:
         pytest.skip("more ranks than time levels")
