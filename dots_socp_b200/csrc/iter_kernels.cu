@@ -286,7 +286,8 @@ __global__ void __launch_bounds__(128, 4) k_tri(dots_ctx_t c)
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_tri with TMA-staged input.  Same arithmetic as k_tri<0/1>; what changes is how the 24 input planes of a
+// k_tri with TMA-staged input (MODE 0 / 1 as k_tri; 2: accumulate the triangle term of KKT #1 instead of storing z_mid; 3: the
+// dual rescaling of a penalty update: E and beta_mid divided by `factor`, corner terms recomputed).  Same arithmetic as k_tri<0/1>; what changes is how the 24 input planes of a
 // (time level, 128-triangle tile) reach the SM: thread 0 issues one 1-D bulk async copy (cp.async.bulk, 1 KB)
 // per plane into a 3-stage shared-memory ring guarded by mbarriers, two time levels ahead of the math.  The
 // bytes in flight per SM (up to 3 blocks x 2 stages x 24 KB) no longer depend on registers or occupancy, which is
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(128, 4) k_tri(dots_ctx_t c)
 #define TRI_ROW_OF(ODD) (TRI_TILE + ((ODD) ? 2 : 0))
 #define TRI_TMA_SMEM_OF(ODD) (TRI_STAGES * TRI_PLANES * TRI_ROW_OF(ODD) * 8 + 64)
 template <int MODE, bool ODD>
-__global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c, int tch)
+__global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c, int tch, double factor)
 {
     constexpr int TRI_ROW = TRI_ROW_OF(ODD);
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c, int tch)
         const bool has0 = tau < nT, has1 = tau > 0;
         // gathers first: they overlap the wait for the bulk copies
         double ph[3] = {0.0, 0.0, 0.0}, lamk[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
-        if (active) {
+        if (active && MODE != 3) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 ph[k] = c.phi[(size_t)tau * V + vk[k]];
@@ -406,6 +407,15 @@ __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c, int tch)
             auto sm_B = [&](int x) -> double { return srow[(18 + x) * TRI_ROW + ((mB + (unsigned)x * todd) & 1u)]; };
             auto sm_E = [&](int x) -> double { return srow[(21 + x) * TRI_ROW + ((mE + (unsigned)x * todd) & 1u)]; };
             double Bn[3], En[3], Eo[3], dx[3], bs[3];
+            if (MODE == 3) {                                                // penalty update: E / factor, B as it is (:370)
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    Bn[x] = sm_B(x);
+                    En[x] = sm_E(x) / factor;
+                    Ep[x * T] = En[x];
+                    Eo[x] = dx[x] = bs[x] = 0.0;
+                }
+            } else {
 #pragma unroll
             for (int x = 0; x < 3; ++x) {
                 const double Bo = sm_B(x);
@@ -440,6 +450,7 @@ __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c, int tch)
                 Bp[x * T] = Bn[x];
                 Ep[x * T] = En[x];
             }
+            }
             double *zm = c.z_mid + (size_t)tau * 18 * T + f;
             double *cn = c.corner_nrm + (size_t)tau * 6 * T + f;
 #pragma unroll
@@ -453,6 +464,13 @@ __global__ void __launch_bounds__(TRI_TILE, 3) k_tri_tma(dots_ctx_t c, int tch)
 #pragma unroll
                         for (int x = 0; x < 3; ++x) {
                             double b = sm_b((sd * 3 + k) * 3 + x);
+                            if (MODE == 3) {                                                  // penalty update: beta_mid / factor (:370)
+                                b = b / factor;
+                                bm[((sd * 3 + k) * 3 + x) * T] = b;
+                                const double w3 = __dmul_rn(dg[k], __fma_rn(cs, Bn[x], -b));
+                                acc += w3 * w3;
+                                continue;
+                            }
                             const double zz = lt * (dg[k] * (bs[x] - b));                     // same arithmetic as pass one
                             // explicit fused operations: the rounding of the update must not depend on what else a MODE does with
                             // zz (the compiler contracted this line differently with and without the z_mid store: 1 ulp in b_mid)
@@ -600,57 +618,70 @@ extern "C" int dots_step_vertex(const dots_ctx_t *c, void *stream)
     return pdl_launch2(k_vertex, dim3(ceil_div(c->n_vert, 256), dots_t_end(c) - c->lvl_begin), 256, (cudaStream_t)stream, c->ring_pdl != 0, *c);
 }
 
+// mode 0 / 1 / 2: the triangle half of an iteration (write_z); 3: E, beta_mid /= factor + corner terms (dots_scale_dual)
+static int launch_tri_tma(const dots_ctx_t *c, int mode, double factor, cudaStream_t st)
+{
+    static bool configured[64] = {false};                  // per device (a second engine on another GPU of the process)
+    int dev = 0;
+    DOTS_CUDA(cudaGetDevice(&dev));
+    dev = (dev >= 0 && dev < 64) ? dev : 0;
+    if (!configured[dev]) {
+        DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(false)));
+        DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(false)));
+        DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(false)));
+        DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(false)));
+        DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(true)));
+        DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(true)));
+        DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(true)));
+        DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(true)));
+        configured[dev] = true;
+    }
+    int tch = 0;
+    const int n_blocks = dots_tri_tma_blocks(c, &tch);
+    const unsigned gx = (unsigned)ceil_div(c->n_tri, TRI_TILE), gy = (unsigned)(n_blocks / (int)gx);
+    if (mode == 2 && (!c->kkt1_part || c->kkt1_blocks < n_blocks)) {
+        dots_set_error("dots_step_tri(write_z = 2): kkt1_part holds %d partials, the grid has %d blocks", c->kkt1_part ? c->kkt1_blocks : 0, n_blocks);
+        return DOTS_ERR_BAD_ARG;
+    }
+    const bool odd = (c->n_tri & 1) != 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, gy);
+    cfg.blockDim = dim3(TRI_TILE);
+    cfg.dynamicSmemBytes = odd ? TRI_TMA_SMEM_OF(true) : TRI_TMA_SMEM_OF(false);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (c->ring_pdl && mode != 3) ? 1 : 0;     // the rescaling follows plain launches: ordinary stream order
+    if (odd) {
+        switch (mode) {
+        case 3: DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<3, true>, *c, tch, factor)); break;
+        case 2: DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<2, true>, *c, tch, factor)); break;
+        case 1: DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<1, true>, *c, tch, factor)); break;
+        default: DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<0, true>, *c, tch, factor)); break;
+        }
+    } else {
+        switch (mode) {
+        case 3: DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<3, false>, *c, tch, factor)); break;
+        case 2: DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<2, false>, *c, tch, factor)); break;
+        case 1: DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<1, false>, *c, tch, factor)); break;
+        default: DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<0, false>, *c, tch, factor)); break;
+        }
+    }
+    return 0;
+}
+
 extern "C" int dots_step_tri(const dots_ctx_t *c, int write_z, void *stream)
 {
     if (int e = dots_check_ctx(c)) return e;
-    if (!(c->ring_flags & 4)) {                            // TMA-staged kernel (ring_flags bit 2 selects the plain-load one: diagnostics)
-        static bool configured[64] = {false};                  // per device (a second engine on another GPU of the process)
-        int dev = 0;
-        DOTS_CUDA(cudaGetDevice(&dev));
-        dev = (dev >= 0 && dev < 64) ? dev : 0;
-        if (!configured[dev]) {
-            DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(false)));
-            DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(false)));
-            DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(false)));
-            DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(true)));
-            DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(true)));
-            DOTS_CUDA(cudaFuncSetAttribute(k_tri_tma<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRI_TMA_SMEM_OF(true)));
-            configured[dev] = true;
-        }
-        int tch = 0;
-        const int n_blocks = dots_tri_tma_blocks(c, &tch);
-        const unsigned gx = (unsigned)ceil_div(c->n_tri, TRI_TILE), gy = (unsigned)(n_blocks / (int)gx);
-        if (write_z == 2 && (!c->kkt1_part || c->kkt1_blocks < n_blocks)) {
-            dots_set_error("dots_step_tri(write_z = 2): kkt1_part holds %d partials, the grid has %d blocks", c->kkt1_part ? c->kkt1_blocks : 0, n_blocks);
-            return DOTS_ERR_BAD_ARG;
-        }
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(gx, gy);
-        cfg.blockDim = dim3(TRI_TILE);
-        const bool odd = (c->n_tri & 1) != 0;
-        cfg.dynamicSmemBytes = odd ? TRI_TMA_SMEM_OF(true) : TRI_TMA_SMEM_OF(false);
-        cfg.stream = (cudaStream_t)stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = c->ring_pdl ? 1 : 0;
-        if (odd) {
-            if (write_z == 2) DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<2, true>, *c, tch));
-            else if (write_z) DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<1, true>, *c, tch));
-            else DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<0, true>, *c, tch));
-        } else {
-            if (write_z == 2) DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<2, false>, *c, tch));
-            else if (write_z) DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<1, false>, *c, tch));
-            else DOTS_CUDA(cudaLaunchKernelEx(&cfg, k_tri_tma<0, false>, *c, tch));
-        }
-        return 0;
-    } else {
-        if (write_z == 2) { dots_set_error("dots_step_tri(write_z = 2) needs the TMA triangle kernel (ring_flags bit 2 is set)"); return DOTS_ERR_BAD_ARG; }
-        dim3 grid(ceil_div(c->n_tri, 128), ceil_div(c->lvl_end - c->lvl_begin, TRI_TCH));
-        if (write_z) k_tri<1><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);
-        else k_tri<0><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);
-    }
+    if (write_z < 0 || write_z > 2) { dots_set_error("dots_step_tri: write_z = %d (0, 1 or 2)", write_z); return DOTS_ERR_BAD_ARG; }
+    if (!(c->ring_flags & 4)) return launch_tri_tma(c, write_z, 1.0, (cudaStream_t)stream);   // TMA-staged kernel
+    // ring_flags bit 2: the plain-load kernel (diagnostics)
+    if (write_z == 2) { dots_set_error("dots_step_tri(write_z = 2) needs the TMA triangle kernel (ring_flags bit 2 is set)"); return DOTS_ERR_BAD_ARG; }
+    dim3 grid(ceil_div(c->n_tri, 128), ceil_div(c->lvl_end - c->lvl_begin, TRI_TCH));
+    if (write_z) k_tri<1><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);
+    else k_tri<0><<<grid, 128, 0, (cudaStream_t)stream>>>(*c);
     DOTS_LAUNCH_CHECK();
     return 0;
 }
@@ -707,12 +738,14 @@ extern "C" int dots_scale_dual(const dots_ctx_t *c, double factor, void *stream)
     int e;
     // mu carries one halo step in front (t = lvl_begin-1), scaled here so that it stays consistent without an exchange
     if ((e = launch_div(c->mu + ((long long)l0 - 1) * (long long)V, (nt + 1) * V, factor, c->n_sm, st))) return e;     // :370
-    if ((e = launch_div(c->E + l0 * 3 * T, nl * 3 * T, factor, c->n_sm, st))) return e;
     if ((e = launch_div(c->bnd0, V, factor, c->n_sm, st))) return e;
     if ((e = launch_div(c->bnd1, V, factor, c->n_sm, st))) return e;
     if ((e = launch_div(c->b_fst + l0 * V, nt * V, factor, c->n_sm, st))) return e;
-    if ((e = launch_div(c->b_mid + l0 * 18 * T, nl * 18 * T, factor, c->n_sm, st))) return e;
     if ((e = launch_div(c->b_end + l0 * V, nt * V, factor, c->n_sm, st))) return e;
+    if (!(c->ring_flags & 4))                              // E, beta_mid / factor inside the TMA-staged pass that recomputes the corner terms
+        return launch_tri_tma(c, 3, factor, st);
+    if ((e = launch_div(c->E + l0 * 3 * T, nl * 3 * T, factor, c->n_sm, st))) return e;
+    if ((e = launch_div(c->b_mid + l0 * 18 * T, nl * 18 * T, factor, c->n_sm, st))) return e;
     return dots_refresh_corner_terms(c, stream);
 }
 
