@@ -100,7 +100,7 @@ def load(build_if_missing: bool = True):
         "dots_ring_entry_rows": (i64,) + (vp,) * 8,
         "dots_mesh_create": (i64, i64, vp, vp, C.POINTER(vp)), "dots_mesh_sizes": (vp, C.POINTER(i64)),
         "dots_mesh_export": (vp,) * 10, "dots_mesh_destroy": (vp,), "dots_corner_lists": (i64, i64, vp, vp, vp),
-        "dots_front_maps": (i64, i64) + (vp,) * 11,
+        "dots_front_maps": (i64, i64) + (vp,) * 11, "dots_csr_permute": (i64,) + (vp,) * 8,
     })
     for name, args in protos.items():
         fn = getattr(lib, name)
@@ -116,7 +116,8 @@ EXPORTS = ("dots_abi_version", "dots_ctx_sizeof", "dots_last_error", "dots_step_
            "dots_factor_small_fronts", "dots_front_nmax", "dots_factor_large_fronts", "dots_enable_peer", "dots_ipc_export", "dots_ipc_import",
            "dots_ring_level_times", "dots_ring_entry_rows",
            "dots_order_create", "dots_order_sizes", "dots_order_export", "dots_order_destroy",
-           "dots_mesh_create", "dots_mesh_sizes", "dots_mesh_export", "dots_mesh_destroy", "dots_corner_lists", "dots_front_maps")
+           "dots_mesh_create", "dots_mesh_sizes", "dots_mesh_export", "dots_mesh_destroy", "dots_corner_lists", "dots_front_maps",
+           "dots_csr_permute")
 
 
 def check(code: int, what: str = ""):

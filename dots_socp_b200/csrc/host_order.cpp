@@ -8,12 +8,20 @@
 // permutation and the same front structure bit for bit (tests/test_nested_host.py checks that).
 //
 // Plain C++, no CUDA: geometric recursive bisection with vertex separators, then boundary sets by a post-order sweep.
+// The bisection of the two halves of a part and the per-triangle / per-vertex passes of the mesh operators run on a few
+// host threads (DOTS_HOST_THREADS, default: the hardware's, at most 16); the results do not depend on the thread count
+// (every sum keeps its order, the tree keeps its shape), which tests/test_nested_host.py checks bit for bit.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <memory>
 #include <new>
 #include <numeric>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -39,29 +47,60 @@ struct dots_order {
 
 namespace {
 
-// nested.dissect: split along the longest bounding-box axis at the median (stable order), take as separator the smaller
-// of the two one-sided vertex frontiers, recurse on what is left of the halves until a part has <= leaf_size vertices.
-void dissect(int64_t n, const double *xyz, const int64_t *indptr, const int64_t *indices, int64_t leaf_size,
-             std::vector<TreeNode> &nodes) {
-    std::vector<int8_t> side((size_t)n, -1);
-    struct Frame { int node; std::vector<int64_t> verts; };
-    std::vector<Frame> stack;
-    nodes.emplace_back();
-    {
-        std::vector<int64_t> all((size_t)n);
-        std::iota(all.begin(), all.end(), (int64_t)0);
-        stack.push_back({0, std::move(all)});
+// Host threads for a pass over `items` work items (at least `grain` items per thread).
+int host_threads(int64_t items, int64_t grain) {
+    const char *e = std::getenv("DOTS_HOST_THREADS");                         // read per call: tests vary it within one process
+    const int want = e ? std::atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    const int limit = std::max(1, std::min(want, 64));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(limit, items / std::max<int64_t>(grain, 1)));
+}
+
+// Stable sort of (column, value) pairs by column: insertion sort for the short rows of a surface mesh.
+inline void sort_row_stable(std::vector<std::pair<int64_t, double>> &row) {
+    if (row.size() > 256) {
+        std::stable_sort(row.begin(), row.end(),
+                         [](const std::pair<int64_t, double> &x, const std::pair<int64_t, double> &y) { return x.first < y.first; });
+        return;
     }
-    std::vector<int64_t> left, right;
+    for (size_t i = 1; i < row.size(); ++i) {
+        const std::pair<int64_t, double> x = row[i];
+        size_t j = i;
+        for (; j > 0 && row[j - 1].first > x.first; --j) row[j] = row[j - 1];
+        row[j] = x;
+    }
+}
+
+// fn(tid, lo, hi) over contiguous ranges of [0, n); the first exception of a worker is rethrown on the caller.
+template <class F>
+void parallel_ranges(int64_t n, int n_threads, F fn) {
+    if (n_threads <= 1) { fn(0, (int64_t)0, n); return; }
+    std::vector<std::thread> pool;
+    std::vector<std::exception_ptr> err((size_t)n_threads);
+    for (int t = 0; t < n_threads; ++t)
+        pool.emplace_back([&, t] {
+            try { fn(t, n * t / n_threads, n * (t + 1) / n_threads); } catch (...) { err[t] = std::current_exception(); }
+        });
+    for (auto &th : pool) th.join();
+    for (auto &e : err)
+        if (e) std::rethrow_exception(e);
+}
+
+// One bisection step of nested.dissect: split `verts` along the longest bounding-box axis at the median (stable order), take
+// as separator the smaller of the two one-sided vertex frontiers.  `side` (one byte per vertex, -1 outside this call) is
+// scratch; `sep`, `left`, `right` receive the three parts.
+struct Bisector {
+    const double *xyz;
+    const int64_t *indptr, *indices;
+    std::vector<int8_t> side;
     std::vector<std::pair<double, int64_t>> keyed;
     std::vector<char> fl, fr;
-    while (!stack.empty()) {
-        Frame fr_ = std::move(stack.back());
-        stack.pop_back();
-        const int me = fr_.node;
-        std::vector<int64_t> &verts = fr_.verts;
+    std::vector<int64_t> keep;
+
+    Bisector(int64_t n, const double *xyz_, const int64_t *indptr_, const int64_t *indices_)
+        : xyz(xyz_), indptr(indptr_), indices(indices_), side((size_t)n, -1) {}
+
+    void split(const std::vector<int64_t> &verts, std::vector<int64_t> &sep, std::vector<int64_t> &left, std::vector<int64_t> &right) {
         const int64_t m = (int64_t)verts.size();
-        if (m <= leaf_size) { nodes[me].own = std::move(verts); continue; }
         double lo[3], hi[3];
         for (int a = 0; a < 3; ++a) lo[a] = hi[a] = xyz[3 * verts[0] + a];
         for (int64_t i = 1; i < m; ++i)
@@ -93,15 +132,32 @@ void dissect(int64_t n, const double *xyz, const int64_t *indptr, const int64_t 
             return cnt;
         };
         const int64_t nl = frontier(left, 1, fl), nr = frontier(right, 0, fr);
-        std::vector<int64_t> sep, keep;
-        auto split = [&](std::vector<int64_t> &part, const std::vector<char> &mask) {
+        sep.clear();
+        auto take = [&](std::vector<int64_t> &part, const std::vector<char> &mask) {
             keep.clear();
             for (size_t i = 0; i < part.size(); ++i) (mask[i] ? sep : keep).push_back(part[i]);
             part.swap(keep);
         };
-        if (nl <= nr) split(left, fl); else split(right, fr);
+        if (nl <= nr) take(left, fl); else take(right, fr);
         for (int64_t i = 0; i < m; ++i) side[verts[i]] = -1;
-        nodes[me].own = std::move(sep);
+    }
+};
+
+// The subtree below `verts`, root at nodes[0] (kid indices local to `nodes`), on the calling thread.
+void dissect_serial(Bisector &bis, std::vector<int64_t> verts, int64_t leaf_size, std::vector<TreeNode> &nodes) {
+    struct Frame { int node; std::vector<int64_t> verts; };
+    std::vector<Frame> stack;
+    nodes.clear();
+    nodes.emplace_back();
+    stack.push_back({0, std::move(verts)});
+    std::vector<int64_t> sep, left, right;
+    while (!stack.empty()) {
+        Frame fr_ = std::move(stack.back());
+        stack.pop_back();
+        const int me = fr_.node;
+        if ((int64_t)fr_.verts.size() <= leaf_size) { nodes[me].own = std::move(fr_.verts); continue; }
+        bis.split(fr_.verts, sep, left, right);
+        nodes[me].own = sep;
         for (std::vector<int64_t> *part : {&left, &right}) {
             if (part->empty()) continue;
             const int kid = (int)nodes.size();
@@ -110,6 +166,61 @@ void dissect(int64_t n, const double *xyz, const int64_t *indptr, const int64_t 
             stack.push_back({kid, *part});
         }
     }
+}
+
+// nested.dissect: recurse on what is left of the halves until a part has <= leaf_size vertices.  While threads are left
+// (`budget` > 1) and the part is large, the left half goes to a new thread (own scratch) and the right half stays here; the
+// two subtrees are then appended behind their root.  The shape of the tree (left kid first) is that of the serial
+// recursion, and the numbering the solver uses (post-order, `symbolic`) depends on nothing else.
+void dissect_rec(int64_t n, const double *xyz, const int64_t *indptr, const int64_t *indices, int64_t leaf_size, int budget,
+                 Bisector &bis, std::vector<int64_t> verts, std::vector<TreeNode> &nodes) {
+    if (budget <= 1 || (int64_t)verts.size() <= std::max<int64_t>(leaf_size, 4096)) {
+        dissect_serial(bis, std::move(verts), leaf_size, nodes);
+        return;
+    }
+    std::vector<int64_t> sep, left, right;
+    bis.split(verts, sep, left, right);
+    std::vector<int64_t>().swap(verts);
+    std::vector<TreeNode> sub[2];
+    std::exception_ptr err;
+    const int b_left = budget / 2;
+    std::thread other;
+    if (!left.empty())
+        other = std::thread([&] {
+            try {
+                Bisector mine(n, xyz, indptr, indices);
+                dissect_rec(n, xyz, indptr, indices, leaf_size, b_left, mine, std::move(left), sub[0]);
+            } catch (...) { err = std::current_exception(); }
+        });
+    try {
+        if (!right.empty()) dissect_rec(n, xyz, indptr, indices, leaf_size, budget - b_left, bis, std::move(right), sub[1]);
+    } catch (...) {
+        if (other.joinable()) other.join();
+        throw;
+    }
+    if (other.joinable()) other.join();
+    if (err) std::rethrow_exception(err);
+    nodes.clear();
+    nodes.reserve(1 + sub[0].size() + sub[1].size());
+    nodes.emplace_back();
+    nodes[0].own = std::move(sep);
+    for (auto &part : sub) {
+        if (part.empty()) continue;
+        const int base = (int)nodes.size();
+        nodes[0].kid[nodes[0].n_kids++] = base;
+        for (TreeNode &nd : part) {
+            for (int k = 0; k < nd.n_kids; ++k) nd.kid[k] += base;
+            nodes.push_back(std::move(nd));
+        }
+    }
+}
+
+void dissect(int64_t n, const double *xyz, const int64_t *indptr, const int64_t *indices, int64_t leaf_size,
+             std::vector<TreeNode> &nodes) {
+    std::vector<int64_t> all((size_t)n);
+    std::iota(all.begin(), all.end(), (int64_t)0);
+    Bisector bis(n, xyz, indptr, indices);
+    dissect_rec(n, xyz, indptr, indices, leaf_size, host_threads(n, 8192), bis, std::move(all), nodes);
 }
 
 // nested.symbolic: post-order numbering, boundary sets B(i) = (neighbours of S(i) and children's boundaries) beyond the
@@ -151,51 +262,69 @@ void symbolic(int64_t n, const int64_t *indptr, const int64_t *indices, const st
     }
     std::vector<int64_t> iperm((size_t)n);
     for (int64_t i = 0; i < n; ++i) iperm[o.perm[i]] = i;
+    // Boundary sets, level by level (leaves first): the nodes of one level only read their children's sets, so threads
+    // share a level's nodes; every set is the sorted union of the same candidates whatever the thread count.
     std::vector<std::vector<int64_t>> bset(N);
-    std::vector<int64_t> cand;
-    for (int64_t i = 0; i < N; ++i) {                                  // post-order: children are ready
-        const int64_t hi = off[i + 1];
-        cand.clear();
-        for (int64_t r = off[i]; r < hi; ++r) {
-            const int64_t v = o.perm[r];
-            for (int64_t q = indptr[v]; q < indptr[v + 1]; ++q) {
-                const int64_t w = iperm[indices[q]];
-                if (w >= hi) cand.push_back(w);
+    int64_t n_levels = 0;
+    for (int64_t i = 0; i < N; ++i) n_levels = std::max(n_levels, o.level[i] + 1);
+    std::vector<int64_t> lvl_ptr(n_levels + 1, 0), lvl_nodes(N);
+    for (int64_t i = 0; i < N; ++i) ++lvl_ptr[o.level[i] + 1];
+    for (int64_t l = 0; l < n_levels; ++l) lvl_ptr[l + 1] += lvl_ptr[l];
+    {
+        std::vector<int64_t> at(lvl_ptr.begin(), lvl_ptr.end() - 1);
+        for (int64_t i = 0; i < N; ++i) lvl_nodes[at[o.level[i]]++] = i;
+    }
+    const int nt = host_threads(n, 8192);
+    for (int64_t l = 0; l < n_levels; ++l) {
+        const int64_t *ids = lvl_nodes.data() + lvl_ptr[l];
+        const int64_t cnt = lvl_ptr[l + 1] - lvl_ptr[l];
+        parallel_ranges(cnt, (int)std::min<int64_t>(nt, std::max<int64_t>(1, cnt / 8)), [&](int, int64_t q0, int64_t q1) {
+            std::vector<int64_t> cand;
+            for (int64_t q = q0; q < q1; ++q) {
+                const int64_t i = ids[q], hi = off[i + 1];
+                cand.clear();
+                for (int64_t r = off[i]; r < hi; ++r) {
+                    const int64_t v = o.perm[r];
+                    for (int64_t e = indptr[v]; e < indptr[v + 1]; ++e) {
+                        const int64_t w = iperm[indices[e]];
+                        if (w >= hi) cand.push_back(w);
+                    }
+                }
+                for (int slot = 0; slot < 2; ++slot) {
+                    const int64_t k = o.child[2 * i + slot];
+                    if (k < 0) continue;
+                    for (int64_t w : bset[k])
+                        if (w >= hi) cand.push_back(w);
+                }
+                std::sort(cand.begin(), cand.end());
+                cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+                bset[i] = cand;
+                o.b[i] = (int64_t)cand.size();
             }
-        }
-        for (int slot = 0; slot < 2; ++slot) {
-            const int64_t k = o.child[2 * i + slot];
-            if (k < 0) continue;
-            for (int64_t w : bset[k])
-                if (w >= hi) cand.push_back(w);
-        }
-        std::sort(cand.begin(), cand.end());
-        cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
-        bset[i] = cand;
-        o.b[i] = (int64_t)cand.size();
+        });
     }
     std::vector<int64_t> front_off(N + 1, 0);
     for (int64_t i = 0; i < N; ++i) front_off[i + 1] = front_off[i] + o.s[i] + o.b[i];
     o.front_total = front_off[N];
     o.front_idx.assign((size_t)o.front_total, 0);
     o.child_pos.assign((size_t)(2 * o.front_total), -1);
-    for (int64_t i = 0; i < N; ++i) {
-        int64_t *rows = o.front_idx.data() + front_off[i];
-        const int64_t nf = o.s[i] + o.b[i];
-        for (int64_t r = 0; r < o.s[i]; ++r) rows[r] = off[i] + r;
-        std::copy(bset[i].begin(), bset[i].end(), rows + o.s[i]);
-        for (int slot = 0; slot < 2; ++slot) {
-            const int64_t k = o.child[2 * i + slot];
-            if (k < 0 || o.b[k] == 0) continue;
-            int64_t *cp = o.child_pos.data() + (size_t)slot * o.front_total + front_off[i];
-            for (int64_t j = 0; j < o.b[k]; ++j) {
-                const int64_t *hit = std::lower_bound(rows, rows + nf, bset[k][j]);
-                cp[hit - rows] = j;                                     // the child's boundary always embeds in the parent's front
+    parallel_ranges(N, (int)std::min<int64_t>(nt, std::max<int64_t>(1, N / 256)), [&](int, int64_t i0, int64_t i1) {
+        for (int64_t i = i0; i < i1; ++i) {
+            int64_t *rows = o.front_idx.data() + front_off[i];
+            const int64_t nf = o.s[i] + o.b[i];
+            for (int64_t r = 0; r < o.s[i]; ++r) rows[r] = off[i] + r;
+            std::copy(bset[i].begin(), bset[i].end(), rows + o.s[i]);
+            for (int slot = 0; slot < 2; ++slot) {
+                const int64_t k = o.child[2 * i + slot];
+                if (k < 0 || o.b[k] == 0) continue;
+                int64_t *cp = o.child_pos.data() + (size_t)slot * o.front_total + front_off[i];
+                for (int64_t j = 0; j < o.b[k]; ++j) {
+                    const int64_t *hit = std::lower_bound(rows, rows + nf, bset[k][j]);
+                    cp[hit - rows] = j;                                 // the child's boundary always embeds in the parent's front
+                }
             }
         }
-        if (o.child[2 * i] >= 0) std::vector<int64_t>().swap(bset[o.child[2 * i]]);
-        if (o.child[2 * i + 1] >= 0) std::vector<int64_t>().swap(bset[o.child[2 * i + 1]]);
-    }
+    });
 }
 
 }  // namespace
@@ -208,19 +337,17 @@ extern "C" int dots_order_create(int64_t n_vert, const double *vertices, const i
     }
     *out = nullptr;
     try {
-        dots_order *o = new dots_order();
+        std::unique_ptr<dots_order> o(new dots_order());
         std::vector<TreeNode> nodes;
         dissect(n_vert, vertices, adj_ptr, adj_idx, leaf_size, nodes);
         symbolic(n_vert, adj_ptr, adj_idx, nodes, *o);
         if ((int64_t)o->perm.size() != n_vert) {
-            const long long covered = (long long)o->perm.size();
-            delete o;
-            dots_set_error("dots_order_create: dissection covered %lld of %lld vertices", covered, (long long)n_vert);
+            dots_set_error("dots_order_create: dissection covered %lld of %lld vertices", (long long)o->perm.size(), (long long)n_vert);
             return -1;
         }
-        *out = o;
-    } catch (const std::bad_alloc &) {
-        dots_set_error("dots_order_create: out of host memory");
+        *out = o.release();
+    } catch (const std::exception &) {
+        dots_set_error("dots_order_create: out of host memory or threads");
         return -1;
     }
     return 0;
@@ -301,74 +428,123 @@ inline double norm3(const double *a) { return std::sqrt(dot3(a, a)); }
 extern "C" int dots_mesh_create(int64_t V, int64_t T, const double *vertices, const int64_t *triangles, dots_mesh_t **out)
 {
     if (!vertices || !triangles || !out || V <= 0 || T <= 0) { dots_set_error("dots_mesh_create: bad arguments"); return -1; }
-    dots_mesh *m = new (std::nothrow) dots_mesh;
-    if (!m) { dots_set_error("dots_mesh_create: out of memory"); return -1; }
-    m->V = V; m->T = T;
-    m->area_f.assign(T, 0.0); m->hat.assign(9 * T, 0.0); m->area_sum.assign(V, 0.0);
-    std::vector<double> w(3 * T);                                          // half cotangent of the angle at corner k
-    for (int64_t f = 0; f < T; ++f) {
-        const int64_t *t = triangles + 3 * f;
-        for (int k = 0; k < 3; ++k)
-            if (t[k] < 0 || t[k] >= V) { dots_set_error("dots_mesh_create: triangle %lld has vertex %lld", (long long)f, (long long)t[k]); delete m; return -1; }
-        const double *p0 = vertices + 3 * t[0], *p1 = vertices + 3 * t[1], *p2 = vertices + 3 * t[2];
-        double e[3][3], n[3];                                              // e01, e12, e20
-        sub3(p1, p0, e[0]); sub3(p2, p1, e[1]); sub3(p0, p2, e[2]);
-        cross3(e[0], e[1], n);
-        m->area_f[f] = 0.5 * norm3(n);
-        for (int k = 0; k < 3; ++k) {                                      // altitude(into = e[k], along = e[(k+1)%3])
-            const double *into = e[k], *along = e[(k + 1) % 3];
-            const double coef = dot3(into, along) / dot3(along, along);
-            double h[3] = {-into[0] + along[0] * coef, -into[1] + along[1] * coef, -into[2] + along[2] * coef};
-            const double hh = dot3(h, h);
-            for (int x = 0; x < 3; ++x) m->hat[(size_t)f * 9 + k * 3 + x] = h[x] / hh;
-            const double *a = e[k], *bb = e[(k + 2) % 3];                  // cot(e[k], -e[(k+2)%3]) = angle at corner k
-            double nb[3] = {-bb[0], -bb[1], -bb[2]}, c[3];
-            cross3(a, nb, c);
-            w[3 * f + k] = 0.5 * (dot3(a, nb) / norm3(c));
+    *out = nullptr;
+    dots_mesh *m = nullptr;
+    try {
+        m = new dots_mesh;
+        m->V = V; m->T = T;
+        m->area_f.assign(T, 0.0); m->hat.assign(9 * T, 0.0); m->area_sum.assign(V, 0.0);
+        std::vector<double> w(3 * T);                                      // half cotangent of the angle at corner k
+        // ---- per triangle (threads over triangle ranges): area, hat gradients, corner cotangents
+        const int nt_tri = host_threads(T, 16384);
+        std::vector<int64_t> bad((size_t)nt_tri, -1);                      // first triangle with a vertex id out of range
+        parallel_ranges(T, nt_tri, [&](int tid, int64_t f0, int64_t f1) {
+            for (int64_t f = f0; f < f1; ++f) {
+                const int64_t *t = triangles + 3 * f;
+                if (t[0] < 0 || t[0] >= V || t[1] < 0 || t[1] >= V || t[2] < 0 || t[2] >= V) { bad[tid] = f; return; }
+                const double *p0 = vertices + 3 * t[0], *p1 = vertices + 3 * t[1], *p2 = vertices + 3 * t[2];
+                double e[3][3], n[3];                                      // e01, e12, e20
+                sub3(p1, p0, e[0]); sub3(p2, p1, e[1]); sub3(p0, p2, e[2]);
+                cross3(e[0], e[1], n);
+                m->area_f[f] = 0.5 * norm3(n);
+                for (int k = 0; k < 3; ++k) {                              // altitude(into = e[k], along = e[(k+1)%3])
+                    const double *into = e[k], *along = e[(k + 1) % 3];
+                    const double coef = dot3(into, along) / dot3(along, along);
+                    double h[3] = {-into[0] + along[0] * coef, -into[1] + along[1] * coef, -into[2] + along[2] * coef};
+                    const double hh = dot3(h, h);
+                    for (int x = 0; x < 3; ++x) m->hat[(size_t)f * 9 + k * 3 + x] = h[x] / hh;
+                    const double *a = e[k], *bb = e[(k + 2) % 3];          // cot(e[k], -e[(k+2)%3]) = angle at corner k
+                    double nb[3] = {-bb[0], -bb[1], -bb[2]}, c[3];
+                    cross3(a, nb, c);
+                    w[3 * f + k] = 0.5 * (dot3(a, nb) / norm3(c));
+                }
+            }
+        });
+        for (int64_t f : bad)
+            if (f >= 0) {
+                const int64_t *t = triangles + 3 * f;
+                const int64_t v = (t[0] < 0 || t[0] >= V) ? t[0] : ((t[1] < 0 || t[1] >= V) ? t[1] : t[2]);
+                dots_set_error("dots_mesh_create: triangle %lld has vertex %lld", (long long)f, (long long)v);
+                delete m;
+                return -1;
+            }
+        // ---- corners around every vertex, ordered by (corner, triangle): column k*T + f of the reference's incidence map.
+        // Counts per (corner slot, vertex) give every list entry its place, so threads can fill disjoint vertex ranges.
+        std::vector<int64_t> cnt_k(3 * (size_t)V, 0);
+        for (int64_t f = 0; f < T; ++f)
+            for (int k = 0; k < 3; ++k) ++cnt_k[(size_t)k * V + triangles[3 * f + k]];
+        m->cptr.assign(V + 1, 0);
+        for (int64_t v = 0; v < V; ++v) m->cptr[v + 1] = m->cptr[v] + cnt_k[v] + cnt_k[V + v] + cnt_k[2 * V + v];
+        m->ctri.assign(3 * T, 0); m->ccorner.assign(3 * T, 0);
+        const int nt_v = host_threads(V, 8192);
+        // ---- per vertex (threads over vertex ranges): incident area sum and row v of the cotan stiffness matrix K = -L.
+        // Every corner k of a triangle weights its opposite edge (a, b): K[a][b] -= w, K[b][a] -= w, K[a][a] += w, K[b][b] += w;
+        // a row collects its terms triangle by triangle (ascending), corner by corner, then sums equal columns in that order.
+        std::vector<std::vector<int64_t>> row_idx((size_t)nt_v);
+        std::vector<std::vector<double>> row_val((size_t)nt_v);
+        std::vector<int64_t> row_nnz((size_t)V, 0);
+        parallel_ranges(V, nt_v, [&](int tid, int64_t v0, int64_t v1) {
+            {   // this range's share of the corner lists: one pass over the triangles, three cursors per vertex
+                std::vector<int64_t> pos(3 * (size_t)(v1 - v0));
+                for (int64_t v = v0; v < v1; ++v) {
+                    int64_t p = m->cptr[v];
+                    for (int k = 0; k < 3; ++k) { pos[(size_t)k * (v1 - v0) + (v - v0)] = p; p += cnt_k[(size_t)k * V + v]; }
+                }
+                for (int64_t f = 0; f < T; ++f)
+                    for (int k = 0; k < 3; ++k) {
+                        const int64_t v = triangles[3 * f + k];
+                        if (v < v0 || v >= v1) continue;
+                        const int64_t p = pos[(size_t)k * (v1 - v0) + (v - v0)]++;
+                        m->ctri[p] = f; m->ccorner[p] = k;
+                    }
+            }
+            std::vector<int64_t> &kidx = row_idx[tid];
+            std::vector<double> &kval = row_val[tid];
+            kidx.reserve(8 * (size_t)(v1 - v0)); kval.reserve(8 * (size_t)(v1 - v0));
+            std::vector<int64_t> tris;
+            std::vector<std::pair<int64_t, double>> row;
+            for (int64_t v = v0; v < v1; ++v) {
+                tris.assign(m->ctri.begin() + m->cptr[v], m->ctri.begin() + m->cptr[v + 1]);
+                std::sort(tris.begin(), tris.end());
+                double asum = 0.0;
+                for (int64_t f : tris) asum += m->area_f[f];               // once per incident corner, ascending triangles
+                m->area_sum[v] = asum;
+                tris.erase(std::unique(tris.begin(), tris.end()), tris.end());
+                row.clear();
+                for (int64_t f : tris) {
+                    const int64_t *t = triangles + 3 * f;
+                    for (int k = 0; k < 3; ++k) {
+                        const int64_t a = t[(k + 1) % 3], b = t[(k + 2) % 3];
+                        const double wk = w[3 * f + k];
+                        if (a == v) { row.emplace_back(b, -wk); row.emplace_back(a, wk); }
+                        if (b == v) { row.emplace_back(a, -wk); row.emplace_back(b, wk); }
+                    }
+                }
+                sort_row_stable(row);                                      // by column; equal columns keep their order
+                const size_t before = kidx.size();
+                for (size_t q = 0; q < row.size();) {
+                    size_t e2 = q;
+                    double sum = 0.0;
+                    while (e2 < row.size() && row[e2].first == row[q].first) sum += row[e2++].second;
+                    kidx.push_back(row[q].first); kval.push_back(sum);
+                    q = e2;
+                }
+                row_nnz[v] = (int64_t)(kidx.size() - before);
+            }
+        });
+        m->kptr.assign(V + 1, 0);
+        for (int64_t v = 0; v < V; ++v) m->kptr[v + 1] = m->kptr[v] + row_nnz[v];
+        m->kidx.resize((size_t)m->kptr[V]); m->kval.resize((size_t)m->kptr[V]);
+        for (int t = 0; t < nt_v; ++t) {
+            const int64_t at = m->kptr[V * t / nt_v];
+            std::copy(row_idx[t].begin(), row_idx[t].end(), m->kidx.begin() + at);
+            std::copy(row_val[t].begin(), row_val[t].end(), m->kval.begin() + at);
         }
-        for (int k = 0; k < 3; ++k) m->area_sum[t[k]] += m->area_f[f];
+    } catch (const std::exception &) {
+        delete m;
+        dots_set_error("dots_mesh_create: out of host memory or threads");
+        return -1;
     }
-    // ---- K: every corner k weights its opposite edge (a, b): K[a][b] -= w, K[b][a] -= w, K[a][a] += w, K[b][b] += w
-    std::vector<int64_t> cnt(V + 1, 0);
-    for (int64_t f = 0; f < T; ++f)
-        for (int k = 0; k < 3; ++k) { cnt[triangles[3 * f + (k + 1) % 3] + 1] += 2; cnt[triangles[3 * f + (k + 2) % 3] + 1] += 2; }
-    for (int64_t v = 0; v < V; ++v) cnt[v + 1] += cnt[v];
-    std::vector<int64_t> col(cnt[V]), fill(cnt.begin(), cnt.end() - 1);
-    std::vector<double> val(cnt[V]);
-    for (int64_t f = 0; f < T; ++f)
-        for (int k = 0; k < 3; ++k) {
-            const int64_t a = triangles[3 * f + (k + 1) % 3], b = triangles[3 * f + (k + 2) % 3];
-            const double wk = w[3 * f + k];
-            col[fill[a]] = b; val[fill[a]++] = -wk; col[fill[a]] = a; val[fill[a]++] = wk;
-            col[fill[b]] = a; val[fill[b]++] = -wk; col[fill[b]] = b; val[fill[b]++] = wk;
-        }
-    m->kptr.assign(V + 1, 0);
-    m->kidx.reserve(8 * V); m->kval.reserve(8 * V);
-    std::vector<std::pair<int64_t, double>> row;
-    for (int64_t v = 0; v < V; ++v) {
-        row.clear();
-        for (int64_t q = cnt[v]; q < cnt[v + 1]; ++q) row.emplace_back(col[q], val[q]);
-        std::stable_sort(row.begin(), row.end(), [](const std::pair<int64_t, double> &x, const std::pair<int64_t, double> &y) { return x.first < y.first; });
-        for (size_t q = 0; q < row.size();) {
-            size_t e2 = q;
-            double sum = 0.0;
-            while (e2 < row.size() && row[e2].first == row[q].first) sum += row[e2++].second;
-            m->kidx.push_back(row[q].first); m->kval.push_back(sum);
-            q = e2;
-        }
-        m->kptr[v + 1] = (int64_t)m->kidx.size();
-    }
-    // ---- corners around every vertex, ordered by (corner, triangle): column k*T + f of the reference's incidence map
-    m->cptr.assign(V + 1, 0);
-    for (int64_t i = 0; i < 3 * T; ++i) ++m->cptr[triangles[i] + 1];
-    for (int64_t v = 0; v < V; ++v) m->cptr[v + 1] += m->cptr[v];
-    m->ctri.assign(3 * T, 0); m->ccorner.assign(3 * T, 0);
-    std::vector<int64_t> pos(m->cptr.begin(), m->cptr.end() - 1);
-    for (int k = 0; k < 3; ++k)
-        for (int64_t f = 0; f < T; ++f) {
-            const int64_t v = triangles[3 * f + k];
-            m->ctri[pos[v]] = f; m->ccorner[pos[v]++] = k;
-        }
     *out = m;
     return 0;
 }
@@ -423,7 +599,10 @@ extern "C" int dots_front_maps(int64_t n_vert, int64_t n_nodes, const int64_t *s
         dots_set_error("dots_front_maps: bad arguments");
         return -1;
     }
-    for (int64_t k = 0; k < n_nodes; ++k) {
+    std::atomic<int64_t> failed{-1};                                       // a node whose boundary does not embed in its parent's front
+    try {
+    parallel_ranges(n_nodes, host_threads(n_nodes, 512), [&](int, int64_t k0, int64_t k1) {
+    for (int64_t k = k0; k < k1; ++k) {
         const int64_t *fi = front_idx + front_off[k];
         const int64_t nf = s[k] + b[k];
         for (int64_t r = off[k]; r < off[k] + s[k]; ++r) {
@@ -450,9 +629,42 @@ extern "C" int dots_front_maps(int64_t n_vert, int64_t n_nodes, const int64_t *s
         for (int64_t p = 0; p < b[k]; ++p) {
             const int64_t vtx = fi[s[k] + p];
             while (j < npf && pf[j] < vtx) ++j;
-            if (j >= npf || pf[j] != vtx) { dots_set_error("dots_front_maps: boundary of node %lld does not embed in its parent's front", (long long)k); return -1; }
+            if (j >= npf || pf[j] != vtx) { failed.store(k); return; }
             pp[p] = (int32_t)j;
         }
     }
+    });
+    } catch (const std::exception &) { dots_set_error("dots_front_maps: out of host memory or threads"); return -1; }
+    if (failed.load() >= 0) {
+        dots_set_error("dots_front_maps: boundary of node %lld does not embed in its parent's front", (long long)failed.load());
+        return -1;
+    }
+    return 0;
+}
+
+// Symmetric permutation of a CSR matrix: out = A[perm][:, perm] with ascending columns in every row (what the numeric
+// assembly reads; scipy's two fancy-indexing passes + sort_indices took 45 ms at V = 164k).  perm: new -> old; iperm: old -> new.
+extern "C" int dots_csr_permute(int64_t n, const int64_t *a_ptr, const int64_t *a_idx, const double *a_val, const int64_t *perm,
+                                const int64_t *iperm, int64_t *o_ptr, int64_t *o_idx, double *o_val)
+{
+    if (!a_ptr || !a_idx || !a_val || !perm || !iperm || !o_ptr || !o_idx || !o_val || n <= 0) { dots_set_error("dots_csr_permute: bad arguments"); return -1; }
+    o_ptr[0] = 0;
+    for (int64_t r = 0; r < n; ++r) {
+        if (perm[r] < 0 || perm[r] >= n) { dots_set_error("dots_csr_permute: perm[%lld] = %lld", (long long)r, (long long)perm[r]); return -1; }
+        o_ptr[r + 1] = o_ptr[r] + (a_ptr[perm[r] + 1] - a_ptr[perm[r]]);
+    }
+    try {
+    parallel_ranges(n, host_threads(n, 8192), [&](int, int64_t r0, int64_t r1) {
+        std::vector<std::pair<int64_t, double>> row;
+        for (int64_t r = r0; r < r1; ++r) {
+            const int64_t old = perm[r];
+            row.clear();
+            for (int64_t q = a_ptr[old]; q < a_ptr[old + 1]; ++q) row.emplace_back(iperm[a_idx[q]], a_val[q]);
+            sort_row_stable(row);
+            int64_t at = o_ptr[r];
+            for (const auto &e : row) { o_idx[at] = e.first; o_val[at++] = e.second; }
+        }
+    });
+    } catch (const std::exception &) { dots_set_error("dots_csr_permute: out of host memory or threads"); return -1; }
     return 0;
 }

@@ -40,6 +40,18 @@ def time_basis(n_time: int):
     return Q, lam
 
 
+def _stable_argsort(keys, bound):
+    """``np.argsort(keys, kind="stable")`` for integer keys in [0, bound): numpy sorts 16-bit keys with a radix sort, so two
+    stable passes over the 16-bit halves (4x faster than its merge sort of 64-bit keys at 330k triangles)."""
+    keys = np.asarray(keys)
+    if bound > 1 << 32 or keys.size < 1 << 14:
+        return np.argsort(keys, kind="stable")
+    low = np.argsort((keys & 0xffff).astype(np.uint16), kind="stable")
+    if bound <= 1 << 16:
+        return low
+    return low[np.argsort((keys >> 16).astype(np.uint16)[low], kind="stable")]
+
+
 def _cut(nodes, lengths, step):
     """Work items (node, first output, n outputs <= step) covering ``lengths[i]`` outputs of ``nodes[i]``, node by node."""
     lengths = np.asarray(lengths, dtype=np.int64)
@@ -127,7 +139,7 @@ class Engine:
         self.sym = sym
         self.perm_v = sym.perm                                                          # new -> old
         tri_new = sym.iperm[tri_old]                                                    # (T,3) in new vertex ids
-        self.perm_f = np.argsort(tri_new.min(axis=1), kind="stable")                    # new -> old triangle
+        self.perm_f = _stable_argsort(tri_new.min(axis=1), V)                           # new -> old triangle
         tri_new = tri_new[self.perm_f]
         tm["ordering"] = time.perf_counter() - t0
         # ---- which sweep kernels, how many padded modes ---------------------------------------------------

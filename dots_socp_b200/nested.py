@@ -373,6 +373,26 @@ def front_maps_native(lib, sym: Symbolic, Kp: sp.csr_matrix):
     return a_pos, parent_pos
 
 
+def permuted_matrix(lib, sym: Symbolic, K: sp.csr_matrix) -> sp.csr_matrix:
+    """``K[perm][:, perm]`` with sorted column indices: by ``dots_csr_permute`` (csrc/host_order.cpp) when the library is
+    there, by scipy otherwise (the checker, tests/test_nested_host.py)."""
+    if lib is None:
+        Kp = K[sym.perm][:, sym.perm].tocsr()
+        Kp.sort_indices()
+        return Kp
+    from . import capi
+    K = K.tocsr()
+    i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+    a_ptr, a_idx, a_val = i64(K.indptr), i64(K.indices), np.ascontiguousarray(K.data, dtype=np.float64)
+    perm, iperm = i64(sym.perm), i64(sym.iperm)
+    o_ptr, o_idx, o_val = np.empty(sym.n + 1, np.int64), np.empty(a_idx.size, np.int64), np.empty(a_idx.size)
+    capi.check(lib.dots_csr_permute(sym.n, *(a.ctypes.data for a in (a_ptr, a_idx, a_val, perm, iperm, o_ptr, o_idx, o_val))),
+               "dots_csr_permute")
+    Kp = sp.csr_matrix((o_val, o_idx, o_ptr), shape=K.shape)
+    Kp.has_sorted_indices = True
+    return Kp
+
+
 def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shifts: np.ndarray, m_pad: int, device, lib,
                          stream_fn, stats: dict | None = None, front_nmax: int | None = None, use_library: bool = False):
     """Numeric factorisation on the GPU, level by level, with hand-written kernels only: small fronts by ``k_front_small``
@@ -386,8 +406,7 @@ def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shif
 
     n_modes = int(len(shifts))
     nmax = int(lib.dots_front_nmax()) if front_nmax is None else int(front_nmax)   # 0: every front through the library path
-    Kp = K[sym.perm][:, sym.perm].tocsr()
-    Kp.sort_indices()
+    Kp = permuted_matrix(lib, sym, K)
     a_pos, parent_pos = front_maps_native(lib, sym, Kp) if lib is not None else front_maps(sym, Kp)
     dev = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device=device)
     shifts_t = dev(shifts, np.float64)

@@ -333,6 +333,11 @@ int dots_front_maps(int64_t n_vert, int64_t n_nodes, const int64_t *s, const int
                     const int64_t *front_idx, const int64_t *upd_off, const int64_t *parent, const int64_t *a_ptr,
                     const int64_t *a_idx, int32_t *a_pos, int32_t *parent_pos);
 
+/* out = A[perm][:, perm] of a CSR matrix, ascending columns in every row (perm: new -> old vertex, iperm: old -> new; o_ptr [n+1],
+ * o_idx / o_val [nnz] caller-allocated): the permuted stiffness matrix the numeric assembly reads.  HOST pointers.       */
+int dots_csr_permute(int64_t n, const int64_t *a_ptr, const int64_t *a_idx, const double *a_val, const int64_t *perm,
+                     const int64_t *iperm, int64_t *o_ptr, int64_t *o_idx, double *o_val);
+
 /* ---- setup, host side: per-entry operand rows of the ring-streamed sweeps (sweep_mode 4).  HOST pointers.  For every
  * panel entry in streaming order (rows_fwd: row-major panels, rows_bwd: column-major copy) the row of Z = [hat | ywork]
  * the entry is multiplied with; bit 31 = last entry of its output.  s, b, off, front_off [n_nodes(+1)], panel_off

@@ -195,6 +195,63 @@ def test_native_ordering_on_open_and_higher_genus_surfaces():
         _same_symbolic(nested.analyse(v, K, leaf_size=12), nested.analyse_native(capi.load(), v, K, leaf_size=12))
 
 
+def test_threaded_host_analysis_does_not_depend_on_the_thread_count(monkeypatch):
+    """csrc/host_order.cpp runs the bisection of the two halves of a part, the boundary sets of a tree level and the
+    per-triangle / per-vertex passes of the mesh operators on DOTS_HOST_THREADS host threads once the mesh is large enough
+    (V = 40 962 here: 5 threads at most).  Ordering, front structure, areas, hat gradients, stiffness matrix and corner lists
+    must be the same bit for bit at every thread count, and the single-thread result is the numpy statement's."""
+    from dots_socp_b200 import capi
+    lib = capi.load()
+    geo, _ = synth.example("icosphere6")
+    v = np.ascontiguousarray(geo["vertices"], dtype=np.float64)
+    t = np.ascontiguousarray(geo["triangles"], dtype=np.int64)
+    results = {}
+    for threads in (1, 2, 5, 16):
+        monkeypatch.setenv("DOTS_HOST_THREADS", str(threads))
+        m = surface.mesh_operators_native(lib, v, t)
+        results[threads] = (m, nested.analyse_native(lib, v, m["K"], leaf_size=16))
+    m1, sym1 = results[1]
+    for threads, (m, sym) in results.items():
+        _same_symbolic(sym1, sym)
+        for key in ("area_f", "hat", "area_sum"):
+            assert np.array_equal(m1[key], m[key]), (threads, key)
+        assert all(np.array_equal(getattr(m1["K"], a), getattr(m["K"], a)) for a in ("indptr", "indices", "data")), threads
+        assert all(np.array_equal(a, b) for a, b in zip(m1["corners"], m["corners"])), threads
+    # the permuted matrix and the assembly index maps: threads over row / node ranges, same output
+    maps = {}
+    for threads in (1, 3, 16):
+        monkeypatch.setenv("DOTS_HOST_THREADS", str(threads))
+        Kp = nested.permuted_matrix(lib, sym1, m1["K"])
+        maps[threads] = (Kp, nested.front_maps_native(lib, sym1, Kp))
+    Kp_ref = nested.permuted_matrix(None, sym1, m1["K"])                       # scipy
+    for threads, (Kp, (a_pos, parent_pos)) in maps.items():
+        assert all(np.array_equal(getattr(Kp, a), getattr(Kp_ref, a)) for a in ("indptr", "indices", "data")), threads
+        assert np.array_equal(a_pos, maps[1][1][0]) and np.array_equal(parent_pos, maps[1][1][1]), threads
+    a_ref, p_ref = nested.front_maps(sym1, Kp_ref)
+    assert np.array_equal(a_ref, maps[1][1][0]) and np.array_equal(p_ref, maps[1][1][1])
+    K = surface.stiffness_matrix(v, t)
+    _same_symbolic(nested.analyse(v, K, leaf_size=16), sym1)
+    assert np.array_equal(m1["area_sum"], surface.incident_area_sum(v.shape[0], t, surface.triangle_areas(v, t)))
+    assert np.array_equal(m1["K"].indices, K.indices) and np.abs(m1["K"].data - K.data).max() <= 1e-14 * np.abs(K.data).max()
+
+
+@pytest.mark.parametrize("example,leaf", [("icosphere2", 8), ("plane8", 6), ("knot", 16)])
+def test_native_matrix_permutation_equals_scipy(example, leaf):
+    """dots_csr_permute against scipy's K[perm][:, perm] + sort_indices: same pattern, same values, sorted columns."""
+    from dots_socp_b200 import capi
+    geo, _ = synth.example(example)
+    K = surface.stiffness_matrix(geo["vertices"], geo["triangles"])
+    sym = nested.analyse(geo["vertices"], K, leaf_size=leaf)
+    got, ref = nested.permuted_matrix(capi.load(), sym, K), nested.permuted_matrix(None, sym, K)
+    assert all(np.array_equal(getattr(got, a), getattr(ref, a)) for a in ("indptr", "indices", "data"))
+    assert np.all(np.diff(got.indices)[np.setdiff1d(np.arange(got.nnz - 1), got.indptr[1:-1] - 1)] > 0)
+    bad = sym.perm.copy()
+    bad[0] = -1
+    with pytest.raises(capi.DotsError, match="perm"):
+        nested.permuted_matrix(capi.load(), sym._replace(perm=bad) if hasattr(sym, "_replace") else
+                               __import__("dataclasses").replace(sym, perm=bad), K)
+
+
 def test_native_ordering_rejects_bad_arguments():
     from dots_socp_b200 import capi
     geo, _ = synth.example("icosphere1")

@@ -76,3 +76,14 @@ def test_host_translation_of_checkpoints(geo):
     sol3 = dict(checkpoints=None)
     solver_mod._dot_checkpoints(sol3, geo, centred=False)
     assert "checkpoints" not in sol3
+
+
+@pytest.mark.parametrize("n,bound", [(100, 50), (1 << 14, 1 << 10), (40000, 1 << 16), (50000, 70000), (330000, 163842),
+                                     (20000, (1 << 32) + 5)])
+def test_triangle_renumbering_sort_is_numpys_stable_argsort(n, bound):
+    """Engine orders the triangles by their smallest new vertex id with two radix passes over 16-bit halves; the triangle
+    numbering (and with it every triangle-indexed array) must be exactly that of ``np.argsort(kind="stable")``."""
+    from dots_socp_b200.engine import _stable_argsort
+    keys = np.random.default_rng(n).integers(0, bound, n)
+    keys[::7] = keys[0]                                               # many ties: stability matters
+    assert np.array_equal(_stable_argsort(keys, bound), np.argsort(keys, kind="stable"))
