@@ -9,7 +9,7 @@
 //
 // Plain C++, no CUDA: geometric recursive bisection with vertex separators, then boundary sets by a post-order sweep.
 // The bisection of the two halves of a part and the per-triangle / per-vertex passes of the mesh operators run on a few
-// host threads (DOTS_HOST_THREADS, default: the hardware's, at most 16); the results do not depend on the thread count
+// host threads (DOTS_HOST_THREADS, default: the hardware's share of this rank, at most 16); the results do not depend on the thread count
 // (every sum keeps its order, the tree keeps its shape), which tests/test_nested_host.py checks bit for bit.
 #include <algorithm>
 #include <atomic>
@@ -50,7 +50,9 @@ namespace {
 // Host threads for a pass over `items` work items (at least `grain` items per thread).
 int host_threads(int64_t items, int64_t grain) {
     const char *e = std::getenv("DOTS_HOST_THREADS");                         // read per call: tests vary it within one process
-    const int want = e ? std::atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    const char *lw = std::getenv("LOCAL_WORLD_SIZE");                         // torchrun: the ranks of a node share its cores
+    const unsigned ranks = lw ? (unsigned)std::max(1, std::atoi(lw)) : 1u;
+    const int want = e ? std::atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency() / ranks));
     const int limit = std::max(1, std::min(want, 64));
     return (int)std::max<int64_t>(1, std::min<int64_t>(limit, items / std::max<int64_t>(grain, 1)));
 }
