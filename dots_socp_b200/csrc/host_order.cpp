@@ -603,39 +603,39 @@ extern "C" int dots_front_maps(int64_t n_vert, int64_t n_nodes, const int64_t *s
     }
     std::atomic<int64_t> failed{-1};                                       // a node whose boundary does not embed in its parent's front
     try {
-    parallel_ranges(n_nodes, host_threads(n_nodes, 512), [&](int, int64_t k0, int64_t k1) {
-    for (int64_t k = k0; k < k1; ++k) {
-        const int64_t *fi = front_idx + front_off[k];
-        const int64_t nf = s[k] + b[k];
-        for (int64_t r = off[k]; r < off[k] + s[k]; ++r) {
-            int64_t j = 0;
-            for (int64_t q = a_ptr[r]; q < a_ptr[r + 1]; ++q) {
-                const int64_t col = a_idx[q];
-                int32_t pos = -1;
-                if (col >= off[k]) {
-                    while (j < nf && fi[j] < col) ++j;
-                    if (j < nf && fi[j] == col) pos = (int32_t)j;
+        parallel_ranges(n_nodes, host_threads(n_nodes, 512), [&](int, int64_t k0, int64_t k1) {
+            for (int64_t k = k0; k < k1; ++k) {
+                const int64_t *fi = front_idx + front_off[k];
+                const int64_t nf = s[k] + b[k];
+                for (int64_t r = off[k]; r < off[k] + s[k]; ++r) {
+                    int64_t j = 0;
+                    for (int64_t q = a_ptr[r]; q < a_ptr[r + 1]; ++q) {
+                        const int64_t col = a_idx[q];
+                        int32_t pos = -1;
+                        if (col >= off[k]) {
+                            while (j < nf && fi[j] < col) ++j;
+                            if (j < nf && fi[j] == col) pos = (int32_t)j;
+                        }
+                        a_pos[q] = pos;
+                    }
                 }
-                a_pos[q] = pos;
+                const int64_t par = parent[k];
+                int32_t *pp = parent_pos + upd_off[k];
+                if (par < 0) {
+                    for (int64_t p = 0; p < b[k]; ++p) pp[p] = -1;
+                    continue;
+                }
+                const int64_t *pf = front_idx + front_off[par];
+                const int64_t npf = s[par] + b[par];
+                int64_t j = 0;
+                for (int64_t p = 0; p < b[k]; ++p) {
+                    const int64_t vtx = fi[s[k] + p];
+                    while (j < npf && pf[j] < vtx) ++j;
+                    if (j >= npf || pf[j] != vtx) { failed.store(k); return; }
+                    pp[p] = (int32_t)j;
+                }
             }
-        }
-        const int64_t par = parent[k];
-        int32_t *pp = parent_pos + upd_off[k];
-        if (par < 0) {
-            for (int64_t p = 0; p < b[k]; ++p) pp[p] = -1;
-            continue;
-        }
-        const int64_t *pf = front_idx + front_off[par];
-        const int64_t npf = s[par] + b[par];
-        int64_t j = 0;
-        for (int64_t p = 0; p < b[k]; ++p) {
-            const int64_t vtx = fi[s[k] + p];
-            while (j < npf && pf[j] < vtx) ++j;
-            if (j >= npf || pf[j] != vtx) { failed.store(k); return; }
-            pp[p] = (int32_t)j;
-        }
-    }
-    });
+        });
     } catch (const std::exception &) { dots_set_error("dots_front_maps: out of host memory or threads"); return -1; }
     if (failed.load() >= 0) {
         dots_set_error("dots_front_maps: boundary of node %lld does not embed in its parent's front", (long long)failed.load());
@@ -656,17 +656,17 @@ extern "C" int dots_csr_permute(int64_t n, const int64_t *a_ptr, const int64_t *
         o_ptr[r + 1] = o_ptr[r] + (a_ptr[perm[r] + 1] - a_ptr[perm[r]]);
     }
     try {
-    parallel_ranges(n, host_threads(n, 8192), [&](int, int64_t r0, int64_t r1) {
-        std::vector<std::pair<int64_t, double>> row;
-        for (int64_t r = r0; r < r1; ++r) {
-            const int64_t old = perm[r];
-            row.clear();
-            for (int64_t q = a_ptr[old]; q < a_ptr[old + 1]; ++q) row.emplace_back(iperm[a_idx[q]], a_val[q]);
-            sort_row_stable(row);
-            int64_t at = o_ptr[r];
-            for (const auto &e : row) { o_idx[at] = e.first; o_val[at++] = e.second; }
-        }
-    });
+        parallel_ranges(n, host_threads(n, 8192), [&](int, int64_t r0, int64_t r1) {
+            std::vector<std::pair<int64_t, double>> row;
+            for (int64_t r = r0; r < r1; ++r) {
+                const int64_t old = perm[r];
+                row.clear();
+                for (int64_t q = a_ptr[old]; q < a_ptr[old + 1]; ++q) row.emplace_back(iperm[a_idx[q]], a_val[q]);
+                sort_row_stable(row);
+                int64_t at = o_ptr[r];
+                for (const auto &e : row) { o_idx[at] = e.first; o_val[at++] = e.second; }
+            }
+        });
     } catch (const std::exception &) { dots_set_error("dots_csr_permute: out of host memory or threads"); return -1; }
     return 0;
 }
