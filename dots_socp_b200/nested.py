@@ -423,6 +423,11 @@ def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shif
     u_view = {}                                           # node -> (b, b, m_pad) view of its update matrix
     level_buf = {}
     levels = level_schedule(sym)
+    # One pinned snapshot of the pointer table per level: a pageable copy of this size (> 64 KB) blocks the host until the
+    # stream has drained, which serialised the enqueue of a level with the factorisation of the one before (measured with
+    # tools/setup_levels.py: 0.19 s of enqueue for 0.185 s of kernels, so nothing of the caller's host planning overlapped).
+    u_ptr_stage = (torch.zeros((len(levels), sym.n_nodes), dtype=torch.int64).pin_memory()
+                   if torch.device(device).type == "cuda" else None)
     last_use = {}
     for lv, nodes in enumerate(levels):
         par = sym.parent[nodes]
@@ -514,7 +519,11 @@ def factor_hybrid_device(sym: Symbolic, K: sp.csr_matrix, mass: np.ndarray, shif
             for nd, o0, bb in zip(nodes, offs[:-1], b_l):
                 if bb:
                     u_view[int(nd)] = buf[int(o0):int(o0 + bb * bb)].view(int(bb), int(bb), m_pad)
-        u_ptr_dev.copy_(torch.from_numpy(u_ptr_host))
+        if u_ptr_stage is not None:
+            u_ptr_stage[lv].copy_(torch.from_numpy(u_ptr_host))
+            u_ptr_dev.copy_(u_ptr_stage[lv], non_blocking=True)
+        else:
+            u_ptr_dev.copy_(torch.from_numpy(u_ptr_host))
         nfront = sym.s[nodes] + sym.b[nodes]
         small = nodes[nfront <= nmax]
         large = nodes[nfront > nmax]
