@@ -21,6 +21,7 @@
 #include <memory>
 #include <new>
 #include <numeric>
+#include <system_error>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -78,10 +79,14 @@ void parallel_ranges(int64_t n, int n_threads, F fn) {
     if (n_threads <= 1) { fn(0, (int64_t)0, n); return; }
     std::vector<std::thread> pool;
     std::vector<std::exception_ptr> err((size_t)n_threads);
-    for (int t = 0; t < n_threads; ++t)
-        pool.emplace_back([&, t] {
-            try { fn(t, n * t / n_threads, n * (t + 1) / n_threads); } catch (...) { err[t] = std::current_exception(); }
-        });
+    auto work = [&](int t) {
+        try { fn(t, n * t / n_threads, n * (t + 1) / n_threads); } catch (...) { err[t] = std::current_exception(); }
+    };
+    pool.reserve((size_t)n_threads);
+    for (int t = 1; t < n_threads; ++t) {
+        try { pool.emplace_back(work, t); } catch (...) { work(t); }        // no thread to be had: this range runs here
+    }
+    work(0);
     for (auto &th : pool) th.join();
     for (auto &e : err)
         if (e) std::rethrow_exception(e);
@@ -187,13 +192,15 @@ void dissect_rec(int64_t n, const double *xyz, const int64_t *indptr, const int6
     std::exception_ptr err;
     const int b_left = budget / 2;
     std::thread other;
-    if (!left.empty())
-        other = std::thread([&] {
-            try {
-                Bisector mine(n, xyz, indptr, indices);
-                dissect_rec(n, xyz, indptr, indices, leaf_size, b_left, mine, std::move(left), sub[0]);
-            } catch (...) { err = std::current_exception(); }
-        });
+    auto do_left = [&] {
+        try {
+            Bisector mine(n, xyz, indptr, indices);
+            dissect_rec(n, xyz, indptr, indices, leaf_size, b_left, mine, std::move(left), sub[0]);
+        } catch (...) { err = std::current_exception(); }
+    };
+    if (!left.empty()) {
+        try { other = std::thread(do_left); } catch (const std::system_error &) { do_left(); }   // no thread to be had: inline
+    }
     try {
         if (!right.empty()) dissect_rec(n, xyz, indptr, indices, leaf_size, budget - b_left, bis, std::move(right), sub[1]);
     } catch (...) {
